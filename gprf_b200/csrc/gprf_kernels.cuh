@@ -1,0 +1,704 @@
+// Device kernels of the GPRF llgrad path (sm_100a).
+//
+// Per evaluation every *unit* (a block, or an edge's stacked pair of blocks;
+// gprf.py:299-330) goes through the same pipeline.  With s points in the unit,
+// sp = s rounded up to 64, nt = sp/64, yr = dy rounded up to 64:
+//
+//   working matrix M : (sp + yr) x sp doubles, row major, in HBM
+//     rows [0,sp)      lower triangle: K -> L -> K^-1 ; upper triangle: U = L^-T
+//     rows [sp,sp+yr)  Y^T -> Z^T = (L^-1 Y)^T          ("augmented rows")
+//   D : per diagonal tile, W_kk = L_kk^-1 and U_kk = W_kk^T (64x64 each)
+//
+//   prep            gather x rows, Y^T rows                       (gprf.py:299-330)
+//   potrf_diag(k)   C_kk = K_kk - sum_j L_kj L_kj^T ; L_kk, W_kk   (jitchol, gpy_linalg.py:77-97)
+//   potrf_panel(k)  L_ik = (K_ik - sum_j L_ij L_kj^T) W_kk^T       (dpotrf; also forward solve of dpotrs)
+//   trtri(d)        U_{k,k+d} = -(sum_j U_kj L_ij^T) W_ii^T        (dpotri part 1)
+//   lauum           K^-1_ij = sum_m U_im U_jm^T ; Alpha_i = sum_m U_im Z_m   (dpotri part 2, dpotrs back solve)
+//   grad            G_ij = Alpha_i Alpha_j^T - dy K^-1_ij, contracted in registers with
+//                   dk/dx and dk/dtheta recomputed from x (gprf.py:547-584); dK never stored
+//   unit_finalize   ll_u, unit gradX rows, unit grad theta          (gprf.py:542-544)
+//   combine         weighted sums over units                        (gprf.py:245-291)
+//
+// K is generated from x inside the potrf epilogues, fused with the noise /
+// jitter diagonal (gprf.py:333-343) - there is no separate kernel-matrix pass.
+// Padding rows/cols behave as an identity block, so tile kernels need no edge
+// handling and the padded problem has the same logdet / inverse / Alpha.
+#pragma once
+#include "covfn.cuh"
+#include "tile_gemm.cuh"
+
+namespace gprf {
+
+constexpr int PART_STRIDE = 392;   // per tile task: row sums 64x3, col sums 64x3, theta 5 (+pad)
+constexpr int PART_COL = 192;
+constexpr int PART_TH = 384;
+
+struct UnitDesc {
+  int s, ni, nt, sp;
+  int a_start, b_start;       // offsets of the two blocks' rows in perm
+  int active, pad_;
+  long long m_off, d_off, al_off, xs_off, part_off, ld_off, gx_off;
+  double weight;
+};
+
+struct EvalParams {
+  const UnitDesc* units;
+  const int* ulist;           // active unit list for this launch
+  double* arena;
+  const double* X;            // n x dx
+  const double* Y;            // n x dy
+  const long long* perm;
+  const double* jitter;       // per unit
+  int* info;                  // per unit: 0 ok, >0 = 1 + first failing row
+  int* nfail;
+  int dx, dy, yr, nya;
+  CovParams cp;
+};
+
+struct TileRef {
+  const double* p;
+  long long ld;
+};
+
+__device__ __forceinline__ long long unit_point(const UnitDesc& u, const long long* perm, int p) {
+  return p < u.ni ? perm[u.a_start + p] : perm[u.b_start + (p - u.ni)];
+}
+
+__device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
+
+__device__ __forceinline__ void tri_decode(int x, int& i, int& j) {
+  i = (int)((sqrtf(8.0f * (float)x + 1.0f) - 1.0f) * 0.5f);
+  while (tri(i + 1) <= x) ++i;
+  while (tri(i) > x) --i;
+  j = x - tri(i);
+}
+
+// gemm with per-tile leading dimensions (tile sources may live in M or in D)
+template <class FA, class FB>
+__device__ __forceinline__ void gemm_nt_ref(Acc& acc, int nk, FA tileA, FB tileB, double* pipe) {
+  constexpr int CPT = T / KC;
+  const int nc = nk * CPT;
+  if (nc == 0) return;
+  double* sA[2] = {pipe, pipe + 2 * STAGE_DOUBLES};
+  double* sB[2] = {pipe + STAGE_DOUBLES, pipe + 3 * STAGE_DOUBLES};
+  {
+    TileRef a = tileA(0), b = tileB(0);
+    stage_chunk(sA[0], a.p, a.ld);
+    stage_chunk(sB[0], b.p, b.ld);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nc; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nc) {
+      const int j = (c + 1) / CPT, ko = ((c + 1) % CPT) * KC;
+      TileRef a = tileA(j), b = tileB(j);
+      stage_chunk(sA[cur ^ 1], a.p + ko, a.ld);
+      stage_chunk(sB[cur ^ 1], b.p + ko, b.ld);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    mma_chunk(acc, sA[cur], sB[cur]);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// prep: gather x rows and Y^T rows of each unit (gprf.py:299-330)
+// grid (nt_max, nlist), 128 threads
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS) k_prep(EvalParams P) {
+  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  const int i = blockIdx.x;
+  if (i >= u.nt) return;
+  __shared__ double sY[T][T + 1];
+  __shared__ long long sidx[T];
+  const int tid = threadIdx.x;
+  double* M = P.arena + u.m_off;
+  double* xs = P.arena + u.xs_off;
+  if (tid < T) {
+    int p = i * T + tid;
+    long long idx = -1;
+    if (p < u.s) idx = unit_point(u, P.perm, p);
+    sidx[tid] = idx;
+#pragma unroll
+    for (int d = 0; d < MAX_DX + 1; ++d)
+      xs[(long long)p * 4 + d] = (idx >= 0 && d < P.dx) ? P.X[idx * P.dx + d] : 0.0;
+  }
+  __syncthreads();
+  for (int a = 0; a < P.nya; ++a) {
+    // load 64 points x 64 outputs, coalesced along the output index
+    for (int e = tid; e < T * T; e += NTHREADS) {
+      int r = e / T, c = e % T;
+      int cc = a * T + c;
+      long long idx = sidx[r];
+      sY[r][c] = (idx >= 0 && cc < P.dy) ? P.Y[idx * P.dy + cc] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < T * T; e += NTHREADS) {
+      int c = e / T, r = e % T;
+      M[(long long)(u.sp + a * T + c) * u.sp + i * T + r] = sY[r][c];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// potrf_diag(k): one CTA per unit.  grid (1, nlist)
+// ---------------------------------------------------------------------------
+template <int DFN, int WFN>
+__global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
+  const int uid = P.ulist[blockIdx.y];
+  const UnitDesc u = P.units[uid];
+  if (k >= u.nt) return;
+  extern __shared__ __align__(16) double smem[];
+  double* pipe = smem;
+  __shared__ double sx[T][4];
+  __shared__ int sfail;
+  const int tid = threadIdx.x;
+  double* M = P.arena + u.m_off;
+  const long long ld = u.sp;
+  const double* xs = P.arena + u.xs_off;
+  if (tid < T) {
+#pragma unroll
+    for (int d = 0; d < 4; ++d) sx[tid][d] = xs[(long long)(k * T + tid) * 4 + d];
+  }
+  if (tid == 0) sfail = 0;
+
+  Acc acc;
+  acc_zero(acc);
+  const double* rowk = M + (long long)k * T * ld;
+  auto tA = [&](int j) { return TileRef{rowk + j * T, ld}; };
+  gemm_nt_ref(acc, k, tA, tA, pipe);
+  __syncthreads();
+
+  // C = K_kk - acc  -> scalar scratch tile S (stride SQLD) in the pipe buffers
+  double* S = pipe;
+  double* W = pipe + T * SQLD;
+  const double diag_add = P.cp.nv + P.jitter[uid];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int r = acc_row(m);
+    const int p = k * T + r;
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = acc_col(n) + e;
+        const int q = k * T + c;
+        double kv;
+        if (p < u.s && q < u.s) {
+          kv = cov_value<DFN, WFN>(sx[r], sx[c], P.cp);
+          if (r == c) kv = P.cp.s2 + diag_add;
+        } else {
+          kv = (r == c) ? 1.0 : 0.0;
+        }
+        S[r * SQLD + c] = kv - acc.c[m][n][e];
+      }
+  }
+  __syncthreads();
+
+  // unblocked right-looking Cholesky of the 64x64 tile (lower)
+  for (int c = 0; c < T; ++c) {
+    const double piv = S[c * SQLD + c];
+    if (!(piv > 0.0)) {
+      if (tid == 0 && sfail == 0) sfail = k * T + c + 1;
+    }
+    const double dsq = sqrt(piv);
+    __syncthreads();
+    if (tid == c) S[c * SQLD + c] = dsq;
+    if (tid > c && tid < T) S[tid * SQLD + c] /= dsq;
+    __syncthreads();
+    {
+      const int r = tid & (T - 1);
+      if (r > c) {
+        const double lrc = S[r * SQLD + c];
+        for (int cc = c + 1 + (tid >> 6); cc <= r; cc += 2) S[r * SQLD + cc] -= lrc * S[cc * SQLD + c];
+      }
+    }
+    __syncthreads();
+  }
+
+  // W = L^-1: two lanes per column, forward substitution down the rows
+  {
+    const int c = tid >> 1, h = tid & 1;
+    for (int r = 0; r < T; ++r) {
+      double part = 0.0;
+      if (r > c)
+        for (int m = c + h; m < r; m += 2) part += S[r * SQLD + m] * W[m * SQLD + c];
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      if (h == 0) {
+        double v = 0.0;
+        if (r == c) v = 1.0 / S[r * SQLD + r];
+        else if (r > c) v = -part / S[r * SQLD + r];
+        W[r * SQLD + c] = v;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // outputs: L_kk (upper part zero), W_kk, U_kk = W_kk^T, logdet partial, status
+  double* Lout = M + (long long)k * T * ld + k * T;
+  double* Wd = P.arena + u.d_off + (long long)k * T * T;
+  double* Ud = P.arena + u.d_off + (long long)(u.nt + k) * T * T;
+  for (int e = tid; e < T * T; e += NTHREADS) {
+    int r = e / T, c = e % T;
+    Lout[(long long)r * ld + c] = (c <= r) ? S[r * SQLD + c] : 0.0;
+    Wd[e] = W[r * SQLD + c];
+    Ud[e] = W[c * SQLD + r];
+  }
+  if (tid == 0) {
+    double lsum = 0.0;
+    for (int r = 0; r < T; ++r) lsum += log(S[r * SQLD + r]);
+    (P.arena + u.ld_off)[k] = lsum;
+    if (sfail != 0 && atomicCAS(&P.info[uid], 0, sfail) == 0) atomicAdd(P.nfail, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// potrf_panel(k): grid (ntmax - k - 1 + nya, nlist).  Row tiles below the
+// diagonal and the augmented Y^T row tiles.
+// ---------------------------------------------------------------------------
+template <int DFN, int WFN>
+__global__ void __launch_bounds__(NTHREADS) k_potrf_panel(EvalParams P, int k) {
+  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  if (k >= u.nt) return;
+  const int below = u.nt - k - 1;
+  int it;           // row-tile index in M (aug tiles follow the square)
+  bool aug = false;
+  if ((int)blockIdx.x < below) {
+    it = k + 1 + blockIdx.x;
+  } else {
+    int a = blockIdx.x - below;
+    if (a >= P.nya) return;
+    it = u.nt + a;
+    aug = true;
+  }
+  extern __shared__ __align__(16) double smem[];
+  double* pipe = smem;
+  __shared__ double sxr[T][4];
+  __shared__ double sxc[T][4];
+  const int tid = threadIdx.x;
+  double* M = P.arena + u.m_off;
+  const long long ld = u.sp;
+  if (!aug && tid < T) {
+    const double* xs = P.arena + u.xs_off;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      sxr[tid][d] = xs[(long long)(it * T + tid) * 4 + d];
+      sxc[tid][d] = xs[(long long)(k * T + tid) * 4 + d];
+    }
+  }
+  Acc acc;
+  acc_zero(acc);
+  const double* rowi = M + (long long)it * T * ld;
+  const double* rowk = M + (long long)k * T * ld;
+  auto tA = [&](int j) { return TileRef{rowi + j * T, ld}; };
+  auto tB = [&](int j) { return TileRef{rowk + j * T, ld}; };
+  gemm_nt_ref(acc, k, tA, tB, pipe);
+  __syncthreads();
+
+  // C = C0 - acc
+  double* out = M + (long long)it * T * ld + k * T;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int r = acc_row(m);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int c = acc_col(n);
+      double c0, c1;
+      if (aug) {
+        double2 v = *reinterpret_cast<const double2*>(out + (long long)r * ld + c);
+        c0 = v.x;
+        c1 = v.y;
+      } else {
+        const int p = it * T + r;
+        c0 = (p < u.s && k * T + c < u.s) ? cov_value<DFN, WFN>(sxr[r], sxc[c], P.cp) : 0.0;
+        c1 = (p < u.s && k * T + c + 1 < u.s) ? cov_value<DFN, WFN>(sxr[r], sxc[c + 1], P.cp) : 0.0;
+      }
+      acc.c[m][n][0] = c0 - acc.c[m][n][0];
+      acc.c[m][n][1] = c1 - acc.c[m][n][1];
+    }
+  }
+  // L_ik = C * W_kk^T
+  const double* Wd = P.arena + u.d_off + (long long)k * T * T;
+  stage_full(pipe, Wd, T);
+  Acc res;
+  mul_acc_by_wt(res, acc, pipe, 1.0);
+  acc_store(res, out, ld);
+}
+
+// ---------------------------------------------------------------------------
+// trtri(d): U_{k,k+d} = -(sum_{j=k}^{i-1} U_kj L_ij^T) W_ii^T.  grid (ntmax - d, nlist)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS) k_trtri(EvalParams P, int d) {
+  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  const int k = blockIdx.x;
+  const int i = k + d;
+  if (i >= u.nt) return;
+  extern __shared__ __align__(16) double smem[];
+  double* pipe = smem;
+  double* M = P.arena + u.m_off;
+  const long long ld = u.sp;
+  const double* Ud = P.arena + u.d_off + (long long)(u.nt + k) * T * T;
+  const double* rowk = M + (long long)k * T * ld;
+  const double* rowi = M + (long long)i * T * ld;
+  Acc acc;
+  acc_zero(acc);
+  auto tA = [&](int jj) {
+    return jj == 0 ? TileRef{Ud, T} : TileRef{rowk + (long long)(k + jj) * T, ld};
+  };
+  auto tB = [&](int jj) { return TileRef{rowi + (long long)(k + jj) * T, ld}; };
+  gemm_nt_ref(acc, d, tA, tB, pipe);
+  __syncthreads();
+  const double* Wd = P.arena + u.d_off + (long long)i * T * T;
+  stage_full(pipe, Wd, T);
+  Acc res;
+  mul_acc_by_wt(res, acc, pipe, -1.0);
+  acc_store(res, M + (long long)k * T * ld + (long long)i * T, ld);
+}
+
+// ---------------------------------------------------------------------------
+// lauum: K^-1 lower tiles and Alpha.  grid (ntri_max + ntmax*nya, nlist)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS) k_lauum(EvalParams P, int ntri_max) {
+  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  int i, j;
+  bool aug = false;
+  if ((int)blockIdx.x < ntri_max) {
+    if ((int)blockIdx.x >= tri(u.nt)) return;
+    tri_decode(blockIdx.x, i, j);
+  } else {
+    int idx = blockIdx.x - ntri_max;
+    i = idx / P.nya;
+    j = u.nt + idx % P.nya;
+    if (i >= u.nt) return;
+    aug = true;
+  }
+  extern __shared__ __align__(16) double smem[];
+  double* pipe = smem;
+  double* M = P.arena + u.m_off;
+  const long long ld = u.sp;
+  const double* Udi = P.arena + u.d_off + (long long)(u.nt + i) * T * T;
+  const double* rowi = M + (long long)i * T * ld;
+  const double* rowj = M + (long long)j * T * ld;
+  Acc acc;
+  acc_zero(acc);
+  auto tA = [&](int jj) {
+    return jj == 0 ? TileRef{Udi, T} : TileRef{rowi + (long long)(i + jj) * T, ld};
+  };
+  auto tB = [&](int jj) {
+    return (j == i && jj == 0) ? TileRef{Udi, T} : TileRef{rowj + (long long)(i + jj) * T, ld};
+  };
+  gemm_nt_ref(acc, u.nt - i, tA, tB, pipe);
+  if (aug) {
+    double* Al = P.arena + u.al_off;
+    acc_store(acc, Al + (long long)i * T * P.yr + (long long)(j - u.nt) * T, P.yr);
+  } else {
+    acc_store(acc, M + (long long)i * T * ld + (long long)j * T, ld);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// grad: G tile in registers, contracted with dk/dx, dk/dtheta.  grid (ntri_max, nlist)
+// ---------------------------------------------------------------------------
+template <int DFN, int WFN>
+__global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
+  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  if ((int)blockIdx.x >= tri(u.nt)) return;
+  int i, j;
+  tri_decode(blockIdx.x, i, j);
+  extern __shared__ __align__(16) double smem[];
+  double* pipe = smem;
+  __shared__ double sxi[T][4];
+  __shared__ double sxj[T][4];
+  __shared__ double scol[4][T][3];
+  __shared__ double sth[4][MAX_NCOV];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* M = P.arena + u.m_off;
+  const long long ld = u.sp;
+  const double* Al = P.arena + u.al_off;
+  if (tid < T) {
+    const double* xs = P.arena + u.xs_off;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      sxi[tid][d] = xs[(long long)(i * T + tid) * 4 + d];
+      sxj[tid][d] = xs[(long long)(j * T + tid) * 4 + d];
+    }
+  }
+  Acc acc;
+  acc_zero(acc);
+  const double* ai = Al + (long long)i * T * P.yr;
+  const double* aj = Al + (long long)j * T * P.yr;
+  auto tA = [&](int c) { return TileRef{ai + c * T, (long long)P.yr}; };
+  auto tB = [&](int c) { return TileRef{aj + c * T, (long long)P.yr}; };
+  gemm_nt_ref(acc, P.nya, tA, tB, pipe);
+  __syncthreads();
+
+  const double* Kt = M + (long long)i * T * ld + (long long)j * T;
+  const double dyd = (double)P.dy;
+  const double inv_s2 = 1.0 / P.cp.s2;
+  double rs[2][3];
+  double th[MAX_NCOV];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) rs[m][0] = rs[m][1] = rs[m][2] = 0.0;
+#pragma unroll
+  for (int t = 0; t < MAX_NCOV; ++t) th[t] = 0.0;
+
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    double2 kin[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+      kin[m] = *reinterpret_cast<const double2*>(Kt + (long long)acc_row(m) * ld + acc_col(n));
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = acc_col(n) + e;
+      const int q = j * T + c;
+      double cs[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int r = acc_row(m);
+        const int p = i * T + r;
+        const double G = acc.c[m][n][e] - dyd * (e == 0 ? kin[m].x : kin[m].y);
+        if (p < u.s && q < u.s) {
+          if (i != j || q < p) {
+            double kv, gp[3], gq[3], gl[3];
+            cov_grad<DFN, WFN>(sxi[r], sxj[c], P.cp, kv, gp, gq, gl);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              rs[m][d] += G * gp[d];
+              cs[d] += G * gq[d];
+              th[2 + d] += G * gl[d];
+            }
+            th[1] += G * kv * inv_s2;
+          } else if (q == p) {
+            th[0] += 0.5 * G;
+            th[1] += 0.5 * G;
+          }
+        }
+      }
+      // column sums: reduce over the 8 row-lanes (g) of the warp
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double v = cs[d];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if ((lane >> 2) == 0) scol[warp][c][d] = v;
+      }
+    }
+  }
+  double* part = P.arena + u.part_off + (long long)blockIdx.x * PART_STRIDE;
+  // row sums: reduce over the 4 lanes of a quad; each row is owned by one warp
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double v = rs[m][d];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if ((lane & 3) == 0) part[acc_row(m) * 3 + d] = v;
+    }
+#pragma unroll
+  for (int t = 0; t < MAX_NCOV; ++t) {
+    double v = th[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sth[warp][t] = v;
+  }
+  __syncthreads();
+  for (int e = tid; e < T * 3; e += NTHREADS) {
+    int c = e / 3, d = e % 3;
+    part[PART_COL + e] = ((scol[0][c][d] + scol[1][c][d]) + scol[2][c][d]) + scol[3][c][d];
+  }
+  if (tid < MAX_NCOV) part[PART_TH + tid] = ((sth[0][tid] + sth[1][tid]) + sth[2][tid]) + sth[3][tid];
+}
+
+// ---------------------------------------------------------------------------
+// unit_finalize: grid (nlist), 128 threads.  ll_u (gprf.py:542-544), unit gradX
+// rows, unit grad theta; everything summed in a fixed order.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS) k_unit_finalize(EvalParams P, double* ll_u, double* gth_u,
+                                                          int want_grad) {
+  const int uid = P.ulist[blockIdx.x];
+  const UnitDesc u = P.units[uid];
+  const int tid = threadIdx.x;
+  __shared__ double red[NTHREADS];
+  const double* M = P.arena + u.m_off;
+  // quadratic term ||Z||^2 over the augmented rows
+  double q = 0.0;
+  const long long tot = (long long)P.yr * u.sp;
+  const double* Z = M + (long long)u.sp * u.sp;
+  for (long long e = tid; e < tot; e += NTHREADS) {
+    double z = Z[e];
+    q += z * z;
+  }
+  red[tid] = q;
+  __syncthreads();
+  for (int o = NTHREADS / 2; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double lsum = 0.0;
+    const double* ldp = P.arena + u.ld_off;
+    for (int k = 0; k < u.nt; ++k) lsum += ldp[k];
+    const double logdet = 2.0 * lsum;
+    ll_u[uid] = -0.5 * red[0] - 0.5 * P.dy * logdet - 0.5 * P.dy * (double)u.s * 1.8378770664093454836;
+  }
+  if (!want_grad) return;
+  const double* part = P.arena + u.part_off;
+  double* gx = P.arena + u.gx_off;
+  for (int p = tid; p < u.s; p += NTHREADS) {
+    const int ip = p / T, r = p % T;
+    double g[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j <= ip; ++j) {
+      const double* pr = part + (long long)(tri(ip) + j) * PART_STRIDE + r * 3;
+      g[0] += pr[0]; g[1] += pr[1]; g[2] += pr[2];
+    }
+    for (int i = ip; i < u.nt; ++i) {
+      const double* pc = part + (long long)(tri(i) + ip) * PART_STRIDE + PART_COL + r * 3;
+      g[0] += pc[0]; g[1] += pc[1]; g[2] += pc[2];
+    }
+    gx[(long long)p * 3 + 0] = g[0];
+    gx[(long long)p * 3 + 1] = g[1];
+    gx[(long long)p * 3 + 2] = g[2];
+  }
+  if (tid < MAX_NCOV) {
+    double v = 0.0;
+    const int ntile = tri(u.nt);
+    for (int t = 0; t < ntile; ++t) v += part[(long long)t * PART_STRIDE + PART_TH + tid];
+    gth_u[(long long)uid * MAX_NCOV + tid] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// combine (gprf.py:245-291)
+// ---------------------------------------------------------------------------
+struct CombineParams {
+  const UnitDesc* units;
+  const double* arena;
+  const long long* perm;
+  const int* pos_block;       // perm position -> block id
+  const long long* block_ptr; // B+1
+  const int* adj_ptr;         // B+1   CSR of incident edges per block
+  const int* adj_edge;        // edge id
+  const int* adj_side;        // 0: block is edge's i (rows first), 1: block is j
+  int B, dx;
+  long long plen;
+};
+
+// one thread per perm position; deterministic gather over the units containing the point
+__global__ void k_combine_gradx(CombineParams C, double* gradX) {
+  const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= C.plen) return;
+  const int b = C.pos_block[pos];
+  const int lp = (int)(pos - C.block_ptr[b]);
+  double g[3] = {0.0, 0.0, 0.0};
+  {
+    const UnitDesc u = C.units[b];
+    if (u.active && u.s > 0) {
+      const double* gx = C.arena + u.gx_off + (long long)lp * 3;
+      g[0] += u.weight * gx[0]; g[1] += u.weight * gx[1]; g[2] += u.weight * gx[2];
+    }
+  }
+  for (int a = C.adj_ptr[b]; a < C.adj_ptr[b + 1]; ++a) {
+    const UnitDesc u = C.units[C.B + C.adj_edge[a]];
+    if (!u.active || u.s == 0) continue;
+    const int l = lp + (C.adj_side[a] ? u.ni : 0);
+    const double* gx = C.arena + u.gx_off + (long long)l * 3;
+    g[0] += u.weight * gx[0]; g[1] += u.weight * gx[1]; g[2] += u.weight * gx[2];
+  }
+  const long long n = C.perm[pos];
+  for (int d = 0; d < C.dx; ++d) gradX[n * C.dx + d] = g[d];
+}
+
+// single CTA: out[0] = sum_u w_u ll_u ; out[1+t] = sum_u w_u gth_u[t]
+__global__ void k_combine_scalars(const UnitDesc* units, int U, const double* ll_u, const double* gth_u,
+                                  int want_cov, double* out) {
+  __shared__ double red[256][1 + MAX_NCOV];
+  const int tid = threadIdx.x;
+  double v[1 + MAX_NCOV];
+#pragma unroll
+  for (int t = 0; t < 1 + MAX_NCOV; ++t) v[t] = 0.0;
+  for (int uix = tid; uix < U; uix += 256) {
+    const UnitDesc u = units[uix];
+    if (!u.active || u.s == 0) continue;
+    v[0] += u.weight * ll_u[uix];
+    if (want_cov)
+#pragma unroll
+      for (int t = 0; t < MAX_NCOV; ++t) v[1 + t] += u.weight * gth_u[(long long)uix * MAX_NCOV + t];
+  }
+#pragma unroll
+  for (int t = 0; t < 1 + MAX_NCOV; ++t) red[tid][t] = v[t];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o)
+#pragma unroll
+      for (int t = 0; t < 1 + MAX_NCOV; ++t) red[tid][t] += red[tid + o][t];
+    __syncthreads();
+  }
+  if (tid < 1 + MAX_NCOV) out[tid] = red[0][tid];
+}
+
+// ---------------------------------------------------------------------------
+// auxiliary kernels: GPRF.kernel (gprf.py:333-343), compute_neighbors (gprf.py:119-150)
+// ---------------------------------------------------------------------------
+template <int DFN, int WFN>
+__global__ void k_kernel_matrix(const double* X1, long long n1, const double* X2, long long n2, int dx,
+                                CovParams cp, int add_noise, double* K) {
+  const long long tot = n1 * n2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / n2, q = e % n2;
+    double xp[4] = {0, 0, 0, 0}, xq[4] = {0, 0, 0, 0};
+    for (int d = 0; d < dx; ++d) {
+      xp[d] = X1[p * dx + d];
+      xq[d] = X2[q * dx + d];
+    }
+    double kv = cov_value<DFN, WFN>(xp, xq, cp);
+    if (add_noise && p == q) kv += cp.nv;
+    K[e] = kv;
+  }
+}
+
+// one CTA per ordered block pair index (i*B + j), j < i
+template <int DFN, int WFN>
+__global__ void k_block_maxk(const double* X, int dx, const long long* perm, const long long* block_ptr, int B,
+                             CovParams cp, double* maxk) {
+  const int i = blockIdx.x / B, j = blockIdx.x % B;
+  if (j >= i) {
+    if (threadIdx.x == 0 && i == j) maxk[(long long)i * B + i] = 1.0;
+    return;
+  }
+  const long long ai = block_ptr[i], ni = block_ptr[i + 1] - ai;
+  const long long aj = block_ptr[j], nj = block_ptr[j + 1] - aj;
+  double best = -1.0;   // np.max over an empty block pair is never taken (reference would raise)
+  for (long long e = threadIdx.x; e < ni * nj; e += blockDim.x) {
+    const long long p = perm[ai + e / nj], q = perm[aj + e % nj];
+    double xp[4] = {0, 0, 0, 0}, xq[4] = {0, 0, 0, 0};
+    for (int d = 0; d < dx; ++d) {
+      xp[d] = X[p * dx + d];
+      xq[d] = X[q * dx + d];
+    }
+    double kv = fabs(cov_value<DFN, WFN>(xp, xq, cp)) / cp.s2;
+    best = fmax(best, kv);
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = best;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    maxk[(long long)i * B + j] = red[0];
+    maxk[(long long)j * B + i] = red[0];
+  }
+}
+
+}  // namespace gprf

@@ -1,0 +1,604 @@
+// Host side of libgprf_b200.so: device context, per-evaluation launch plan and
+// the C-ABI declared in include/gprf_b200.h.  No torch types cross this
+// boundary; PyTorch (when used at all) only lends device pointers and a stream.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gprf_b200.h"
+#include "gprf_kernels.cuh"
+
+using namespace gprf;
+
+#define CUDA_OK(call)                                                                     \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      char buf_[512];                                                                     \
+      snprintf(buf_, sizeof buf_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      h->err = buf_;                                                                      \
+      return GPRF_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+struct gprf_ctx {
+  int device = 0;
+  long long n = 0;
+  int dx = 0, dy = 0, yr = 0, nya = 0, dfn = 0, wfn = 0, nls = 0;
+  std::string err;
+
+  cudaStream_t stream = nullptr;   // used by the host-buffer entry
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int last_launches = 0;
+
+  double* dY = nullptr;
+  double* dX = nullptr;            // staging for host-buffer entry
+  double* dOut = nullptr;          // [ll, gth(5), gradX(n*dx)]
+  double* hX = nullptr;            // pinned
+  double* hOut = nullptr;          // pinned
+
+  // structure
+  bool have_structure = false;
+  int B = 0, E = 0, U = 0;
+  long long plen = 0;
+  std::vector<UnitDesc> units;
+  std::vector<int> all_list;       // active, non-empty units, largest first
+  int ntmax = 0;
+  UnitDesc* dUnits = nullptr;
+  int* dList = nullptr;      // scratch list (jitter retries)
+  int* dListAll = nullptr;   // all active, non-empty units
+  long long* dPerm = nullptr;
+  long long* dBlockPtr = nullptr;
+  int* dPosBlock = nullptr;
+  int *dAdjPtr = nullptr, *dAdjEdge = nullptr, *dAdjSide = nullptr;
+  size_t capUnits = 0, capPerm = 0, capPos = 0, capB = 0, capAdj = 0;
+
+  double* arena = nullptr;
+  size_t arena_cap = 0;            // doubles
+  double *dLLu = nullptr, *dGthU = nullptr, *dJitter = nullptr;
+  int *dInfo = nullptr, *dNfail = nullptr;
+  std::vector<double> jitter;
+  std::vector<int> tries;
+};
+
+static size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+template <class Tp>
+static cudaError_t ensure(Tp** p, size_t* cap, size_t need) {
+  if (need <= *cap && *p) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  size_t c = std::max<size_t>(need + need / 4, 16);
+  cudaError_t e = cudaMalloc((void**)p, c * sizeof(Tp));
+  *cap = (e == cudaSuccess) ? c : 0;
+  return e;
+}
+
+static int make_cov(const gprf_ctx* h, const double* theta, int ncov, CovParams* cp) {
+  if (ncov != 2 + h->nls) return GPRF_ERR_ARG;
+  cp->nv = theta[0];
+  cp->s2 = theta[1];
+  cp->dx = h->dx;
+  cp->nls = h->nls;
+  for (int t = 0; t < MAX_NLS; ++t) {
+    if (t < h->nls) {
+      double l = theta[2 + t];
+      cp->il2[t] = 1.0 / (l * l);
+      cp->il3[t] = 1.0 / (l * l * l);
+    } else {
+      cp->il2[t] = 0.0;
+      cp->il3[t] = 0.0;
+    }
+  }
+  return GPRF_OK;
+}
+
+static const size_t PIPE_BYTES = PIPE_DOUBLES * sizeof(double);
+
+template <int DFN, int WFN>
+static void set_attrs_t() {
+  cudaFuncSetAttribute(k_potrf_diag<DFN, WFN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
+  cudaFuncSetAttribute(k_potrf_panel<DFN, WFN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
+  cudaFuncSetAttribute(k_grad<DFN, WFN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
+}
+static void set_attrs() {
+  set_attrs_t<0, 0>();
+  set_attrs_t<0, 1>();
+  set_attrs_t<1, 0>();
+  set_attrs_t<1, 1>();
+  cudaFuncSetAttribute(k_trtri, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
+  cudaFuncSetAttribute(k_lauum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
+}
+
+#define DISPATCH_COV(h, CALL)                                  \
+  do {                                                         \
+    if ((h)->dfn == 0 && (h)->wfn == 0) { CALL(0, 0); }        \
+    else if ((h)->dfn == 0 && (h)->wfn == 1) { CALL(0, 1); }   \
+    else if ((h)->dfn == 1 && (h)->wfn == 0) { CALL(1, 0); }   \
+    else { CALL(1, 1); }                                       \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+extern "C" int gprf_abi_version(void) { return 1; }
+
+extern "C" const char* gprf_strerror(int code) {
+  switch (code) {
+    case GPRF_OK: return "ok";
+    case GPRF_ERR_NOT_PD: return "not positive definite, even with jitter.";
+    case GPRF_ERR_NONPOS_DIAG: return "not pd: non-positive diagonal elements";
+    case GPRF_ERR_ARG: return "invalid argument";
+    case GPRF_ERR_CUDA: return "CUDA error";
+    case GPRF_ERR_NO_STRUCTURE: return "gprf_set_structure has not been called";
+  }
+  return "unknown";
+}
+
+extern "C" const char* gprf_last_error(gprf_handle h) { return h ? h->err.c_str() : ""; }
+
+extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, int dy, const double* Y,
+                           int dfn_id, int wfn_id) {
+  if (!out || n <= 0 || dx < 1 || dx > MAX_DX || dy < 1 || !Y) return GPRF_ERR_ARG;
+  if (dfn_id < 0 || dfn_id > 1 || wfn_id < 0 || wfn_id > 1) return GPRF_ERR_ARG;
+  if (dfn_id == GPRF_DFN_LLD && dx != 3) return GPRF_ERR_ARG;
+  gprf_ctx* h = new gprf_ctx();
+  *out = h;
+  h->device = device;
+  h->n = n;
+  h->dx = dx;
+  h->dy = dy;
+  h->yr = ((dy + T - 1) / T) * T;
+  h->nya = h->yr / T;
+  h->dfn = dfn_id;
+  h->wfn = wfn_id;
+  h->nls = (dfn_id == GPRF_DFN_LLD) ? 2 : dx;
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&h->ev0));
+  CUDA_OK(cudaEventCreate(&h->ev1));
+  const size_t outlen = 1 + MAX_NCOV + (size_t)n * dx;
+  CUDA_OK(cudaMalloc((void**)&h->dY, (size_t)n * dy * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&h->dX, (size_t)n * dx * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&h->dOut, outlen * sizeof(double)));
+  CUDA_OK(cudaMallocHost((void**)&h->hX, (size_t)n * dx * sizeof(double)));
+  CUDA_OK(cudaMallocHost((void**)&h->hOut, outlen * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&h->dNfail, sizeof(int)));
+  CUDA_OK(cudaMemcpy(h->dY, Y, (size_t)n * dy * sizeof(double), cudaMemcpyHostToDevice));
+  set_attrs();
+  CUDA_OK(cudaGetLastError());
+  return GPRF_OK;
+}
+
+extern "C" int gprf_destroy(gprf_handle h) {
+  if (!h) return GPRF_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->dY); cudaFree(h->dX); cudaFree(h->dOut);
+  cudaFreeHost(h->hX); cudaFreeHost(h->hOut);
+  cudaFree(h->dUnits); cudaFree(h->dList); cudaFree(h->dListAll); cudaFree(h->dPerm); cudaFree(h->dBlockPtr);
+  cudaFree(h->dPosBlock); cudaFree(h->dAdjPtr); cudaFree(h->dAdjEdge); cudaFree(h->dAdjSide);
+  cudaFree(h->arena); cudaFree(h->dLLu); cudaFree(h->dGthU); cudaFree(h->dJitter);
+  cudaFree(h->dInfo); cudaFree(h->dNfail);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return GPRF_OK;
+}
+
+extern "C" int gprf_set_structure(gprf_handle h, int B, const long long* block_ptr, const long long* perm,
+                                  int E, const int* edges, const unsigned char* unit_mask) {
+  if (!h || B < 1 || !block_ptr || E < 0 || (E > 0 && !edges)) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  const long long plen = block_ptr[B];
+  if (block_ptr[0] != 0 || plen < 0 || plen > h->n || (plen > 0 && !perm)) {
+    h->err = "block_ptr must start at 0 and cover at most n points";
+    return GPRF_ERR_ARG;
+  }
+  {
+    std::vector<unsigned char> seen((size_t)h->n, 0);
+    for (long long p = 0; p < plen; ++p) {
+      if (perm[p] < 0 || perm[p] >= h->n || seen[(size_t)perm[p]]) {
+        h->err = "block index lists must be disjoint indices in [0, n)";
+        return GPRF_ERR_ARG;
+      }
+      seen[(size_t)perm[p]] = 1;
+    }
+  }
+  for (int b = 0; b < B; ++b)
+    if (block_ptr[b + 1] < block_ptr[b]) return GPRF_ERR_ARG;
+  for (int e = 0; e < E; ++e) {
+    int i = edges[2 * e], j = edges[2 * e + 1];
+    if (i < 0 || i >= B || j < 0 || j >= B || i == j) {
+      h->err = "edge endpoints must be distinct block ids";
+      return GPRF_ERR_ARG;
+    }
+  }
+  h->have_structure = false;
+  h->B = B;
+  h->E = E;
+  h->U = B + E;
+  h->plen = plen;
+  const int U = h->U;
+
+  std::vector<int> deg(B, 0);
+  for (int e = 0; e < E; ++e) {
+    deg[edges[2 * e]]++;
+    deg[edges[2 * e + 1]]++;
+  }
+  // CSR of incident edges per block, in edge order (fixed summation order)
+  std::vector<int> adj_ptr(B + 1, 0), adj_edge(2 * (size_t)E), adj_side(2 * (size_t)E);
+  for (int b = 0; b < B; ++b) adj_ptr[b + 1] = adj_ptr[b] + deg[b];
+  {
+    std::vector<int> fill(adj_ptr.begin(), adj_ptr.end() - 1);
+    for (int e = 0; e < E; ++e) {
+      int i = edges[2 * e], j = edges[2 * e + 1];
+      adj_edge[fill[i]] = e; adj_side[fill[i]++] = 0;
+      adj_edge[fill[j]] = e; adj_side[fill[j]++] = 1;
+    }
+  }
+  std::vector<int> pos_block((size_t)plen);
+  for (int b = 0; b < B; ++b)
+    for (long long p = block_ptr[b]; p < block_ptr[b + 1]; ++p) pos_block[(size_t)p] = b;
+
+  h->units.assign(U, UnitDesc());
+  size_t off = 0;
+  h->ntmax = 0;
+  h->all_list.clear();
+  for (int uix = 0; uix < U; ++uix) {
+    UnitDesc& u = h->units[uix];
+    int bi, bj = -1;
+    if (uix < B) {
+      bi = uix;
+      u.weight = 1.0 - (double)deg[bi];
+    } else {
+      bi = edges[2 * (uix - B)];
+      bj = edges[2 * (uix - B) + 1];
+      u.weight = 1.0;
+    }
+    u.ni = (int)(block_ptr[bi + 1] - block_ptr[bi]);
+    u.a_start = (int)block_ptr[bi];
+    int nj = 0;
+    u.b_start = 0;
+    if (bj >= 0) {
+      nj = (int)(block_ptr[bj + 1] - block_ptr[bj]);
+      u.b_start = (int)block_ptr[bj];
+    }
+    u.s = u.ni + nj;
+    u.nt = (u.s + T - 1) / T;
+    u.sp = u.nt * T;
+    u.active = (!unit_mask || unit_mask[uix]) ? 1 : 0;
+    u.pad_ = 0;
+    if (u.active && u.s > 0) {
+      const size_t sp = u.sp, nt = u.nt;
+      u.m_off = off;   off += align16((sp + h->yr) * sp);
+      u.d_off = off;   off += align16(2 * nt * T * T);
+      u.al_off = off;  off += align16(sp * h->yr);
+      u.xs_off = off;  off += align16(sp * 4);
+      u.part_off = off; off += align16((nt * (nt + 1) / 2) * PART_STRIDE);
+      u.ld_off = off;  off += align16(nt);
+      u.gx_off = off;  off += align16(sp * 3);
+      h->all_list.push_back(uix);
+      h->ntmax = std::max(h->ntmax, u.nt);
+    } else {
+      u.m_off = u.d_off = u.al_off = u.xs_off = u.part_off = u.ld_off = u.gx_off = 0;
+    }
+  }
+  std::stable_sort(h->all_list.begin(), h->all_list.end(),
+                   [&](int a, int b) { return h->units[a].s > h->units[b].s; });
+
+  size_t acap = h->arena_cap;
+  CUDA_OK(ensure(&h->arena, &acap, off));
+  h->arena_cap = acap;
+  size_t cu = h->capUnits;
+  if ((size_t)U > cu || !h->dUnits) {
+    cudaFree(h->dUnits); cudaFree(h->dList); cudaFree(h->dListAll); cudaFree(h->dLLu); cudaFree(h->dGthU);
+    cudaFree(h->dJitter); cudaFree(h->dInfo);
+    h->dUnits = nullptr; h->dList = nullptr; h->dListAll = nullptr; h->dLLu = nullptr; h->dGthU = nullptr;
+    h->dJitter = nullptr; h->dInfo = nullptr;
+    cu = (size_t)U + U / 4 + 16;
+    CUDA_OK(cudaMalloc((void**)&h->dUnits, cu * sizeof(UnitDesc)));
+    CUDA_OK(cudaMalloc((void**)&h->dList, cu * sizeof(int)));
+    CUDA_OK(cudaMalloc((void**)&h->dListAll, cu * sizeof(int)));
+    CUDA_OK(cudaMalloc((void**)&h->dLLu, cu * sizeof(double)));
+    CUDA_OK(cudaMalloc((void**)&h->dGthU, cu * MAX_NCOV * sizeof(double)));
+    CUDA_OK(cudaMalloc((void**)&h->dJitter, cu * sizeof(double)));
+    CUDA_OK(cudaMalloc((void**)&h->dInfo, cu * sizeof(int)));
+    h->capUnits = cu;
+  }
+  CUDA_OK(ensure(&h->dPerm, &h->capPerm, (size_t)std::max<long long>(plen, 1)));
+  CUDA_OK(ensure(&h->dPosBlock, &h->capPos, (size_t)std::max<long long>(plen, 1)));
+  {
+    size_t cb = h->capB;
+    if ((size_t)(B + 1) > cb || !h->dBlockPtr) {
+      cudaFree(h->dBlockPtr); cudaFree(h->dAdjPtr);
+      cb = (size_t)B + 1 + B / 4;
+      CUDA_OK(cudaMalloc((void**)&h->dBlockPtr, cb * sizeof(long long)));
+      CUDA_OK(cudaMalloc((void**)&h->dAdjPtr, cb * sizeof(int)));
+      h->capB = cb;
+    }
+    size_t ca = h->capAdj;
+    if ((size_t)(2 * E + 1) > ca || !h->dAdjEdge) {
+      cudaFree(h->dAdjEdge); cudaFree(h->dAdjSide);
+      ca = (size_t)2 * E + 16;
+      CUDA_OK(cudaMalloc((void**)&h->dAdjEdge, ca * sizeof(int)));
+      CUDA_OK(cudaMalloc((void**)&h->dAdjSide, ca * sizeof(int)));
+      h->capAdj = ca;
+    }
+  }
+  CUDA_OK(cudaMemcpy(h->dUnits, h->units.data(), (size_t)U * sizeof(UnitDesc), cudaMemcpyHostToDevice));
+  if (!h->all_list.empty())
+    CUDA_OK(cudaMemcpy(h->dListAll, h->all_list.data(), h->all_list.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (plen > 0) {
+    CUDA_OK(cudaMemcpy(h->dPerm, perm, (size_t)plen * sizeof(long long), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->dPosBlock, pos_block.data(), (size_t)plen * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  CUDA_OK(cudaMemcpy(h->dBlockPtr, block_ptr, (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(h->dAdjPtr, adj_ptr.data(), (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  if (E > 0) {
+    CUDA_OK(cudaMemcpy(h->dAdjEdge, adj_edge.data(), (size_t)2 * E * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->dAdjSide, adj_side.data(), (size_t)2 * E * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  h->jitter.assign(U, 0.0);
+  h->tries.assign(U, 0);
+  h->have_structure = true;
+  return GPRF_OK;
+}
+
+// Enqueue the per-unit pipeline for the units in `list` (already on device as
+// dList[0..nlist)).  Returns the number of kernel launches.
+static int launch_units(gprf_ctx* h, const EvalParams& P, int nlist, int ntmax, bool want_grad,
+                        cudaStream_t st) {
+  int launches = 0;
+  if (nlist == 0) return 0;
+  const int ntri_max = ntmax * (ntmax + 1) / 2;
+  const int CH = 32768;   // gridDim.y limit is 65535
+  for (int base = 0; base < nlist; base += CH) {
+    const int cnt = std::min(CH, nlist - base);
+    EvalParams Pc = P;
+    Pc.ulist = P.ulist + base;
+    k_prep<<<dim3(ntmax, cnt), NTHREADS, 0, st>>>(Pc);
+    ++launches;
+    for (int k = 0; k < ntmax; ++k) {
+#define CALL_DIAG(D, W) k_potrf_diag<D, W><<<dim3(1, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, k)
+      DISPATCH_COV(h, CALL_DIAG);
+      ++launches;
+      const int gx = ntmax - k - 1 + h->nya;
+#define CALL_PANEL(D, W) k_potrf_panel<D, W><<<dim3(gx, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, k)
+      DISPATCH_COV(h, CALL_PANEL);
+      ++launches;
+    }
+    if (want_grad) {
+      for (int d = 1; d < ntmax; ++d) {
+        k_trtri<<<dim3(ntmax - d, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, d);
+        ++launches;
+      }
+      k_lauum<<<dim3(ntri_max + ntmax * h->nya, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, ntri_max);
+      ++launches;
+#define CALL_GRAD(D, W) k_grad<D, W><<<dim3(ntri_max, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc)
+      DISPATCH_COV(h, CALL_GRAD);
+      ++launches;
+    }
+    k_unit_finalize<<<cnt, NTHREADS, 0, st>>>(Pc, h->dLLu, h->dGthU, want_grad ? 1 : 0);
+    ++launches;
+  }
+  return launches;
+}
+
+static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int ncov, int grad_X, int grad_cov,
+                    double* out_dev, cudaStream_t st, int* failed_unit) {
+  if (failed_unit) *failed_unit = -1;
+  if (!h->have_structure) return GPRF_ERR_NO_STRUCTURE;
+  CovParams cp;
+  int rc = make_cov(h, theta, ncov, &cp);
+  if (rc != GPRF_OK) {
+    h->err = "theta must have 2 + (number of lengthscales) entries";
+    return rc;
+  }
+  const bool want_grad = grad_X || grad_cov;
+  const int U = h->U;
+  EvalParams P;
+  P.units = h->dUnits;
+  P.ulist = h->dList;
+  P.arena = h->arena;
+  P.X = X_dev;
+  P.Y = h->dY;
+  P.perm = h->dPerm;
+  P.jitter = h->dJitter;
+  P.info = h->dInfo;
+  P.nfail = h->dNfail;
+  P.dx = h->dx;
+  P.dy = h->dy;
+  P.yr = h->yr;
+  P.nya = h->nya;
+  P.cp = cp;
+
+  std::fill(h->jitter.begin(), h->jitter.end(), 0.0);
+  std::fill(h->tries.begin(), h->tries.end(), 0);
+  CUDA_OK(cudaEventRecord(h->ev0, st));
+  CUDA_OK(cudaMemsetAsync(h->dJitter, 0, (size_t)U * sizeof(double), st));
+  CUDA_OK(cudaMemsetAsync(h->dInfo, 0, (size_t)U * sizeof(int), st));
+  CUDA_OK(cudaMemsetAsync(h->dNfail, 0, sizeof(int), st));
+  CUDA_OK(cudaMemsetAsync(h->dLLu, 0, (size_t)U * sizeof(double), st));
+  const size_t outlen = 1 + MAX_NCOV + (grad_X ? (size_t)h->n * h->dx : 0);
+  CUDA_OK(cudaMemsetAsync(out_dev, 0, outlen * sizeof(double), st));
+  const int nlist = (int)h->all_list.size();
+  P.ulist = h->dListAll;
+  int launches = launch_units(h, P, nlist, h->ntmax, want_grad, st);
+  P.ulist = h->dList;
+  CUDA_OK(cudaGetLastError());
+
+  // jitter rule (gpy_linalg.py:77-97): host-driven retry of the failed units only
+  int nfail = 0;
+  CUDA_OK(cudaMemcpyAsync(&nfail, h->dNfail, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<int> info;
+  while (nfail > 0) {
+    if (!(cp.s2 + cp.nv > 0.0)) return GPRF_ERR_NONPOS_DIAG;
+    info.resize(U);
+    CUDA_OK(cudaMemcpy(info.data(), h->dInfo, (size_t)U * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> failed;
+    int ntm = 0;
+    for (int uix = 0; uix < U; ++uix) {
+      if (info[uix] == 0) continue;
+      if (h->tries[uix] >= 5) {
+        if (failed_unit) *failed_unit = uix;
+        return GPRF_ERR_NOT_PD;
+      }
+      h->jitter[uix] = (cp.s2 + cp.nv) * 1e-6 * std::pow(10.0, h->tries[uix]);
+      h->tries[uix]++;
+      if (!std::isfinite(h->jitter[uix])) {
+        if (failed_unit) *failed_unit = uix;
+        return GPRF_ERR_NOT_PD;
+      }
+      failed.push_back(uix);
+      ntm = std::max(ntm, h->units[uix].nt);
+    }
+    CUDA_OK(cudaMemcpyAsync(h->dJitter, h->jitter.data(), (size_t)U * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemsetAsync(h->dInfo, 0, (size_t)U * sizeof(int), st));
+    CUDA_OK(cudaMemsetAsync(h->dNfail, 0, sizeof(int), st));
+    CUDA_OK(cudaMemcpyAsync(h->dList, failed.data(), failed.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    launches += launch_units(h, P, (int)failed.size(), ntm, want_grad, st);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(&nfail, h->dNfail, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+
+  k_combine_scalars<<<1, 256, 0, st>>>(h->dUnits, U, h->dLLu, h->dGthU, grad_cov ? 1 : 0, out_dev);
+  ++launches;
+  if (grad_X && h->plen > 0) {
+    CombineParams C;
+    C.units = h->dUnits;
+    C.arena = h->arena;
+    C.perm = h->dPerm;
+    C.pos_block = h->dPosBlock;
+    C.block_ptr = h->dBlockPtr;
+    C.adj_ptr = h->dAdjPtr;
+    C.adj_edge = h->dAdjEdge;
+    C.adj_side = h->dAdjSide;
+    C.B = h->B;
+    C.dx = h->dx;
+    C.plen = h->plen;
+    const int tb = 256;
+    k_combine_gradx<<<(unsigned)((h->plen + tb - 1) / tb), tb, 0, st>>>(C, out_dev + 1 + MAX_NCOV);
+    ++launches;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(h->ev1, st));
+  h->last_launches = launches;
+  return GPRF_OK;
+}
+
+extern "C" int gprf_llgrad_device(gprf_handle h, const double* X_dev, const double* theta, int ncov,
+                                  int grad_X, int grad_cov, double* out_dev, void* stream, int* failed_unit) {
+  if (!h || !X_dev || !theta || !out_dev) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = run_eval(h, X_dev, theta, ncov, grad_X, grad_cov, out_dev, st, failed_unit);
+  if (rc != GPRF_OK) return rc;
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  return GPRF_OK;
+}
+
+extern "C" int gprf_llgrad(gprf_handle h, const double* X, const double* theta, int ncov, int grad_X,
+                           int grad_cov, double* ll, double* gradX, double* gradTheta, int* failed_unit) {
+  if (!h || !X || !theta || !ll) return GPRF_ERR_ARG;
+  if ((grad_X && !gradX) || (grad_cov && !gradTheta)) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  const size_t xb = (size_t)h->n * h->dx * sizeof(double);
+  memcpy(h->hX, X, xb);
+  CUDA_OK(cudaMemcpyAsync(h->dX, h->hX, xb, cudaMemcpyHostToDevice, h->stream));
+  int rc = run_eval(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, failed_unit);
+  if (rc != GPRF_OK) return rc;
+  const size_t outlen = 1 + MAX_NCOV + (grad_X ? (size_t)h->n * h->dx : 0);
+  CUDA_OK(cudaMemcpyAsync(h->hOut, h->dOut, outlen * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  *ll = h->hOut[0];
+  if (grad_cov)
+    for (int t = 0; t < ncov; ++t) gradTheta[t] = h->hOut[1 + t];
+  if (grad_X) memcpy(gradX, h->hOut + 1 + MAX_NCOV, xb);
+  return GPRF_OK;
+}
+
+extern "C" int gprf_unit_results(gprf_handle h, double* ll_units, double* jitter_units) {
+  if (!h || !h->have_structure) return GPRF_ERR_NO_STRUCTURE;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (ll_units) CUDA_OK(cudaMemcpy(ll_units, h->dLLu, (size_t)h->U * sizeof(double), cudaMemcpyDeviceToHost));
+  if (jitter_units) memcpy(jitter_units, h->jitter.data(), (size_t)h->U * sizeof(double));
+  return GPRF_OK;
+}
+
+extern "C" int gprf_last_timing(gprf_handle h, float* ms, int* launches) {
+  if (!h) return GPRF_ERR_ARG;
+  if (ms) *ms = h->last_ms;
+  if (launches) *launches = h->last_launches;
+  return GPRF_OK;
+}
+
+extern "C" int gprf_debug_unit(gprf_handle h, int unit, int* s, int* sp, int* yr, double* M, double* alpha,
+                               double* gx_unit) {
+  if (!h || !h->have_structure) return GPRF_ERR_NO_STRUCTURE;
+  if (unit < 0 || unit >= h->U) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  const UnitDesc& u = h->units[unit];
+  if (s) *s = u.s;
+  if (sp) *sp = u.sp;
+  if (yr) *yr = h->yr;
+  if (!u.active || u.s == 0) return GPRF_OK;
+  if (M) CUDA_OK(cudaMemcpy(M, h->arena + u.m_off, (size_t)(u.sp + h->yr) * u.sp * sizeof(double), cudaMemcpyDeviceToHost));
+  if (alpha) CUDA_OK(cudaMemcpy(alpha, h->arena + u.al_off, (size_t)u.sp * h->yr * sizeof(double), cudaMemcpyDeviceToHost));
+  if (gx_unit) CUDA_OK(cudaMemcpy(gx_unit, h->arena + u.gx_off, (size_t)u.sp * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  return GPRF_OK;
+}
+
+extern "C" int gprf_kernel_matrix(gprf_handle h, const double* X1, long long n1, const double* X2, long long n2,
+                                  const double* theta, int ncov, double* K) {
+  if (!h || !X1 || !theta || !K || n1 < 0) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  CovParams cp;
+  if (make_cov(h, theta, ncov, &cp) != GPRF_OK) return GPRF_ERR_ARG;
+  const bool self = (X2 == nullptr);
+  if (self) n2 = n1;
+  if (n1 == 0 || n2 == 0) return GPRF_OK;
+  double *d1 = nullptr, *d2 = nullptr, *dK = nullptr;
+  CUDA_OK(cudaMalloc((void**)&d1, (size_t)n1 * h->dx * sizeof(double)));
+  CUDA_OK(cudaMemcpy(d1, X1, (size_t)n1 * h->dx * sizeof(double), cudaMemcpyHostToDevice));
+  if (!self) {
+    CUDA_OK(cudaMalloc((void**)&d2, (size_t)n2 * h->dx * sizeof(double)));
+    CUDA_OK(cudaMemcpy(d2, X2, (size_t)n2 * h->dx * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  CUDA_OK(cudaMalloc((void**)&dK, (size_t)n1 * n2 * sizeof(double)));
+  const int grid = (int)std::min<long long>((n1 * n2 + 255) / 256, 148 * 16);
+#define CALL_KM(D, W) k_kernel_matrix<D, W><<<grid, 256>>>(d1, n1, self ? d1 : d2, n2, h->dx, cp, self ? 1 : 0, dK)
+  DISPATCH_COV(h, CALL_KM);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpy(K, dK, (size_t)n1 * n2 * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d1); cudaFree(d2); cudaFree(dK);
+  return GPRF_OK;
+}
+
+extern "C" int gprf_block_max_kernel(gprf_handle h, const double* X, const double* theta, int ncov, double* maxk) {
+  if (!h || !X || !theta || !maxk) return GPRF_ERR_ARG;
+  if (!h->have_structure) return GPRF_ERR_NO_STRUCTURE;
+  CUDA_OK(cudaSetDevice(h->device));
+  CovParams cp;
+  if (make_cov(h, theta, ncov, &cp) != GPRF_OK) return GPRF_ERR_ARG;
+  const size_t xb = (size_t)h->n * h->dx * sizeof(double);
+  CUDA_OK(cudaMemcpy(h->dX, X, xb, cudaMemcpyHostToDevice));
+  double* dM = nullptr;
+  const size_t BB = (size_t)h->B * h->B;
+  CUDA_OK(cudaMalloc((void**)&dM, BB * sizeof(double)));
+  CUDA_OK(cudaMemset(dM, 0, BB * sizeof(double)));
+#define CALL_MK(D, W) k_block_maxk<D, W><<<(unsigned)BB, 256>>>(h->dX, h->dx, h->dPerm, h->dBlockPtr, h->B, cp, dM)
+  DISPATCH_COV(h, CALL_MK);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpy(maxk, dM, BB * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dM);
+  return GPRF_OK;
+}

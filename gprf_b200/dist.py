@@ -1,0 +1,122 @@
+"""Multi-GPU evaluation: one process per GPU, units sharded across ranks.
+
+The reference's only parallelism is data-parallel over independent units
+(``Pool.map_async`` over blocks, then over edges - gprf.py:218-233) followed by
+a serial reduction in the parent (gprf.py:245-291).  Here every rank holds X, Y
+and the full structure (X is n*dx*8 bytes - 3.2 MB at n = 200k - so replicating
+it costs less than any halo bookkeeping), evaluates its share of the units on
+its own GPU and the partial ``[ll, grad_theta, gradX]`` vectors are summed with
+ONE all-reduce over NCCL/NVLink.  No other data-path collective exists.
+
+``shard_units`` is pure host logic (tested with gloo on CPU).
+"""
+import ctypes as C
+import heapq
+
+import numpy as np
+
+from . import _lib
+from .gprf import GPRF, LinAlgError
+
+COST_DY = 50.0
+
+
+def unit_costs(block_ptr, edges):
+    """Work model W(s) = s^3 + 4 s^2 dy per unit."""
+    sizes = np.diff(np.asarray(block_ptr, dtype=np.int64)).astype(np.float64)
+    e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    s = np.concatenate([sizes, sizes[e[:, 0]] + sizes[e[:, 1]]]) if len(e) else sizes
+    return s ** 3 + 4.0 * COST_DY * s ** 2
+
+
+def shard_units(block_ptr, edges, rank, world):
+    """uint8 mask over units (blocks, then edges): 1 = evaluated on ``rank``.
+
+    Longest-processing-time greedy on the work model; deterministic, so every
+    rank derives the same global assignment without communication.
+    """
+    cost = unit_costs(block_ptr, edges)
+    owner = np.zeros(len(cost), dtype=np.int64)
+    if world > 1:
+        order = np.argsort(-cost, kind="stable")
+        heap = [(0.0, r) for r in range(world)]
+        heapq.heapify(heap)
+        for u in order:
+            load, r = heapq.heappop(heap)
+            owner[u] = r
+            heapq.heappush(heap, (load + cost[u], r))
+    return np.ascontiguousarray((owner == rank).astype(np.uint8))
+
+
+def pack(ll, gX, gC, n, dx):
+    """[ll, gC(5, zero padded), gX.ravel()] - the layout of gprf_llgrad_device's out buffer."""
+    buf = np.zeros(1 + _lib.MAX_NCOV + n * dx, dtype=np.float64)
+    buf[0] = ll
+    if gC is not None and gC.size:
+        buf[1:1 + gC.size] = gC.ravel()
+    if gX is not None and gX.size:
+        buf[1 + _lib.MAX_NCOV:] = gX.ravel()
+    return buf
+
+
+def unpack(buf, n, dx, ncov, grad_X, grad_cov):
+    ll = np.float64(buf[0])
+    gC = np.array(buf[1:1 + ncov], dtype=np.float64).reshape(1, -1) if grad_cov else np.zeros((0, 0))
+    gX = np.array(buf[1 + _lib.MAX_NCOV:1 + _lib.MAX_NCOV + n * dx], dtype=np.float64).reshape(n, dx) \
+        if grad_X else np.zeros((0, 0))
+    return ll, gX, gC
+
+
+class ShardedGPRF(GPRF):
+    """GPRF whose ``llgrad`` evaluates this rank's units and all-reduces.
+
+    Requires an initialised ``torch.distributed`` process group (NCCL on GPUs)
+    with one process per GPU; the result is identical on every rank.
+    """
+
+    def __init__(self, *args, **kwargs):
+        import torch
+        import torch.distributed as dist
+        self._torch = torch
+        self._dist = dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        kwargs.setdefault("device", torch.cuda.current_device())
+        kwargs["unit_shard"] = (rank, world)
+        super(ShardedGPRF, self).__init__(*args, **kwargs)
+        self._out = None
+        self._Xd = None
+
+    def llgrad(self, parallel=False, local=True, **kwargs):
+        torch, dist = self._torch, self._dist
+        grad_X = bool(kwargs.get("grad_X", False))
+        grad_cov = bool(kwargs.get("grad_cov", False))
+        edges = self.neighbors if local else [(i, j) for i in range(self.n_blocks) for j in range(i)]
+        self._push_structure(edges)
+        n, dx = self.X.shape
+        dev = torch.device("cuda", self.device)
+        if self._out is None:
+            # slot 0 carries the per-rank status so that a failed factorisation on one
+            # rank cannot leave the others waiting in the collective
+            self._out = torch.empty(2 + _lib.MAX_NCOV + n * dx, dtype=torch.float64, device=dev)
+            self._Xd = torch.empty((n, dx), dtype=torch.float64, device=dev)
+            self._Xh = torch.empty((n, dx), dtype=torch.float64).pin_memory()
+            self._outh = torch.empty(2 + _lib.MAX_NCOV + n * dx, dtype=torch.float64).pin_memory()
+        self._Xh.numpy()[...] = self.X
+        self._Xd.copy_(self._Xh, non_blocking=True)
+        th = self._theta()
+        failed = C.c_int(-1)
+        stream = torch.cuda.current_stream(dev)
+        rc = self._lib.gprf_llgrad_device(self._h, C.c_void_p(self._Xd.data_ptr()), _lib.ptr(th), len(th),
+                                          int(grad_X), int(grad_cov), C.c_void_p(self._out.data_ptr() + 8),
+                                          C.c_void_p(stream.cuda_stream), C.byref(failed))
+        used = 2 + _lib.MAX_NCOV + (n * dx if grad_X else 0)
+        if rc != _lib.OK:
+            self._out[:used].zero_()
+        self._out[0] = float(rc)
+        dist.all_reduce(self._out[:used])
+        self._outh[:used].copy_(self._out[:used], non_blocking=True)
+        stream.synchronize()
+        self._check(rc, failed.value)
+        if self._outh[0].item() != 0.0:
+            raise LinAlgError("a unit on another rank was not positive definite")
+        return unpack(self._outh.numpy()[1:], n, dx, len(th), grad_X, grad_cov)

@@ -1,0 +1,119 @@
+/*
+ * gprf_b200 - C-ABI of the B200-native GPRF objective-and-gradient hot path.
+ *
+ * The reference (davmre/gprf) has no FFI of its own: its boundary for this
+ * path is the Python method surface of `GPRF` (gprf.py:85-331).  This header
+ * is the plain-C boundary a maintainer binds from Python with ctypes (see
+ * INTEGRATION.md); `gprf_b200/gprf.py` is that binding, mirroring the
+ * reference class.  Each entry point names the reference code it replaces.
+ *
+ * All pointers are HOST pointers unless the parameter name ends in `_dev`.
+ * All floating point is IEEE double; indices are int64 (numpy default) for
+ * point indices and int32 for block ids.  Every call is synchronous with
+ * respect to the host on return unless stated otherwise.
+ *
+ * theta = [noise_var, signal_var, l_0, ..., l_{nls-1}]   (gprf.py:160-167)
+ *   nls = dx for dfn "euclidean", 2 for dfn "lld";  ncov = 2 + nls.
+ */
+#ifndef GPRF_B200_H
+#define GPRF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gprf_ctx* gprf_handle;
+
+/* distance / weight functions of treegp's VectorTree used by the reference
+ * (synthetic.py:149, run_seismic.py:299-301) */
+enum { GPRF_DFN_EUCLIDEAN = 0, GPRF_DFN_LLD = 1 };
+enum { GPRF_WFN_SE = 0, GPRF_WFN_MATERN32 = 1 };
+
+/* return codes */
+enum {
+  GPRF_OK = 0,
+  GPRF_ERR_NOT_PD = 1,        /* jitchol: "not positive definite, even with jitter." gpy_linalg.py:97 */
+  GPRF_ERR_NONPOS_DIAG = 2,   /* jitchol: "not pd: non-positive diagonal elements"   gpy_linalg.py:85 */
+  GPRF_ERR_ARG = 3,
+  GPRF_ERR_CUDA = 4,
+  GPRF_ERR_NO_STRUCTURE = 5
+};
+
+#define GPRF_MAX_NCOV 5
+
+/* Replaces GPRF.__init__'s data capture (gprf.py:85-97): Y (n x dy, C order) is
+ * uploaded once and stays resident in HBM; X changes every evaluation. */
+int gprf_create(gprf_handle* out, int device, long long n, int dx, int dy,
+                const double* Y, int dfn_id, int wfn_id);
+
+int gprf_destroy(gprf_handle h);
+
+/* Replaces the structure consumed by llgrad (gprf.py:206-216, 299-330):
+ *   block_ptr[B+1], perm[block_ptr[B]] : concatenated GPRF.block_idxs
+ *   edges[2E] : GPRF.neighbors as (i, j) pairs; pair unit e stacks block i's
+ *               rows first, then block j's (gprf.py:310-330)
+ *   unit_mask[B+E] or NULL : multi-GPU sharding - only units with mask != 0
+ *               are evaluated on this device (replaces Pool.map_async,
+ *               gprf.py:218-233).  Unit u < B is the unary of block u,
+ *               unit B+e the pair of edge e.
+ * Called whenever block membership changes (GPRF.update_X, gprf.py:169-174). */
+int gprf_set_structure(gprf_handle h, int n_blocks, const long long* block_ptr,
+                       const long long* perm, int n_edges, const int* edges,
+                       const unsigned char* unit_mask);
+
+/* Replaces GPRF.llgrad (gprf.py:206-296) for host buffers:
+ *   ll         <- sum_e ll_e + sum_i (1 - deg_i) ll_i
+ *   gradX      <- n x dx (C order) or NULL   (grad_X=False)
+ *   gradTheta  <- ncov or NULL               (grad_cov=False)
+ *   failed_unit<- first unit that was not PD after jitter (or -1)
+ * H2D of X and D2H of the results happen inside the call.  With a unit_mask
+ * the outputs are this device's partial sums. */
+int gprf_llgrad(gprf_handle h, const double* X, const double* theta, int ncov,
+                int grad_X, int grad_cov, double* ll, double* gradX,
+                double* gradTheta, int* failed_unit);
+
+/* Same evaluation with X already in HBM and the result left in HBM:
+ *   out_dev[0] = ll, out_dev[1..GPRF_MAX_NCOV] = gradTheta (zero padded),
+ *   out_dev[1+GPRF_MAX_NCOV ...] = gradX (n*dx) when grad_X.
+ * Work is enqueued on `stream` (a cudaStream_t); the call returns after the
+ * stream has drained (the per-unit Cholesky status must be read to apply the
+ * jitter rule). */
+int gprf_llgrad_device(gprf_handle h, const double* X_dev, const double* theta,
+                       int ncov, int grad_X, int grad_cov, double* out_dev,
+                       void* stream, int* failed_unit);
+
+/* Per-unit results of the last evaluation (llgrad_unary / llgrad_joint,
+ * gprf.py:299-330): ll_units[B+E]; jitter_units[B+E] (0 = none); either may
+ * be NULL. */
+int gprf_unit_results(gprf_handle h, double* ll_units, double* jitter_units);
+
+/* Replaces GPRF.compute_neighbors (gprf.py:119-150): for every block pair
+ * (i, j), j < i, max |k(x_p, x_q)| / signal_var over p in i, q in j
+ * (noise-free kernel).  maxk[B*B] symmetric, diagonal 1.  Uses the structure's
+ * blocks and the given X / theta. */
+int gprf_block_max_kernel(gprf_handle h, const double* X, const double* theta,
+                          int ncov, double* maxk);
+
+/* Replaces GPRF.kernel (gprf.py:333-343): K (n1 x n2).  X2 == NULL -> K(X1,X1)
+ * + noise_var*I; else cross kernel without noise. */
+int gprf_kernel_matrix(gprf_handle h, const double* X1, long long n1,
+                       const double* X2, long long n2, const double* theta,
+                       int ncov, double* K);
+
+/* Debug / test access: copy unit u's working matrix ((sp+yr) x sp, row major)
+ * and sizes after the last evaluation.  Any pointer may be NULL. */
+int gprf_debug_unit(gprf_handle h, int unit, int* s, int* sp, int* yr,
+                    double* M, double* alpha, double* gx_unit);
+
+/* Device time of the kernels of the last evaluation, in milliseconds
+ * (CUDA events on the launching stream), and the number of kernel launches. */
+int gprf_last_timing(gprf_handle h, float* ms, int* launches);
+
+const char* gprf_strerror(int code);
+const char* gprf_last_error(gprf_handle h);
+int gprf_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPRF_B200_H */

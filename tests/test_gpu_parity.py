@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via gprf_b200.GPRF) against
+the CPU oracle on identical X, Y, blocks, edges and theta.
+
+Tolerances (BASELINE.json north_star): objective 1e-9 relative, gradients 1e-7
+relative (norm-wise: max abs error / max abs gradient), fp64 throughout; block
+assignments and edge lists bit-exact.
+"""
+import ctypes as C
+import json
+import os
+import pickle
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from test_oracle_props import COVS, make_points  # noqa: E402
+
+LL_RTOL = 1e-9
+GRAD_RTOL = 1e-7
+
+
+def _cuda():
+    import torch
+    return torch.cuda.is_available()
+
+
+def prod_cov(cov):
+    from gprf_b200 import GPCov
+    return GPCov(cov.wfn_params, cov.dfn_params, cov.dfn_str, cov.wfn_str)
+
+
+def build_pair(name, sizes, edges, dy=7, seed=0, nv=0.05):
+    """Same structure on the oracle and on the CUDA-backed GPRF."""
+    from oracle.gprf_oracle import OracleGPRF
+    from gprf_b200 import GPRF
+    cov, dx = COVS[name]
+    rng = np.random.RandomState(seed)
+    n = int(np.sum(sizes))
+    X = make_points(n, dx, rng)
+    Y = rng.randn(n, dy)
+    perm = rng.permutation(n)
+    ptr = np.concatenate([[0], np.cumsum(sizes)])
+    blocks = [np.sort(perm[ptr[b]:ptr[b + 1]]) for b in range(len(sizes))]
+    o = OracleGPRF(X, Y, None, cov, nv, block_idxs=blocks, neighbors=list(edges))
+    g = GPRF(X, Y, None, prod_cov(cov), nv, block_idxs=blocks, neighbors=list(edges))
+    return o, g
+
+
+def assert_parity(want, got, what=""):
+    ll_w, gx_w, gc_w = want
+    ll_g, gx_g, gc_g = got
+    assert abs(ll_g - ll_w) <= LL_RTOL * abs(ll_w), "%s ll %r vs %r" % (what, ll_g, ll_w)
+    assert gx_g.shape == gx_w.shape and gc_g.shape == gc_w.shape
+    if gx_w.size:
+        err = np.abs(gx_g - gx_w).max()
+        assert err <= GRAD_RTOL * np.abs(gx_w).max(), "%s gradX err %g (scale %g)" % (what, err, np.abs(gx_w).max())
+    if gc_w.size:
+        assert np.all(np.abs(gc_g - gc_w) <= GRAD_RTOL * np.maximum(np.abs(gc_w), 1e-3 * np.abs(gc_w).max())), \
+            "%s gradCov %r vs %r" % (what, gc_g, gc_w)
+
+
+def test_device_present():
+    assert _cuda(), "no CUDA device: the product has no CPU fallback"
+
+
+@pytest.mark.parametrize("s", [1, 5, 64, 65, 130, 200])
+def test_single_unit_stages(s):
+    """One block, no edges: check L, U = L^-T, K^-1, Alpha stage by stage (localises a failure)."""
+    from gprf_b200 import _lib
+    o, g = build_pair("euclid_se", [s], [], dy=7, seed=s)
+    want = o.llgrad(grad_X=True, grad_cov=True)
+    got = g.llgrad(grad_X=True, grad_cov=True)
+    sz, sp, yr = C.c_int(), C.c_int(), C.c_int()
+    g._lib.gprf_debug_unit(g._h, 0, C.byref(sz), C.byref(sp), C.byref(yr), None, None, None)
+    assert sz.value == s and sp.value == ((s + 63) // 64) * 64 and yr.value == 64
+    M = np.zeros((sp.value + yr.value, sp.value))
+    Al = np.zeros((sp.value, yr.value))
+    gxu = np.zeros((sp.value, 3))
+    g._lib.gprf_debug_unit(g._h, 0, None, None, None, _lib.ptr(M), _lib.ptr(Al), _lib.ptr(gxu))
+    idx = o.block_idxs[0]
+    K = o.kernel(o.X[idx])
+    Kinv = np.linalg.inv(K)
+    L = np.linalg.cholesky(K)
+    A = np.linalg.solve(K, o.Y[idx])
+    Z = np.linalg.solve(L, o.Y[idx])
+    sq = M[:sp.value]
+    nt = sp.value // 64
+    scale = np.abs(Kinv).max()
+    assert np.abs(np.tril(sq)[:s, :s] - np.tril(Kinv)).max() <= 1e-9 * scale, "K^-1 (lower) wrong"
+    Uref = np.linalg.inv(L).T
+    for a in range(nt):
+        for b in range(a + 1, nt):
+            blk = sq[a * 64:(a + 1) * 64, b * 64:(b + 1) * 64]
+            ref = np.zeros((64, 64))
+            r1, c1 = min(s, (a + 1) * 64) - a * 64, min(s, (b + 1) * 64) - b * 64
+            if c1 > 0:
+                ref[:r1, :c1] = Uref[a * 64:a * 64 + r1, b * 64:b * 64 + c1]
+            assert np.abs(blk - ref).max() <= 1e-9 * np.abs(Uref).max(), "U tile (%d,%d) wrong" % (a, b)
+    assert np.abs(M[sp.value:sp.value + 7, :s] - Z.T).max() <= 1e-9 * np.abs(Z).max(), "Z = L^-1 Y wrong"
+    assert np.abs(Al[:s, :7] - A).max() <= 1e-9 * np.abs(A).max(), "Alpha wrong"
+    assert np.abs(Al[s:]).max() == 0 if s < sp.value else True
+    assert np.abs(gxu[:s, :2] - want[1][idx]).max() <= GRAD_RTOL * max(np.abs(want[1]).max(), 1e-300)
+    assert_parity(want, got, "single unit s=%d" % s)
+
+
+@pytest.mark.parametrize("name", sorted(COVS))
+@pytest.mark.parametrize("flags", [(True, True), (True, False), (False, True), (False, False)])
+def test_llgrad_parity_small(name, flags):
+    sizes = [40, 70, 0, 1, 64, 90, 129]
+    edges = [(1, 0), (4, 1), (5, 4), (6, 5), (3, 1), (2, 1), (6, 0), (5, 3)]
+    o, g = build_pair(name, sizes, edges)
+    kw = dict(grad_X=flags[0], grad_cov=flags[1])
+    assert_parity(o.llgrad(**kw), g.llgrad(**kw), name)
+    # no kwargs at all: objective only, empty gradients (gprf.py:275,291)
+    ll, gx, gc = g.llgrad()
+    assert gx.shape == (0, 0) and gc.shape == (0, 0)
+    lls, jit = g.unit_results()
+    for u in range(len(sizes)):
+        assert abs(lls[u] - o.llgrad_unary(u)[0]) <= LL_RTOL * max(1.0, abs(o.llgrad_unary(u)[0]))
+    assert np.all(jit == 0)
+
+
+def test_llgrad_nonlocal_all_pairs():
+    o, g = build_pair("euclid_se", [30, 45, 20, 33], [(1, 0)])
+    kw = dict(grad_X=True, grad_cov=True)
+    assert_parity(o.llgrad(local=False, **kw), g.llgrad(local=False, **kw), "local=False")
+    assert_parity(o.llgrad(**kw), g.llgrad(**kw), "back to local")
+
+
+def test_update_X_and_update_covs():
+    from oracle.blocking import Blocker as OB, grid_centers
+    from gprf_b200 import Blocker, GPRF
+    from oracle.gprf_oracle import OracleGPRF
+    cov, _ = COVS["euclid_se"]
+    rng = np.random.RandomState(7)
+    X = rng.rand(600, 2)
+    Y = rng.randn(600, 6)
+    bo, bp = OB(np.asarray(grid_centers(9))), Blocker(grid_centers(9))
+    o = OracleGPRF(X, Y, bo.block_clusters, cov, 0.02, neighbors=bo.neighbors())
+    g = GPRF(X, Y, bp.block_clusters, prod_cov(cov), 0.02, neighbors=bp.neighbors())
+    assert g.neighbors == o.neighbors
+    kw = dict(grad_X=True, grad_cov=True)
+    assert_parity(o.llgrad(**kw), g.llgrad(**kw), "initial")
+    for step in range(3):
+        X2 = np.clip(X + rng.randn(*X.shape) * 0.05, 0, 1)
+        th = np.array([[0.02 * (step + 1), 1.0 + 0.1 * step, 0.2, 0.15 + 0.02 * step]])
+        o.update_X(X2); g.update_X(X2)
+        o.update_covs(th); g.update_covs(th)
+        assert all(np.array_equal(a, b) for a, b in zip(o.block_idxs, g.block_idxs))
+        assert_parity(o.llgrad(**kw), g.llgrad(**kw), "step %d" % step)
+
+
+def test_kernel_and_compute_neighbors():
+    for name in sorted(COVS):
+        o, g = build_pair(name, [50, 60, 45, 30], [])
+        Xa, Xb = o.X[:37], o.X[37:80]
+        np.testing.assert_allclose(g.kernel(Xa), o.kernel(Xa), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(g.kernel(Xa, X2=Xb), o.kernel(Xa, X2=Xb), rtol=1e-12, atol=1e-15)
+        for thr in (1e-3, 0.3, 0.6):
+            o.compute_neighbors(thr)
+            g.compute_neighbors(thr)
+            assert g.neighbors == o.neighbors, (name, thr)
+        g.compute_neighbors(1.0)
+        assert g.neighbors == []
+
+
+def test_golden_values_n2000(golden_data):
+    """Known-answer test on the device: the reference's shipped objective values."""
+    from gprf_b200 import GPRF
+    runs = json.load(open(os.path.join(HERE, "golden", "gprf_results_golden.json")))["runs"]
+    done = 0
+    for run in runs:
+        if run["ntrain"] != 2000 or run["task"] != "x":
+            continue
+        sd = golden_data(2000, run["nblocks"], run["local_dist"])
+        for X, key in ((sd.X_obs, "step0_ll"), (sd.SX, "trueX_ll")):
+            gp = sd.build_gprf(X=X, local_dist=run["local_dist"], cls=_prod_cls())
+            val = gp.llgrad()[0]
+            if key == "step0_ll":
+                val += sd.x_prior(sd.X_obs.flatten())[0]
+            assert abs(val - run[key]) < 0.006, (run["dir"], key, val, run[key])
+            gp.close()
+        done += 1
+    assert done == 4
+
+
+def _prod_cls():
+    from gprf_b200 import GPRF
+
+    def make(X, Y, block_fn, cov, noise_var, **kw):
+        return GPRF(X, Y, block_fn, prod_cov(cov), noise_var, **kw)
+    return make
+
+
+def test_readme_config_golden_and_parity(golden_data):
+    """BASELINE cfg 2/3: n=10000, 100 blocks, 342 edges, dy=50 - golden objective and
+    oracle parity for X and hyperparameter gradients."""
+    sd = golden_data(10000, 100, 0.1)
+    g = sd.build_gprf(local_dist=0.1, cls=_prod_cls())
+    assert len(g.neighbors) == 342
+    ll, gX, gC = g.llgrad(grad_X=True, grad_cov=True)
+    assert abs(ll + sd.x_prior(sd.X_obs.flatten())[0] - (-6563678.10)) < 0.006
+    o = sd.build_gprf(local_dist=0.1)
+    assert_parity(o.llgrad(grad_X=True, grad_cov=True), (ll, gX, gC), "cfg2/3")
+    g.update_X(sd.SX)           # blocks recomputed on SX - not the golden trueX setup
+    g2 = sd.build_gprf(X=sd.SX, local_dist=0.1, cls=_prod_cls())
+    assert abs(g2.llgrad()[0] - 414491.46) < 0.006
+
+
+def test_jitter_sequence_and_failures():
+    """jitchol semantics (gpy_linalg.py:77-97) through the device path."""
+    from gprf_b200 import GPRF, LinAlgError
+    from oracle.gprf_oracle import OracleGPRF
+    cov, _ = COVS["euclid_se"]
+    rng = np.random.RandomState(11)
+    base = rng.rand(12, 2)
+    X = np.repeat(base, 8, axis=0) + 1e-9 * rng.randn(96, 2)      # 12 clusters of 8 near-duplicates
+    Y = rng.randn(96, 5)
+    blocks = [np.arange(0, 48), np.arange(48, 96)]
+    s2 = cov.wfn_params[0]
+    # K_noise-free is numerically rank 12; nv < 0 shifts its spectrum down by |nv|
+    nv = -2e-4 * s2
+    o = OracleGPRF(X, Y, None, cov, nv, block_idxs=blocks, neighbors=[(1, 0)])
+    g = GPRF(X, Y, None, prod_cov(cov), nv, block_idxs=blocks, neighbors=[(1, 0)])
+    want = o.llgrad(grad_X=True, grad_cov=True)
+    got = g.llgrad(grad_X=True, grad_cov=True)
+    _, jit = g.unit_results()
+    assert np.allclose(jit, (s2 + nv) * 1e-3, rtol=1e-12), jit      # 1e-6, 1e-5, 1e-4 fail, 1e-3 succeeds
+    assert abs(got[0] - want[0]) <= 1e-7 * abs(want[0])             # ill-conditioned by construction
+    assert np.abs(got[1] - want[1]).max() <= 1e-4 * np.abs(want[1]).max()
+    g.noise_var = -0.5 * s2
+    with pytest.raises(LinAlgError, match="even with jitter"):
+        g.llgrad()
+    g.noise_var = -2.0 * s2
+    with pytest.raises(LinAlgError, match="non-positive diagonal"):
+        g.llgrad()
+    g.noise_var = 0.05          # and the handle is still usable afterwards
+    o.noise_var = 0.05
+    assert_parity(o.llgrad(grad_X=True), g.llgrad(grad_X=True), "after failures")
+
+
+def test_pickle_roundtrip_and_unit_entry_points():
+    o, g = build_pair("euclid_m32", [33, 47, 20], [(1, 0), (2, 1)])
+    g2 = pickle.loads(pickle.dumps(g))
+    assert_parity(o.llgrad(grad_X=True, grad_cov=True), g2.llgrad(grad_X=True, grad_cov=True), "unpickled")
+    a = o.llgrad_joint(1, 0, grad_X=True, grad_cov=True)
+    b = g.llgrad_joint(1, 0, grad_X=True, grad_cov=True)
+    assert abs(a[0] - b[0]) <= LL_RTOL * abs(a[0])
+    assert np.abs(a[1] - b[1]).max() <= GRAD_RTOL * np.abs(a[1]).max()
+    assert np.abs(a[2] - b[2]).max() <= GRAD_RTOL * np.abs(a[2]).max()
+    assert g.gaussian_llgrad(o.X[:0], o.Y[:0], grad_X=True)[0] == 0.0
+
+
+def test_large_units_property():
+    """Units of ~500 / ~1000 points (the n=200k shape): cross-check against the oracle on a
+    few units and through the additive structure of the objective."""
+    o, g = build_pair("euclid_se", [480, 520, 505], [(1, 0), (2, 1)], dy=50, seed=2, nv=0.01)
+    o.cov.dfn_params[:] = 0.05
+    g.cov.dfn_params[:] = 0.05
+    assert_parity(o.llgrad(grad_X=True, grad_cov=True), g.llgrad(grad_X=True, grad_cov=True), "large")
+    lls, _ = g.unit_results()
+    w = np.array([1 - 1, 1 - 2, 1 - 1, 1, 1], dtype=float)
+    assert abs(np.dot(w, lls) - g.llgrad()[0]) <= 1e-12 * abs(g.llgrad()[0])
