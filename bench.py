@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""Benchmark of the GPRF llgrad hot path (BASELINE.json metric: llgrad evals/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+
+One "step" = one objective-and-gradient evaluation (GPRF.llgrad with grad_X, as one
+L-BFGS function evaluation of gprfopt.py:377-417) of the named workload.
+
+  value      device-resident: X already in HBM, result left in HBM; CUDA events per step on
+             the launching stream, L2 flushed between steps, max over ranks.
+  e2e        the call a user makes: GPRF.update_X(X_host) + GPRF.llgrad(grad_X=True) returning
+             host numpy arrays - host block assignment, H2D, kernels, (all-reduce), D2H.
+  roofline   dominant kernel family, algorithmic FP64 flops / measured device time against
+             the FP64 tensor (DMMA) peak measured live with a cuBLAS DGEMM.
+  cpu_baseline   the CPU oracle (a port of the reference's algorithm) timed on this host.
+
+N > 1 (torchrun, one rank per GPU): the SAME problem is sharded by units over the ranks
+(strong scaling); partial [ll, grad] vectors are summed with one NCCL all-reduce.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+DY = 50
+FAMILY_FLOPS = {                 # algorithmic flops per unit of s points (sum = s^3 + 4 s^2 dy)
+    "potrf": lambda s, dy: s ** 3 / 3.0 + s ** 2 * dy,      # dpotrf + forward half of dpotrs
+    "trtri": lambda s, dy: s ** 3 / 3.0,                    # dpotri, triangular inverse
+    "lauum": lambda s, dy: s ** 3 / 3.0 + s ** 2 * dy,      # dpotri, U U^T + back half of dpotrs
+    "grad": lambda s, dy: 2.0 * s ** 2 * dy,                # Alpha Alpha^T for G
+}
+
+
+# --------------------------------------------------------------------------- workloads
+def make_workload(name):
+    """Returns dict(X, Y, block_fn, block_idxs, neighbors, cov, noise_var, grad_cov, desc)."""
+    from gprf_b200 import GPCov, Blocker, grid_centers
+    from gprf_b200.synthetic import readme_dataset, SampledData
+    if name in ("cfg2", "cfg3"):
+        sd = readme_dataset(ntrain=10000, nblocks=100, ntest=500, yd=DY, seed=0)
+        return dict(X=sd.X_obs, Y=sd.SY, block_fn=sd.reblock, block_idxs=sd.block_idxs, neighbors=sd.neighbors,
+                    cov=sd.cov, noise_var=sd.noise_var, grad_cov=(name == "cfg3"),
+                    desc="gprfopt README config: n=10000 yd=50 nblocks=100 (342 edges) lscale=0.06 obs_std=0.02 "
+                         "seed=0, X=X_obs, task=%s" % ("xcov" if name == "cfg3" else "x"))
+    if name == "cfg1":
+        sd = SampledData(noise_var=0.01, n=2500, ntrain=2000, lscale=0.06, obs_std=0.006, yd=DY, seed=0)
+        sd.set_centers(grid_centers(20))
+        return dict(X=sd.X_obs, Y=sd.SY, block_fn=sd.reblock, block_idxs=sd.block_idxs, neighbors=sd.neighbors,
+                    cov=sd.cov, noise_var=0.01, grad_cov=False,
+                    desc="gprfopt synthetic n=2000 yd=50 lscale=0.06 nblocks=20 (25 blocks, 72 edges) task=x")
+    if name == "cfg5":
+        n = 200000
+        rng = np.random.RandomState(0)
+        X = rng.rand(n, 2)
+        Y = rng.randn(n, DY)       # exact GP sampling at n=200k is infeasible; timing is data independent
+        bl = Blocker(grid_centers(400))
+        lscale = 6.0 / np.sqrt(n)
+        return dict(X=X, Y=Y, block_fn=bl.block_clusters, block_idxs=bl.block_clusters(X), neighbors=bl.neighbors(),
+                    cov=GPCov([1.0], [lscale, lscale], "euclidean", "se"), noise_var=0.01, grad_cov=False,
+                    desc="synthetic n=200000 yd=50 400 blocks (~500 pts, 1482 edges) lscale=6/sqrt(n) Y=randn task=x")
+    raise SystemExit("unknown workload %r" % name)
+
+
+def unit_sizes(block_idxs, neighbors):
+    b = np.array([len(x) for x in block_idxs], dtype=np.float64)
+    e = np.array(neighbors, dtype=np.int64).reshape(-1, 2)
+    return np.concatenate([b, b[e[:, 0]] + b[e[:, 1]]]) if len(e) else b
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference / CPU arm
+def oracle_gprf(wl, mode="fast"):
+    from oracle.gprf_oracle import OracleGPRF
+    from oracle.kernels import GPCov as OCov
+    c = wl["cov"]
+    return OracleGPRF(wl["X"], wl["Y"], None, OCov(c.wfn_params, c.dfn_params, c.dfn_str, c.wfn_str),
+                      wl["noise_var"], block_idxs=wl["block_idxs"], neighbors=wl["neighbors"], mode=mode)
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(wl, budget_s=20.0):
+    """Oracle port on this host in the reference's own parallel mode (Pool(cpu_count) over units,
+    gprf.py:218-233), 1 BLAS thread per worker - the fastest way the reference's algorithm runs on
+    CPU (1 process x all BLAS threads is ~5x slower on these 100-200 point units).  Bounded sample:
+    one warm-up evaluation, then whole evaluations until ~budget_s seconds are spent."""
+    o = oracle_gprf(wl)
+    kw = dict(grad_X=True, grad_cov=wl["grad_cov"])
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)
+    except Exception:
+        limiter = None
+    try:
+        t0 = time.perf_counter()
+        o.llgrad(parallel=True, **kw)
+        first = time.perf_counter() - t0
+        ts = []
+        while not ts or (sum(ts) + first + min(ts) < budget_s and len(ts) < 5):
+            t0 = time.perf_counter()
+            o.llgrad(parallel=True, **kw)
+            ts.append(time.perf_counter() - t0)
+    finally:
+        if limiter is not None:
+            limiter.restore_original_limits()
+    sec = float(np.median(ts))
+    return {"value": 1.0 / sec, "unit": "evals/s", "cores": cores, "kind": "port",
+            "sample": "%d full evals after 1 warm-up (median), all %d units, grad_X" % (len(ts), o.n_blocks + len(o.neighbors)),
+            "sec_per_eval": sec,
+            "note": "oracle port, Pool(%d) x 1 BLAS thread (the reference's --parallel mode)" % cores}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm on the host cores.  The reference itself
+    (Python 2 + un-vendored treegp) cannot run, so this is the oracle port, using the reference's
+    own parallel mode (Pool(cpu_count) over units, gprf.py:218-233) with 1 BLAS thread per worker."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload(args.workload)
+    o = oracle_gprf(wl)
+    kw = dict(grad_X=True, grad_cov=wl["grad_cov"])
+    cores = os.cpu_count() or 1
+    sizes = unit_sizes(wl["block_idxs"], wl["neighbors"])
+    w = sizes ** 3 + 4 * sizes ** 2 * DY
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
+    # bounded sample: keep every step under ~20 s by evaluating a prefix of the edge list
+    t0 = time.perf_counter()
+    o.llgrad_joint(*o.neighbors[0], **kw)
+    est = (time.perf_counter() - t0) * w.sum() / w[o.n_blocks] / max(1, cores)
+    frac = 1.0
+    if est > 20.0:
+        keep = max(cores, int(len(o.neighbors) * 20.0 / est))
+        used = np.zeros(len(sizes), dtype=bool)
+        used[:o.n_blocks] = True
+        used[o.n_blocks:o.n_blocks + keep] = True
+        frac = w[used].sum() / w.sum()
+        o.neighbors = o.neighbors[:keep]
+        o.compute_neighbor_count()
+    for _ in range(max(1, args.warmup if frac == 1.0 else 1)):
+        o.llgrad(parallel=True, **kw)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.llgrad(parallel=True, **kw)
+    sec = (time.perf_counter() - t0) / args.steps / frac
+    sample = ("full eval per step" if frac == 1.0 else
+              "%.1f%% of the eval's flops per step (all blocks + first %d edges), scaled by flops"
+              % (100 * frac, len(o.neighbors)))
+    val = 1.0 / sec
+    line = {"impl": "reference", "metric": "GPRF llgrad evals/sec", "value": val, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": wl["desc"]},
+            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "reference is Python 2 + un-vendored treegp (cannot run); oracle port in the "
+                                     "reference's --parallel mode: Pool(%d) x 1 BLAS thread" % cores},
+            "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def dgemm_peak_tflops(torch, n=6144, reps=4):
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / best * 1e-9
+
+
+class Runner(object):
+    """One workload on this rank's GPU: device-resident steps, end-to-end steps, profiling."""
+
+    def __init__(self, torch, dist, wl, rank, world, local_rank):
+        from gprf_b200 import GPRF
+        from gprf_b200 import _lib
+        self.torch, self.dist, self.wl, self.rank, self.world = torch, dist, wl, rank, world
+        self.n, self.dx = wl["X"].shape
+        self.dev = torch.device("cuda", local_rank)
+        self.g = GPRF(wl["X"], wl["Y"], wl["block_fn"], wl["cov"], wl["noise_var"], block_idxs=wl["block_idxs"],
+                      neighbors=wl["neighbors"], device=local_rank,
+                      unit_shard=(rank, world) if world > 1 else None)
+        self.outlen = 1 + _lib.MAX_NCOV + self.n * self.dx
+        self.Xd = torch.tensor(wl["X"], dtype=torch.float64, device=self.dev)
+        self.out = torch.zeros(self.outlen, dtype=torch.float64, device=self.dev)
+        self.Xh = torch.empty((self.n, self.dx), dtype=torch.float64).pin_memory()
+        self.outh = torch.empty(self.outlen, dtype=torch.float64).pin_memory()
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.grad_cov = wl["grad_cov"]
+
+    def flush_l2(self):
+        self.flush_buf.zero_()
+
+    def device_step(self):
+        st = self.torch.cuda.current_stream(self.dev)
+        self.g.llgrad_device(self.Xd.data_ptr(), self.out.data_ptr(), st.cuda_stream,
+                             grad_X=True, grad_cov=self.grad_cov)
+        if self.world > 1:
+            self.dist.all_reduce(self.out)
+
+    def timed_device_steps(self, k):
+        torch = self.torch
+        total = 0.0
+        launches = 0
+        for _ in range(k):
+            self.flush_l2()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.device_step()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+            launches += self.g.last_timing()[1] + (1 if self.world > 1 else 0)
+        return total, launches
+
+    def e2e_step(self, X_host):
+        """update_X (host block assignment) + llgrad through host buffers."""
+        torch = self.torch
+        if self.world == 1:
+            self.g.update_X(X_host)
+            return self.g.llgrad(grad_X=True, grad_cov=self.grad_cov)
+        self.g.update_X(X_host)
+        self.Xh.numpy()[...] = X_host
+        self.Xd.copy_(self.Xh, non_blocking=True)
+        self.device_step()
+        self.outh.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self.outh[0].item()
+
+    def e2e_bytes(self):
+        nb, ne = len(self.wl["block_idxs"]), len(self.wl["neighbors"])
+        h2d = self.n * self.dx * 8 + self.n * 8 + self.n * 4 + (nb + 1) * 12 + ne * 8 * 2 + ne * 8 + (nb + ne) * 96
+        d2h = (1 + 5 + self.n * self.dx) * 8 + 4
+        return h2d, d2h
+
+    def family_profile(self, reps=3):
+        self.g.set_profiling(True)
+        acc = {}
+        for _ in range(reps):
+            self.flush_l2()
+            self.device_step()
+            for k, (ms, nl) in self.g.family_timing().items():
+                a = acc.setdefault(k, [0.0, 0])
+                a[0] += ms / reps
+                a[1] = nl
+        self.g.set_profiling(False)
+        return acc
+
+
+def roofline_from_profile(fam, sizes_local, dy, peak_tflops, peak_note):
+    merged = {"potrf": [fam["potrf_diag"][0] + fam["potrf_panel"][0], fam["potrf_diag"][1] + fam["potrf_panel"][1]],
+              "trtri": fam["trtri"], "lauum": fam["lauum"], "grad": fam["grad"]}
+    name = max(merged, key=lambda k: merged[k][0])
+    ms, nl = merged[name]
+    flops = float(np.sum(FAMILY_FLOPS[name](sizes_local, dy)))
+    achieved = flops / (ms * 1e-3) * 1e-12 if ms > 0 else 0.0
+    return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": achieved / peak_tflops, "traffic": None, "peak_source": peak_note,
+            "launches_per_eval": nl, "ms_per_eval": ms,
+            "families_ms": dict((k, round(v[0], 4)) for k, v in fam.items())}
+
+
+def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, with_cpu):
+    wl = make_workload(wl_name)
+    R = Runner(torch, dist, wl, rank, world, local_rank)
+    sizes = unit_sizes(wl["block_idxs"], wl["neighbors"])
+    flops_eval = float(np.sum(sizes ** 3 + 4 * sizes ** 2 * DY))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi needs a few 100 ms to start: cover warm-up too
+    t_w, n_w = time.perf_counter(), 0
+    while n_w < max(3, warmup) or (time.perf_counter() - t_w < 0.8 and n_w < 400):
+        R.device_step()
+        n_w += 1
+    barrier()
+    total_ms, launches = R.timed_device_steps(steps)
+    barrier()
+    t_w = time.perf_counter()
+    while len(sampler.rows) < 4 and time.perf_counter() - t_w < 2.0:
+        R.device_step()                  # keep the load on until the sampler has seen it (untimed)
+    clocks = sampler.stop()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=R.dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / steps
+
+    # end to end through the public host API
+    Xh = np.array(wl["X"])
+    for _ in range(2):
+        R.e2e_step(Xh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R.e2e_step(Xh)
+    barrier()
+    te = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=R.dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_sec = te.item()
+    h2d, d2h = R.e2e_bytes()
+
+    peak = dgemm_peak_tflops(torch)
+    peak_note = ("measured live: cuBLAS DGEMM 6144^3 fp64 on this GPU (MEASURED_PEAKS.json has no fp64 entry; raw DMMA "
+                 "issue peak measured at 37.1 TFLOP/s, profiles/r01_fp64_peak_dmma_dfma.txt)")
+    fam = R.family_profile()
+    if world > 1:
+        from gprf_b200.dist import shard_units
+        from gprf_b200.gprf import _blocks_to_csr
+        ptr, _ = _blocks_to_csr(wl["block_idxs"])
+        mask = shard_units(ptr, np.asarray(wl["neighbors"]), rank, world).astype(bool)
+        sizes_local = sizes[mask]
+    else:
+        sizes_local = sizes
+    roof = roofline_from_profile(fam, sizes_local, DY, peak, peak_note)
+    roof["eval_tflops"] = flops_eval / (ms_per_step * 1e-3) * 1e-12
+    roof["eval_frac_of_peak_all_gpus"] = roof["eval_tflops"] / (peak * world)
+    res = {"wl": wl, "ms_per_step": ms_per_step, "value": 1e3 / ms_per_step, "launches": launches // steps,
+           "clocks": clocks, "e2e": {"value": 1.0 / e2e_sec, "unit": "evals/s", "h2d_bytes_per_step": h2d,
+                                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec * 1e3},
+           "roofline": roof, "flops_per_eval": flops_eval}
+    if with_cpu and rank == 0 and world == 1:
+        res["cpu_baseline"] = cpu_baseline(wl)
+    R.g.close()
+    del R
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--no-n200k", action="store_true", help="skip the extra n=200k measurement")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+
+    r = measure(torch, dist, args, args.workload, rank, world, local_rank, args.steps, args.warmup,
+                with_cpu=not args.no_cpu)
+    line = {"metric": "GPRF llgrad evals/sec", "value": r["value"], "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": r["wl"]["desc"], "parallelism": "units sharded over %d GPU(s), 1 all-reduce" % world,
+                       "l2": "flushed between timed steps (256 MiB write)",
+                       "flops_per_eval": r["flops_per_eval"]},
+            "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["launches"] * args.steps,
+            "roofline": r["roofline"]}
+    if "cpu_baseline" in r:
+        line["cpu_baseline"] = r["cpu_baseline"]
+    if not args.no_n200k and args.workload != "cfg5":
+        k5 = max(2, min(args.steps, 5))
+        r5 = measure(torch, dist, args, "cfg5", rank, world, local_rank, k5, 1, with_cpu=False)
+        line["n200k"] = {"workload": r5["wl"]["desc"], "value": r5["value"], "unit": "evals/s",
+                         "ms_per_step": r5["ms_per_step"], "steps": k5, "e2e": r5["e2e"], "roofline": r5["roofline"],
+                         "clocks": r5["clocks"], "scaling": "strong"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -65,7 +65,51 @@ struct gprf_ctx {
   int *dInfo = nullptr, *dNfail = nullptr;
   std::vector<double> jitter;
   std::vector<int> tries;
+
+  // optional per-kernel-family timing (CUDA events around every launch)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Rec { int fam; size_t a, b; };
+  std::vector<Rec> recs;
+  float fam_ms[GPRF_N_FAMILIES] = {0};
+  int fam_launches[GPRF_N_FAMILIES] = {0};
+
+  size_t prof_begin(int fam, cudaStream_t st) {
+    if (!profile) return 0;
+    while (ev_pool.size() < ev_used + 2) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev_pool.push_back(e);
+    }
+    size_t a = ev_used;
+    ev_used += 2;
+    cudaEventRecord(ev_pool[a], st);
+    recs.push_back({fam, a, a + 1});
+    return a;
+  }
+  void prof_end(size_t a, cudaStream_t st) {
+    if (profile) cudaEventRecord(ev_pool[a + 1], st);
+  }
+  void prof_resolve() {
+    for (int f = 0; f < GPRF_N_FAMILIES; ++f) { fam_ms[f] = 0.f; fam_launches[f] = 0; }
+    for (auto& r : recs) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev_pool[r.a], ev_pool[r.b]) == cudaSuccess) fam_ms[r.fam] += ms;
+      fam_launches[r.fam]++;
+    }
+    recs.clear();
+    ev_used = 0;
+  }
 };
+
+#define LAUNCH(fam, ...)                          \
+  do {                                            \
+    size_t pa_ = h->prof_begin(fam, st);          \
+    __VA_ARGS__;                                  \
+    h->prof_end(pa_, st);                         \
+    ++launches;                                   \
+  } while (0)
 
 static size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
@@ -183,6 +227,7 @@ extern "C" int gprf_destroy(gprf_handle h) {
   cudaFree(h->dPosBlock); cudaFree(h->dAdjPtr); cudaFree(h->dAdjEdge); cudaFree(h->dAdjSide);
   cudaFree(h->arena); cudaFree(h->dLLu); cudaFree(h->dGthU); cudaFree(h->dJitter);
   cudaFree(h->dInfo); cudaFree(h->dNfail);
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -361,30 +406,23 @@ static int launch_units(gprf_ctx* h, const EvalParams& P, int nlist, int ntmax, 
     const int cnt = std::min(CH, nlist - base);
     EvalParams Pc = P;
     Pc.ulist = P.ulist + base;
-    k_prep<<<dim3(ntmax, cnt), NTHREADS, 0, st>>>(Pc);
-    ++launches;
+    LAUNCH(0, (k_prep<<<dim3(ntmax, cnt), NTHREADS, 0, st>>>(Pc)));
     for (int k = 0; k < ntmax; ++k) {
 #define CALL_DIAG(D, W) k_potrf_diag<D, W><<<dim3(1, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, k)
-      DISPATCH_COV(h, CALL_DIAG);
-      ++launches;
+      LAUNCH(1, DISPATCH_COV(h, CALL_DIAG));
       const int gx = ntmax - k - 1 + h->nya;
 #define CALL_PANEL(D, W) k_potrf_panel<D, W><<<dim3(gx, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, k)
-      DISPATCH_COV(h, CALL_PANEL);
-      ++launches;
+      LAUNCH(2, DISPATCH_COV(h, CALL_PANEL));
     }
     if (want_grad) {
       for (int d = 1; d < ntmax; ++d) {
-        k_trtri<<<dim3(ntmax - d, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, d);
-        ++launches;
+        LAUNCH(3, (k_trtri<<<dim3(ntmax - d, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, d)));
       }
-      k_lauum<<<dim3(ntri_max + ntmax * h->nya, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, ntri_max);
-      ++launches;
+      LAUNCH(4, (k_lauum<<<dim3(ntri_max + ntmax * h->nya, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, ntri_max)));
 #define CALL_GRAD(D, W) k_grad<D, W><<<dim3(ntri_max, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc)
-      DISPATCH_COV(h, CALL_GRAD);
-      ++launches;
+      LAUNCH(5, DISPATCH_COV(h, CALL_GRAD));
     }
-    k_unit_finalize<<<cnt, NTHREADS, 0, st>>>(Pc, h->dLLu, h->dGthU, want_grad ? 1 : 0);
-    ++launches;
+    LAUNCH(6, (k_unit_finalize<<<cnt, NTHREADS, 0, st>>>(Pc, h->dLLu, h->dGthU, want_grad ? 1 : 0)));
   }
   return launches;
 }
@@ -468,8 +506,7 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
     CUDA_OK(cudaStreamSynchronize(st));
   }
 
-  k_combine_scalars<<<1, 256, 0, st>>>(h->dUnits, U, h->dLLu, h->dGthU, grad_cov ? 1 : 0, out_dev);
-  ++launches;
+  LAUNCH(7, (k_combine_scalars<<<1, 256, 0, st>>>(h->dUnits, U, h->dLLu, h->dGthU, grad_cov ? 1 : 0, out_dev)));
   if (grad_X && h->plen > 0) {
     CombineParams C;
     C.units = h->dUnits;
@@ -484,8 +521,7 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
     C.dx = h->dx;
     C.plen = h->plen;
     const int tb = 256;
-    k_combine_gradx<<<(unsigned)((h->plen + tb - 1) / tb), tb, 0, st>>>(C, out_dev + 1 + MAX_NCOV);
-    ++launches;
+    LAUNCH(7, (k_combine_gradx<<<(unsigned)((h->plen + tb - 1) / tb), tb, 0, st>>>(C, out_dev + 1 + MAX_NCOV)));
   }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(h->ev1, st));
@@ -502,6 +538,7 @@ extern "C" int gprf_llgrad_device(gprf_handle h, const double* X_dev, const doub
   if (rc != GPRF_OK) return rc;
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  if (h->profile) h->prof_resolve();
   return GPRF_OK;
 }
 
@@ -519,6 +556,7 @@ extern "C" int gprf_llgrad(gprf_handle h, const double* X, const double* theta, 
   CUDA_OK(cudaMemcpyAsync(h->hOut, h->dOut, outlen * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  if (h->profile) h->prof_resolve();
   *ll = h->hOut[0];
   if (grad_cov)
     for (int t = 0; t < ncov; ++t) gradTheta[t] = h->hOut[1 + t];
@@ -538,6 +576,27 @@ extern "C" int gprf_last_timing(gprf_handle h, float* ms, int* launches) {
   if (!h) return GPRF_ERR_ARG;
   if (ms) *ms = h->last_ms;
   if (launches) *launches = h->last_launches;
+  return GPRF_OK;
+}
+
+extern "C" int gprf_set_profiling(gprf_handle h, int on) {
+  if (!h) return GPRF_ERR_ARG;
+  h->profile = (on != 0);
+  return GPRF_OK;
+}
+
+extern "C" const char* gprf_family_name(int fam) {
+  static const char* names[GPRF_N_FAMILIES] = {"prep", "potrf_diag", "potrf_panel", "trtri",
+                                               "lauum", "grad", "unit_finalize", "combine"};
+  return (fam >= 0 && fam < GPRF_N_FAMILIES) ? names[fam] : "";
+}
+
+extern "C" int gprf_family_timing(gprf_handle h, float* ms, int* launches) {
+  if (!h) return GPRF_ERR_ARG;
+  for (int f = 0; f < GPRF_N_FAMILIES; ++f) {
+    if (ms) ms[f] = h->fam_ms[f];
+    if (launches) launches[f] = h->fam_launches[f];
+  }
   return GPRF_OK;
 }
 

@@ -222,6 +222,21 @@ class GPRF(object):
         gradCov = gC.reshape((1, -1)) if grad_cov else np.zeros((0, 0))
         return np.float64(ll.value), gradX, gradCov
 
+    def llgrad_device(self, X_dev_ptr, out_dev_ptr, stream_ptr=0, local=True, grad_X=False, grad_cov=False):
+        """Device-resident variant (gprf_llgrad_device): X already in HBM at ``X_dev_ptr``
+        (n x dx doubles), results left in HBM at ``out_dev_ptr`` as
+        [ll, grad_theta (5, zero padded), gradX (n*dx)].  Pointers are plain integers
+        (e.g. ``tensor.data_ptr()``, ``torch.cuda.current_stream().cuda_stream``).
+        Uses the block structure of the last ``update_X`` / constructor."""
+        edges = self.neighbors if local else [(i, j) for i in range(self.n_blocks) for j in range(i)]
+        self._push_structure(edges)
+        th = self._theta()
+        failed = C.c_int(-1)
+        rc = self._lib.gprf_llgrad_device(self._h, C.c_void_p(X_dev_ptr), _lib.ptr(th), len(th), int(grad_X),
+                                          int(grad_cov), C.c_void_p(out_dev_ptr), C.c_void_p(stream_ptr),
+                                          C.byref(failed))
+        self._check(rc, failed.value)
+
     def unit_results(self):
         """Per-unit log-likelihoods and applied jitter of the last evaluation
         (units: blocks 0..B-1, then edges in ``neighbors`` order)."""
@@ -236,6 +251,16 @@ class GPRF(object):
         n = C.c_int()
         self._lib.gprf_last_timing(self._h, C.byref(ms), C.byref(n))
         return ms.value, n.value
+
+    def set_profiling(self, on=True):
+        self._lib.gprf_set_profiling(self._h, int(bool(on)))
+
+    def family_timing(self):
+        """{family: (ms, launches)} of the last evaluation (needs set_profiling(True))."""
+        ms = (C.c_float * _lib.N_FAMILIES)()
+        nl = (C.c_int * _lib.N_FAMILIES)()
+        self._lib.gprf_family_timing(self._h, ms, nl)
+        return dict((self._lib.gprf_family_name(i).decode(), (ms[i], nl[i])) for i in range(_lib.N_FAMILIES))
 
     # -- single-unit entry points (gprf.py:299-330, 496-591) -------------------
     def gaussian_llgrad(self, X, Y, grad_X=False, grad_cov=False, **_unused):

@@ -1,0 +1,96 @@
+"""Synthetic experiment data (the reference's ``synthetic.sample_synthetic`` and
+``gprfopt.SampledData``; synthetic.py:103-114,139-153, gprfopt.py:19-74,172-182).
+
+Host-side set-up code for drivers, benchmarks and examples - not part of the
+per-evaluation hot path.  The legacy global ``np.random.seed`` stream is used
+because the reference's shipped results are keyed to it.
+"""
+import numpy as np
+from scipy.linalg import lapack
+
+from .blocking import Blocker, grid_centers
+from .cov import GPCov
+from .gprf import GPRF
+
+
+def _se_gram(X, lscales, signal_var):
+    r2 = np.zeros((X.shape[0], X.shape[0]))
+    for i in range(X.shape[1]):
+        d = (X[:, i][:, None] - X[:, i][None, :]) / lscales[i]
+        d *= d
+        r2 += d
+    np.sqrt(r2, out=r2)          # mirror r = sqrt(r2); w = exp(-r*r) of the evaluator
+    r2 *= r2
+    np.negative(r2, out=r2)
+    np.exp(r2, out=r2)
+    r2 *= signal_var
+    return r2
+
+
+def sample_y(X, cov, noise_var, yd):
+    """GP-prior draw Y = chol(K + nv I) Z with Z = randn(n, yd) (dense branch, n < 40000)."""
+    if cov.dfn_str != "euclidean" or cov.wfn_str != "se":
+        raise NotImplementedError("host sampling is provided for the synthetic (euclidean, se) family")
+    K = _se_gram(np.asarray(X, dtype=float), cov.dfn_params, cov.wfn_params[0])
+    K[np.diag_indices_from(K)] += noise_var
+    L, info = lapack.dpotrf(K, lower=1)
+    if info != 0:
+        raise np.linalg.LinAlgError("prior covariance is not positive definite")
+    Z = np.random.randn(X.shape[0], yd)
+    return np.dot(L, Z)
+
+
+def sample_synthetic(seed=1, n=400, xd=2, yd=10, lscale=0.1, noise_var=0.01):
+    if seed >= 1000:
+        raise NotImplementedError("shaped synthetic sets (seed >= 1000) are not provided")
+    np.random.seed(seed)
+    X = np.random.rand(n, xd)
+    cov = GPCov(wfn_params=[1.0], dfn_params=[lscale, lscale], dfn_str="euclidean", wfn_str="se")
+    return X, sample_y(X, cov, noise_var, yd), cov
+
+
+class SampledData(object):
+    """Train/test split, noisy observed locations, grid blocks and the location prior."""
+
+    def __init__(self, noise_var=0.01, n=30, ntrain=20, lscale=0.5, obs_std=0.05, yd=10, seed=1):
+        self.noise_var, self.n, self.ntrain, self.lscale, self.obs_std = noise_var, n, ntrain, lscale, obs_std
+        Xfull, Yfull, self.cov = sample_synthetic(n=n, noise_var=noise_var, yd=yd, lscale=lscale, seed=seed)
+        self.SX, self.SY = Xfull[:ntrain, :], Yfull[:ntrain, :]
+        self.Xtest, self.Ytest = Xfull[ntrain:, :], Yfull[ntrain:, :]
+        np.random.seed(seed)
+        self.X_obs = self.SX + np.random.randn(*self.SX.shape) * obs_std
+        self.block_idxs = None
+        self.neighbors = None
+
+    def set_centers(self, centers):
+        self.centers = np.asarray(centers)
+        blocker = Blocker(self.centers)
+        self.block_idxs = blocker.block_clusters(self.X_obs)
+        self.reblock = blocker.block_clusters
+        self.neighbors = blocker.neighbors(diag_connections=True)
+
+    def build_gprf(self, X=None, cov=None, local_dist=1e-4, cls=GPRF, **extra):
+        X = self.X_obs if X is None else X
+        noise_var = self.noise_var
+        if cov is None:
+            cov = self.cov
+        else:
+            cov = np.asarray(cov)
+            noise_var = cov[0, 0]
+            cov = GPCov(wfn_params=[cov[0, 1]], dfn_params=cov[0, 2:], dfn_str="euclidean", wfn_str="se")
+        return cls(X, self.SY, self.reblock, cov, noise_var, neighbor_threshold=local_dist,
+                   block_idxs=self.block_idxs, neighbors=self.neighbors if local_dist < 1.0 else [], **extra)
+
+    def x_prior(self, xx):
+        resid = xx - self.X_obs.ravel()
+        ll = -.5 * np.sum((resid / self.obs_std) ** 2) - .5 * len(xx) * np.log(2 * np.pi * self.obs_std ** 2)
+        return ll, -resid / self.obs_std ** 2
+
+
+def readme_dataset(ntrain=10000, nblocks=100, ntest=500, yd=50, seed=0, noise_var=0.01):
+    """The reference's README / results configuration: lscale = 6/sqrt(n), obs_std = 2/sqrt(n)
+    (gprfopt_analyze.py:206-207), grid blocks, 8-connected edges."""
+    sd = SampledData(noise_var=noise_var, n=ntrain + ntest, ntrain=ntrain, lscale=6.0 / np.sqrt(ntrain),
+                     obs_std=2.0 / np.sqrt(ntrain), yd=yd, seed=seed)
+    sd.set_centers(grid_centers(nblocks))
+    return sd

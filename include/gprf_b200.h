@@ -109,6 +109,15 @@ int gprf_debug_unit(gprf_handle h, int unit, int* s, int* sp, int* yr,
  * (CUDA events on the launching stream), and the number of kernel launches. */
 int gprf_last_timing(gprf_handle h, float* ms, int* launches);
 
+/* Optional per-kernel-family timing: when on, every launch is bracketed by CUDA
+ * events on the launching stream; gprf_family_timing returns, for the last
+ * evaluation, the summed device time (ms) and launch count of each family
+ * (gprf_family_name(i), i < GPRF_N_FAMILIES). */
+#define GPRF_N_FAMILIES 8
+int gprf_set_profiling(gprf_handle h, int on);
+int gprf_family_timing(gprf_handle h, float* ms, int* launches);
+const char* gprf_family_name(int fam);
+
 const char* gprf_strerror(int code);
 const char* gprf_last_error(gprf_handle h);
 int gprf_abi_version(void);

@@ -144,3 +144,16 @@ def test_sharded_reduction_world2_gloo():
     for p in procs:
         p.join(60)
     assert res == [(0, True), (1, True)]
+
+
+def test_product_synthetic_matches_oracle_bitwise():
+    """The product's data generator (used by bench.py) equals the golden-pinned oracle recipe."""
+    from gprf_b200.synthetic import readme_dataset
+    from oracle.synthetic import golden_run
+    a = readme_dataset(ntrain=700, nblocks=9, ntest=100, yd=6)
+    b = golden_run(700, 9, 0.1, yd=6, ntest=100)
+    assert np.array_equal(a.SX, b.SX) and np.array_equal(a.SY, b.SY) and np.array_equal(a.X_obs, b.X_obs)
+    assert a.neighbors == b.neighbors
+    assert all(np.array_equal(x, y) for x, y in zip(a.block_idxs, b.block_idxs))
+    xx = a.SX.flatten()
+    assert a.x_prior(xx)[0] == b.x_prior(xx)[0]
