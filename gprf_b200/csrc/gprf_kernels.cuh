@@ -26,6 +26,7 @@
 #pragma once
 #include "covfn.cuh"
 #include "tile_gemm.cuh"
+#include "smem_chol.cuh"
 
 namespace gprf {
 
@@ -174,16 +175,18 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
   gemm_nt_ref(acc, k, tA, tA, pipe);
   __syncthreads();
 
-  // C = K_kk - acc  -> scalar scratch tile S (stride SQLD) in the pipe buffers
+  // C = K_kk - acc  -> shared tile S (stride WLD); S2 receives U_kk = L_kk^-T
   double* S = pipe;
-  double* W = pipe + T * SQLD;
+  double* S2 = pipe + T * WLD;
+  double* Wsm = pipe + 2 * T * WLD;
   const double diag_add = P.cp.nv + P.jitter[uid];
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
     const int r = acc_row(m);
     const int p = k * T + r;
 #pragma unroll
-    for (int n = 0; n < 8; ++n)
+    for (int n = 0; n < 8; ++n) {
+      double v[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int c = acc_col(n) + e;
@@ -195,64 +198,31 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
         } else {
           kv = (r == c) ? 1.0 : 0.0;
         }
-        S[r * SQLD + c] = kv - acc.c[m][n][e];
+        v[e] = kv - acc.c[m][n][e];
       }
+      *reinterpret_cast<double2*>(S + r * WLD + acc_col(n)) = make_double2(v[0], v[1]);
+    }
   }
+  for (int e = tid; e < T * WLD; e += NTHREADS) S2[e] = 0.0;
   __syncthreads();
 
-  // unblocked right-looking Cholesky of the 64x64 tile (lower)
-  for (int c = 0; c < T; ++c) {
-    const double piv = S[c * SQLD + c];
-    if (!(piv > 0.0)) {
-      if (tid == 0 && sfail == 0) sfail = k * T + c + 1;
-    }
-    const double dsq = sqrt(piv);
-    __syncthreads();
-    if (tid == c) S[c * SQLD + c] = dsq;
-    if (tid > c && tid < T) S[tid * SQLD + c] /= dsq;
-    __syncthreads();
-    {
-      const int r = tid & (T - 1);
-      if (r > c) {
-        const double lrc = S[r * SQLD + c];
-        for (int cc = c + 1 + (tid >> 6); cc <= r; cc += 2) S[r * SQLD + cc] -= lrc * S[cc * SQLD + c];
-      }
-    }
-    __syncthreads();
-  }
+  smem_potrf_trtri(S, S2, Wsm, WLD, T / 8, &sfail, k * T);
 
-  // W = L^-1: two lanes per column, forward substitution down the rows
-  {
-    const int c = tid >> 1, h = tid & 1;
-    for (int r = 0; r < T; ++r) {
-      double part = 0.0;
-      if (r > c)
-        for (int m = c + h; m < r; m += 2) part += S[r * SQLD + m] * W[m * SQLD + c];
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      if (h == 0) {
-        double v = 0.0;
-        if (r == c) v = 1.0 / S[r * SQLD + r];
-        else if (r > c) v = -part / S[r * SQLD + r];
-        W[r * SQLD + c] = v;
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-
-  // outputs: L_kk (upper part zero), W_kk, U_kk = W_kk^T, logdet partial, status
+  // outputs: L_kk (upper part zero), W_kk = U_kk^T, U_kk, logdet partial, status
   double* Lout = M + (long long)k * T * ld + k * T;
   double* Wd = P.arena + u.d_off + (long long)k * T * T;
   double* Ud = P.arena + u.d_off + (long long)(u.nt + k) * T * T;
   for (int e = tid; e < T * T; e += NTHREADS) {
     int r = e / T, c = e % T;
-    Lout[(long long)r * ld + c] = (c <= r) ? S[r * SQLD + c] : 0.0;
-    Wd[e] = W[r * SQLD + c];
-    Ud[e] = W[c * SQLD + r];
+    Lout[(long long)r * ld + c] = (c <= r) ? S[r * WLD + c] : 0.0;
+    Ud[e] = S2[r * WLD + c];
+    Wd[e] = S2[c * WLD + r];
   }
+  if (tid < T) Wsm[tid] = log(S[tid * WLD + tid]);
+  __syncthreads();
   if (tid == 0) {
     double lsum = 0.0;
-    for (int r = 0; r < T; ++r) lsum += log(S[r * SQLD + r]);
+    for (int r = 0; r < T; ++r) lsum += Wsm[r];
     (P.arena + u.ld_off)[k] = lsum;
     if (sfail != 0 && atomicCAS(&P.info[uid], 0, sfail) == 0) atomicAdd(P.nfail, 1);
   }
