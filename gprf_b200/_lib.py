@@ -29,6 +29,17 @@ _SIGNATURES = {
     "gprf_destroy": (C.c_int, [C.c_void_p]),
     "gprf_set_structure": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p]),
+    "gprf_set_edges": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "gprf_set_blocks": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "gprf_set_grid_partitioner": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "gprf_set_tree_partitioner": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]),
+    "gprf_reblock": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gprf_reblock_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gprf_block_count": (C.c_int, [C.c_void_p, _ip, _llp]),
+    "gprf_get_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gprf_llgrad_reblock": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      _dp, C.c_void_p, C.c_void_p, _ip]),
     "gprf_llgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                               _dp, C.c_void_p, C.c_void_p, _ip]),
     "gprf_llgrad_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

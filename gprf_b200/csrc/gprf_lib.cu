@@ -12,6 +12,9 @@
 
 #include "../../include/gprf_b200.h"
 #include "gprf_kernels.cuh"
+#include "partition.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <queue>
 
 using namespace gprf;
 
@@ -57,7 +60,25 @@ struct gprf_ctx {
   long long* dBlockPtr = nullptr;
   int* dPosBlock = nullptr;
   int *dAdjPtr = nullptr, *dAdjEdge = nullptr, *dAdjSide = nullptr;
-  size_t capUnits = 0, capPerm = 0, capPos = 0, capB = 0, capAdj = 0;
+  size_t capUnits = 0, capPerm = 0, capPos = 0, capB = 0, capAdj = 0, capAdj2 = 0, capAdjPtr = 0;
+  UnitDesc* hUnits = nullptr;      // pinned staging
+  int* hList = nullptr;
+  cudaEvent_t evStage = nullptr;
+  std::vector<int> edges, deg;
+  std::vector<long long> block_ptr_h;
+  std::vector<unsigned char> explicit_mask, lpt, seen;
+  bool use_explicit_mask = false, adj_dirty = true, blocks_from_device = false;
+  int shard_rank = 0, shard_world = 1;
+
+  // device partitioner (K8)
+  int part_kind = 0, part_B = 0, part_mode = 0, part_root = 0, part_launches = 0;
+  double part_wrap_add = 22.0, part_wrap_mod = 360.0;
+  double *dPartA = nullptr, *dPartB = nullptr, *dPartC = nullptr;
+  int* dPartChild = nullptr;
+  int *dOwner = nullptr, *dIota = nullptr, *dIdxSorted = nullptr;
+  size_t capOwner = 0, capIota = 0, capIdxS = 0, capCub = 0, capHB = 0;
+  void* dCub = nullptr;
+  long long* hBlockPtr = nullptr;  // pinned
 
   double* arena = nullptr;
   size_t arena_cap = 0;            // doubles
@@ -205,6 +226,7 @@ extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, in
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreate(&h->ev0));
   CUDA_OK(cudaEventCreate(&h->ev1));
+  CUDA_OK(cudaEventCreateWithFlags(&h->evStage, cudaEventDisableTiming));
   const size_t outlen = 1 + MAX_NCOV + (size_t)n * dx;
   CUDA_OK(cudaMalloc((void**)&h->dY, (size_t)n * dy * sizeof(double)));
   CUDA_OK(cudaMalloc((void**)&h->dX, (size_t)n * dx * sizeof(double)));
@@ -227,6 +249,12 @@ extern "C" int gprf_destroy(gprf_handle h) {
   cudaFree(h->dPosBlock); cudaFree(h->dAdjPtr); cudaFree(h->dAdjEdge); cudaFree(h->dAdjSide);
   cudaFree(h->arena); cudaFree(h->dLLu); cudaFree(h->dGthU); cudaFree(h->dJitter);
   cudaFree(h->dInfo); cudaFree(h->dNfail);
+  cudaFree(h->dPartA); cudaFree(h->dPartB); cudaFree(h->dPartC); cudaFree(h->dPartChild);
+  cudaFree(h->dOwner); cudaFree(h->dIota); cudaFree(h->dIdxSorted); cudaFree(h->dCub);
+  if (h->hUnits) cudaFreeHost(h->hUnits);
+  if (h->hList) cudaFreeHost(h->hList);
+  if (h->hBlockPtr) cudaFreeHost(h->hBlockPtr);
+  if (h->evStage) cudaEventDestroy(h->evStage);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -235,27 +263,10 @@ extern "C" int gprf_destroy(gprf_handle h) {
   return GPRF_OK;
 }
 
-extern "C" int gprf_set_structure(gprf_handle h, int B, const long long* block_ptr, const long long* perm,
-                                  int E, const int* edges, const unsigned char* unit_mask) {
-  if (!h || B < 1 || !block_ptr || E < 0 || (E > 0 && !edges)) return GPRF_ERR_ARG;
-  CUDA_OK(cudaSetDevice(h->device));
-  const long long plen = block_ptr[B];
-  if (block_ptr[0] != 0 || plen < 0 || plen > h->n || (plen > 0 && !perm)) {
-    h->err = "block_ptr must start at 0 and cover at most n points";
-    return GPRF_ERR_ARG;
-  }
-  {
-    std::vector<unsigned char> seen((size_t)h->n, 0);
-    for (long long p = 0; p < plen; ++p) {
-      if (perm[p] < 0 || perm[p] >= h->n || seen[(size_t)perm[p]]) {
-        h->err = "block index lists must be disjoint indices in [0, n)";
-        return GPRF_ERR_ARG;
-      }
-      seen[(size_t)perm[p]] = 1;
-    }
-  }
-  for (int b = 0; b < B; ++b)
-    if (block_ptr[b + 1] < block_ptr[b]) return GPRF_ERR_ARG;
+// ---------------------------------------------------------------------------
+// structure = edges (static) + blocks (per update_X) -> units
+// ---------------------------------------------------------------------------
+static int validate_edges(gprf_ctx* h, int B, int E, const int* edges) {
   for (int e = 0; e < E; ++e) {
     int i = edges[2 * e], j = edges[2 * e + 1];
     if (i < 0 || i >= B || j < 0 || j >= B || i == j) {
@@ -263,21 +274,22 @@ extern "C" int gprf_set_structure(gprf_handle h, int B, const long long* block_p
       return GPRF_ERR_ARG;
     }
   }
-  h->have_structure = false;
-  h->B = B;
-  h->E = E;
-  h->U = B + E;
-  h->plen = plen;
-  const int U = h->U;
+  return GPRF_OK;
+}
 
-  std::vector<int> deg(B, 0);
+// Adjacency (CSR of incident edges per block, in edge order = fixed summation order) and degrees.
+static int rebuild_adjacency(gprf_ctx* h) {
+  const int B = h->B, E = h->E;
+  const int* edges = h->edges.data();
+  int rc = validate_edges(h, B, E, edges);
+  if (rc != GPRF_OK) return rc;
+  h->deg.assign(B, 0);
   for (int e = 0; e < E; ++e) {
-    deg[edges[2 * e]]++;
-    deg[edges[2 * e + 1]]++;
+    h->deg[edges[2 * e]]++;
+    h->deg[edges[2 * e + 1]]++;
   }
-  // CSR of incident edges per block, in edge order (fixed summation order)
-  std::vector<int> adj_ptr(B + 1, 0), adj_edge(2 * (size_t)E), adj_side(2 * (size_t)E);
-  for (int b = 0; b < B; ++b) adj_ptr[b + 1] = adj_ptr[b] + deg[b];
+  std::vector<int> adj_ptr(B + 1, 0), adj_edge(2 * (size_t)E + 1), adj_side(2 * (size_t)E + 1);
+  for (int b = 0; b < B; ++b) adj_ptr[b + 1] = adj_ptr[b] + h->deg[b];
   {
     std::vector<int> fill(adj_ptr.begin(), adj_ptr.end() - 1);
     for (int e = 0; e < E; ++e) {
@@ -286,10 +298,63 @@ extern "C" int gprf_set_structure(gprf_handle h, int B, const long long* block_p
       adj_edge[fill[j]] = e; adj_side[fill[j]++] = 1;
     }
   }
-  std::vector<int> pos_block((size_t)plen);
-  for (int b = 0; b < B; ++b)
-    for (long long p = block_ptr[b]; p < block_ptr[b + 1]; ++p) pos_block[(size_t)p] = b;
+  CUDA_OK(ensure(&h->dAdjPtr, &h->capAdjPtr, (size_t)B + 1));
+  CUDA_OK(ensure(&h->dAdjEdge, &h->capAdj, (size_t)2 * E + 1));
+  CUDA_OK(ensure(&h->dAdjSide, &h->capAdj2, (size_t)2 * E + 1));
+  CUDA_OK(cudaMemcpy(h->dAdjPtr, adj_ptr.data(), (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  if (E > 0) {
+    CUDA_OK(cudaMemcpy(h->dAdjEdge, adj_edge.data(), (size_t)2 * E * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->dAdjSide, adj_side.data(), (size_t)2 * E * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  h->adj_dirty = false;
+  return GPRF_OK;
+}
 
+// Longest-processing-time sharding of the units over `world` ranks on the work model
+// W(s) = s^3 + 4 s^2 * 50 - the same rule as gprf_b200/dist.py::shard_units.
+static void lpt_mask(const std::vector<double>& sizes, int rank, int world, std::vector<unsigned char>& mask) {
+  const size_t U = sizes.size();
+  mask.assign(U, 1);
+  if (world <= 1) return;
+  std::vector<double> cost(U);
+  for (size_t u = 0; u < U; ++u) cost[u] = sizes[u] * sizes[u] * sizes[u] + 4.0 * 50.0 * sizes[u] * sizes[u];
+  std::vector<int> order(U);
+  for (size_t u = 0; u < U; ++u) order[u] = (int)u;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  typedef std::pair<double, int> LR;
+  std::priority_queue<LR, std::vector<LR>, std::greater<LR>> heap;
+  for (int r = 0; r < world; ++r) heap.push(LR(0.0, r));
+  for (int u : order) {
+    LR t = heap.top();
+    heap.pop();
+    mask[u] = (t.second == rank) ? 1 : 0;
+    heap.push(LR(t.first + cost[u], t.second));
+  }
+}
+
+// Units from h->block_ptr_h + edges (+ mask / shard).  Uploads descriptors on `st` from pinned staging.
+static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
+  const int B = h->B;
+  if ((int)h->block_ptr_h.size() != B + 1) return GPRF_ERR_NO_STRUCTURE;
+  if (h->adj_dirty) {
+    int rc = rebuild_adjacency(h);
+    if (rc != GPRF_OK) return rc;
+  }
+  const int E = h->E, U = B + E;
+  h->U = U;
+  const long long* block_ptr = h->block_ptr_h.data();
+  const int* edges = h->edges.data();
+  const unsigned char* mask = nullptr;
+  if (h->use_explicit_mask) {
+    if ((int)h->explicit_mask.size() != U) return GPRF_ERR_ARG;
+    mask = h->explicit_mask.data();
+  } else if (h->shard_world > 1) {
+    std::vector<double> sizes(U);
+    for (int b = 0; b < B; ++b) sizes[b] = (double)(block_ptr[b + 1] - block_ptr[b]);
+    for (int e = 0; e < E; ++e) sizes[B + e] = sizes[edges[2 * e]] + sizes[edges[2 * e + 1]];
+    lpt_mask(sizes, h->shard_rank, h->shard_world, h->lpt);
+    mask = h->lpt.data();
+  }
   h->units.assign(U, UnitDesc());
   size_t off = 0;
   h->ntmax = 0;
@@ -299,7 +364,7 @@ extern "C" int gprf_set_structure(gprf_handle h, int B, const long long* block_p
     int bi, bj = -1;
     if (uix < B) {
       bi = uix;
-      u.weight = 1.0 - (double)deg[bi];
+      u.weight = 1.0 - (double)h->deg[bi];
     } else {
       bi = edges[2 * (uix - B)];
       bj = edges[2 * (uix - B) + 1];
@@ -316,7 +381,7 @@ extern "C" int gprf_set_structure(gprf_handle h, int B, const long long* block_p
     u.s = u.ni + nj;
     u.nt = (u.s + T - 1) / T;
     u.sp = u.nt * T;
-    u.active = (!unit_mask || unit_mask[uix]) ? 1 : 0;
+    u.active = (!mask || mask[uix]) ? 1 : 0;
     u.pad_ = 0;
     if (u.active && u.s > 0) {
       const size_t sp = u.sp, nt = u.nt;
@@ -336,16 +401,21 @@ extern "C" int gprf_set_structure(gprf_handle h, int B, const long long* block_p
   std::stable_sort(h->all_list.begin(), h->all_list.end(),
                    [&](int a, int b) { return h->units[a].s > h->units[b].s; });
 
-  size_t acap = h->arena_cap;
-  CUDA_OK(ensure(&h->arena, &acap, off));
-  h->arena_cap = acap;
-  size_t cu = h->capUnits;
-  if ((size_t)U > cu || !h->dUnits) {
+  if (off > h->arena_cap || !h->arena) {
+    CUDA_OK(cudaStreamSynchronize(st));
+    size_t acap = h->arena_cap;
+    CUDA_OK(ensure(&h->arena, &acap, off));
+    h->arena_cap = acap;
+  }
+  if ((size_t)U > h->capUnits || !h->dUnits) {
+    CUDA_OK(cudaStreamSynchronize(st));
     cudaFree(h->dUnits); cudaFree(h->dList); cudaFree(h->dListAll); cudaFree(h->dLLu); cudaFree(h->dGthU);
     cudaFree(h->dJitter); cudaFree(h->dInfo);
+    if (h->hUnits) cudaFreeHost(h->hUnits);
+    if (h->hList) cudaFreeHost(h->hList);
     h->dUnits = nullptr; h->dList = nullptr; h->dListAll = nullptr; h->dLLu = nullptr; h->dGthU = nullptr;
-    h->dJitter = nullptr; h->dInfo = nullptr;
-    cu = (size_t)U + U / 4 + 16;
+    h->dJitter = nullptr; h->dInfo = nullptr; h->hUnits = nullptr; h->hList = nullptr;
+    size_t cu = (size_t)U + U / 4 + 16;
     CUDA_OK(cudaMalloc((void**)&h->dUnits, cu * sizeof(UnitDesc)));
     CUDA_OK(cudaMalloc((void**)&h->dList, cu * sizeof(int)));
     CUDA_OK(cudaMalloc((void**)&h->dListAll, cu * sizeof(int)));
@@ -353,44 +423,280 @@ extern "C" int gprf_set_structure(gprf_handle h, int B, const long long* block_p
     CUDA_OK(cudaMalloc((void**)&h->dGthU, cu * MAX_NCOV * sizeof(double)));
     CUDA_OK(cudaMalloc((void**)&h->dJitter, cu * sizeof(double)));
     CUDA_OK(cudaMalloc((void**)&h->dInfo, cu * sizeof(int)));
+    CUDA_OK(cudaMallocHost((void**)&h->hUnits, cu * sizeof(UnitDesc)));
+    CUDA_OK(cudaMallocHost((void**)&h->hList, cu * sizeof(int)));
     h->capUnits = cu;
   }
-  CUDA_OK(ensure(&h->dPerm, &h->capPerm, (size_t)std::max<long long>(plen, 1)));
-  CUDA_OK(ensure(&h->dPosBlock, &h->capPos, (size_t)std::max<long long>(plen, 1)));
-  {
-    size_t cb = h->capB;
-    if ((size_t)(B + 1) > cb || !h->dBlockPtr) {
-      cudaFree(h->dBlockPtr); cudaFree(h->dAdjPtr);
-      cb = (size_t)B + 1 + B / 4;
-      CUDA_OK(cudaMalloc((void**)&h->dBlockPtr, cb * sizeof(long long)));
-      CUDA_OK(cudaMalloc((void**)&h->dAdjPtr, cb * sizeof(int)));
-      h->capB = cb;
-    }
-    size_t ca = h->capAdj;
-    if ((size_t)(2 * E + 1) > ca || !h->dAdjEdge) {
-      cudaFree(h->dAdjEdge); cudaFree(h->dAdjSide);
-      ca = (size_t)2 * E + 16;
-      CUDA_OK(cudaMalloc((void**)&h->dAdjEdge, ca * sizeof(int)));
-      CUDA_OK(cudaMalloc((void**)&h->dAdjSide, ca * sizeof(int)));
-      h->capAdj = ca;
-    }
-  }
-  CUDA_OK(cudaMemcpy(h->dUnits, h->units.data(), (size_t)U * sizeof(UnitDesc), cudaMemcpyHostToDevice));
+  // pinned staging must not be overwritten while a previous upload is in flight
+  CUDA_OK(cudaEventSynchronize(h->evStage));
+  memcpy(h->hUnits, h->units.data(), (size_t)U * sizeof(UnitDesc));
+  if (!h->all_list.empty()) memcpy(h->hList, h->all_list.data(), h->all_list.size() * sizeof(int));
+  CUDA_OK(cudaMemcpyAsync(h->dUnits, h->hUnits, (size_t)U * sizeof(UnitDesc), cudaMemcpyHostToDevice, st));
   if (!h->all_list.empty())
-    CUDA_OK(cudaMemcpy(h->dListAll, h->all_list.data(), h->all_list.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpyAsync(h->dListAll, h->hList, h->all_list.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaEventRecord(h->evStage, st));
+  h->jitter.assign(U, 0.0);
+  h->tries.assign(U, 0);
+  h->have_structure = true;
+  return GPRF_OK;
+}
+
+static int store_blocks_host(gprf_ctx* h, int B, const long long* block_ptr, const long long* perm) {
+  const long long plen = block_ptr[B];
+  if (block_ptr[0] != 0 || plen < 0 || plen > h->n || (plen > 0 && !perm)) {
+    h->err = "block_ptr must start at 0 and cover at most n points";
+    return GPRF_ERR_ARG;
+  }
+  for (int b = 0; b < B; ++b)
+    if (block_ptr[b + 1] < block_ptr[b]) return GPRF_ERR_ARG;
+  h->seen.assign((size_t)h->n, 0);
+  for (long long p = 0; p < plen; ++p) {
+    if (perm[p] < 0 || perm[p] >= h->n || h->seen[(size_t)perm[p]]) {
+      h->err = "block index lists must be disjoint indices in [0, n)";
+      return GPRF_ERR_ARG;
+    }
+    h->seen[(size_t)perm[p]] = 1;
+  }
+  if (B != h->B) h->adj_dirty = true;
+  h->B = B;
+  h->plen = plen;
+  h->block_ptr_h.assign(block_ptr, block_ptr + B + 1);
+  std::vector<int> pos_block((size_t)plen);
+  for (int b = 0; b < B; ++b)
+    for (long long p = block_ptr[b]; p < block_ptr[b + 1]; ++p) pos_block[(size_t)p] = b;
+  CUDA_OK(ensure(&h->dPerm, &h->capPerm, (size_t)std::max<long long>(h->n, 1)));
+  CUDA_OK(ensure(&h->dPosBlock, &h->capPos, (size_t)std::max<long long>(h->n, 1)));
+  CUDA_OK(ensure(&h->dBlockPtr, &h->capB, (size_t)B + 1));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
   if (plen > 0) {
     CUDA_OK(cudaMemcpy(h->dPerm, perm, (size_t)plen * sizeof(long long), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(h->dPosBlock, pos_block.data(), (size_t)plen * sizeof(int), cudaMemcpyHostToDevice));
   }
   CUDA_OK(cudaMemcpy(h->dBlockPtr, block_ptr, (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(h->dAdjPtr, adj_ptr.data(), (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice));
-  if (E > 0) {
-    CUDA_OK(cudaMemcpy(h->dAdjEdge, adj_edge.data(), (size_t)2 * E * sizeof(int), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(h->dAdjSide, adj_side.data(), (size_t)2 * E * sizeof(int), cudaMemcpyHostToDevice));
+  h->blocks_from_device = false;
+  return GPRF_OK;
+}
+
+extern "C" int gprf_set_edges(gprf_handle h, int E, const int* edges, int shard_rank, int shard_world) {
+  if (!h || E < 0 || (E > 0 && !edges) || shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world)
+    return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  h->edges.assign(edges, edges + 2 * (size_t)E);
+  h->E = E;
+  h->shard_rank = shard_rank;
+  h->shard_world = shard_world;
+  h->use_explicit_mask = false;
+  h->adj_dirty = true;
+  h->have_structure = false;
+  if ((int)h->block_ptr_h.size() == h->B + 1 && h->B > 0) {
+    int rc = rebuild_units(h, h->stream);
+    if (rc != GPRF_OK) return rc;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
   }
-  h->jitter.assign(U, 0.0);
-  h->tries.assign(U, 0);
-  h->have_structure = true;
+  return GPRF_OK;
+}
+
+extern "C" int gprf_set_blocks(gprf_handle h, int B, const long long* block_ptr, const long long* perm) {
+  if (!h || B < 1 || !block_ptr) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  h->have_structure = false;
+  int rc = store_blocks_host(h, B, block_ptr, perm);
+  if (rc != GPRF_OK) return rc;
+  rc = rebuild_units(h, h->stream);
+  if (rc != GPRF_OK) return rc;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return GPRF_OK;
+}
+
+extern "C" int gprf_set_structure(gprf_handle h, int B, const long long* block_ptr, const long long* perm,
+                                  int E, const int* edges, const unsigned char* unit_mask) {
+  if (!h || B < 1 || !block_ptr || E < 0 || (E > 0 && !edges)) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  h->have_structure = false;
+  int rc = validate_edges(h, B, E, edges);
+  if (rc != GPRF_OK) return rc;
+  h->edges.assign(edges, edges + 2 * (size_t)E);
+  h->E = E;
+  h->adj_dirty = true;
+  h->use_explicit_mask = (unit_mask != nullptr);
+  if (unit_mask) h->explicit_mask.assign(unit_mask, unit_mask + B + E);
+  else { h->shard_rank = 0; h->shard_world = 1; }
+  rc = store_blocks_host(h, B, block_ptr, perm);
+  if (rc != GPRF_OK) return rc;
+  rc = rebuild_units(h, h->stream);
+  if (rc != GPRF_OK) return rc;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return GPRF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// device partitioners (K8)
+// ---------------------------------------------------------------------------
+extern "C" int gprf_set_grid_partitioner(gprf_handle h, int B, const double* centers, const double* csq,
+                                         int dot_mode) {
+  if (!h || B < 1 || !centers || !csq || dot_mode < 0 || dot_mode > 2) return GPRF_ERR_ARG;
+  if ((size_t)B * (h->dx + 1) * sizeof(double) > 200 * 1024) {
+    h->err = "too many block centres for the shared-memory assignment kernel";
+    return GPRF_ERR_ARG;
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->dPartA); cudaFree(h->dPartB);
+  h->dPartA = h->dPartB = nullptr;
+  CUDA_OK(cudaMalloc((void**)&h->dPartA, (size_t)B * h->dx * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&h->dPartB, (size_t)B * sizeof(double)));
+  CUDA_OK(cudaMemcpy(h->dPartA, centers, (size_t)B * h->dx * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(h->dPartB, csq, (size_t)B * sizeof(double), cudaMemcpyHostToDevice));
+  h->part_kind = 1;
+  h->part_B = B;
+  h->part_mode = dot_mode;
+  return GPRF_OK;
+}
+
+extern "C" int gprf_set_tree_partitioner(gprf_handle h, int n_nodes, const double* center, const double* direction,
+                                         const double* cut, const int* child, int root, int n_leaves,
+                                         double wrap_add, double wrap_mod, int dot_mode) {
+  if (!h || n_nodes < 0 || n_leaves < 1 || dot_mode < 0 || dot_mode > 2 || h->dx < 2) return GPRF_ERR_ARG;
+  if (n_nodes > 0 && (!center || !direction || !cut || !child)) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->dPartA); cudaFree(h->dPartB); cudaFree(h->dPartC); cudaFree(h->dPartChild);
+  h->dPartA = h->dPartB = h->dPartC = nullptr;
+  h->dPartChild = nullptr;
+  const size_t nn = (size_t)std::max(n_nodes, 1);
+  CUDA_OK(cudaMalloc((void**)&h->dPartA, nn * 2 * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&h->dPartB, nn * 2 * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&h->dPartC, nn * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&h->dPartChild, nn * 2 * sizeof(int)));
+  if (n_nodes > 0) {
+    CUDA_OK(cudaMemcpy(h->dPartA, center, nn * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->dPartB, direction, nn * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->dPartC, cut, nn * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->dPartChild, child, nn * 2 * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  h->part_kind = 2;
+  h->part_B = n_leaves;
+  h->part_mode = dot_mode;
+  h->part_root = root;
+  h->part_wrap_add = wrap_add;
+  h->part_wrap_mod = wrap_mod;
+  return GPRF_OK;
+}
+
+// Block membership of X_dev on the device: assignment kernel, stable radix sort, bounds.
+// Leaves perm / pos_block / block_ptr on the device, block_ptr on the host, and rebuilds the units.
+static int reblock_device(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
+  if (h->part_kind == 0) {
+    h->err = "no device partitioner set";
+    return GPRF_ERR_ARG;
+  }
+  const long long n = h->n;
+  const int B = h->part_B;
+  CUDA_OK(ensure(&h->dPerm, &h->capPerm, (size_t)n));
+  CUDA_OK(ensure(&h->dPosBlock, &h->capPos, (size_t)n));
+  CUDA_OK(ensure(&h->dBlockPtr, &h->capB, (size_t)B + 1));
+  CUDA_OK(ensure(&h->dOwner, &h->capOwner, (size_t)n));
+  CUDA_OK(ensure(&h->dIdxSorted, &h->capIdxS, (size_t)n));
+  if (!h->dIota || h->capIota < (size_t)n) {
+    CUDA_OK(ensure(&h->dIota, &h->capIota, (size_t)n));
+    k_iota<<<(unsigned)((h->capIota + 255) / 256), 256, 0, st>>>(h->dIota, (long long)h->capIota);
+  }
+  int bits = 1;
+  while ((1 << bits) < B) ++bits;
+  size_t need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, h->dOwner, h->dPosBlock, h->dIota, h->dIdxSorted, (int)n, 0, bits, st);
+  if (need > h->capCub || !h->dCub) {
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(h->dCub);
+    h->dCub = nullptr;
+    CUDA_OK(cudaMalloc(&h->dCub, need + 256));
+    h->capCub = need + 256;
+  }
+  const int tb = 256;
+  const unsigned gb = (unsigned)((n + tb - 1) / tb);
+  if (h->part_kind == 1) {
+    const size_t sm = (size_t)B * (h->dx + 1) * sizeof(double);
+#define CALL_ASSIGN(MODE)                                                                                         \
+  do {                                                                                                            \
+    if (sm > 48 * 1024) cudaFuncSetAttribute(k_assign_grid<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+    k_assign_grid<MODE><<<gb, tb, sm, st>>>(X_dev, n, h->dx, h->dPartA, h->dPartB, B, h->dOwner);              \
+  } while (0)
+    if (h->part_mode == 0) CALL_ASSIGN(0);
+    else if (h->part_mode == 1) CALL_ASSIGN(1);
+    else CALL_ASSIGN(2);
+  } else {
+    TreeParams Tp;
+    Tp.center = h->dPartA;
+    Tp.direction = h->dPartB;
+    Tp.cut = h->dPartC;
+    Tp.child = h->dPartChild;
+    Tp.root = h->part_root;
+    Tp.wrap_add = h->part_wrap_add;
+    Tp.wrap_mod = h->part_wrap_mod;
+    if (h->part_mode == 0) k_assign_tree<0><<<gb, tb, 0, st>>>(X_dev, n, h->dx, Tp, h->dOwner);
+    else if (h->part_mode == 1) k_assign_tree<1><<<gb, tb, 0, st>>>(X_dev, n, h->dx, Tp, h->dOwner);
+    else k_assign_tree<2><<<gb, tb, 0, st>>>(X_dev, n, h->dx, Tp, h->dOwner);
+  }
+  size_t tmp = h->capCub;
+  cub::DeviceRadixSort::SortPairs(h->dCub, tmp, h->dOwner, h->dPosBlock, h->dIota, h->dIdxSorted, (int)n, 0, bits, st);
+  const long long nthr = std::max<long long>(n, B + 1);
+  k_block_bounds<<<(unsigned)((nthr + tb - 1) / tb), tb, 0, st>>>(h->dPosBlock, h->dIdxSorted, n, B, h->dBlockPtr,
+                                                                    h->dPerm);
+  CUDA_OK(cudaGetLastError());
+  if (!h->hBlockPtr || h->capHB < (size_t)B + 1) {
+    if (h->hBlockPtr) cudaFreeHost(h->hBlockPtr);
+    h->hBlockPtr = nullptr;
+    CUDA_OK(cudaMallocHost((void**)&h->hBlockPtr, ((size_t)B + 1) * sizeof(long long)));
+    h->capHB = (size_t)B + 1;
+  }
+  CUDA_OK(cudaMemcpyAsync(h->hBlockPtr, h->dBlockPtr, ((size_t)B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (B != h->B) h->adj_dirty = true;
+  h->B = B;
+  h->plen = n;
+  h->block_ptr_h.assign(h->hBlockPtr, h->hBlockPtr + B + 1);
+  h->blocks_from_device = true;
+  h->part_launches = 5;
+  return rebuild_units(h, st);
+}
+
+extern "C" int gprf_reblock_device(gprf_handle h, const double* X_dev, void* stream) {
+  if (!h || !X_dev) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  h->have_structure = false;
+  return reblock_device(h, X_dev, (cudaStream_t)stream);
+}
+
+extern "C" int gprf_reblock(gprf_handle h, const double* X) {
+  if (!h || !X) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  h->have_structure = false;
+  const size_t xb = (size_t)h->n * h->dx * sizeof(double);
+  memcpy(h->hX, X, xb);
+  CUDA_OK(cudaMemcpyAsync(h->dX, h->hX, xb, cudaMemcpyHostToDevice, h->stream));
+  int rc = reblock_device(h, h->dX, h->stream);
+  if (rc != GPRF_OK) return rc;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return GPRF_OK;
+}
+
+extern "C" int gprf_block_count(gprf_handle h, int* n_blocks, long long* plen) {
+  if (!h) return GPRF_ERR_ARG;
+  if ((int)h->block_ptr_h.size() != h->B + 1) return GPRF_ERR_NO_STRUCTURE;
+  if (n_blocks) *n_blocks = h->B;
+  if (plen) *plen = h->plen;
+  return GPRF_OK;
+}
+
+extern "C" int gprf_get_blocks(gprf_handle h, long long* block_ptr, long long* perm) {
+  if (!h) return GPRF_ERR_ARG;
+  if ((int)h->block_ptr_h.size() != h->B + 1) return GPRF_ERR_NO_STRUCTURE;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (block_ptr) memcpy(block_ptr, h->block_ptr_h.data(), (size_t)(h->B + 1) * sizeof(long long));
+  if (perm && h->plen > 0) {
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaMemcpy(perm, h->dPerm, (size_t)h->plen * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
   return GPRF_OK;
 }
 
@@ -557,6 +863,32 @@ extern "C" int gprf_llgrad(gprf_handle h, const double* X, const double* theta, 
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   if (h->profile) h->prof_resolve();
+  *ll = h->hOut[0];
+  if (grad_cov)
+    for (int t = 0; t < ncov; ++t) gradTheta[t] = h->hOut[1 + t];
+  if (grad_X) memcpy(gradX, h->hOut + 1 + MAX_NCOV, xb);
+  return GPRF_OK;
+}
+
+extern "C" int gprf_llgrad_reblock(gprf_handle h, const double* X, const double* theta, int ncov, int grad_X,
+                                   int grad_cov, double* ll, double* gradX, double* gradTheta, int* failed_unit) {
+  if (!h || !X || !theta || !ll) return GPRF_ERR_ARG;
+  if ((grad_X && !gradX) || (grad_cov && !gradTheta)) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  const size_t xb = (size_t)h->n * h->dx * sizeof(double);
+  memcpy(h->hX, X, xb);
+  CUDA_OK(cudaMemcpyAsync(h->dX, h->hX, xb, cudaMemcpyHostToDevice, h->stream));
+  h->have_structure = false;
+  int rc = reblock_device(h, h->dX, h->stream);
+  if (rc != GPRF_OK) return rc;
+  rc = run_eval(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, failed_unit);
+  if (rc != GPRF_OK) return rc;
+  const size_t outlen = 1 + MAX_NCOV + (grad_X ? (size_t)h->n * h->dx : 0);
+  CUDA_OK(cudaMemcpyAsync(h->hOut, h->dOut, outlen * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  if (h->profile) h->prof_resolve();
+  h->last_launches += h->part_launches;
   *ll = h->hOut[0];
   if (grad_cov)
     for (int t = 0; t < ncov; ++t) gradTheta[t] = h->hOut[1 + t];

@@ -1,0 +1,129 @@
+// Point -> block assignment on the device (K8), bit-exact with the reference's
+// numpy expressions.
+//
+//  grid  : Blocker.block_clusters (block_clustering.py:17-26):
+//            argmin_b sqrt((|x|^2 * 1 - 2 x.c_b) + 1 * |c_b|^2)
+//          with numpy's operation order and rounding: the squares and their sum
+//          are separately rounded, the dot product is rounded the way the host
+//          BLAS rounds it (dot_mode, probed by the Python layer on the actual
+//          data), first index wins ties, the first NaN wins over everything
+//          (np.argmin).  |c_b|^2 is computed by numpy on the host and passed in.
+//  tree  : PDTree.recluster (pdtree_clustering.py:65-77) on (lon wrapped, lat):
+//            a = dot(x - center, direction);  a < cut -> left, a >= cut -> right
+//
+// dot_mode: 0  acc = x0*c0; acc = fma(x1, c1, acc); ...      (k-ascending FMA)
+//           1  acc = x_{d-1}*c_{d-1}; acc = fma(x_{d-2}, ...) (k-descending FMA)
+//           2  acc = x0*c0 + x1*c1 + ...  each product and sum rounded (no FMA)
+//
+// Bucketing: stable radix sort of (owner, index) pairs (CUB) - ascending point
+// index inside every block, as numpy's boolean-mask selection yields.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace gprf {
+
+template <int MODE>
+__device__ __forceinline__ double dot_rounded(const double* x, const double* c, int d) {
+  if (MODE == 0) {
+    double acc = __dmul_rn(x[0], c[0]);
+    for (int i = 1; i < d; ++i) acc = __fma_rn(x[i], c[i], acc);
+    return acc;
+  } else if (MODE == 1) {
+    double acc = __dmul_rn(x[d - 1], c[d - 1]);
+    for (int i = d - 2; i >= 0; --i) acc = __fma_rn(x[i], c[i], acc);
+    return acc;
+  } else {
+    double acc = __dmul_rn(x[0], c[0]);
+    for (int i = 1; i < d; ++i) acc = __dadd_rn(acc, __dmul_rn(x[i], c[i]));
+    return acc;
+  }
+}
+
+// centers: B x dx, csq: B (numpy's sum(c**2)), owner out: int32 per point
+template <int MODE>
+__global__ void k_assign_grid(const double* X, long long n, int dx, const double* centers, const double* csq,
+                              int B, int* owner) {
+  extern __shared__ double sc[];     // B * (dx + 1)
+  for (int e = threadIdx.x; e < B * dx; e += blockDim.x) sc[e] = centers[e];
+  for (int e = threadIdx.x; e < B; e += blockDim.x) sc[B * dx + e] = csq[e];
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double x[3] = {0.0, 0.0, 0.0};
+  for (int i = 0; i < dx; ++i) x[i] = X[p * dx + i];
+  double a = __dmul_rn(x[0], x[0]);
+  for (int i = 1; i < dx; ++i) a = __dadd_rn(a, __dmul_rn(x[i], x[i]));
+  int best = 0;
+  double bestd = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const double dot = dot_rounded<MODE>(x, sc + b * dx, dx);
+    const double t = __dadd_rn(__dsub_rn(a, 2.0 * dot), sc[B * dx + b]);
+    const double dist = __dsqrt_rn(t);
+    if (dist != dist) {          // np.argmin: the first NaN is the minimum
+      best = b;
+      break;
+    }
+    if (b == 0 || dist < bestd) {
+      best = b;
+      bestd = dist;
+    }
+  }
+  owner[p] = best;
+}
+
+struct TreeParams {
+  const double* center;      // nnodes x 2
+  const double* direction;   // nnodes x 2
+  const double* cut;         // nnodes
+  const int* child;          // nnodes x 2; negative = -(leaf id) - 1
+  int root;
+  double wrap_add, wrap_mod; // lon -> (lon + wrap_add) % wrap_mod - wrap_add   (22, 360)
+};
+
+template <int MODE>
+__global__ void k_assign_tree(const double* X, long long n, int dx, TreeParams Tp, int* owner) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double q[2];
+  {
+    // numpy float remainder: fmod, then shift into the sign of the divisor
+    double r = fmod(__dadd_rn(X[p * dx], Tp.wrap_add), Tp.wrap_mod);
+    if (r != 0.0) {
+      if (r < 0.0) r = __dadd_rn(r, Tp.wrap_mod);
+    } else {
+      r = 0.0;
+    }
+    q[0] = __dsub_rn(r, Tp.wrap_add);
+    q[1] = X[p * dx + 1];
+  }
+  int node = Tp.root;
+  int guard = 0;
+  while (node >= 0 && guard++ < 64) {
+    double v[2] = {__dsub_rn(q[0], Tp.center[2 * node]), __dsub_rn(q[1], Tp.center[2 * node + 1])};
+    const double a = dot_rounded<MODE>(v, Tp.direction + 2 * node, 2);
+    node = (a < Tp.cut[node]) ? Tp.child[2 * node] : Tp.child[2 * node + 1];
+  }
+  owner[p] = -node - 1;
+}
+
+__global__ void k_iota(int* idx, long long n) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) idx[p] = (int)p;
+}
+
+// sorted owner keys -> block_ptr[b] = first position with key >= b; perm64 from the sorted indices
+__global__ void k_block_bounds(const int* keys, const int* idx_sorted, long long n, int B, long long* block_ptr,
+                               long long* perm64) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) perm64[t] = idx_sorted[t];
+  if (t <= B) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+      long long mid = (lo + hi) >> 1;
+      if (keys[mid] < (int)t) lo = mid + 1; else hi = mid;
+    }
+    block_ptr[t] = lo;
+  }
+}
+
+}  // namespace gprf

@@ -90,8 +90,6 @@ class ShardedGPRF(GPRF):
         torch, dist = self._torch, self._dist
         grad_X = bool(kwargs.get("grad_X", False))
         grad_cov = bool(kwargs.get("grad_cov", False))
-        edges = self.neighbors if local else [(i, j) for i in range(self.n_blocks) for j in range(i)]
-        self._push_structure(edges)
         n, dx = self.X.shape
         dev = torch.device("cuda", self.device)
         if self._out is None:
@@ -103,20 +101,23 @@ class ShardedGPRF(GPRF):
             self._outh = torch.empty(2 + _lib.MAX_NCOV + n * dx, dtype=torch.float64).pin_memory()
         self._Xh.numpy()[...] = self.X
         self._Xd.copy_(self._Xh, non_blocking=True)
-        th = self._theta()
-        failed = C.c_int(-1)
         stream = torch.cuda.current_stream(dev)
-        rc = self._lib.gprf_llgrad_device(self._h, C.c_void_p(self._Xd.data_ptr()), _lib.ptr(th), len(th),
-                                          int(grad_X), int(grad_cov), C.c_void_p(self._out.data_ptr() + 8),
-                                          C.c_void_p(stream.cuda_stream), C.byref(failed))
         used = 2 + _lib.MAX_NCOV + (n * dx if grad_X else 0)
-        if rc != _lib.OK:
+        error = None
+        try:
+            self.llgrad_device(self._Xd.data_ptr(), self._out.data_ptr() + 8, stream.cuda_stream, local=local,
+                               grad_X=grad_X, grad_cov=grad_cov,
+                               reblock=self._blocks_stale and self._device_part is not None)
+            self._out[0] = 0.0
+        except LinAlgError as exc:
+            error = exc
             self._out[:used].zero_()
-        self._out[0] = float(rc)
+            self._out[0] = 1.0
         dist.all_reduce(self._out[:used])
         self._outh[:used].copy_(self._out[:used], non_blocking=True)
         stream.synchronize()
-        self._check(rc, failed.value)
+        if error is not None:
+            raise error
         if self._outh[0].item() != 0.0:
             raise LinAlgError("a unit on another rank was not positive definite")
-        return unpack(self._outh.numpy()[1:], n, dx, len(th), grad_X, grad_cov)
+        return unpack(self._outh.numpy()[1:], n, dx, 2 + len(self.cov.dfn_params), grad_X, grad_cov)

@@ -4,12 +4,20 @@ Same constructor, mutators, attributes and return conventions as the
 reference so that its L-BFGS drivers (gprfopt.py:377-417,
 run_seismic.py:121-199) drive it unchanged:
 
+    gprf.update_X(XX)
     ll, gX, gC = gprf.llgrad(local=True, grad_X=True, grad_cov=True, parallel=False)
 
 ``ll`` is a float, ``gX`` an (n, dx) array or ``zeros((0, 0))``, ``gC`` a
 (1, ncov) array or ``zeros((0, 0))`` (gprf.py:275,288,291).  All numerics run
 in libgprf_b200.so (hand-written sm_100a kernels); this file only marshals
 numpy arrays across the C-ABI.  There is no CPU fallback.
+
+Block membership (``block_idxs = block_fn(X)``, recomputed by every
+``update_X``, gprf.py:169-174) is evaluated on the GPU when ``block_fn`` is one
+of this package's partitioners (``Blocker.block_clusters`` or the ``reblock``
+closure of ``pdtree_cluster``) AND the device result has been proven identical
+to the host numpy result on the construction-time X (see ``partition_probe``);
+any other ``block_fn`` is called on the host exactly like the reference does.
 """
 import ctypes as C
 from collections import defaultdict
@@ -18,6 +26,7 @@ import numpy as np
 from numpy.linalg import LinAlgError
 
 from . import _lib
+from . import partition_probe
 from .blocking import symmetrize_neighbors
 from .cov import GPCov
 
@@ -33,14 +42,20 @@ def _blocks_to_csr(block_idxs):
     return ptr, perm
 
 
+def _edge_array(edges):
+    if len(edges) == 0:
+        return np.zeros((0, 2), dtype=np.int32)
+    return np.ascontiguousarray(np.asarray(edges, dtype=np.int32).reshape(-1, 2))
+
+
 class GPRF(object):
 
     def __init__(self, X, Y, block_fn, cov, noise_var, kernelized=False, dy=None,
                  neighbor_threshold=1e-3, nonstationary=False, nonstationary_prec=False,
-                 block_idxs=None, neighbors=None, device=0, unit_shard=None):
-        """gprf.py:85-117.  Extra keywords: ``device`` (CUDA ordinal) and
-        ``unit_shard`` = (rank, world) to evaluate only this rank's share of the
-        units (multi-GPU; see gprf_b200.dist)."""
+                 block_idxs=None, neighbors=None, device=0, unit_shard=None, device_blocks=True):
+        """gprf.py:85-117.  Extra keywords: ``device`` (CUDA ordinal), ``unit_shard`` =
+        (rank, world) to evaluate only this rank's share of the units (multi-GPU; see
+        gprf_b200.dist) and ``device_blocks`` (allow the on-device partitioner)."""
         if kernelized or nonstationary or nonstationary_prec:
             raise NotImplementedError("kernelized / nonstationary variants are dead code in the reference "
                                       "(gprf.py:104,674-736) and outside the hot path")
@@ -54,20 +69,22 @@ class GPRF(object):
         self.neighbor_threshold = neighbor_threshold
         self.device = device
         self.unit_shard = unit_shard
+        self.device_blocks = device_blocks
         self._lib = None
         self._h = None
-        self._structure_key = None
+        self._device_part = None
         self._open()
         if block_idxs is None:
             block_idxs = block_fn(X)
         self.block_idxs = block_idxs
-        self.n_blocks = len(block_idxs)
         if neighbors is not None:
             self.neighbors = neighbors
         else:
             self.compute_neighbors(threshold=neighbor_threshold)
         self.compute_neighbor_count()
         self.neighbor_dict = symmetrize_neighbors(self.neighbors)
+        if device_blocks and block_fn is not None:
+            self._setup_device_partitioner()
 
     # -- native handle ---------------------------------------------------
     def _open(self):
@@ -80,7 +97,9 @@ class GPRF(object):
                                    self._Yc.shape[1], _lib.ptr(self._Yc), dfn_id, wfn_id)
         self._h = h
         self._check(rc)
-        self._structure_key = None
+        self._edges_key = None
+        self._blocks_key = None
+        self._blocks_stale = False
 
     def _check(self, rc, failed_unit=-1):
         if rc == _lib.OK:
@@ -109,7 +128,9 @@ class GPRF(object):
     def __getstate__(self):
         # gprf.py:738-741 drops the native evaluator when pickling
         d = self.__dict__.copy()
-        for k in ("_lib", "_h", "_structure_key", "_Yc"):
+        d["_block_idxs"] = self.block_idxs          # materialise device-held blocks
+        for k in ("_lib", "_h", "_edges_key", "_blocks_key", "_Yc", "_keep_edges", "_keep_blocks",
+                  "_device_part", "_blocks_stale"):
             d.pop(k, None)
         return d
 
@@ -117,7 +138,65 @@ class GPRF(object):
         self.__dict__ = d
         self._lib = None
         self._h = None
+        self._device_part = None
         self._open()
+        if self.device_blocks and self.block_fn is not None:
+            self._setup_device_partitioner()
+
+    # -- block membership ------------------------------------------------------
+    @property
+    def block_idxs(self):
+        """List of index arrays, one per block (gprf.py:98-100).  When membership lives on
+        the device it is downloaded on first access."""
+        if self._block_idxs is None:
+            if self._blocks_stale:
+                Xc = np.ascontiguousarray(self.X, dtype=np.float64)
+                self._check(self._lib.gprf_reblock(self._h, _lib.ptr(Xc)))
+                self._blocks_stale = False
+            B = C.c_int()
+            plen = C.c_longlong()
+            self._check(self._lib.gprf_block_count(self._h, C.byref(B), C.byref(plen)))
+            ptr = np.zeros(B.value + 1, dtype=np.int64)
+            perm = np.zeros(plen.value, dtype=np.int64)
+            self._check(self._lib.gprf_get_blocks(self._h, _lib.ptr(ptr), _lib.ptr(perm)))
+            self._block_idxs = [perm[ptr[b]:ptr[b + 1]] for b in range(B.value)]
+            self._blocks_key = id(self._block_idxs)      # already on the device
+            self._keep_blocks = self._block_idxs
+        return self._block_idxs
+
+    @block_idxs.setter
+    def block_idxs(self, value):
+        self._block_idxs = value
+        self._blocks_stale = False
+        self.n_blocks = len(value)
+
+    def _setup_device_partitioner(self):
+        """Enable on-device block assignment iff it reproduces the host partition of the
+        current X bit for bit (and the BLAS rounding mode could be identified)."""
+        spec = partition_probe.describe(self.block_fn, np.asarray(self.X, dtype=np.float64))
+        if spec is None:
+            return
+        if spec["kind"] == "grid":
+            rc = self._lib.gprf_set_grid_partitioner(self._h, spec["n_blocks"], _lib.ptr(spec["centers"]),
+                                                     _lib.ptr(spec["csq"]), spec["dot_mode"])
+        else:
+            rc = self._lib.gprf_set_tree_partitioner(self._h, spec["n_nodes"], _lib.ptr(spec["center"]),
+                                                     _lib.ptr(spec["direction"]), _lib.ptr(spec["cut"]),
+                                                     _lib.ptr(spec["child"]), spec["root"], spec["n_leaves"],
+                                                     spec["wrap_add"], spec["wrap_mod"], spec["dot_mode"])
+        self._check(rc)
+        # proof on the actual data: device partition == host partition
+        host = self.block_fn(self.X)
+        Xc = np.ascontiguousarray(self.X, dtype=np.float64)
+        self._check(self._lib.gprf_reblock(self._h, _lib.ptr(Xc)))
+        saved = self._block_idxs
+        self._block_idxs = None
+        dev = self.block_idxs
+        same = len(dev) == len(host) and all(np.array_equal(a, b) for a, b in zip(dev, host))
+        self._block_idxs = saved
+        self._blocks_key = None                   # device now holds `dev`, not `saved`
+        if same:
+            self._device_part = spec["kind"]
 
     # -- parameters --------------------------------------------------------
     def _theta(self):
@@ -138,7 +217,11 @@ class GPRF(object):
         """gprf.py:169-174."""
         self.X = new_X
         if self.block_fn is not None:
-            self.block_idxs = self.block_fn(new_X)
+            if self._device_part is not None:
+                self._block_idxs = None           # recomputed on the GPU by the next llgrad
+                self._blocks_stale = True
+            else:
+                self.block_idxs = self.block_fn(new_X)
         if recompute_neighbors:
             self.compute_neighbors(threshold=self.neighbor_threshold)
             self.compute_neighbor_count()
@@ -156,35 +239,45 @@ class GPRF(object):
             count[j] += 1
         self.neighbor_count = count
 
-    def _shard_mask(self, n_units, ptr, edges):
-        if self.unit_shard is None:
-            return None
-        from .dist import shard_units
-        rank, world = self.unit_shard
-        return shard_units(ptr, edges, rank, world)
+    def _edges_for(self, local):
+        if local:
+            return self.neighbors
+        if getattr(self, "_all_pairs_B", None) != self.n_blocks:
+            self._all_pairs = [(i, j) for i in range(self.n_blocks) for j in range(i)]
+            self._all_pairs_B = self.n_blocks
+        return self._all_pairs
 
-    def _push_structure(self, edges, force=False):
-        """Hand block membership + edge list to the device (gprf_set_structure)."""
-        key = (id(self.block_idxs), id(edges), len(edges))
-        if not force and key == self._structure_key:
+    def _sync_edges(self, edges):
+        key = (id(edges), len(edges))
+        if key == self._edges_key:
             return
-        ptr, perm = _blocks_to_csr(self.block_idxs)
-        e = np.ascontiguousarray(np.asarray(edges, dtype=np.int32).reshape(-1, 2)) if len(edges) else \
-            np.zeros((0, 2), dtype=np.int32)
-        mask = self._shard_mask(len(self.block_idxs) + len(e), ptr, e)
-        rc = self._lib.gprf_set_structure(self._h, len(self.block_idxs), _lib.ptr(ptr), _lib.ptr(perm),
-                                          len(e), _lib.ptr(e), _lib.ptr(mask))
-        self._check(rc)
-        self._structure_key = key
-        self._keep = (ptr, perm, e, mask, self.block_idxs, edges)   # keep ids alive while cached
+        e = _edge_array(edges)
+        rank, world = self.unit_shard if self.unit_shard is not None else (0, 1)
+        self._check(self._lib.gprf_set_edges(self._h, len(e), _lib.ptr(e), int(rank), int(world)))
+        self._edges_key = key
+        self._keep_edges = (edges, e)             # keeps id(edges) unique while cached
+
+    def _sync_blocks(self):
+        """Host-held block lists -> device (no-op when the device already holds them)."""
+        if self._blocks_stale:
+            return
+        key = id(self._block_idxs)
+        if key == self._blocks_key:
+            return
+        ptr, perm = _blocks_to_csr(self._block_idxs)
+        self._check(self._lib.gprf_set_blocks(self._h, len(self._block_idxs), _lib.ptr(ptr), _lib.ptr(perm)))
+        self._blocks_key = key
+        self._keep_blocks = self._block_idxs
 
     def compute_neighbors(self, threshold=1e-3):
         """gprf.py:119-150: edge (i, j), j < i, iff max |k(X_i, X_j)| / signal_var > threshold."""
         self.neighbors = []
         if threshold == 1.0:
             return
-        self._push_structure([], force=True)
-        B = len(self.block_idxs)
+        blocks = self.block_idxs
+        self._sync_edges(self.neighbors)
+        self._sync_blocks()
+        B = len(blocks)
         maxk = np.empty((B, B), dtype=np.float64)
         Xc = np.ascontiguousarray(self.X, dtype=np.float64)
         th = self._theta()
@@ -201,35 +294,47 @@ class GPRF(object):
         grad_cov = bool(kwargs.get("grad_cov", False))
         if kwargs.get("sparse", False):
             raise NotImplementedError("sparse (CHOLMOD) unit likelihoods are outside the hot path")
-        if local:
-            edges = self.neighbors
-        else:
-            if getattr(self, "_all_pairs_B", None) != self.n_blocks:
-                self._all_pairs = [(i, j) for i in range(self.n_blocks) for j in range(i)]
-                self._all_pairs_B = self.n_blocks
-            edges = self._all_pairs
-        self._push_structure(edges)
+        self._sync_edges(self._edges_for(local))
         Xc = np.ascontiguousarray(self.X, dtype=np.float64)
         th = self._theta()
         ll = C.c_double()
         failed = C.c_int(-1)
         gX = np.empty(Xc.shape, dtype=np.float64) if grad_X else None
         gC = np.empty(len(th), dtype=np.float64) if grad_cov else None
-        rc = self._lib.gprf_llgrad(self._h, _lib.ptr(Xc), _lib.ptr(th), len(th), int(grad_X), int(grad_cov),
-                                   C.byref(ll), _lib.ptr(gX), _lib.ptr(gC), C.byref(failed))
+        if self._blocks_stale:
+            fn = self._lib.gprf_llgrad_reblock      # update_X's re-blocking happens on the GPU
+            self._blocks_stale = False
+            self._blocks_key = None
+        else:
+            self._sync_blocks()
+            fn = self._lib.gprf_llgrad
+        rc = fn(self._h, _lib.ptr(Xc), _lib.ptr(th), len(th), int(grad_X), int(grad_cov),
+                C.byref(ll), _lib.ptr(gX), _lib.ptr(gC), C.byref(failed))
         self._check(rc, failed.value)
         gradX = gX if grad_X else np.zeros((0, 0))
         gradCov = gC.reshape((1, -1)) if grad_cov else np.zeros((0, 0))
         return np.float64(ll.value), gradX, gradCov
 
-    def llgrad_device(self, X_dev_ptr, out_dev_ptr, stream_ptr=0, local=True, grad_X=False, grad_cov=False):
+    def llgrad_device(self, X_dev_ptr, out_dev_ptr, stream_ptr=0, local=True, grad_X=False, grad_cov=False,
+                      reblock=False):
         """Device-resident variant (gprf_llgrad_device): X already in HBM at ``X_dev_ptr``
         (n x dx doubles), results left in HBM at ``out_dev_ptr`` as
         [ll, grad_theta (5, zero padded), gradX (n*dx)].  Pointers are plain integers
         (e.g. ``tensor.data_ptr()``, ``torch.cuda.current_stream().cuda_stream``).
-        Uses the block structure of the last ``update_X`` / constructor."""
-        edges = self.neighbors if local else [(i, j) for i in range(self.n_blocks) for j in range(i)]
-        self._push_structure(edges)
+        ``reblock`` recomputes block membership from the device X first (needs the
+        on-device partitioner); otherwise the current blocks are used."""
+        self._sync_edges(self._edges_for(local))
+        if reblock:
+            if self._device_part is None:
+                raise RuntimeError("reblock=True needs the on-device partitioner")
+            self._check(self._lib.gprf_reblock_device(self._h, C.c_void_p(X_dev_ptr), C.c_void_p(stream_ptr)))
+            self._block_idxs = None
+            self._blocks_stale = False
+            self._blocks_key = None
+        elif self._blocks_stale:
+            _ = self.block_idxs
+        else:
+            self._sync_blocks()
         th = self._theta()
         failed = C.c_int(-1)
         rc = self._lib.gprf_llgrad_device(self._h, C.c_void_p(X_dev_ptr), _lib.ptr(th), len(th), int(grad_X),
@@ -240,7 +345,7 @@ class GPRF(object):
     def unit_results(self):
         """Per-unit log-likelihoods and applied jitter of the last evaluation
         (units: blocks 0..B-1, then edges in ``neighbors`` order)."""
-        U = self.n_blocks + len(self._keep[2])
+        U = self.n_blocks + len(self._keep_edges[1])
         lls = np.zeros(U)
         jit = np.zeros(U)
         self._check(self._lib.gprf_unit_results(self._h, _lib.ptr(lls), _lib.ptr(jit)))

@@ -61,6 +61,45 @@ int gprf_set_structure(gprf_handle h, int n_blocks, const long long* block_ptr,
                        const long long* perm, int n_edges, const int* edges,
                        const unsigned char* unit_mask);
 
+/* The same structure in two halves: the edge list is fixed at construction
+ * (gprf.py:111-116) while block membership changes with every update_X.
+ * gprf_set_edges also selects the multi-GPU share: with shard_world > 1 this
+ * device evaluates the units a longest-processing-time split on the work model
+ * W(s) = s^3 + 4 s^2 dy assigns to shard_rank (same rule on every rank). */
+int gprf_set_edges(gprf_handle h, int n_edges, const int* edges, int shard_rank,
+                   int shard_world);
+int gprf_set_blocks(gprf_handle h, int n_blocks, const long long* block_ptr,
+                    const long long* perm);
+
+/* Device-side partitioners: block membership is recomputed from X on the GPU,
+ * bit-exact with the reference's numpy expressions.
+ *   grid: Blocker.block_clusters (block_clustering.py:17-26).  centers B x dx,
+ *         csq[b] = numpy's sum(c_b**2).
+ *   tree: PDTree.recluster + pdtree_cluster's longitude wrap
+ *         (pdtree_clustering.py:65-94).  Flattened nodes: center/direction
+ *         (n_nodes x 2), cut, child (n_nodes x 2, negative = -(leaf)-1).
+ *   dot_mode selects how the host BLAS rounds the length-dx dot product
+ *         (0: k-ascending FMA, 1: k-descending FMA, 2: no FMA); the Python
+ *         layer probes it against numpy on the actual data. */
+int gprf_set_grid_partitioner(gprf_handle h, int n_blocks, const double* centers,
+                              const double* csq, int dot_mode);
+int gprf_set_tree_partitioner(gprf_handle h, int n_nodes, const double* center,
+                              const double* direction, const double* cut,
+                              const int* child, int root, int n_leaves,
+                              double wrap_add, double wrap_mod, int dot_mode);
+
+/* Replaces GPRF.update_X's `block_idxs = block_fn(new_X)` (gprf.py:169-174):
+ * recompute block membership on the device from X (host) / X_dev. */
+int gprf_reblock(gprf_handle h, const double* X);
+int gprf_reblock_device(gprf_handle h, const double* X_dev, void* stream);
+int gprf_block_count(gprf_handle h, int* n_blocks, long long* plen);
+int gprf_get_blocks(gprf_handle h, long long* block_ptr, long long* perm);
+
+/* update_X + llgrad in one call: H2D of X, device reblock, evaluation, D2H. */
+int gprf_llgrad_reblock(gprf_handle h, const double* X, const double* theta,
+                        int ncov, int grad_X, int grad_cov, double* ll,
+                        double* gradX, double* gradTheta, int* failed_unit);
+
 /* Replaces GPRF.llgrad (gprf.py:206-296) for host buffers:
  *   ll         <- sum_e ll_e + sum_i (1 - deg_i) ll_i
  *   gradX      <- n x dx (C order) or NULL   (grad_X=False)

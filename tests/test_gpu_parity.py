@@ -266,3 +266,89 @@ def test_large_units_property():
     lls, _ = g.unit_results()
     w = np.array([1 - 1, 1 - 2, 1 - 1, 1, 1], dtype=float)
     assert abs(np.dot(w, lls) - g.llgrad()[0]) <= 1e-12 * abs(g.llgrad()[0])
+
+
+def test_device_partitioner_grid_bit_exact():
+    """K8 on the device: block membership after update_X equals the host numpy partition,
+    including points on cell boundaries (ties) and outside the unit square."""
+    from gprf_b200 import GPRF, Blocker, grid_centers
+    from oracle.blocking import Blocker as OB, grid_centers as ogc
+    cov, _ = COVS["euclid_se"]
+    rng = np.random.RandomState(21)
+    n = 4000
+    X = rng.rand(n, 2)
+    Y = rng.randn(n, 3)
+    bp = Blocker(grid_centers(36))
+    bo = OB(np.asarray(ogc(36)))
+    g = GPRF(X, Y, bp.block_clusters, prod_cov(cov), 0.05, neighbors=bp.neighbors())
+    assert g._device_part == "grid"
+    for trial in range(4):
+        X2 = rng.rand(n, 2) * 1.2 - 0.1
+        m = n // 4
+        X2[:m] = np.round(X2[:m] * 6) / 6.0                 # exactly on cell boundaries / corners
+        X2[m:2 * m, 0] = np.round(X2[m:2 * m, 0] * 12) / 12.0
+        g.update_X(X2)
+        ll = g.llgrad()[0]                                   # reblocks on the GPU
+        host = bo.block_clusters(X2)
+        dev = g.block_idxs
+        assert len(dev) == len(host)
+        for a, b in zip(dev, host):
+            assert a.dtype == np.int64 and np.array_equal(a, b)
+        assert np.isfinite(ll)
+    g.close()
+
+
+def test_device_partitioner_tree_and_lld_parity():
+    """Seismic-style configuration: lon/lat/depth, PDTree blocks, threshold edges, lld+Matern."""
+    from gprf_b200 import GPRF, pdtree_cluster
+    from oracle.blocking import pdtree_cluster as o_pdtree
+    from oracle.gprf_oracle import OracleGPRF
+    cov, _ = COVS["lld_m32"]
+    rng = np.random.RandomState(5)
+    n = 1500
+    X = np.column_stack([rng.uniform(-30, 330, n) % 360 - 180 + 180, rng.uniform(-60, 60, n), rng.rand(n) * 3])
+    X[:, 0] = 80 + 0.4 * rng.randn(n)            # compact cluster so that neighbouring blocks correlate
+    X[:, 1] = 35 + 0.3 * rng.randn(n)
+    Y = rng.randn(n, 4)
+    idx_p, reblock_p = pdtree_cluster(X, blocksize=210)
+    idx_o, reblock_o = o_pdtree(X, blocksize=210)
+    g = GPRF(X, Y, reblock_p, prod_cov(cov), 0.1, neighbor_threshold=0.6, block_idxs=idx_p)
+    o = OracleGPRF(X, Y, reblock_o, cov, 0.1, neighbor_threshold=0.6, block_idxs=idx_o)
+    assert g._device_part == "tree"
+    assert g.neighbors == o.neighbors and len(g.neighbors) > 0
+    kw = dict(grad_X=True, grad_cov=True)
+    assert_parity(o.llgrad(**kw), g.llgrad(**kw), "pdtree initial")
+    for step in range(3):
+        X2 = X + rng.randn(*X.shape) * [0.02, 0.02, 0.2]
+        o.update_X(X2)
+        g.update_X(X2)
+        assert_parity(o.llgrad(**kw), g.llgrad(**kw), "pdtree step %d" % step)
+        assert all(np.array_equal(a, b) for a, b in zip(o.block_idxs, g.block_idxs))
+    g.close()
+
+
+def test_unit_sharding_partial_sums():
+    """Multi-GPU algebra on one device: the shards' partial results add up to the full result and
+    the C++ LPT split equals gprf_b200.dist.shard_units."""
+    from gprf_b200 import GPRF
+    from gprf_b200.dist import shard_units
+    from gprf_b200.gprf import _blocks_to_csr
+    o, g = build_pair("euclid_se", [40, 70, 55, 64, 90, 33], [(1, 0), (2, 1), (3, 2), (4, 3), (5, 4), (5, 0)])
+    kw = dict(grad_X=True, grad_cov=True)
+    full = g.llgrad(**kw)
+    ptr, _ = _blocks_to_csr(g.block_idxs)
+    for world in (2, 3):
+        tot = [0.0, np.zeros_like(full[1]), np.zeros_like(full[2])]
+        for rank in range(world):
+            gs = GPRF(o.X, o.Y, None, g.cov, g.noise_var, block_idxs=g.block_idxs, neighbors=g.neighbors,
+                      unit_shard=(rank, world))
+            part = gs.llgrad(**kw)
+            lls, _ = gs.unit_results()
+            mask = shard_units(ptr, np.asarray(g.neighbors), rank, world).astype(bool)
+            assert np.array_equal(lls != 0, mask)
+            for t in range(3):
+                tot[t] = tot[t] + part[t]
+            gs.close()
+        assert abs(tot[0] - full[0]) <= 1e-12 * abs(full[0])
+        assert np.abs(tot[1] - full[1]).max() <= 1e-12 * np.abs(full[1]).max()
+        assert np.abs(tot[2] - full[2]).max() <= 1e-12 * np.abs(full[2]).max()
