@@ -358,7 +358,7 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
     barrier()
     t_w = time.perf_counter()
     while len(sampler.rows) < 4 and time.perf_counter() - t_w < 2.0:
-        R.device_step()                  # keep the load on until the sampler has seen it (untimed)
+        R.device_step(reblock=R.reblock)  # keep the load on until the sampler has seen it (untimed)
     clocks = sampler.stop()
     t = torch.tensor([total_ms], dtype=torch.float64, device=R.dev)
     if world > 1:

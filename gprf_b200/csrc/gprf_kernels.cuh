@@ -56,11 +56,6 @@ struct EvalParams {
   CovParams cp;
 };
 
-struct TileRef {
-  const double* p;
-  long long ld;
-};
-
 __device__ __forceinline__ long long unit_point(const UnitDesc& u, const long long* perm, int p) {
   return p < u.ni ? perm[u.a_start + p] : perm[u.b_start + (p - u.ni)];
 }
@@ -74,36 +69,10 @@ __device__ __forceinline__ void tri_decode(int x, int& i, int& j) {
   j = x - tri(i);
 }
 
-// gemm with per-tile leading dimensions (tile sources may live in M or in D)
-template <class FA, class FB>
-__device__ __forceinline__ void gemm_nt_ref(Acc& acc, int nk, FA tileA, FB tileB, double* pipe) {
-  constexpr int CPT = T / KC;
-  const int nc = nk * CPT;
-  if (nc == 0) return;
-  double* sA[2] = {pipe, pipe + 2 * STAGE_DOUBLES};
-  double* sB[2] = {pipe + STAGE_DOUBLES, pipe + 3 * STAGE_DOUBLES};
-  {
-    TileRef a = tileA(0), b = tileB(0);
-    stage_chunk(sA[0], a.p, a.ld);
-    stage_chunk(sB[0], b.p, b.ld);
-    cp_async_commit();
-  }
-  for (int c = 0; c < nc; ++c) {
-    const int cur = c & 1;
-    if (c + 1 < nc) {
-      const int j = (c + 1) / CPT, ko = ((c + 1) % CPT) * KC;
-      TileRef a = tileA(j), b = tileB(j);
-      stage_chunk(sA[cur ^ 1], a.p + ko, a.ld);
-      stage_chunk(sB[cur ^ 1], b.p + ko, b.ld);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    mma_chunk(acc, sA[cur], sB[cur]);
-    __syncthreads();
-  }
+// Non-padding 8x8 block rows of point tile t of a unit with s points (1..8; tiles t < nt).
+__device__ __forceinline__ int ext8(int s, int t) {
+  const int r = s - t * T;
+  return r >= T ? NB8 : (r + 7) >> 3;
 }
 
 // ---------------------------------------------------------------------------
@@ -170,12 +139,14 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
 
   Acc acc;
   acc_zero(acc);
+  const int e8 = ext8(u.s, k);           // non-padding 8x8 block rows of this tile
   const double* rowk = M + (long long)k * T * ld;
-  auto tA = [&](int j) { return TileRef{rowk + j * T, ld}; };
-  gemm_nt_ref(acc, k, tA, tA, pipe);
+  auto tA = [&](int j) { return tile_ref(rowk + j * T, ld); };
+  gemm_nt<true>(acc, k, tA, tA, e8, e8, pipe);
   __syncthreads();
 
-  // C = K_kk - acc  -> shared tile S (stride WLD); S2 receives U_kk = L_kk^-T
+  // C = K_kk - acc (lower block triangle only) -> shared tile S (stride WLD); S2 receives
+  // U_kk = L_kk^-T.  Padding rows/cols form an identity block in S and S2.
   double* S = pipe;
   double* S2 = pipe + T * WLD;
   double* Wsm = pipe + 2 * T * WLD;
@@ -184,6 +155,7 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
   for (int m = 0; m < 2; ++m) {
     const int r = acc_row(m);
     const int p = k * T + r;
+    const bool rowact = acc_brow(m) < e8;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       double v[2];
@@ -192,7 +164,7 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
         const int c = acc_col(n) + e;
         const int q = k * T + c;
         double kv;
-        if (p < u.s && q < u.s) {
+        if (rowact && n <= acc_brow(m) && p < u.s && q < u.s) {
           kv = cov_value<DFN, WFN>(sx[r], sx[c], P.cp);
           if (r == c) kv = P.cp.s2 + diag_add;
         } else {
@@ -203,10 +175,13 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
       *reinterpret_cast<double2*>(S + r * WLD + acc_col(n)) = make_double2(v[0], v[1]);
     }
   }
-  for (int e = tid; e < T * WLD; e += NTHREADS) S2[e] = 0.0;
+  for (int e = tid; e < T * WLD; e += NTHREADS) {
+    const int r = e / WLD, c = e % WLD;
+    S2[e] = (r == c && r >= e8 * 8) ? 1.0 : 0.0;
+  }
   __syncthreads();
 
-  smem_potrf_trtri(S, S2, Wsm, WLD, T / 8, &sfail, k * T);
+  smem_potrf_trtri(S, S2, Wsm, WLD, e8, &sfail, k * T);
 
   // outputs: L_kk (upper part zero), W_kk = U_kk^T, U_kk, logdet partial, status
   double* Lout = M + (long long)k * T * ld + k * T;
@@ -264,11 +239,14 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_panel(EvalParams P, int k) {
   }
   Acc acc;
   acc_zero(acc);
+  // block masks: rows of this tile (points of tile `it`, or outputs of Y^T), columns = points of tile k
+  const int mlim = aug ? min(NB8, (P.dy - (it - u.nt) * T + 7) >> 3) : ext8(u.s, it);
+  const int nlim = ext8(u.s, k);
   const double* rowi = M + (long long)it * T * ld;
   const double* rowk = M + (long long)k * T * ld;
-  auto tA = [&](int j) { return TileRef{rowi + j * T, ld}; };
-  auto tB = [&](int j) { return TileRef{rowk + j * T, ld}; };
-  gemm_nt_ref(acc, k, tA, tB, pipe);
+  auto tA = [&](int j) { return tile_ref(rowi + j * T, ld); };
+  auto tB = [&](int j) { return tile_ref(rowk + j * T, ld); };
+  gemm_nt<false>(acc, k, tA, tB, mlim, nlim, pipe);
   __syncthreads();
 
   // C = C0 - acc
@@ -276,18 +254,21 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_panel(EvalParams P, int k) {
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
     const int r = acc_row(m);
+    const bool rowact = acc_brow(m) < mlim;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       const int c = acc_col(n);
-      double c0, c1;
-      if (aug) {
-        double2 v = *reinterpret_cast<const double2*>(out + (long long)r * ld + c);
-        c0 = v.x;
-        c1 = v.y;
-      } else {
-        const int p = it * T + r;
-        c0 = (p < u.s && k * T + c < u.s) ? cov_value<DFN, WFN>(sxr[r], sxc[c], P.cp) : 0.0;
-        c1 = (p < u.s && k * T + c + 1 < u.s) ? cov_value<DFN, WFN>(sxr[r], sxc[c + 1], P.cp) : 0.0;
+      double c0 = 0.0, c1 = 0.0;
+      if (rowact && n < nlim) {
+        if (aug) {
+          double2 v = *reinterpret_cast<const double2*>(out + (long long)r * ld + c);
+          c0 = v.x;
+          c1 = v.y;
+        } else {
+          const int p = it * T + r;
+          c0 = (p < u.s && k * T + c < u.s) ? cov_value<DFN, WFN>(sxr[r], sxc[c], P.cp) : 0.0;
+          c1 = (p < u.s && k * T + c + 1 < u.s) ? cov_value<DFN, WFN>(sxr[r], sxc[c + 1], P.cp) : 0.0;
+        }
       }
       acc.c[m][n][0] = c0 - acc.c[m][n][0];
       acc.c[m][n][1] = c1 - acc.c[m][n][1];
@@ -297,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_panel(EvalParams P, int k) {
   const double* Wd = P.arena + u.d_off + (long long)k * T * T;
   stage_full(pipe, Wd, T);
   Acc res;
-  mul_acc_by_wt(res, acc, pipe, 1.0);
+  mul_acc_by_wt(res, acc, pipe, 1.0, mlim, nlim);
   acc_store(res, out, ld);
 }
 
@@ -318,16 +299,17 @@ __global__ void __launch_bounds__(NTHREADS) k_trtri(EvalParams P, int d) {
   const double* rowi = M + (long long)i * T * ld;
   Acc acc;
   acc_zero(acc);
+  const int nlim = ext8(u.s, i);      // tile k < i is never the padded one
   auto tA = [&](int jj) {
-    return jj == 0 ? TileRef{Ud, T} : TileRef{rowk + (long long)(k + jj) * T, ld};
+    return jj == 0 ? tile_ref(Ud, T, NB8, 1, 0) : tile_ref(rowk + (long long)(k + jj) * T, ld);
   };
-  auto tB = [&](int jj) { return TileRef{rowi + (long long)(k + jj) * T, ld}; };
-  gemm_nt_ref(acc, d, tA, tB, pipe);
+  auto tB = [&](int jj) { return tile_ref(rowi + (long long)(k + jj) * T, ld); };
+  gemm_nt<false>(acc, d, tA, tB, NB8, nlim, pipe);
   __syncthreads();
   const double* Wd = P.arena + u.d_off + (long long)i * T * T;
   stage_full(pipe, Wd, T);
   Acc res;
-  mul_acc_by_wt(res, acc, pipe, -1.0);
+  mul_acc_by_wt(res, acc, pipe, -1.0, NB8, nlim);
   acc_store(res, M + (long long)k * T * ld + (long long)i * T, ld);
 }
 
@@ -357,13 +339,19 @@ __global__ void __launch_bounds__(NTHREADS) k_lauum(EvalParams P, int ntri_max) 
   const double* rowj = M + (long long)j * T * ld;
   Acc acc;
   acc_zero(acc);
+  const int mlim = ext8(u.s, i);
+  const int nlim = aug ? min(NB8, (P.dy - (j - u.nt) * T + 7) >> 3) : ext8(u.s, j);
+  // contraction over point tiles m = i + jj; U_ii is upper triangular
   auto tA = [&](int jj) {
-    return jj == 0 ? TileRef{Udi, T} : TileRef{rowi + (long long)(i + jj) * T, ld};
+    const int kl = ext8(u.s, i + jj);
+    return jj == 0 ? tile_ref(Udi, T, kl, 1, 0) : tile_ref(rowi + (long long)(i + jj) * T, ld, kl);
   };
   auto tB = [&](int jj) {
-    return (j == i && jj == 0) ? TileRef{Udi, T} : TileRef{rowj + (long long)(i + jj) * T, ld};
+    const int kl = ext8(u.s, i + jj);
+    return (j == i && jj == 0) ? tile_ref(Udi, T, kl, 0, 2) : tile_ref(rowj + (long long)(i + jj) * T, ld, kl);
   };
-  gemm_nt_ref(acc, u.nt - i, tA, tB, pipe);
+  if (j == i) gemm_nt<true>(acc, u.nt - i, tA, tB, mlim, nlim, pipe);
+  else gemm_nt<false>(acc, u.nt - i, tA, tB, mlim, nlim, pipe);
   if (aug) {
     double* Al = P.arena + u.al_off;
     acc_store(acc, Al + (long long)i * T * P.yr + (long long)(j - u.nt) * T, P.yr);
@@ -403,9 +391,11 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
   acc_zero(acc);
   const double* ai = Al + (long long)i * T * P.yr;
   const double* aj = Al + (long long)j * T * P.yr;
-  auto tA = [&](int c) { return TileRef{ai + c * T, (long long)P.yr}; };
-  auto tB = [&](int c) { return TileRef{aj + c * T, (long long)P.yr}; };
-  gemm_nt_ref(acc, P.nya, tA, tB, pipe);
+  const int mlim = ext8(u.s, i), nlim = ext8(u.s, j);
+  auto tA = [&](int c) { return tile_ref(ai + c * T, (long long)P.yr, min(NB8, (P.dy - c * T + 7) >> 3)); };
+  auto tB = [&](int c) { return tile_ref(aj + c * T, (long long)P.yr, min(NB8, (P.dy - c * T + 7) >> 3)); };
+  if (i == j) gemm_nt<true>(acc, P.nya, tA, tB, mlim, nlim, pipe);
+  else gemm_nt<false>(acc, P.nya, tA, tB, mlim, nlim, pipe);
   __syncthreads();
 
   const double* Kt = M + (long long)i * T * ld + (long long)j * T;
@@ -418,12 +408,29 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
 #pragma unroll
   for (int t = 0; t < MAX_NCOV; ++t) th[t] = 0.0;
 
+  // block (m, n) of the tile holds real entries of the strictly-lower-or-diagonal part?
+  bool mact[2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) mact[m] = acc_brow(m) < mlim;
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
+    bool bact[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) bact[m] = mact[m] && n < nlim && (i != j || n <= acc_brow(m));
+    if (!bact[0] && !bact[1]) {           // warp-uniform: nothing of this block column is ours
+      if ((lane >> 2) == 0) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) scol[warp][acc_col(n) + e][d] = 0.0;
+      }
+      continue;
+    }
     double2 kin[2];
 #pragma unroll
     for (int m = 0; m < 2; ++m)
-      kin[m] = *reinterpret_cast<const double2*>(Kt + (long long)acc_row(m) * ld + acc_col(n));
+      kin[m] = bact[m] ? *reinterpret_cast<const double2*>(Kt + (long long)acc_row(m) * ld + acc_col(n))
+                       : make_double2(0.0, 0.0);
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int c = acc_col(n) + e;
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
         const int r = acc_row(m);
         const int p = i * T + r;
         const double G = acc.c[m][n][e] - dyd * (e == 0 ? kin[m].x : kin[m].y);
-        if (p < u.s && q < u.s) {
+        if (bact[m] && p < u.s && q < u.s) {
           if (i != j || q < p) {
             double kv, gp[3], gq[3], gl[3];
             cov_grad<DFN, WFN>(sxi[r], sxj[c], P.cp, kv, gp, gq, gl);

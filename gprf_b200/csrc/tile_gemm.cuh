@@ -1,15 +1,29 @@
 // FP64 tensor-core tile engine shared by every dense kernel of the path.
 //
-// One CTA (128 threads = 4 warps) owns one 64x64 output tile.  Warp w owns
-// rows 16w..16w+15 and all 64 columns: 2 x 8 DMMA (m8n8k4, f64) accumulator
-// tiles = 32 doubles per thread.  Every product on the path is of the form
+// One CTA (128 threads = 4 warps) owns one 64x64 output tile, seen as 8x8 blocks
+// of 8x8 doubles (the DMMA m8n8k4 fragment).  Warp w owns block rows {w, 7-w}
+// (a folded assignment: triangular operands and triangular outputs then cost
+// every warp the same) and all 8 block columns: 2 x 8 accumulator fragments =
+// 32 doubles per thread.  Every product on the path is of the form
 //
 //     C(64x64) += sum_j  A_j(64x64) * B_j(64x64)^T          ("NT")
 //
-// with A_j, B_j row-major tiles in HBM/L2, so a single staging pattern
-// serves the Cholesky update, the triangular inverse, K^-1 = U U^T, Alpha and
+// with A_j, B_j row-major tiles in HBM/L2, so a single staging pattern serves
+// the Cholesky update, the triangular inverse, K^-1 = U U^T, Alpha and
 // G = Alpha Alpha^T.  Operands are staged through shared memory in K-chunks
 // of 32 with cp.async (16-byte, L2 only), double buffered.
+//
+// Block masks.  Units are padded to multiples of 64 points, diagonal tiles of
+// L / U / W are triangular and diagonal output tiles are symmetric.  Executing
+// those as dense 64^3 products costs 2-4x the useful flops on 100-200 point
+// units, so every product carries a mask at 8x8-block granularity:
+//   mlim / nlim   number of non-padding block rows / block columns of C
+//   klim(j)       number of non-padding block columns of A_j, B_j
+//   atri          A_j is upper triangular (block (m,k) is zero for k < m)
+//   btri          B_j is upper triangular (2: block (n,k) is zero for k < n)
+//   CLOW          only the lower block triangle of C is needed (n <= m)
+// A skipped block leaves its accumulator fragment at zero, which is exactly the
+// value of the padded / structurally-zero entry, so stores stay dense.
 //
 // Fragment trick: the contraction index may be visited in any order as long
 // as A and B agree.  A thread loads (row g, cols 2q,2q+1) with one LDS.128 and
@@ -25,6 +39,7 @@
 namespace gprf {
 
 constexpr int T = 64;            // tile edge
+constexpr int NB8 = T / 8;       // 8x8 blocks per tile edge
 constexpr int KC = 32;           // K chunk staged per pipeline stage
 constexpr int SLD = KC + 8;      // smem row stride (doubles): 320 B = 64 mod 128
 constexpr int NTHREADS = 128;
@@ -44,6 +59,15 @@ __device__ __forceinline__ void acc_zero(Acc& a) {
     for (int n = 0; n < 8; ++n) a.c[m][n][0] = a.c[m][n][1] = 0.0;
 }
 
+// Block row (0..7) of accumulator slot m for this thread's warp.
+__device__ __forceinline__ int acc_brow(int m) {
+  const int w = threadIdx.x >> 5;
+  return m == 0 ? w : 7 - w;
+}
+// Accumulator element coordinates inside the 64x64 tile.
+__device__ __forceinline__ int acc_row(int m) { return acc_brow(m) * 8 + ((threadIdx.x & 31) >> 2); }
+__device__ __forceinline__ int acc_col(int n) { return n * 8 + 2 * (threadIdx.x & 3); }
+
 // D(8x8) += A(8x4) * B(4x8);  a = A[g][q], b = B[q][g], c = {C[g][2q], C[g][2q+1]}
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -61,69 +85,144 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// Stage one 64 x KC chunk (row-major source, leading dimension ld) into smem.
-__device__ __forceinline__ void stage_chunk(double* dst, const double* src, long long ld) {
+// One source tile of a product and its block mask.
+struct TileRef {
+  const double* p;    // element (0,0)
+  long long ld;
+  int klim;           // non-padding block columns (1..8)
+  int atri;           // used as A: upper triangular
+  int btri;           // used as B: 2 = upper triangular
+};
+__device__ __forceinline__ TileRef tile_ref(const double* p, long long ld, int klim = NB8, int atri = 0,
+                                            int btri = 0) {
+  TileRef t;
+  t.p = p; t.ld = ld; t.klim = klim; t.atri = atri; t.btri = btri;
+  return t;
+}
+
+// Stage the first `rows` rows of one 64 x KC chunk (row-major source, leading dimension ld).
+__device__ __forceinline__ void stage_chunk(double* dst, const double* src, long long ld, int rows) {
   const int tid = threadIdx.x;
 #pragma unroll
   for (int it = 0; it < (T * KC / 2) / NTHREADS; ++it) {
     int id = tid + it * NTHREADS;
     int row = id / (KC / 2);
     int cu = id % (KC / 2);
-    cp_async16(dst + row * SLD + cu * 2, src + (long long)row * ld + cu * 2);
+    if (row < rows) cp_async16(dst + row * SLD + cu * 2, src + (long long)row * ld + cu * 2);
   }
 }
 
-// One staged chunk: acc += A_chunk(64 x KC) * B_chunk(64 x KC)^T
-__device__ __forceinline__ void mma_chunk(Acc& acc, const double* sA, const double* sB) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// One staged chunk: acc += A_chunk(64 x KC) * B_chunk(64 x KC)^T under the block mask.
+// kk0 = block-column index of the chunk's first column inside its tile (0 or 4).
+// A chunk without any masked block takes the branch-free path (all LDS.128 issued up front,
+// 32 back-to-back DMMAs per 8 columns); the masked path keeps the loads unconditional and
+// predicates only the DMMAs, so the scheduler can still hoist the loads.
+template <bool CLOW>
+__device__ __forceinline__ void mma_chunk(Acc& acc, const double* sA, const double* sB, int kk0, int mlim,
+                                          int nlim, int klim, int atri, int btri) {
+  const int lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const double* pa = sA + (warp * 16 + g) * SLD + 2 * q;
+  const int br0 = acc_brow(0), br1 = acc_brow(1);
+  const double* pa0 = sA + (br0 * 8 + g) * SLD + 2 * q;
+  const double* pa1 = sA + (br1 * 8 + g) * SLD + 2 * q;
   const double* pb = sB + g * SLD + 2 * q;
+  if (!CLOW && mlim == NB8 && nlim == NB8 && klim >= kk0 + KC / 8 && atri == 0 && btri == 0) {
+#pragma unroll
+    for (int k8 = 0; k8 < KC / 8; ++k8) {
+      double2 a[2], b[8];
+      a[0] = *reinterpret_cast<const double2*>(pa0 + k8 * 8);
+      a[1] = *reinterpret_cast<const double2*>(pa1 + k8 * 8);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) b[n] = *reinterpret_cast<const double2*>(pb + n * 8 * SLD + k8 * 8);
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          dmma884(acc.c[m][n][0], acc.c[m][n][1], a[m].x, b[n].x);
+          dmma884(acc.c[m][n][0], acc.c[m][n][1], a[m].y, b[n].y);
+        }
+    }
+    return;
+  }
+  // Masked path.  A predicated-off DMMA occupies the FP64 pipe exactly like an executed one
+  // (measured: scripts/dmma_pred.cu, profiles/r01_dmma_predication.txt), so blocks are skipped
+  // with real forward branches: per block row an ascending loop over the block columns that
+  // breaks at the first masked one (every mask on the path is an upper limit on n).
+  const bool row0 = br0 < mlim, row1 = br1 < mlim;
 #pragma unroll
   for (int k8 = 0; k8 < KC / 8; ++k8) {
+    const int kk = kk0 + k8;
+    if (kk >= klim) break;
+    int nhi = nlim;
+    if (btri == 2) nhi = min(nhi, kk + 1);
+    int nh0 = (row0 && (!atri || kk >= br0)) ? nhi : 0;
+    int nh1 = (row1 && (!atri || kk >= br1)) ? nhi : 0;
+    if (CLOW) {
+      nh0 = min(nh0, br0 + 1);
+      nh1 = min(nh1, br1 + 1);
+    }
+    if (nh0 == 0 && nh1 == 0) continue;
     double2 a[2], b[8];
-#pragma unroll
-    for (int m = 0; m < 2; ++m) a[m] = *reinterpret_cast<const double2*>(pa + m * 8 * SLD + k8 * 8);
+    a[0] = *reinterpret_cast<const double2*>(pa0 + k8 * 8);
+    a[1] = *reinterpret_cast<const double2*>(pa1 + k8 * 8);
 #pragma unroll
     for (int n = 0; n < 8; ++n) b[n] = *reinterpret_cast<const double2*>(pb + n * 8 * SLD + k8 * 8);
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int n = 0; n < 8; ++n) {
+      if (n >= nh0) break;
+      dmma884(acc.c[0][n][0], acc.c[0][n][1], a[0].x, b[n].x);
+      dmma884(acc.c[0][n][0], acc.c[0][n][1], a[0].y, b[n].y);
+    }
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        dmma884(acc.c[m][n][0], acc.c[m][n][1], a[m].x, b[n].x);
-        dmma884(acc.c[m][n][0], acc.c[m][n][1], a[m].y, b[n].y);
-      }
+    for (int n = 0; n < 8; ++n) {
+      if (n >= nh1) break;
+      dmma884(acc.c[1][n][0], acc.c[1][n][1], a[1].x, b[n].x);
+      dmma884(acc.c[1][n][0], acc.c[1][n][1], a[1].y, b[n].y);
+    }
   }
 }
 
-// acc += sum_{j=0}^{nk-1} A_j * B_j^T.  tileA(j) / tileB(j) return the address of
-// element (0,0) of the j-th 64x64 source tile.  `pipe` = PIPE_DOUBLES of smem.
+// acc += sum_{j=0}^{nk-1} A_j * B_j^T.  tileA(j) / tileB(j) return TileRefs (klim is taken
+// from A's ref and must agree with B's).  `pipe` = PIPE_DOUBLES of smem.
 // Ends with a __syncthreads(): `pipe` may be reused by the caller afterwards.
-template <class FA, class FB>
-__device__ __forceinline__ void gemm_nt(Acc& acc, int nk, FA tileA, long long lda, FB tileB,
-                                        long long ldb, double* pipe) {
-  constexpr int CPT = T / KC;  // chunks per tile
-  const int nc = nk * CPT;
-  if (nc == 0) return;
-  double* sA[2] = {pipe, pipe + 2 * STAGE_DOUBLES};
-  double* sB[2] = {pipe + STAGE_DOUBLES, pipe + 3 * STAGE_DOUBLES};
-  stage_chunk(sA[0], tileA(0), lda);
-  stage_chunk(sB[0], tileB(0), ldb);
+template <bool CLOW, class FA, class FB>
+__device__ __forceinline__ void gemm_nt(Acc& acc, int nk, FA tileA, FB tileB, int mlim, int nlim, double* pipe) {
+  constexpr int CPT = T / KC;        // chunks per tile
+  constexpr int BPC = KC / 8;        // 8-blocks per chunk
+  if (nk <= 0 || mlim <= 0 || nlim <= 0) return;
+  // stage s: A at pipe + 2 s STAGE_DOUBLES, B right after it (plain arithmetic: no pointer arrays,
+  // which would live in local memory once indexed with a run-time stage)
+  const int arows = mlim * 8, brows = nlim * 8;
+  // chunk cursor over (tile j, half h), skipping chunks beyond the tile's klim
+  int j = 0, h = 0;
+  TileRef a = tileA(0), b = tileB(0);
+  stage_chunk(pipe, a.p, a.ld, arows);
+  stage_chunk(pipe + STAGE_DOUBLES, b.p, b.ld, brows);
   cp_async_commit();
-  for (int c = 0; c < nc; ++c) {
-    const int cur = c & 1;
-    if (c + 1 < nc) {
-      const int j = (c + 1) / CPT, ko = ((c + 1) % CPT) * KC;
-      stage_chunk(sA[cur ^ 1], tileA(j) + ko, lda);
-      stage_chunk(sB[cur ^ 1], tileB(j) + ko, ldb);
+  int cur = 0;
+  while (true) {
+    // next chunk
+    int jn = j, hn = h + 1;
+    if (hn == CPT || hn * BPC >= a.klim) { hn = 0; ++jn; }
+    const bool more = jn < nk;
+    TileRef an = a, bn = b;
+    if (more) {
+      if (jn != j) { an = tileA(jn); bn = tileB(jn); }
+      double* nxt = pipe + (cur ^ 1) * 2 * STAGE_DOUBLES;
+      stage_chunk(nxt, an.p + hn * KC, an.ld, arows);
+      stage_chunk(nxt + STAGE_DOUBLES, bn.p + hn * KC, bn.ld, brows);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
-    mma_chunk(acc, sA[cur], sB[cur]);
+    const double* cs = pipe + cur * 2 * STAGE_DOUBLES;
+    mma_chunk<CLOW>(acc, cs, cs + STAGE_DOUBLES, h * BPC, mlim, nlim, a.klim, a.atri, b.btri);
     __syncthreads();
+    if (!more) break;
+    j = jn; h = hn; a = an; b = bn;
+    cur ^= 1;
   }
 }
 
@@ -143,24 +242,34 @@ __device__ __forceinline__ void stage_full(double* dst, const double* src, long 
 }
 
 // out = scale * (C * W^T) with C taken from accumulator registers (used as the
-// A operand, see header) and W a fully staged 64x64 row-major tile (stride WLD).
-__device__ __forceinline__ void mul_acc_by_wt(Acc& out, const Acc& c, const double* sW, double scale) {
+// A operand, see header) and W a fully staged 64x64 row-major LOWER TRIANGULAR
+// tile (stride WLD) with wlim non-padding block rows / columns.  Rows of C beyond
+// mlim blocks are padding.
+__device__ __forceinline__ void mul_acc_by_wt(Acc& out, const Acc& c, const double* sW, double scale, int mlim,
+                                              int wlim) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
+  const int w0 = acc_brow(0) < mlim ? wlim : 0, w1 = acc_brow(1) < mlim ? wlim : 0;
   acc_zero(out);
 #pragma unroll
   for (int k8 = 0; k8 < 8; ++k8) {
+    if (k8 >= wlim) break;
     double2 b[8];
 #pragma unroll
-    for (int n = 0; n < 8; ++n)
+    for (int n = k8; n < 8; ++n)                      // W[n][k] = 0 for k > n
       b[n] = *reinterpret_cast<const double2*>(sW + (n * 8 + g) * WLD + k8 * 8 + 2 * q);
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int n = k8; n < 8; ++n) {
+      if (n >= w0) break;
+      dmma884(out.c[0][n][0], out.c[0][n][1], c.c[0][k8][0], b[n].x);
+      dmma884(out.c[0][n][0], out.c[0][n][1], c.c[0][k8][1], b[n].y);
+    }
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        dmma884(out.c[m][n][0], out.c[m][n][1], c.c[m][k8][0], b[n].x);
-        dmma884(out.c[m][n][0], out.c[m][n][1], c.c[m][k8][1], b[n].y);
-      }
+    for (int n = k8; n < 8; ++n) {
+      if (n >= w1) break;
+      dmma884(out.c[1][n][0], out.c[1][n][1], c.c[1][k8][0], b[n].x);
+      dmma884(out.c[1][n][0], out.c[1][n][1], c.c[1][k8][1], b[n].y);
+    }
   }
   if (scale != 1.0) {
 #pragma unroll
@@ -172,10 +281,6 @@ __device__ __forceinline__ void mul_acc_by_wt(Acc& out, const Acc& c, const doub
       }
   }
 }
-
-// Accumulator element coordinates inside the 64x64 tile.
-__device__ __forceinline__ int acc_row(int m) { return (threadIdx.x >> 5) * 16 + m * 8 + ((threadIdx.x & 31) >> 2); }
-__device__ __forceinline__ int acc_col(int n) { return n * 8 + 2 * (threadIdx.x & 3); }
 
 // Store the accumulator tile row-major (16-byte stores).
 __device__ __forceinline__ void acc_store(const Acc& a, double* dst, long long ld) {

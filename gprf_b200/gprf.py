@@ -259,7 +259,7 @@ class GPRF(object):
 
     def _sync_blocks(self):
         """Host-held block lists -> device (no-op when the device already holds them)."""
-        if self._blocks_stale:
+        if self._blocks_stale or self._block_idxs is None:      # None: membership lives on the device
             return
         key = id(self._block_idxs)
         if key == self._blocks_key:
