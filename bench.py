@@ -305,7 +305,7 @@ class Runner(object):
 
     def e2e_bytes(self):
         nb, ne = len(self.wl["block_idxs"]), len(self.wl["neighbors"])
-        h2d = self.n * self.dx * 8 + self.n * 8 + self.n * 4 + (nb + 1) * 12 + ne * 8 * 2 + ne * 8 + (nb + ne) * 96
+        h2d = self.n * self.dx * 8 + self.n * 8 + self.n * 4 + (nb + 1) * 12 + ne * 8 * 2 + ne * 8 + (nb + ne) * 104
         d2h = (1 + 5 + self.n * self.dx) * 8 + 4
         return h2d, d2h
 

@@ -100,7 +100,10 @@ __device__ __forceinline__ double cov_value(const double* xp, const double* xq, 
 
 // Covariance value and all first derivatives for one ordered pair (p, q), p != q:
 //   gp[i] = dk/dx_{p,i},  gq[i] = dk/dx_{q,i},  gl[t] = dk/dl_t
-template <int DFN, int WFN>
+// HAVE_K: k holds the covariance value on entry (saved by the factorisation, which had to
+// evaluate it anyway), so the exponential is not recomputed:
+//   se: wr = -2 k          matern32: wr = -3 k / (1 + sqrt3 r)
+template <int DFN, int WFN, bool HAVE_K>
 __device__ __forceinline__ void cov_grad(const double* xp, const double* xq, const CovParams& cp,
                                          double& k, double gp[MAX_DX], double gq[MAX_DX],
                                          double gl[MAX_NLS]) {
@@ -113,7 +116,11 @@ __device__ __forceinline__ void cov_grad(const double* xp, const double* xq, con
       d[i] = xp[i] - xq[i];
       r2 += d[i] * d[i] * cp.il2[i];
     }
-    weight_and_wr<WFN>(r2, cp.s2, k, wr);
+    if (HAVE_K) {
+      wr = (WFN == WFN_SE) ? -2.0 * k : -3.0 * k / (1.0 + GPRF_SQRT3 * sqrt(r2));
+    } else {
+      weight_and_wr<WFN>(r2, cp.s2, k, wr);
+    }
 #pragma unroll
     for (int i = 0; i < MAX_DX; ++i) {
       double g = wr * d[i] * cp.il2[i];
@@ -126,7 +133,11 @@ __device__ __forceinline__ void cov_grad(const double* xp, const double* xq, con
     double d = 2.0 * GPRF_EARTH_R * asin(sqrt(t.h));
     double dz = xp[2] - xq[2];
     double r2 = d * d * cp.il2[0] + dz * dz * cp.il2[1];
-    weight_and_wr<WFN>(r2, cp.s2, k, wr);
+    if (HAVE_K) {
+      wr = (WFN == WFN_SE) ? -2.0 * k : -3.0 * k / (1.0 + GPRF_SQRT3 * sqrt(r2));
+    } else {
+      weight_and_wr<WFN>(r2, cp.s2, k, wr);
+    }
     // d * dd/dh / l0^2 ; the reference's 0 * inf at h == 0 is mapped to 0
     double pref = 0.0;
     if (t.h > 0.0) pref = wr * d * (GPRF_EARTH_R / sqrt(t.h * (1.0 - t.h))) * cp.il2[0];

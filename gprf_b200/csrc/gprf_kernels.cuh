@@ -38,7 +38,7 @@ struct UnitDesc {
   int s, ni, nt, sp;
   int a_start, b_start;       // offsets of the two blocks' rows in perm
   int active, pad_;
-  long long m_off, d_off, al_off, xs_off, part_off, ld_off, gx_off;
+  long long m_off, d_off, al_off, xs_off, part_off, ld_off, gx_off, k_off;
   double weight;
 };
 
@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
   double* S2 = pipe + T * WLD;
   double* Wsm = pipe + 2 * T * WLD;
   const double diag_add = P.cp.nv + P.jitter[uid];
+  double* Ks = P.arena + u.k_off + (long long)k * T * ld + k * T;     // saved K tile (k, k)
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
     const int r = acc_row(m);
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
     const bool rowact = acc_brow(m) < e8;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      double v[2];
+      double v[2], kvs[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int c = acc_col(n) + e;
@@ -170,9 +171,12 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
         } else {
           kv = (r == c) ? 1.0 : 0.0;
         }
+        kvs[e] = kv;
         v[e] = kv - acc.c[m][n][e];
       }
       *reinterpret_cast<double2*>(S + r * WLD + acc_col(n)) = make_double2(v[0], v[1]);
+      if (rowact && n <= acc_brow(m))          // noise-free off-diagonal values are what grad re-reads
+        *reinterpret_cast<double2*>(Ks + (long long)r * ld + acc_col(n)) = make_double2(kvs[0], kvs[1]);
     }
   }
   for (int e = tid; e < T * WLD; e += NTHREADS) {
@@ -251,6 +255,7 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_panel(EvalParams P, int k) {
 
   // C = C0 - acc
   double* out = M + (long long)it * T * ld + k * T;
+  double* Ks = P.arena + u.k_off + (long long)it * T * ld + k * T;    // saved K tile (it, k), non-aug only
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
     const int r = acc_row(m);
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_panel(EvalParams P, int k) {
           const int p = it * T + r;
           c0 = (p < u.s && k * T + c < u.s) ? cov_value<DFN, WFN>(sxr[r], sxc[c], P.cp) : 0.0;
           c1 = (p < u.s && k * T + c + 1 < u.s) ? cov_value<DFN, WFN>(sxr[r], sxc[c + 1], P.cp) : 0.0;
+          *reinterpret_cast<double2*>(Ks + (long long)r * ld + c) = make_double2(c0, c1);
         }
       }
       acc.c[m][n][0] = c0 - acc.c[m][n][0];
@@ -392,28 +398,54 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
   const double* ai = Al + (long long)i * T * P.yr;
   const double* aj = Al + (long long)j * T * P.yr;
   const int mlim = ext8(u.s, i), nlim = ext8(u.s, j);
+  // K^-1 and saved-K values of this thread's fragments, fetched in two halves (block columns
+  // 0-3 / 4-7) so that the global-load latency hides behind the G product and behind the first
+  // half of the epilogue instead of being paid once per block column.
+  const double* Kt = M + (long long)i * T * ld + (long long)j * T;
+  const double* Kst = P.arena + u.k_off + (long long)i * T * ld + (long long)j * T;
+  double2 kinA[4][2], ksvA[4][2], kinB[4][2], ksvB[4][2];
+  auto load_half = [&](int h, double2 (&kin)[4][2], double2 (&ksv)[4][2]) {
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn)
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const long long o = (long long)acc_row(m) * ld + acc_col(h * 4 + nn);
+        kin[nn][m] = *reinterpret_cast<const double2*>(Kt + o);
+        ksv[nn][m] = *reinterpret_cast<const double2*>(Kst + o);
+      }
+  };
+  load_half(0, kinA, ksvA);
   auto tA = [&](int c) { return tile_ref(ai + c * T, (long long)P.yr, min(NB8, (P.dy - c * T + 7) >> 3)); };
   auto tB = [&](int c) { return tile_ref(aj + c * T, (long long)P.yr, min(NB8, (P.dy - c * T + 7) >> 3)); };
   if (i == j) gemm_nt<true>(acc, P.nya, tA, tB, mlim, nlim, pipe);
   else gemm_nt<false>(acc, P.nya, tA, tB, mlim, nlim, pipe);
   __syncthreads();
 
-  const double* Kt = M + (long long)i * T * ld + (long long)j * T;
+  load_half(1, kinB, ksvB);
   const double dyd = (double)P.dy;
   const double inv_s2 = 1.0 / P.cp.s2;
+  // Raw sums; for the euclidean family they are scaled by the lengthscale factors at the end:
+  //   t_d = G w'(r)/r (x_p - x_q)_d ;  rs = il2_d sum t_d ; cs = -il2_d sum t_d ; th[2+d] = -il3_d sum t_d (x_p-x_q)_d
   double rs[2][3];
   double th[MAX_NCOV];
 #pragma unroll
   for (int m = 0; m < 2; ++m) rs[m][0] = rs[m][1] = rs[m][2] = 0.0;
 #pragma unroll
   for (int t = 0; t < MAX_NCOV; ++t) th[t] = 0.0;
+  double xi[2][3];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xi[m][d] = sxi[acc_row(m)][d];
 
   // block (m, n) of the tile holds real entries of the strictly-lower-or-diagonal part?
   bool mact[2];
 #pragma unroll
   for (int m = 0; m < 2; ++m) mact[m] = acc_brow(m) < mlim;
+  auto epilogue_half = [&](int h, const double2 (&kinH)[4][2], const double2 (&ksvH)[4][2]) {
 #pragma unroll
-  for (int n = 0; n < 8; ++n) {
+  for (int nn = 0; nn < 4; ++nn) {
+    const int n = h * 4 + nn;
     bool bact[2];
 #pragma unroll
     for (int m = 0; m < 2; ++m) bact[m] = mact[m] && n < nlim && (i != j || n <= acc_brow(m));
@@ -426,47 +458,80 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
       }
       continue;
     }
-    double2 kin[2];
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-      kin[m] = bact[m] ? *reinterpret_cast<const double2*>(Kt + (long long)acc_row(m) * ld + acc_col(n))
-                       : make_double2(0.0, 0.0);
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int c = acc_col(n) + e;
       const int q = j * T + c;
       double cs[3] = {0.0, 0.0, 0.0};
+      double xj[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) xj[d] = sxj[c][d];
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
         const int r = acc_row(m);
         const int p = i * T + r;
-        const double G = acc.c[m][n][e] - dyd * (e == 0 ? kin[m].x : kin[m].y);
-        if (bact[m] && p < u.s && q < u.s) {
-          if (i != j || q < p) {
-            double kv, gp[3], gq[3], gl[3];
-            cov_grad<DFN, WFN>(sxi[r], sxj[c], P.cp, kv, gp, gq, gl);
+        double kv = (e == 0 ? ksvH[nn][m].x : ksvH[nn][m].y);
+        double G = acc.c[m][h * 4 + nn][e] - dyd * (e == 0 ? kinH[nn][m].x : kinH[nn][m].y);
+        const bool inside = bact[m] && p < u.s && q < u.s;
+        if (i == j && inside && q == p) {
+          th[0] += 0.5 * G;
+          th[1] += 0.5 * G * P.cp.s2;     // scaled by inv_s2 below
+        }
+        const bool offd = inside && (i != j || q < p);
+        if (DFN == DFN_EUCLIDEAN) {
+          // branch-free: entries outside the strictly lower part contribute G = 0
+          G = offd ? G : 0.0;
+          kv = offd ? kv : 0.0;           // blocks outside the mask hold unspecified memory
+          double dd[3], r2 = 0.0;
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              rs[m][d] += G * gp[d];
-              cs[d] += G * gq[d];
-              th[2 + d] += G * gl[d];
-            }
-            th[1] += G * kv * inv_s2;
-          } else if (q == p) {
-            th[0] += 0.5 * G;
-            th[1] += 0.5 * G;
+          for (int d = 0; d < 3; ++d) {
+            dd[d] = xi[m][d] - xj[d];
+            if (WFN != WFN_SE) r2 += dd[d] * dd[d] * P.cp.il2[d];
           }
+          const double gk = G * kv;
+          th[1] += gk;
+          const double pw = (WFN == WFN_SE) ? -2.0 * gk : -3.0 * gk / (1.0 + GPRF_SQRT3 * sqrt(r2));
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const double t = pw * dd[d];
+            rs[m][d] += t;
+            cs[d] += t;
+            th[2 + d] += t * dd[d];
+          }
+        } else if (offd) {
+          double kk = kv, gp[3], gq[3], gl[3];
+          cov_grad<DFN, WFN, true>(sxi[r], sxj[c], P.cp, kk, gp, gq, gl);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            rs[m][d] += G * gp[d];
+            cs[d] += G * gq[d];
+            th[2 + d] += G * gl[d];
+          }
+          th[1] += G * kv;
         }
       }
       // column sums: reduce over the 8 row-lanes (g) of the warp
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         double v = cs[d];
+        if (DFN == DFN_EUCLIDEAN) v *= -P.cp.il2[d];
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         if ((lane >> 2) == 0) scol[warp][c][d] = v;
       }
+    }
+  }
+  };
+  epilogue_half(0, kinA, ksvA);
+  epilogue_half(1, kinB, ksvB);
+  th[1] *= inv_s2;
+  if (DFN == DFN_EUCLIDEAN) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      rs[0][d] *= P.cp.il2[d];
+      rs[1][d] *= P.cp.il2[d];
+      th[2 + d] *= -P.cp.il3[d];
     }
   }
   double* part = P.arena + u.part_off + (long long)blockIdx.x * PART_STRIDE;

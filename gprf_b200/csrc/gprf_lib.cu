@@ -392,10 +392,11 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
       u.part_off = off; off += align16((nt * (nt + 1) / 2) * PART_STRIDE);
       u.ld_off = off;  off += align16(nt);
       u.gx_off = off;  off += align16(sp * 3);
+      u.k_off = off;   off += align16(sp * sp);
       h->all_list.push_back(uix);
       h->ntmax = std::max(h->ntmax, u.nt);
     } else {
-      u.m_off = u.d_off = u.al_off = u.xs_off = u.part_off = u.ld_off = u.gx_off = 0;
+      u.m_off = u.d_off = u.al_off = u.xs_off = u.part_off = u.ld_off = u.gx_off = u.k_off = 0;
     }
   }
   std::stable_sort(h->all_list.begin(), h->all_list.end(),
