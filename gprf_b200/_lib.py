@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgprf_b200.so")
 MAX_NCOV = 5
-N_FAMILIES = 8
+N_FAMILIES = 9
 
 OK, ERR_NOT_PD, ERR_NONPOS_DIAG, ERR_ARG, ERR_CUDA, ERR_NO_STRUCTURE = range(6)
 
@@ -50,6 +50,8 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_int, C.c_void_p]),
     "gprf_debug_unit": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _ip, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gprf_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), _ip]),
+    "gprf_debug_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "gprf_set_fused_nt": (C.c_int, [C.c_void_p, C.c_int]),
     "gprf_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gprf_family_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), _ip]),
     "gprf_family_name": (C.c_char_p, [C.c_int]),

@@ -39,13 +39,46 @@ struct CovParams {
 #define GPRF_DEG 0.017453292519943295769  // pi / 180
 #define GPRF_SQRT3 1.7320508075688772935
 
+// exp(-x) for x >= 0, branch free.  libdevice's exp() ends in a range-check branch, which keeps
+// the scheduler from interleaving independent evaluations: 160 cycles each however many are in
+// flight, against ~45 for this one at ILP 4 (scripts/fp64_latency.cu).  The tile kernels evaluate
+// 16-32 covariances per thread back to back, so this is what bounds their prologues.
+// Cody-Waite reduction x = n ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation
+// 4e-18), 2^n through the exponent field.  Max error ~1.5 ulp; results below 2^-1021 (x > 708)
+// are flushed to 0 instead of going subnormal.
+__device__ __forceinline__ double exp_neg(double x) {
+  const double t = fmax(-x, -708.0);
+  const double MAGIC = 6755399441055744.0;               // 2^52 + 2^51: rounds to nearest integer
+  const double kf = fma(t, 1.4426950408889634074, MAGIC);
+  const int ni = __double2loint(kf);
+  const double n = kf - MAGIC;
+  double r = fma(n, -6.93147180369123816490e-01, t);     // ln2 high part (fdlibm split)
+  r = fma(n, -1.90821492927058770002e-10, r);            // ln2 low part
+  double p = 1.6059043836821613e-10;                     // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);                   // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);                  // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);                  // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);                 // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);                   // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);                  // 1/7!
+  p = fma(p, r, 1.388888888888889e-03);                  // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);                  // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);                 // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);                 // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double scale = __hiloint2double((ni + 1023) << 20, 0);
+  return (x > 708.0) ? 0.0 : p * scale;
+}
+
 template <int WFN>
 __device__ __forceinline__ double weight_from_r2(double r2, double s2) {
   if (WFN == WFN_SE) {
-    return s2 * exp(-r2);
+    return s2 * exp_neg(r2);
   } else {
     double a = GPRF_SQRT3 * sqrt(r2);
-    return s2 * (1.0 + a) * exp(-a);
+    return s2 * (1.0 + a) * exp_neg(a);
   }
 }
 
@@ -53,11 +86,11 @@ __device__ __forceinline__ double weight_from_r2(double r2, double s2) {
 template <int WFN>
 __device__ __forceinline__ void weight_and_wr(double r2, double s2, double& w, double& wr) {
   if (WFN == WFN_SE) {
-    w = s2 * exp(-r2);
+    w = s2 * exp_neg(r2);
     wr = -2.0 * w;
   } else {
     double a = GPRF_SQRT3 * sqrt(r2);
-    double e = s2 * exp(-a);
+    double e = s2 * exp_neg(a);
     w = (1.0 + a) * e;
     wr = -3.0 * e;
   }

@@ -54,7 +54,23 @@ struct EvalParams {
   int* nfail;
   int dx, dy, yr, nya;
   CovParams cp;
+  unsigned long long* trace;  // debug: TRACE_SLOTS (tag, ns) pairs per fused CTA, or nullptr
+  int trace_ctas;
 };
+
+constexpr int TRACE_SLOTS = 512;
+// Debug timeline of the fused kernel: thread 0 appends (tag, %globaltimer).  `cursor` lives in
+// shared memory (TileScratch::tcur).  A no-op unless gprf_debug_trace enabled it.
+__device__ __forceinline__ void trace_mark(const EvalParams& P, int* cursor, int tag) {
+  if (P.trace && threadIdx.x == 0 && (int)blockIdx.x < P.trace_ctas && *cursor < TRACE_SLOTS) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    unsigned long long* w = P.trace + ((long long)blockIdx.x * TRACE_SLOTS + *cursor) * 2;
+    w[0] = (unsigned long long)tag;
+    w[1] = t;
+    ++*cursor;
+  }
+}
 
 __device__ __forceinline__ long long unit_point(const UnitDesc& u, const long long* perm, int p) {
   return p < u.ni ? perm[u.a_start + p] : perm[u.b_start + (p - u.ni)];
@@ -75,16 +91,31 @@ __device__ __forceinline__ int ext8(int s, int t) {
   return r >= T ? NB8 : (r + 7) >> 3;
 }
 
+// Small static scratch shared by every tile task (one instance per CTA).  Everything
+// larger lives in the dynamic `pipe` region (PIPE_DOUBLES doubles).
+struct __align__(16) TileScratch {
+  double xa[T][4];            // coordinates of the row-tile points
+  double xb[T][4];            // coordinates of the column-tile points
+  double scol[NW][T][3];      // grad: per-warp column sums
+  double sth[NW][MAX_NCOV];   // grad: per-warp theta partials
+  long long idx[T];           // prep: gathered point indices
+  int fail;                   // diag: first non-positive pivot
+  int tcur;                   // debug trace cursor
+};
+
+// Every tile task below is a __device__ function called either by its own thin
+// __global__ wrapper (multi-launch path: one launch per dependency level, grid =
+// tiles x units) or by k_unit_fused (one CTA walks a whole unit).  Contract: all
+// NTHREADS threads call it; on entry nobody is still using `pipe` / `sc`; the task does
+// NOT synchronise after its last global store.
+
 // ---------------------------------------------------------------------------
 // prep: gather x rows and Y^T rows of each unit (gprf.py:299-330)
-// grid (nt_max, nlist), 128 threads
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS) k_prep(EvalParams P) {
-  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
-  const int i = blockIdx.x;
-  if (i >= u.nt) return;
-  __shared__ double sY[T][T + 1];
-  __shared__ long long sidx[T];
+__device__ __forceinline__ void prep_tile(const EvalParams& P, const UnitDesc& u, int i, double* pipe,
+                                          TileScratch& sc) {
+  double (*sY)[T + 1] = reinterpret_cast<double (*)[T + 1]>(pipe);
+  long long* sidx = sc.idx;
   const int tid = threadIdx.x;
   double* M = P.arena + u.m_off;
   double* xs = P.arena + u.xs_off;
@@ -99,12 +130,21 @@ __global__ void __launch_bounds__(NTHREADS) k_prep(EvalParams P) {
   }
   __syncthreads();
   for (int a = 0; a < P.nya; ++a) {
-    // load 64 points x 64 outputs, coalesced along the output index
-    for (int e = tid; e < T * T; e += NTHREADS) {
-      int r = e / T, c = e % T;
-      int cc = a * T + c;
-      long long idx = sidx[r];
-      sY[r][c] = (idx >= 0 && cc < P.dy) ? P.Y[idx * P.dy + cc] : 0.0;
+    // load 64 points x 64 outputs, coalesced along the output index; all loads of a thread are
+    // issued before the first use (one memory round trip per tile instead of one per element)
+    constexpr int PER = T * T / NTHREADS;
+    double v[PER];
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int e = tid + it * NTHREADS;
+      const int r = e / T, cc = a * T + e % T;
+      const long long idx = sidx[r];
+      v[it] = (idx >= 0 && cc < P.dy) ? __ldg(P.Y + idx * P.dy + cc) : 0.0;
+    }
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int e = tid + it * NTHREADS;
+      sY[e / T][e % T] = v[it];
     }
     __syncthreads();
     for (int e = tid; e < T * T; e += NTHREADS) {
@@ -115,18 +155,25 @@ __global__ void __launch_bounds__(NTHREADS) k_prep(EvalParams P) {
   }
 }
 
+// grid (nt_max, nlist), NTHREADS threads
+#ifndef GPRF_FUSED_ONLY
+__global__ void __launch_bounds__(NTHREADS) k_prep(EvalParams P) {
+  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  if ((int)blockIdx.x >= u.nt) return;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ TileScratch sc;
+  prep_tile(P, u, blockIdx.x, smem, sc);
+}
+#endif
+
 // ---------------------------------------------------------------------------
-// potrf_diag(k): one CTA per unit.  grid (1, nlist)
+// potrf_diag(k): diagonal tile k of one unit
 // ---------------------------------------------------------------------------
 template <int DFN, int WFN>
-__global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
-  const int uid = P.ulist[blockIdx.y];
-  const UnitDesc u = P.units[uid];
-  if (k >= u.nt) return;
-  extern __shared__ __align__(16) double smem[];
-  double* pipe = smem;
-  __shared__ double sx[T][4];
-  __shared__ int sfail;
+__device__ __forceinline__ void diag_tile(const EvalParams& P, int uid, const UnitDesc& u, int k, double* pipe,
+                                          TileScratch& sc) {
+  double (*sx)[4] = sc.xa;
+  int& sfail = sc.fail;
   const int tid = threadIdx.x;
   double* M = P.arena + u.m_off;
   const long long ld = u.sp;
@@ -138,54 +185,66 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
   if (tid == 0) sfail = 0;
 
   Acc acc;
-  acc_zero(acc);
   const int e8 = ext8(u.s, k);           // non-padding 8x8 block rows of this tile
   const double* rowk = M + (long long)k * T * ld;
+  const double diag_add = P.cp.nv + P.jitter[uid];
+  double* Ks = P.arena + u.k_off + (long long)k * T * ld + k * T;     // saved K tile (k, k)
+  // acc = -K_kk (lower block triangle; padding rows/cols form an identity block), evaluated
+  // while the first operand chunk is in flight; the product then accumulates +sum_j L_kj L_kj^T
+  auto init = [&]() {
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      const int r = acc_row(m);
+      const int p = k * T + r;
+      const bool rowact = acc_brow(m) < e8;
+      double xr[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) xr[d] = sx[r][d];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        // evaluated unconditionally and masked by selects (see panel_tile)
+        double kvs[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = acc_col(n) + e;
+          const int q = k * T + c;
+          const double v = cov_value<DFN, WFN>(xr, sx[c], P.cp);
+          const bool in = rowact && n <= acc_brow(m) && p < u.s && q < u.s;
+          double kv = in ? v : 0.0;
+          if (r == c) kv = in ? P.cp.s2 + diag_add : 1.0;
+          kvs[e] = kv;
+          acc.c[m][n][e] = -kv;
+        }
+        if (rowact && n <= acc_brow(m))          // noise-free off-diagonal values are what grad re-reads
+          *reinterpret_cast<double2*>(Ks + (long long)r * ld + acc_col(n)) = make_double2(kvs[0], kvs[1]);
+      }
+    }
+  };
   auto tA = [&](int j) { return tile_ref(rowk + j * T, ld); };
-  gemm_nt<true>(acc, k, tA, tA, e8, e8, pipe);
+  gemm_nt<true>(acc, k, tA, tA, e8, e8, pipe, init);
   __syncthreads();
+  trace_mark(P, &sc.tcur, 31);
 
-  // C = K_kk - acc (lower block triangle only) -> shared tile S (stride WLD); S2 receives
-  // U_kk = L_kk^-T.  Padding rows/cols form an identity block in S and S2.
+  // C = K_kk - sum = -acc -> shared tile S (stride WLD); S2 receives U_kk = L_kk^-T.
   double* S = pipe;
   double* S2 = pipe + T * WLD;
   double* Wsm = pipe + 2 * T * WLD;
-  const double diag_add = P.cp.nv + P.jitter[uid];
-  double* Ks = P.arena + u.k_off + (long long)k * T * ld + k * T;     // saved K tile (k, k)
 #pragma unroll
-  for (int m = 0; m < 2; ++m) {
-    const int r = acc_row(m);
-    const int p = k * T + r;
-    const bool rowact = acc_brow(m) < e8;
+  for (int m = 0; m < MB; ++m)
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      double v[2], kvs[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = acc_col(n) + e;
-        const int q = k * T + c;
-        double kv;
-        if (rowact && n <= acc_brow(m) && p < u.s && q < u.s) {
-          kv = cov_value<DFN, WFN>(sx[r], sx[c], P.cp);
-          if (r == c) kv = P.cp.s2 + diag_add;
-        } else {
-          kv = (r == c) ? 1.0 : 0.0;
-        }
-        kvs[e] = kv;
-        v[e] = kv - acc.c[m][n][e];
-      }
-      *reinterpret_cast<double2*>(S + r * WLD + acc_col(n)) = make_double2(v[0], v[1]);
-      if (rowact && n <= acc_brow(m))          // noise-free off-diagonal values are what grad re-reads
-        *reinterpret_cast<double2*>(Ks + (long long)r * ld + acc_col(n)) = make_double2(kvs[0], kvs[1]);
-    }
-  }
+    for (int n = 0; n < 8; ++n)
+      *reinterpret_cast<double2*>(S + acc_row(m) * WLD + acc_col(n)) =
+          make_double2(-acc.c[m][n][0], -acc.c[m][n][1]);
   for (int e = tid; e < T * WLD; e += NTHREADS) {
     const int r = e / WLD, c = e % WLD;
     S2[e] = (r == c && r >= e8 * 8) ? 1.0 : 0.0;
   }
   __syncthreads();
 
+  trace_mark(P, &sc.tcur, 32);
   smem_potrf_trtri(S, S2, Wsm, WLD, e8, &sfail, k * T);
+  trace_mark(P, &sc.tcur, 33);
 
   // outputs: L_kk (upper part zero), W_kk = U_kk^T, U_kk, logdet partial, status
   double* Lout = M + (long long)k * T * ld + k * T;
@@ -207,29 +266,37 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_diag(EvalParams P, int k) {
   }
 }
 
+// grid (1, nlist)
+template <int DFN, int WFN>
+__global__ void __launch_bounds__(NTHREADS, 2) k_potrf_diag(EvalParams P, int k) {
+  const int uid = P.ulist[blockIdx.y];
+  const UnitDesc u = P.units[uid];
+  if (k >= u.nt) return;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ TileScratch sc;
+  diag_tile<DFN, WFN>(P, uid, u, k, smem, sc);
+}
+
 // ---------------------------------------------------------------------------
-// potrf_panel(k): grid (ntmax - k - 1 + nya, nlist).  Row tiles below the
-// diagonal and the augmented Y^T row tiles.
+// potrf_panel(k): task x < nt-k-1 is the row tile k+1+x below the diagonal, tasks
+// nt-k-1 .. nt-k-1+nya-1 are the augmented Y^T row tiles.
 // ---------------------------------------------------------------------------
 template <int DFN, int WFN>
-__global__ void __launch_bounds__(NTHREADS) k_potrf_panel(EvalParams P, int k) {
-  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
-  if (k >= u.nt) return;
+__device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& u, int k, int x, double* pipe,
+                                           TileScratch& sc) {
   const int below = u.nt - k - 1;
   int it;           // row-tile index in M (aug tiles follow the square)
   bool aug = false;
-  if ((int)blockIdx.x < below) {
-    it = k + 1 + blockIdx.x;
+  if (x < below) {
+    it = k + 1 + x;
   } else {
-    int a = blockIdx.x - below;
+    int a = x - below;
     if (a >= P.nya) return;
     it = u.nt + a;
     aug = true;
   }
-  extern __shared__ __align__(16) double smem[];
-  double* pipe = smem;
-  __shared__ double sxr[T][4];
-  __shared__ double sxc[T][4];
+  double (*sxr)[4] = sc.xa;
+  double (*sxc)[4] = sc.xb;
   const int tid = threadIdx.x;
   double* M = P.arena + u.m_off;
   const long long ld = u.sp;
@@ -242,62 +309,86 @@ __global__ void __launch_bounds__(NTHREADS) k_potrf_panel(EvalParams P, int k) {
     }
   }
   Acc acc;
-  acc_zero(acc);
   // block masks: rows of this tile (points of tile `it`, or outputs of Y^T), columns = points of tile k
   const int mlim = aug ? min(NB8, (P.dy - (it - u.nt) * T + 7) >> 3) : ext8(u.s, it);
   const int nlim = ext8(u.s, k);
   const double* rowi = M + (long long)it * T * ld;
   const double* rowk = M + (long long)k * T * ld;
-  auto tA = [&](int j) { return tile_ref(rowi + j * T, ld); };
-  auto tB = [&](int j) { return tile_ref(rowk + j * T, ld); };
-  gemm_nt<false>(acc, k, tA, tB, mlim, nlim, pipe);
-  __syncthreads();
-
-  // C = C0 - acc
   double* out = M + (long long)it * T * ld + k * T;
   double* Ks = P.arena + u.k_off + (long long)it * T * ld + k * T;    // saved K tile (it, k), non-aug only
+  // acc = -C0 (covariance values K_ik, or the Y^T rows), evaluated while the first operand chunk
+  // is in flight; the product accumulates +sum_j L_ij L_kj^T, so that acc = -(C0 - sum) at the end
+  auto init = [&]() {
+    __syncthreads();
+    if (aug) {
 #pragma unroll
-  for (int m = 0; m < 2; ++m) {
-    const int r = acc_row(m);
-    const bool rowact = acc_brow(m) < mlim;
+      for (int m = 0; m < MB; ++m) {
+        const int r = acc_row(m);
+        const bool rowact = acc_brow(m) < mlim;
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int c = acc_col(n);
-      double c0 = 0.0, c1 = 0.0;
-      if (rowact && n < nlim) {
-        if (aug) {
-          double2 v = *reinterpret_cast<const double2*>(out + (long long)r * ld + c);
-          c0 = v.x;
-          c1 = v.y;
-        } else {
-          const int p = it * T + r;
-          c0 = (p < u.s && k * T + c < u.s) ? cov_value<DFN, WFN>(sxr[r], sxc[c], P.cp) : 0.0;
-          c1 = (p < u.s && k * T + c + 1 < u.s) ? cov_value<DFN, WFN>(sxr[r], sxc[c + 1], P.cp) : 0.0;
-          *reinterpret_cast<double2*>(Ks + (long long)r * ld + c) = make_double2(c0, c1);
+        for (int n = 0; n < 8; ++n) {
+          double2 v = make_double2(0.0, 0.0);
+          if (rowact && n < nlim) v = *reinterpret_cast<const double2*>(out + (long long)r * ld + acc_col(n));
+          acc.c[m][n][0] = -v.x;
+          acc.c[m][n][1] = -v.y;
         }
       }
-      acc.c[m][n][0] = c0 - acc.c[m][n][0];
-      acc.c[m][n][1] = c1 - acc.c[m][n][1];
+    } else {
+      // Covariances are evaluated unconditionally (padding points sit at the origin) and masked
+      // by selects afterwards: straight-line code lets the scheduler interleave the independent
+      // exponentials instead of paying their full latency one after the other.
+#pragma unroll
+      for (int m = 0; m < MB; ++m) {
+        const int r = acc_row(m);
+        const bool rowact = acc_brow(m) < mlim;
+        const bool pin = it * T + r < u.s;
+        double xr[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) xr[d] = sxr[r][d];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          const int c = acc_col(n);
+          const double v0 = cov_value<DFN, WFN>(xr, sxc[c], P.cp);
+          const double v1 = cov_value<DFN, WFN>(xr, sxc[c + 1], P.cp);
+          const bool act = rowact && n < nlim;
+          const double c0 = (act && pin && k * T + c < u.s) ? v0 : 0.0;
+          const double c1 = (act && pin && k * T + c + 1 < u.s) ? v1 : 0.0;
+          if (act) *reinterpret_cast<double2*>(Ks + (long long)r * ld + c) = make_double2(c0, c1);
+          acc.c[m][n][0] = -c0;
+          acc.c[m][n][1] = -c1;
+        }
+      }
     }
-  }
-  // L_ik = C * W_kk^T
+  };
+  auto tA = [&](int j) { return tile_ref(rowi + j * T, ld); };
+  auto tB = [&](int j) { return tile_ref(rowk + j * T, ld); };
+  // W_kk arrives in the idle stage buffer while the last chunk is multiplied
   const double* Wd = P.arena + u.d_off + (long long)k * T * T;
-  stage_full(pipe, Wd, T);
+  const double* sW = gemm_nt<false>(acc, k, tA, tB, mlim, nlim, pipe, init, Wd, T);
+  trace_mark(P, &sc.tcur, 41);
+  // L_ik = (C0 - sum) W_kk^T = -(acc W_kk^T)
   Acc res;
-  mul_acc_by_wt(res, acc, pipe, 1.0, mlim, nlim);
+  mul_acc_by_wt(res, acc, sW, -1.0, mlim, nlim);
+  trace_mark(P, &sc.tcur, 42);
   acc_store(res, out, ld);
 }
 
-// ---------------------------------------------------------------------------
-// trtri(d): U_{k,k+d} = -(sum_{j=k}^{i-1} U_kj L_ij^T) W_ii^T.  grid (ntmax - d, nlist)
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS) k_trtri(EvalParams P, int d) {
+// grid (ntmax - k - 1 + nya, nlist)
+template <int DFN, int WFN>
+__global__ void __launch_bounds__(NTHREADS, 2) k_potrf_panel(EvalParams P, int k) {
   const UnitDesc u = P.units[P.ulist[blockIdx.y]];
-  const int k = blockIdx.x;
+  if (k >= u.nt) return;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ TileScratch sc;
+  panel_tile<DFN, WFN>(P, u, k, blockIdx.x, smem, sc);
+}
+
+// ---------------------------------------------------------------------------
+// trtri(d): U_{k,k+d} = -(sum_{j=k}^{i-1} U_kj L_ij^T) W_ii^T
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void trtri_tile(const EvalParams& P, const UnitDesc& u, int k, int d, double* pipe) {
   const int i = k + d;
   if (i >= u.nt) return;
-  extern __shared__ __align__(16) double smem[];
-  double* pipe = smem;
   double* M = P.arena + u.m_off;
   const long long ld = u.sp;
   const double* Ud = P.arena + u.d_off + (long long)(u.nt + k) * T * T;
@@ -310,34 +401,40 @@ __global__ void __launch_bounds__(NTHREADS) k_trtri(EvalParams P, int d) {
     return jj == 0 ? tile_ref(Ud, T, NB8, 1, 0) : tile_ref(rowk + (long long)(k + jj) * T, ld);
   };
   auto tB = [&](int jj) { return tile_ref(rowi + (long long)(k + jj) * T, ld); };
-  gemm_nt<false>(acc, d, tA, tB, NB8, nlim, pipe);
-  __syncthreads();
   const double* Wd = P.arena + u.d_off + (long long)i * T * T;
-  stage_full(pipe, Wd, T);
+  const double* sW = gemm_nt<false>(acc, d, tA, tB, NB8, nlim, pipe, NoHook(), Wd, T);
   Acc res;
-  mul_acc_by_wt(res, acc, pipe, -1.0, NB8, nlim);
+  mul_acc_by_wt(res, acc, sW, -1.0, NB8, nlim);
   acc_store(res, M + (long long)k * T * ld + (long long)i * T, ld);
 }
 
-// ---------------------------------------------------------------------------
-// lauum: K^-1 lower tiles and Alpha.  grid (ntri_max + ntmax*nya, nlist)
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS) k_lauum(EvalParams P, int ntri_max) {
+// grid (ntmax - d, nlist)
+#ifndef GPRF_FUSED_ONLY
+__global__ void __launch_bounds__(NTHREADS, 2) k_trtri(EvalParams P, int d) {
   const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  extern __shared__ __align__(16) double smem[];
+  trtri_tile(P, u, blockIdx.x, d, smem);
+}
+#endif
+
+// ---------------------------------------------------------------------------
+// lauum: K^-1 lower tiles (tasks x < ntri_max, x = tri(i) + j) and Alpha (tasks
+// ntri_max + i * nya + a)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void lauum_tile(const EvalParams& P, const UnitDesc& u, int x, int ntri_max,
+                                           double* pipe) {
   int i, j;
   bool aug = false;
-  if ((int)blockIdx.x < ntri_max) {
-    if ((int)blockIdx.x >= tri(u.nt)) return;
-    tri_decode(blockIdx.x, i, j);
+  if (x < ntri_max) {
+    if (x >= tri(u.nt)) return;
+    tri_decode(x, i, j);
   } else {
-    int idx = blockIdx.x - ntri_max;
+    int idx = x - ntri_max;
     i = idx / P.nya;
     j = u.nt + idx % P.nya;
     if (i >= u.nt) return;
     aug = true;
   }
-  extern __shared__ __align__(16) double smem[];
-  double* pipe = smem;
   double* M = P.arena + u.m_off;
   const long long ld = u.sp;
   const double* Udi = P.arena + u.d_off + (long long)(u.nt + i) * T * T;
@@ -366,21 +463,28 @@ __global__ void __launch_bounds__(NTHREADS) k_lauum(EvalParams P, int ntri_max) 
   }
 }
 
+// grid (ntri_max + ntmax*nya, nlist)
+#ifndef GPRF_FUSED_ONLY
+__global__ void __launch_bounds__(NTHREADS, 2) k_lauum(EvalParams P, int ntri_max) {
+  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  extern __shared__ __align__(16) double smem[];
+  lauum_tile(P, u, blockIdx.x, ntri_max, smem);
+}
+#endif
+
 // ---------------------------------------------------------------------------
-// grad: G tile in registers, contracted with dk/dx, dk/dtheta.  grid (ntri_max, nlist)
+// grad: G tile (x = tri(i) + j) in registers, contracted with dk/dx, dk/dtheta
 // ---------------------------------------------------------------------------
 template <int DFN, int WFN>
-__global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
-  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
-  if ((int)blockIdx.x >= tri(u.nt)) return;
+__device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u, int x, double* pipe,
+                                          TileScratch& sc) {
+  if (x >= tri(u.nt)) return;
   int i, j;
-  tri_decode(blockIdx.x, i, j);
-  extern __shared__ __align__(16) double smem[];
-  double* pipe = smem;
-  __shared__ double sxi[T][4];
-  __shared__ double sxj[T][4];
-  __shared__ double scol[4][T][3];
-  __shared__ double sth[4][MAX_NCOV];
+  tri_decode(x, i, j);
+  double (*sxi)[4] = sc.xa;
+  double (*sxj)[4] = sc.xb;
+  double (*scol)[T][3] = sc.scol;
+  double (*sth)[MAX_NCOV] = sc.sth;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* M = P.arena + u.m_off;
   const long long ld = u.sp;
@@ -403,12 +507,12 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
   // half of the epilogue instead of being paid once per block column.
   const double* Kt = M + (long long)i * T * ld + (long long)j * T;
   const double* Kst = P.arena + u.k_off + (long long)i * T * ld + (long long)j * T;
-  double2 kinA[4][2], ksvA[4][2], kinB[4][2], ksvB[4][2];
-  auto load_half = [&](int h, double2 (&kin)[4][2], double2 (&ksv)[4][2]) {
+  double2 kinA[4][MB], ksvA[4][MB], kinB[4][MB], ksvB[4][MB];
+  auto load_half = [&](int h, double2 (&kin)[4][MB], double2 (&ksv)[4][MB]) {
 #pragma unroll
     for (int nn = 0; nn < 4; ++nn)
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
+      for (int m = 0; m < MB; ++m) {
         const long long o = (long long)acc_row(m) * ld + acc_col(h * 4 + nn);
         kin[nn][m] = *reinterpret_cast<const double2*>(Kt + o);
         ksv[nn][m] = *reinterpret_cast<const double2*>(Kst + o);
@@ -420,36 +524,40 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
   if (i == j) gemm_nt<true>(acc, P.nya, tA, tB, mlim, nlim, pipe);
   else gemm_nt<false>(acc, P.nya, tA, tB, mlim, nlim, pipe);
   __syncthreads();
+  trace_mark(P, &sc.tcur, 71);
 
   load_half(1, kinB, ksvB);
   const double dyd = (double)P.dy;
   const double inv_s2 = 1.0 / P.cp.s2;
   // Raw sums; for the euclidean family they are scaled by the lengthscale factors at the end:
   //   t_d = G w'(r)/r (x_p - x_q)_d ;  rs = il2_d sum t_d ; cs = -il2_d sum t_d ; th[2+d] = -il3_d sum t_d (x_p-x_q)_d
-  double rs[2][3];
+  double rs[MB][3];
   double th[MAX_NCOV];
 #pragma unroll
-  for (int m = 0; m < 2; ++m) rs[m][0] = rs[m][1] = rs[m][2] = 0.0;
+  for (int m = 0; m < MB; ++m) rs[m][0] = rs[m][1] = rs[m][2] = 0.0;
 #pragma unroll
   for (int t = 0; t < MAX_NCOV; ++t) th[t] = 0.0;
-  double xi[2][3];
+  double xi[MB][3];
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < MB; ++m)
 #pragma unroll
     for (int d = 0; d < 3; ++d) xi[m][d] = sxi[acc_row(m)][d];
 
   // block (m, n) of the tile holds real entries of the strictly-lower-or-diagonal part?
-  bool mact[2];
+  bool mact[MB];
 #pragma unroll
-  for (int m = 0; m < 2; ++m) mact[m] = acc_brow(m) < mlim;
-  auto epilogue_half = [&](int h, const double2 (&kinH)[4][2], const double2 (&ksvH)[4][2]) {
+  for (int m = 0; m < MB; ++m) mact[m] = acc_brow(m) < mlim;
+  auto epilogue_half = [&](int h, const double2 (&kinH)[4][MB], const double2 (&ksvH)[4][MB]) {
 #pragma unroll
   for (int nn = 0; nn < 4; ++nn) {
     const int n = h * 4 + nn;
-    bool bact[2];
+    bool bact[MB];
 #pragma unroll
-    for (int m = 0; m < 2; ++m) bact[m] = mact[m] && n < nlim && (i != j || n <= acc_brow(m));
-    if (!bact[0] && !bact[1]) {           // warp-uniform: nothing of this block column is ours
+    for (int m = 0; m < MB; ++m) bact[m] = mact[m] && n < nlim && (i != j || n <= acc_brow(m));
+    bool anyact = false;
+#pragma unroll
+    for (int m = 0; m < MB; ++m) anyact = anyact || bact[m];
+    if (!anyact) {                        // warp-uniform: nothing of this block column is ours
       if ((lane >> 2) == 0) {
 #pragma unroll
         for (int e = 0; e < 2; ++e)
@@ -467,7 +575,7 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) xj[d] = sxj[c][d];
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
+      for (int m = 0; m < MB; ++m) {
         const int r = acc_row(m);
         const int p = i * T + r;
         double kv = (e == 0 ? ksvH[nn][m].x : ksvH[nn][m].y);
@@ -524,20 +632,22 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
   }
   };
   epilogue_half(0, kinA, ksvA);
+  trace_mark(P, &sc.tcur, 72);
   epilogue_half(1, kinB, ksvB);
+  trace_mark(P, &sc.tcur, 73);
   th[1] *= inv_s2;
   if (DFN == DFN_EUCLIDEAN) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      rs[0][d] *= P.cp.il2[d];
-      rs[1][d] *= P.cp.il2[d];
+#pragma unroll
+      for (int m = 0; m < MB; ++m) rs[m][d] *= P.cp.il2[d];
       th[2 + d] *= -P.cp.il3[d];
     }
   }
-  double* part = P.arena + u.part_off + (long long)blockIdx.x * PART_STRIDE;
+  double* part = P.arena + u.part_off + (long long)x * PART_STRIDE;
   // row sums: reduce over the 4 lanes of a quad; each row is owned by one warp
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < MB; ++m)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       double v = rs[m][d];
@@ -555,21 +665,35 @@ __global__ void __launch_bounds__(NTHREADS) k_grad(EvalParams P) {
   __syncthreads();
   for (int e = tid; e < T * 3; e += NTHREADS) {
     int c = e / 3, d = e % 3;
-    part[PART_COL + e] = ((scol[0][c][d] + scol[1][c][d]) + scol[2][c][d]) + scol[3][c][d];
+    double v = scol[0][c][d];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) v += scol[w][c][d];
+    part[PART_COL + e] = v;
   }
-  if (tid < MAX_NCOV) part[PART_TH + tid] = ((sth[0][tid] + sth[1][tid]) + sth[2][tid]) + sth[3][tid];
+  if (tid < MAX_NCOV) {
+    double v = sth[0][tid];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) v += sth[w][tid];
+    part[PART_TH + tid] = v;
+  }
+}
+
+// grid (ntri_max, nlist)
+template <int DFN, int WFN>
+__global__ void __launch_bounds__(NTHREADS, 2) k_grad(EvalParams P) {
+  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  extern __shared__ __align__(16) double smem[];
+  __shared__ TileScratch sc;
+  grad_tile<DFN, WFN>(P, u, blockIdx.x, smem, sc);
 }
 
 // ---------------------------------------------------------------------------
-// unit_finalize: grid (nlist), 128 threads.  ll_u (gprf.py:542-544), unit gradX
-// rows, unit grad theta; everything summed in a fixed order.
+// unit_finalize: ll_u (gprf.py:542-544), unit gradX rows, unit grad theta;
+// everything summed in a fixed order.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS) k_unit_finalize(EvalParams P, double* ll_u, double* gth_u,
-                                                          int want_grad) {
-  const int uid = P.ulist[blockIdx.x];
-  const UnitDesc u = P.units[uid];
+__device__ __forceinline__ void finalize_unit(const EvalParams& P, int uid, const UnitDesc& u, double* ll_u,
+                                              double* gth_u, int want_grad, double* red) {
   const int tid = threadIdx.x;
-  __shared__ double red[NTHREADS];
   const double* M = P.arena + u.m_off;
   // quadratic term ||Z||^2 over the augmented rows
   double q = 0.0;
@@ -618,6 +742,94 @@ __global__ void __launch_bounds__(NTHREADS) k_unit_finalize(EvalParams P, double
   }
 }
 
+// grid (nlist), NTHREADS threads
+#ifndef GPRF_FUSED_ONLY
+__global__ void __launch_bounds__(NTHREADS) k_unit_finalize(EvalParams P, double* ll_u, double* gth_u,
+                                                          int want_grad) {
+  const int uid = P.ulist[blockIdx.x];
+  const UnitDesc u = P.units[uid];
+  __shared__ double red[NTHREADS];
+  finalize_unit(P, uid, u, ll_u, gth_u, want_grad, red);
+}
+#endif
+
+// ---------------------------------------------------------------------------
+// Fused per-unit pipeline: ONE CTA walks one unit through prep, the left-looking
+// Cholesky, the triangular inverse, K^-1 / Alpha, the gradient contraction and the
+// finalisation.  grid (nlist), units largest first.  Used for units of up to
+// `fused_nt` tiles, where the multi-launch path is bound by its ~20 dependent,
+// mostly empty launches (README config: 442 units of 100-260 points); here units
+// advance independently and the SM interleaves the phases of its resident CTAs.
+// Dependent phases are separated by __threadfence() + __syncthreads() (operands are
+// re-read through L2 by cp.async.cg), independent tasks by __syncthreads() only.
+// ---------------------------------------------------------------------------
+constexpr size_t FUSED_SMEM_BYTES = PIPE_DOUBLES * sizeof(double);
+
+__device__ __forceinline__ void phase_sync() {
+  __threadfence();
+  __syncthreads();
+}
+
+template <int DFN, int WFN>
+__global__ void __launch_bounds__(NTHREADS, 2) k_unit_fused(EvalParams P, double* ll_u, double* gth_u,
+                                                            int want_grad) {
+  const int uid = P.ulist[blockIdx.x];
+  const UnitDesc u = P.units[uid];
+  extern __shared__ __align__(16) double smem[];
+  __shared__ TileScratch sc;
+  double* pipe = smem;
+  const int nt = u.nt;
+  if (threadIdx.x == 0) sc.tcur = 0;
+  __syncthreads();
+  trace_mark(P, &sc.tcur, 1);
+  for (int i = 0; i < nt; ++i) {
+    prep_tile(P, u, i, pipe, sc);       // ends with a __syncthreads()
+  }
+  phase_sync();
+  trace_mark(P, &sc.tcur, 2);
+  for (int k = 0; k < nt; ++k) {
+    diag_tile<DFN, WFN>(P, uid, u, k, pipe, sc);
+    phase_sync();
+    trace_mark(P, &sc.tcur, 3);
+    const int ntask = nt - k - 1 + P.nya;
+    for (int x = 0; x < ntask; ++x) {
+      panel_tile<DFN, WFN>(P, u, k, x, pipe, sc);
+      __syncthreads();
+      trace_mark(P, &sc.tcur, 40);
+    }
+    phase_sync();
+    trace_mark(P, &sc.tcur, 4);
+  }
+  if (want_grad) {
+    for (int d = 1; d < nt; ++d) {
+      for (int k = 0; k + d < nt; ++k) {
+        trtri_tile(P, u, k, d, pipe);
+        __syncthreads();
+        trace_mark(P, &sc.tcur, 50);
+      }
+      phase_sync();
+      trace_mark(P, &sc.tcur, 5);
+    }
+    const int ntri = tri(nt);
+    for (int x = 0; x < ntri + nt * P.nya; ++x) {
+      lauum_tile(P, u, x, ntri, pipe);
+      __syncthreads();
+      trace_mark(P, &sc.tcur, 60);
+    }
+    phase_sync();
+    trace_mark(P, &sc.tcur, 6);
+    for (int x = 0; x < ntri; ++x) {
+      grad_tile<DFN, WFN>(P, u, x, pipe, sc);
+      __syncthreads();
+      trace_mark(P, &sc.tcur, 70);
+    }
+    phase_sync();
+    trace_mark(P, &sc.tcur, 7);
+  }
+  finalize_unit(P, uid, u, ll_u, gth_u, want_grad, pipe);
+  trace_mark(P, &sc.tcur, 8);
+}
+
 // ---------------------------------------------------------------------------
 // combine (gprf.py:245-291)
 // ---------------------------------------------------------------------------
@@ -635,6 +847,7 @@ struct CombineParams {
 };
 
 // one thread per perm position; deterministic gather over the units containing the point
+#ifndef GPRF_FUSED_ONLY
 __global__ void k_combine_gradx(CombineParams C, double* gradX) {
   const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= C.plen) return;
@@ -658,8 +871,10 @@ __global__ void k_combine_gradx(CombineParams C, double* gradX) {
   const long long n = C.perm[pos];
   for (int d = 0; d < C.dx; ++d) gradX[n * C.dx + d] = g[d];
 }
+#endif
 
 // single CTA: out[0] = sum_u w_u ll_u ; out[1+t] = sum_u w_u gth_u[t]
+#ifndef GPRF_FUSED_ONLY
 __global__ void k_combine_scalars(const UnitDesc* units, int U, const double* ll_u, const double* gth_u,
                                   int want_cov, double* out) {
   __shared__ double red[256][1 + MAX_NCOV];
@@ -686,6 +901,7 @@ __global__ void k_combine_scalars(const UnitDesc* units, int U, const double* ll
   }
   if (tid < 1 + MAX_NCOV) out[tid] = red[0][tid];
 }
+#endif
 
 // ---------------------------------------------------------------------------
 // auxiliary kernels: GPRF.kernel (gprf.py:333-343), compute_neighbors (gprf.py:119-150)

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -69,6 +70,9 @@ struct gprf_ctx {
   std::vector<unsigned char> explicit_mask, lpt, seen;
   bool use_explicit_mask = false, adj_dirty = true, blocks_from_device = false;
   int shard_rank = 0, shard_world = 1;
+  int fused_nt = 8;                // units of up to this many 64-point tiles take k_unit_fused
+  unsigned long long* dTrace = nullptr;   // debug trace of the fused kernel (gprf_debug_trace)
+  size_t capTrace = 0;
 
   // device partitioner (K8)
   int part_kind = 0, part_B = 0, part_mode = 0, part_root = 0, part_launches = 0;
@@ -166,17 +170,27 @@ static int make_cov(const gprf_ctx* h, const double* theta, int ncov, CovParams*
 
 static const size_t PIPE_BYTES = PIPE_DOUBLES * sizeof(double);
 
+// k_unit_fused is instantiated in its own translation units (gprf_fused.cu, one per covariance
+// family, compiled in parallel by build.sh); these are their host-side launchers.
+namespace gprf {
+template <int DFN, int WFN> void fused_set_attr();
+template <int DFN, int WFN>
+void fused_launch(const EvalParams& P, double* ll_u, double* gth_u, int want_grad, int nunits, cudaStream_t st);
+}
+
 template <int DFN, int WFN>
 static void set_attrs_t() {
   cudaFuncSetAttribute(k_potrf_diag<DFN, WFN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
   cudaFuncSetAttribute(k_potrf_panel<DFN, WFN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
   cudaFuncSetAttribute(k_grad<DFN, WFN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
+  fused_set_attr<DFN, WFN>();
 }
 static void set_attrs() {
   set_attrs_t<0, 0>();
   set_attrs_t<0, 1>();
   set_attrs_t<1, 0>();
   set_attrs_t<1, 1>();
+  cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
   cudaFuncSetAttribute(k_trtri, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
   cudaFuncSetAttribute(k_lauum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
 }
@@ -236,7 +250,36 @@ extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, in
   CUDA_OK(cudaMalloc((void**)&h->dNfail, sizeof(int)));
   CUDA_OK(cudaMemcpy(h->dY, Y, (size_t)n * dy * sizeof(double), cudaMemcpyHostToDevice));
   set_attrs();
+  if (const char* e = getenv("GPRF_FUSED_NT")) h->fused_nt = atoi(e);
   CUDA_OK(cudaGetLastError());
+  return GPRF_OK;
+}
+
+// Debug: enable (n_ctas > 0) / read back the per-phase timestamps of the fused kernel.
+extern "C" int gprf_debug_trace(gprf_handle h, int n_ctas, unsigned long long* out) {
+  if (!h) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (out && h->dTrace) {
+    CUDA_OK(cudaMemcpy(out, h->dTrace,
+                       std::min((size_t)n_ctas * 2 * TRACE_SLOTS, h->capTrace) * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost));
+    return GPRF_OK;
+  }
+  if (h->dTrace) cudaFree(h->dTrace);
+  h->dTrace = nullptr;
+  h->capTrace = 0;
+  if (n_ctas > 0) {
+    const size_t len = (size_t)n_ctas * 2 * TRACE_SLOTS;
+    CUDA_OK(cudaMalloc((void**)&h->dTrace, len * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemset(h->dTrace, 0, len * sizeof(unsigned long long)));
+    h->capTrace = len;
+  }
+  return GPRF_OK;
+}
+
+extern "C" int gprf_set_fused_nt(gprf_handle h, int nt) {
+  if (!h || nt < 0) return GPRF_ERR_ARG;
+  h->fused_nt = nt;
   return GPRF_OK;
 }
 
@@ -703,8 +746,38 @@ extern "C" int gprf_get_blocks(gprf_handle h, long long* block_ptr, long long* p
 
 // Enqueue the per-unit pipeline for the units in `list` (already on device as
 // dList[0..nlist)).  Returns the number of kernel launches.
-static int launch_units(gprf_ctx* h, const EvalParams& P, int nlist, int ntmax, bool want_grad,
-                        cudaStream_t st) {
+// Units of up to h->fused_nt tiles go through k_unit_fused (one CTA per unit, one launch);
+// larger ones through the multi-launch tile pipeline.  `nt_of(i)` = tile count of list entry i
+// (lists are sorted largest first, so the large units form a prefix).
+static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, int nlist, int ntmax, bool want_grad,
+                              cudaStream_t st);
+
+static int launch_units(gprf_ctx* h, const EvalParams& P, const int* list_host, int nlist, int ntmax,
+                        bool want_grad, cudaStream_t st) {
+  int launches = 0;
+  if (nlist == 0) return 0;
+  int nlarge = 0, ntl = 0;
+  while (nlarge < nlist && h->units[list_host[nlarge]].nt > h->fused_nt) {
+    ntl = std::max(ntl, h->units[list_host[nlarge]].nt);
+    ++nlarge;
+  }
+  if (nlarge > 0) launches += launch_units_tiled(h, P, nlarge, ntl, want_grad, st);
+  const int CH = 1 << 20;
+  for (int base = nlarge; base < nlist; base += CH) {
+    const int cnt = std::min(CH, nlist - base);
+    EvalParams Pc = P;
+    Pc.ulist = P.ulist + base;
+    Pc.trace = h->dTrace;
+    Pc.trace_ctas = (int)(h->capTrace / (2 * TRACE_SLOTS));
+#define CALL_FUSED(D, W) fused_launch<D, W>(Pc, h->dLLu, h->dGthU, want_grad ? 1 : 0, cnt, st)
+    LAUNCH(8, DISPATCH_COV(h, CALL_FUSED));
+  }
+  (void)ntmax;
+  return launches;
+}
+
+static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, int nlist, int ntmax, bool want_grad,
+                              cudaStream_t st) {
   int launches = 0;
   if (nlist == 0) return 0;
   const int ntri_max = ntmax * (ntmax + 1) / 2;
@@ -713,7 +786,7 @@ static int launch_units(gprf_ctx* h, const EvalParams& P, int nlist, int ntmax, 
     const int cnt = std::min(CH, nlist - base);
     EvalParams Pc = P;
     Pc.ulist = P.ulist + base;
-    LAUNCH(0, (k_prep<<<dim3(ntmax, cnt), NTHREADS, 0, st>>>(Pc)));
+    LAUNCH(0, (k_prep<<<dim3(ntmax, cnt), NTHREADS, T * (T + 1) * sizeof(double), st>>>(Pc)));
     for (int k = 0; k < ntmax; ++k) {
 #define CALL_DIAG(D, W) k_potrf_diag<D, W><<<dim3(1, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, k)
       LAUNCH(1, DISPATCH_COV(h, CALL_DIAG));
@@ -761,6 +834,8 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
   P.yr = h->yr;
   P.nya = h->nya;
   P.cp = cp;
+  P.trace = nullptr;        // set for the fused launches only (launch_units)
+  P.trace_ctas = 0;
 
   std::fill(h->jitter.begin(), h->jitter.end(), 0.0);
   std::fill(h->tries.begin(), h->tries.end(), 0);
@@ -773,7 +848,7 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
   CUDA_OK(cudaMemsetAsync(out_dev, 0, outlen * sizeof(double), st));
   const int nlist = (int)h->all_list.size();
   P.ulist = h->dListAll;
-  int launches = launch_units(h, P, nlist, h->ntmax, want_grad, st);
+  int launches = launch_units(h, P, h->all_list.data(), nlist, h->ntmax, want_grad, st);
   P.ulist = h->dList;
   CUDA_OK(cudaGetLastError());
 
@@ -806,8 +881,9 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
     CUDA_OK(cudaMemcpyAsync(h->dJitter, h->jitter.data(), (size_t)U * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(h->dInfo, 0, (size_t)U * sizeof(int), st));
     CUDA_OK(cudaMemsetAsync(h->dNfail, 0, sizeof(int), st));
+    std::stable_sort(failed.begin(), failed.end(), [&](int a, int b) { return h->units[a].s > h->units[b].s; });
     CUDA_OK(cudaMemcpyAsync(h->dList, failed.data(), failed.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    launches += launch_units(h, P, (int)failed.size(), ntm, want_grad, st);
+    launches += launch_units(h, P, failed.data(), (int)failed.size(), ntm, want_grad, st);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(&nfail, h->dNfail, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
@@ -920,7 +996,7 @@ extern "C" int gprf_set_profiling(gprf_handle h, int on) {
 
 extern "C" const char* gprf_family_name(int fam) {
   static const char* names[GPRF_N_FAMILIES] = {"prep", "potrf_diag", "potrf_panel", "trtri",
-                                               "lauum", "grad", "unit_finalize", "combine"};
+                                               "lauum", "grad", "unit_finalize", "combine", "unit_fused"};
   return (fam >= 0 && fam < GPRF_N_FAMILIES) ? names[fam] : "";
 }
 

@@ -32,7 +32,7 @@ __device__ __forceinline__ int chol8_inv8(double a[8], double w[8], int lane) {
   for (int c = 0; c < 8; ++c) {
     const double piv = __shfl_sync(FULL, a[c], c);
     if (!(piv > 0.0) && fail == 0) fail = c + 1;
-    const double dinv = 1.0 / sqrt(piv);
+    const double dinv = rsqrt(piv);        // 75 vs 173 cycles for 1/sqrt on the critical path
     const double l = a[c] * dinv;          // lane r: L[r][c] for r > c ; lane c: sqrt(piv)
     if (lane == c) dinv_own = dinv;
 #pragma unroll

@@ -42,19 +42,30 @@ constexpr int T = 64;            // tile edge
 constexpr int NB8 = T / 8;       // 8x8 blocks per tile edge
 constexpr int KC = 32;           // K chunk staged per pipeline stage
 constexpr int SLD = KC + 8;      // smem row stride (doubles): 320 B = 64 mod 128
-constexpr int NTHREADS = 128;
+// Warps per CTA = warps per 64x64 tile.  4: warp w owns block rows {w, 7-w} (32 accumulator
+// doubles per thread); 8: warp w owns block row w (16 per thread).  One warp can issue one
+// DMMA.8x8x4 every 32 cycles while an SM sub-partition retires one every 16
+// (scripts/fp64_latency.cu, profiles/r01_fp64_latency.txt), so the latency of a tile task is
+// set by DMMAs per warp: 8 warps halve it and leave 4 warps per sub-partition with 2 CTAs/SM.
+#ifndef GPRF_NW
+#define GPRF_NW 8
+#endif
+constexpr int NW = GPRF_NW;
+static_assert(NW == 4 || NW == 8, "4 or 8 warps per tile");
+constexpr int MB = NB8 / NW;     // block rows per warp
+constexpr int NTHREADS = NW * 32;
 constexpr int STAGE_DOUBLES = T * SLD;               // one operand, one stage
 constexpr int PIPE_DOUBLES = 4 * STAGE_DOUBLES;      // A,B x 2 stages
 constexpr int WLD = T + 8;       // stride of a fully staged 64x64 operand (72)
 constexpr int SQLD = T + 1;      // stride of the scalar potf2 scratch tile
 
 struct Acc {
-  double c[2][8][2];
+  double c[MB][8][2];
 };
 
 __device__ __forceinline__ void acc_zero(Acc& a) {
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < MB; ++m)
 #pragma unroll
     for (int n = 0; n < 8; ++n) a.c[m][n][0] = a.c[m][n][1] = 0.0;
 }
@@ -62,7 +73,7 @@ __device__ __forceinline__ void acc_zero(Acc& a) {
 // Block row (0..7) of accumulator slot m for this thread's warp.
 __device__ __forceinline__ int acc_brow(int m) {
   const int w = threadIdx.x >> 5;
-  return m == 0 ? w : 7 - w;
+  return (MB == 1 || m == 0) ? w : 7 - w;
 }
 // Accumulator element coordinates inside the 64x64 tile.
 __device__ __forceinline__ int acc_row(int m) { return acc_brow(m) * 8 + ((threadIdx.x & 31) >> 2); }
@@ -122,20 +133,24 @@ __device__ __forceinline__ void mma_chunk(Acc& acc, const double* sA, const doub
                                           int nlim, int klim, int atri, int btri) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const int br0 = acc_brow(0), br1 = acc_brow(1);
-  const double* pa0 = sA + (br0 * 8 + g) * SLD + 2 * q;
-  const double* pa1 = sA + (br1 * 8 + g) * SLD + 2 * q;
+  int br[MB];
+  const double* pa[MB];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) {
+    br[m] = acc_brow(m);
+    pa[m] = sA + (br[m] * 8 + g) * SLD + 2 * q;
+  }
   const double* pb = sB + g * SLD + 2 * q;
   if (!CLOW && mlim == NB8 && nlim == NB8 && klim >= kk0 + KC / 8 && atri == 0 && btri == 0) {
 #pragma unroll
     for (int k8 = 0; k8 < KC / 8; ++k8) {
-      double2 a[2], b[8];
-      a[0] = *reinterpret_cast<const double2*>(pa0 + k8 * 8);
-      a[1] = *reinterpret_cast<const double2*>(pa1 + k8 * 8);
+      double2 a[MB], b[8];
+#pragma unroll
+      for (int m = 0; m < MB; ++m) a[m] = *reinterpret_cast<const double2*>(pa[m] + k8 * 8);
 #pragma unroll
       for (int n = 0; n < 8; ++n) b[n] = *reinterpret_cast<const double2*>(pb + n * 8 * SLD + k8 * 8);
 #pragma unroll
-      for (int m = 0; m < 2; ++m)
+      for (int m = 0; m < MB; ++m)
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
           dmma884(acc.c[m][n][0], acc.c[m][n][1], a[m].x, b[n].x);
@@ -148,48 +163,71 @@ __device__ __forceinline__ void mma_chunk(Acc& acc, const double* sA, const doub
   // (measured: scripts/dmma_pred.cu, profiles/r01_dmma_predication.txt), so blocks are skipped
   // with real forward branches: per block row an ascending loop over the block columns that
   // breaks at the first masked one (every mask on the path is an upper limit on n).
-  const bool row0 = br0 < mlim, row1 = br1 < mlim;
 #pragma unroll
   for (int k8 = 0; k8 < KC / 8; ++k8) {
     const int kk = kk0 + k8;
     if (kk >= klim) break;
     int nhi = nlim;
     if (btri == 2) nhi = min(nhi, kk + 1);
-    int nh0 = (row0 && (!atri || kk >= br0)) ? nhi : 0;
-    int nh1 = (row1 && (!atri || kk >= br1)) ? nhi : 0;
-    if (CLOW) {
-      nh0 = min(nh0, br0 + 1);
-      nh1 = min(nh1, br1 + 1);
+    int nh[MB];
+    bool any = false;
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      nh[m] = (br[m] < mlim && (!atri || kk >= br[m])) ? nhi : 0;
+      if (CLOW) nh[m] = min(nh[m], br[m] + 1);
+      any = any || nh[m] > 0;
     }
-    if (nh0 == 0 && nh1 == 0) continue;
-    double2 a[2], b[8];
-    a[0] = *reinterpret_cast<const double2*>(pa0 + k8 * 8);
-    a[1] = *reinterpret_cast<const double2*>(pa1 + k8 * 8);
+    if (!any) continue;
+    double2 a[MB], b[8];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) a[m] = *reinterpret_cast<const double2*>(pa[m] + k8 * 8);
 #pragma unroll
     for (int n = 0; n < 8; ++n) b[n] = *reinterpret_cast<const double2*>(pb + n * 8 * SLD + k8 * 8);
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      if (n >= nh0) break;
-      dmma884(acc.c[0][n][0], acc.c[0][n][1], a[0].x, b[n].x);
-      dmma884(acc.c[0][n][0], acc.c[0][n][1], a[0].y, b[n].y);
-    }
+    for (int m = 0; m < MB; ++m) {
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      if (n >= nh1) break;
-      dmma884(acc.c[1][n][0], acc.c[1][n][1], a[1].x, b[n].x);
-      dmma884(acc.c[1][n][0], acc.c[1][n][1], a[1].y, b[n].y);
+      for (int n = 0; n < 8; ++n) {
+        if (n >= nh[m]) break;
+        dmma884(acc.c[m][n][0], acc.c[m][n][1], a[m].x, b[n].x);
+        dmma884(acc.c[m][n][0], acc.c[m][n][1], a[m].y, b[n].y);
+      }
     }
   }
 }
 
+__device__ __forceinline__ void stage_full_async(double* dst, const double* src, long long ld);
+
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+
 // acc += sum_{j=0}^{nk-1} A_j * B_j^T.  tileA(j) / tileB(j) return TileRefs (klim is taken
 // from A's ref and must agree with B's).  `pipe` = PIPE_DOUBLES of smem.
 // Ends with a __syncthreads(): `pipe` may be reused by the caller afterwards.
-template <bool CLOW, class FA, class FB>
-__device__ __forceinline__ void gemm_nt(Acc& acc, int nk, FA tileA, FB tileB, int mlim, int nlim, double* pipe) {
+//
+// Two hooks hide the fixed latencies of a short contraction (units of 100-250 points have
+// 0-3 tiles of K):
+//   overlap()  runs right after the cp.async of the first chunk were issued (the caller
+//              initialises the accumulator there: covariance values, Y^T rows); it may
+//              contain __syncthreads().  Called exactly once, also when nk == 0.
+//   tailW      a full 64x64 row-major tile (leading dimension tail_ld) fetched into the idle
+//              stage buffer while the last chunk is multiplied; the function returns its
+//              address in shared memory (stride WLD), ready to use.
+template <bool CLOW, class FA, class FB, class Hook = NoHook>
+__device__ __forceinline__ const double* gemm_nt(Acc& acc, int nk, FA tileA, FB tileB, int mlim, int nlim,
+                                                 double* pipe, Hook overlap = Hook(),
+                                                 const double* tailW = nullptr, long long tail_ld = T) {
   constexpr int CPT = T / KC;        // chunks per tile
   constexpr int BPC = KC / 8;        // 8-blocks per chunk
-  if (nk <= 0 || mlim <= 0 || nlim <= 0) return;
+  if (nk <= 0 || mlim <= 0 || nlim <= 0) {
+    if (tailW) stage_full_async(pipe, tailW, tail_ld);
+    overlap();
+    if (tailW) {
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    return pipe;
+  }
   // stage s: A at pipe + 2 s STAGE_DOUBLES, B right after it (plain arithmetic: no pointer arrays,
   // which would live in local memory once indexed with a run-time stage)
   const int arows = mlim * 8, brows = nlim * 8;
@@ -199,7 +237,9 @@ __device__ __forceinline__ void gemm_nt(Acc& acc, int nk, FA tileA, FB tileB, in
   stage_chunk(pipe, a.p, a.ld, arows);
   stage_chunk(pipe + STAGE_DOUBLES, b.p, b.ld, brows);
   cp_async_commit();
+  overlap();
   int cur = 0;
+  const double* wsm = pipe;
   while (true) {
     // next chunk
     int jn = j, hn = h + 1;
@@ -213,21 +253,29 @@ __device__ __forceinline__ void gemm_nt(Acc& acc, int nk, FA tileA, FB tileB, in
       stage_chunk(nxt + STAGE_DOUBLES, bn.p + hn * KC, bn.ld, brows);
       cp_async_commit();
       cp_async_wait<1>();
+    } else if (tailW) {
+      double* nxt = pipe + (cur ^ 1) * 2 * STAGE_DOUBLES;
+      stage_full_async(nxt, tailW, tail_ld);
+      wsm = nxt;
+      cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
     const double* cs = pipe + cur * 2 * STAGE_DOUBLES;
     mma_chunk<CLOW>(acc, cs, cs + STAGE_DOUBLES, h * BPC, mlim, nlim, a.klim, a.atri, b.btri);
+    if (!more && tailW) cp_async_wait<0>();
     __syncthreads();
     if (!more) break;
     j = jn; h = hn; a = an; b = bn;
     cur ^= 1;
   }
+  return wsm;
 }
 
-// Stage a full 64x64 row-major operand (ld) into smem with stride WLD.
-__device__ __forceinline__ void stage_full(double* dst, const double* src, long long ld) {
+// Stage a full 64x64 row-major operand (ld) into smem with stride WLD (T * WLD doubles, which
+// fit in one pipeline stage: static_assert below).  _async: issue + commit only.
+__device__ __forceinline__ void stage_full_async(double* dst, const double* src, long long ld) {
   const int tid = threadIdx.x;
 #pragma unroll
   for (int it = 0; it < (T * T / 2) / NTHREADS; ++it) {
@@ -237,6 +285,10 @@ __device__ __forceinline__ void stage_full(double* dst, const double* src, long 
     cp_async16(dst + row * WLD + cu * 2, src + (long long)row * ld + cu * 2);
   }
   cp_async_commit();
+}
+static_assert(T * WLD <= 2 * STAGE_DOUBLES, "a staged full tile must fit in one (A,B) stage");
+__device__ __forceinline__ void stage_full(double* dst, const double* src, long long ld) {
+  stage_full_async(dst, src, ld);
   cp_async_wait<0>();
   __syncthreads();
 }
@@ -249,7 +301,9 @@ __device__ __forceinline__ void mul_acc_by_wt(Acc& out, const Acc& c, const doub
                                               int wlim) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const int w0 = acc_brow(0) < mlim ? wlim : 0, w1 = acc_brow(1) < mlim ? wlim : 0;
+  int wl[MB];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) wl[m] = acc_brow(m) < mlim ? wlim : 0;
   acc_zero(out);
 #pragma unroll
   for (int k8 = 0; k8 < 8; ++k8) {
@@ -259,21 +313,18 @@ __device__ __forceinline__ void mul_acc_by_wt(Acc& out, const Acc& c, const doub
     for (int n = k8; n < 8; ++n)                      // W[n][k] = 0 for k > n
       b[n] = *reinterpret_cast<const double2*>(sW + (n * 8 + g) * WLD + k8 * 8 + 2 * q);
 #pragma unroll
-    for (int n = k8; n < 8; ++n) {
-      if (n >= w0) break;
-      dmma884(out.c[0][n][0], out.c[0][n][1], c.c[0][k8][0], b[n].x);
-      dmma884(out.c[0][n][0], out.c[0][n][1], c.c[0][k8][1], b[n].y);
-    }
+    for (int m = 0; m < MB; ++m) {
 #pragma unroll
-    for (int n = k8; n < 8; ++n) {
-      if (n >= w1) break;
-      dmma884(out.c[1][n][0], out.c[1][n][1], c.c[1][k8][0], b[n].x);
-      dmma884(out.c[1][n][0], out.c[1][n][1], c.c[1][k8][1], b[n].y);
+      for (int n = k8; n < 8; ++n) {
+        if (n >= wl[m]) break;
+        dmma884(out.c[m][n][0], out.c[m][n][1], c.c[m][k8][0], b[n].x);
+        dmma884(out.c[m][n][0], out.c[m][n][1], c.c[m][k8][1], b[n].y);
+      }
     }
   }
   if (scale != 1.0) {
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < MB; ++m)
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
         out.c[m][n][0] *= scale;
@@ -285,7 +336,7 @@ __device__ __forceinline__ void mul_acc_by_wt(Acc& out, const Acc& c, const doub
 // Store the accumulator tile row-major (16-byte stores).
 __device__ __forceinline__ void acc_store(const Acc& a, double* dst, long long ld) {
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
+  for (int m = 0; m < MB; ++m)
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       double2 v = make_double2(a.c[m][n][0], a.c[m][n][1]);

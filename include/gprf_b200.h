@@ -148,11 +148,22 @@ int gprf_debug_unit(gprf_handle h, int unit, int* s, int* sp, int* yr,
  * (CUDA events on the launching stream), and the number of kernel launches. */
 int gprf_last_timing(gprf_handle h, float* ms, int* launches);
 
+/* Debug: timeline of the fused kernel, 512 (tag, %globaltimer ns) pairs per CTA.
+ * out == NULL: allocate for the first n_ctas CTAs (0 frees); out != NULL: copy back
+ * n_ctas * 512 * 2 values.  Tags: see scripts/trace_fused.py. */
+int gprf_debug_trace(gprf_handle h, int n_ctas, unsigned long long* out);
+
+/* Scheduling knob (no effect on results beyond fp64 summation order, which is
+ * identical on both paths): units of up to `nt` 64-point tiles are evaluated by
+ * the fused one-CTA-per-unit kernel, larger ones by the multi-launch tile
+ * pipeline.  Default 8 (environment override GPRF_FUSED_NT); 0 disables fusion. */
+int gprf_set_fused_nt(gprf_handle h, int nt);
+
 /* Optional per-kernel-family timing: when on, every launch is bracketed by CUDA
  * events on the launching stream; gprf_family_timing returns, for the last
  * evaluation, the summed device time (ms) and launch count of each family
  * (gprf_family_name(i), i < GPRF_N_FAMILIES). */
-#define GPRF_N_FAMILIES 8
+#define GPRF_N_FAMILIES 9
 int gprf_set_profiling(gprf_handle h, int on);
 int gprf_family_timing(gprf_handle h, float* ms, int* launches);
 const char* gprf_family_name(int fam);

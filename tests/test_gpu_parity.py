@@ -125,6 +125,26 @@ def test_llgrad_parity_small(name, flags):
     assert np.all(jit == 0)
 
 
+@pytest.mark.parametrize("name", sorted(COVS))
+def test_fused_and_tiled_paths_bit_identical(name):
+    """The fused one-CTA-per-unit kernel and the multi-launch tile pipeline run the same tile
+    tasks in the same arithmetic order: results must agree bit for bit, whichever units each
+    path gets (fused_nt = 0: all tiled; 2: mixed; 8: all fused)."""
+    sizes = [40, 70, 0, 1, 64, 90, 129, 200, 150]
+    edges = [(1, 0), (4, 1), (5, 4), (6, 5), (3, 1), (2, 1), (6, 0), (5, 3), (8, 7), (7, 6)]
+    o, g = build_pair(name, sizes, edges)
+    kw = dict(grad_X=True, grad_cov=True)
+    res = {}
+    for nt in (0, 2, 8):
+        g.set_fused_nt(nt)
+        res[nt] = g.llgrad(**kw)
+        res[nt, "ll"] = g.llgrad()[0]
+    assert_parity(o.llgrad(**kw), res[8], name)
+    for nt in (2, 8):
+        assert res[nt][0] == res[0][0] and res[nt, "ll"] == res[0, "ll"]
+        assert np.array_equal(res[nt][1], res[0][1]) and np.array_equal(res[nt][2], res[0][2])
+
+
 def test_llgrad_nonlocal_all_pairs():
     o, g = build_pair("euclid_se", [30, 45, 20, 33], [(1, 0)])
     kw = dict(grad_X=True, grad_cov=True)
