@@ -323,12 +323,24 @@ class Runner(object):
         return acc
 
 
+FUSED_NT = int(os.environ.get("GPRF_FUSED_NT", "8"))   # library default (include/gprf_b200.h)
+
+
 def roofline_from_profile(fam, sizes_local, dy, peak_tflops, peak_note):
+    """Dominant kernel family of one evaluation.  Units of up to FUSED_NT tiles run the whole pipeline
+    in k_unit_fused (algorithmic flops s^3 + 4 s^2 dy each); larger ones go through the per-family
+    tile kernels, whose algorithmic flops are split as in FAMILY_FLOPS."""
+    fused = np.ceil(sizes_local / 64.0) <= FUSED_NT
+    big = sizes_local[~fused]
     merged = {"potrf": [fam["potrf_diag"][0] + fam["potrf_panel"][0], fam["potrf_diag"][1] + fam["potrf_panel"][1]],
-              "trtri": fam["trtri"], "lauum": fam["lauum"], "grad": fam["grad"]}
+              "trtri": fam["trtri"], "lauum": fam["lauum"], "grad": fam["grad"], "unit_fused": fam["unit_fused"]}
     name = max(merged, key=lambda k: merged[k][0])
     ms, nl = merged[name]
-    flops = float(np.sum(FAMILY_FLOPS[name](sizes_local, dy)))
+    if name == "unit_fused":
+        sf = sizes_local[fused]
+        flops = float(np.sum(sf ** 3 + 4 * sf ** 2 * dy))
+    else:
+        flops = float(np.sum(FAMILY_FLOPS[name](big, dy)))
     achieved = flops / (ms * 1e-3) * 1e-12 if ms > 0 else 0.0
     return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": achieved / peak_tflops, "traffic": None, "peak_source": peak_note,
@@ -349,21 +361,30 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
 
     sampler = ClockSampler(local_rank)
     sampler.start()                      # nvidia-smi needs a few 100 ms to start: cover warm-up too
-    t_w, n_w = time.perf_counter(), 0
-    while n_w < max(3, warmup) or (time.perf_counter() - t_w < 0.8 and n_w < 400):
+    # Every loop below runs the SAME number of steps on every rank (each step holds an all-reduce):
+    # counts are fixed or derived from all-reduced quantities, never from a rank's own clock.
+    t_w = time.perf_counter()
+    for _ in range(max(3, warmup)):
         R.device_step(reblock=R.reblock)
-        n_w += 1
+    torch.cuda.synchronize()
+    tw = torch.tensor([(time.perf_counter() - t_w) / max(3, warmup)], dtype=torch.float64, device=R.dev)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    n_extra = int(min(400, max(0, 0.8 / max(tw.item(), 1e-6))))      # ~0.8 s more of untimed warm-up
+    for _ in range(n_extra):
+        R.device_step(reblock=R.reblock)
     barrier()
     total_ms, launches = R.timed_device_steps(steps)
     barrier()
-    t_w = time.perf_counter()
-    while len(sampler.rows) < 4 and time.perf_counter() - t_w < 2.0:
-        R.device_step(reblock=R.reblock)  # keep the load on until the sampler has seen it (untimed)
-    clocks = sampler.stop()
     t = torch.tensor([total_ms], dtype=torch.float64, device=R.dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = t.item() / steps
+    # keep the load on (untimed) until the clock sampler has seen it: ~1.5 s worth of steps
+    for _ in range(int(min(2000, max(3, 1500.0 / max(ms_per_step, 1e-3))))):
+        R.device_step(reblock=R.reblock)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
 
     # end to end through the public host API
     Xh = np.array(wl["X"])
@@ -430,7 +451,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=150))   # a hang must not eat the GPU budget
     import __graft_entry__
     if rank == 0:
         __graft_entry__.build()

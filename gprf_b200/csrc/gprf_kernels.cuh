@@ -373,14 +373,24 @@ __device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& 
   acc_store(res, out, ld);
 }
 
-// grid (ntmax - k - 1 + nya, nlist)
+// grid (nlist, ntmax - k - 1 + nya): unit = blockIdx.x, task = blockIdx.y.  Look-ahead: the CTA
+// that produced L_{k+1,k} (task 0) goes straight on to the diagonal tile k+1 (its other operands
+// are older), so the serial 64x64 factorisation overlaps with the remaining panel tiles of this
+// launch instead of being a launch of its own with one CTA per unit (k_potrf_diag is launched
+// for k = 0 only).  Task-major grid order dispatches those long CTAs first.
 template <int DFN, int WFN>
 __global__ void __launch_bounds__(NTHREADS, 2) k_potrf_panel(EvalParams P, int k) {
-  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  const int uid = P.ulist[blockIdx.x];
+  const UnitDesc u = P.units[uid];
   if (k >= u.nt) return;
   extern __shared__ __align__(16) double smem[];
   __shared__ TileScratch sc;
-  panel_tile<DFN, WFN>(P, u, k, blockIdx.x, smem, sc);
+  panel_tile<DFN, WFN>(P, u, k, blockIdx.y, smem, sc);
+  if (blockIdx.y == 0 && k + 1 < u.nt) {
+    __threadfence();
+    __syncthreads();
+    diag_tile<DFN, WFN>(P, uid, u, k + 1, smem, sc);
+  }
 }
 
 // ---------------------------------------------------------------------------

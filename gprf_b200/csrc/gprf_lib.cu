@@ -789,9 +789,9 @@ static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, int nlist, int n
     LAUNCH(0, (k_prep<<<dim3(ntmax, cnt), NTHREADS, T * (T + 1) * sizeof(double), st>>>(Pc)));
     for (int k = 0; k < ntmax; ++k) {
 #define CALL_DIAG(D, W) k_potrf_diag<D, W><<<dim3(1, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, k)
-      LAUNCH(1, DISPATCH_COV(h, CALL_DIAG));
+      if (k == 0) LAUNCH(1, DISPATCH_COV(h, CALL_DIAG));   // diag(k+1) rides in panel(k)
       const int gx = ntmax - k - 1 + h->nya;
-#define CALL_PANEL(D, W) k_potrf_panel<D, W><<<dim3(gx, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, k)
+#define CALL_PANEL(D, W) k_potrf_panel<D, W><<<dim3(cnt, gx), NTHREADS, PIPE_BYTES, st>>>(Pc, k)
       LAUNCH(2, DISPATCH_COV(h, CALL_PANEL));
     }
     if (want_grad) {
