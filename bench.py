@@ -34,8 +34,8 @@ DY = 50
 FAMILY_FLOPS = {                 # algorithmic flops per unit of s points (sum = s^3 + 4 s^2 dy)
     "potrf": lambda s, dy: s ** 3 / 3.0 + s ** 2 * dy,      # dpotrf + forward half of dpotrs
     "trtri": lambda s, dy: s ** 3 / 3.0,                    # dpotri, triangular inverse
-    "lauum": lambda s, dy: s ** 3 / 3.0 + s ** 2 * dy,      # dpotri, U U^T + back half of dpotrs
-    "grad": lambda s, dy: 2.0 * s ** 2 * dy,                # Alpha Alpha^T for G
+    "alpha": lambda s, dy: s ** 2 * dy,                             # back half of dpotrs
+    "kinv_grad": lambda s, dy: s ** 3 / 3.0 + 2.0 * s ** 2 * dy,    # dpotri's U U^T + Alpha Alpha^T for G
 }
 
 
@@ -333,7 +333,8 @@ def roofline_from_profile(fam, sizes_local, dy, peak_tflops, peak_note):
     fused = np.ceil(sizes_local / 64.0) <= FUSED_NT
     big = sizes_local[~fused]
     merged = {"potrf": [fam["potrf_diag"][0] + fam["potrf_panel"][0], fam["potrf_diag"][1] + fam["potrf_panel"][1]],
-              "trtri": fam["trtri"], "lauum": fam["lauum"], "grad": fam["grad"], "unit_fused": fam["unit_fused"]}
+              "trtri": fam["trtri"], "alpha": fam["alpha"], "kinv_grad": fam["kinv_grad"],
+              "unit_fused": fam["unit_fused"]}
     name = max(merged, key=lambda k: merged[k][0])
     ms, nl = merged[name]
     if name == "unit_fused":

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "gprf_debug_unit": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _ip, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gprf_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), _ip]),
     "gprf_debug_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "gprf_set_keep_kinv": (C.c_int, [C.c_void_p, C.c_int]),
     "gprf_set_fused_nt": (C.c_int, [C.c_void_p, C.c_int]),
     "gprf_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gprf_family_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), _ip]),

@@ -53,6 +53,7 @@ struct EvalParams {
   int* info;                  // per unit: 0 ok, >0 = 1 + first failing row
   int* nfail;
   int dx, dy, yr, nya;
+  int keep_kinv;              // write K^-1 tiles back to M (debug / predictor); llgrad itself needs only G
   CovParams cp;
   unsigned long long* trace;  // debug: TRACE_SLOTS (tag, ns) pairs per fused CTA, or nullptr
   int trace_ctas;
@@ -428,24 +429,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_trtri(EvalParams P, int d) {
 #endif
 
 // ---------------------------------------------------------------------------
-// lauum: K^-1 lower tiles (tasks x < ntri_max, x = tri(i) + j) and Alpha (tasks
-// ntri_max + i * nya + a)
+// alpha: Alpha_i = sum_{m >= i} U_im Z_m  (back half of dpotrs, gpy_linalg.py:139-148).
+// Task x = i * nya + a  ->  row tile i, output tile a.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void lauum_tile(const EvalParams& P, const UnitDesc& u, int x, int ntri_max,
-                                           double* pipe) {
-  int i, j;
-  bool aug = false;
-  if (x < ntri_max) {
-    if (x >= tri(u.nt)) return;
-    tri_decode(x, i, j);
-  } else {
-    int idx = x - ntri_max;
-    i = idx / P.nya;
-    j = u.nt + idx % P.nya;
-    if (i >= u.nt) return;
-    aug = true;
-  }
-  double* M = P.arena + u.m_off;
+__device__ __forceinline__ void alpha_tile(const EvalParams& P, const UnitDesc& u, int x, double* pipe) {
+  const int i = x / P.nya, a = x % P.nya;
+  if (i >= u.nt) return;
+  const int j = u.nt + a;
+  const double* M = P.arena + u.m_off;
   const long long ld = u.sp;
   const double* Udi = P.arena + u.d_off + (long long)(u.nt + i) * T * T;
   const double* rowi = M + (long long)i * T * ld;
@@ -453,37 +444,35 @@ __device__ __forceinline__ void lauum_tile(const EvalParams& P, const UnitDesc& 
   Acc acc;
   acc_zero(acc);
   const int mlim = ext8(u.s, i);
-  const int nlim = aug ? min(NB8, (P.dy - (j - u.nt) * T + 7) >> 3) : ext8(u.s, j);
+  const int nlim = min(NB8, (P.dy - a * T + 7) >> 3);
   // contraction over point tiles m = i + jj; U_ii is upper triangular
   auto tA = [&](int jj) {
     const int kl = ext8(u.s, i + jj);
     return jj == 0 ? tile_ref(Udi, T, kl, 1, 0) : tile_ref(rowi + (long long)(i + jj) * T, ld, kl);
   };
-  auto tB = [&](int jj) {
-    const int kl = ext8(u.s, i + jj);
-    return (j == i && jj == 0) ? tile_ref(Udi, T, kl, 0, 2) : tile_ref(rowj + (long long)(i + jj) * T, ld, kl);
-  };
-  if (j == i) gemm_nt<true>(acc, u.nt - i, tA, tB, mlim, nlim, pipe);
-  else gemm_nt<false>(acc, u.nt - i, tA, tB, mlim, nlim, pipe);
-  if (aug) {
-    double* Al = P.arena + u.al_off;
-    acc_store(acc, Al + (long long)i * T * P.yr + (long long)(j - u.nt) * T, P.yr);
-  } else {
-    acc_store(acc, M + (long long)i * T * ld + (long long)j * T, ld);
-  }
+  auto tB = [&](int jj) { return tile_ref(rowj + (long long)(i + jj) * T, ld, ext8(u.s, i + jj)); };
+  gemm_nt<false>(acc, u.nt - i, tA, tB, mlim, nlim, pipe);
+  double* Al = P.arena + u.al_off;
+  acc_store(acc, Al + (long long)i * T * P.yr + (long long)a * T, P.yr);
 }
 
-// grid (ntri_max + ntmax*nya, nlist)
+// grid (ntmax*nya, nlist)
 #ifndef GPRF_FUSED_ONLY
-__global__ void __launch_bounds__(NTHREADS, 2) k_lauum(EvalParams P, int ntri_max) {
+__global__ void __launch_bounds__(NTHREADS, 2) k_alpha(EvalParams P) {
   const UnitDesc u = P.units[P.ulist[blockIdx.y]];
   extern __shared__ __align__(16) double smem[];
-  lauum_tile(P, u, blockIdx.x, ntri_max, smem);
+  alpha_tile(P, u, blockIdx.x, smem);
 }
 #endif
 
 // ---------------------------------------------------------------------------
-// grad: G tile (x = tri(i) + j) in registers, contracted with dk/dx, dk/dtheta
+// kinv_grad: tile (i, j), x = tri(i) + j, of
+//   K^-1_ij = sum_{m >= i} U_im U_jm^T                      (dpotri's U U^T, gpy_linalg.py:150-171)
+//   G_ij    = Alpha_i Alpha_j^T - dy K^-1_ij                (gprf.py:547-551)
+// The K^-1 tile never leaves the registers: the accumulator is scaled by -dy and the
+// Alpha product is accumulated on top of it, then G is contracted with dk/dx and dk/dtheta
+// recomputed from x and the saved covariance values (gprf.py:553-584).  K^-1 is written to
+// the lower triangle of M only when P.keep_kinv is set (tests, predictor).
 // ---------------------------------------------------------------------------
 template <int DFN, int WFN>
 __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u, int x, double* pipe,
@@ -512,23 +501,45 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
   const double* ai = Al + (long long)i * T * P.yr;
   const double* aj = Al + (long long)j * T * P.yr;
   const int mlim = ext8(u.s, i), nlim = ext8(u.s, j);
-  // K^-1 and saved-K values of this thread's fragments, fetched in two halves (block columns
-  // 0-3 / 4-7) so that the global-load latency hides behind the G product and behind the first
-  // half of the epilogue instead of being paid once per block column.
-  const double* Kt = M + (long long)i * T * ld + (long long)j * T;
+  // K^-1_ij: contraction over point tiles m = i + jj; U_ii is upper triangular
+  {
+    const double* Udi = P.arena + u.d_off + (long long)(u.nt + i) * T * T;
+    const double* rowi = M + (long long)i * T * ld;
+    const double* rowj = M + (long long)j * T * ld;
+    auto uA = [&](int jj) {
+      const int kl = ext8(u.s, i + jj);
+      return jj == 0 ? tile_ref(Udi, T, kl, 1, 0) : tile_ref(rowi + (long long)(i + jj) * T, ld, kl);
+    };
+    auto uB = [&](int jj) {
+      const int kl = ext8(u.s, i + jj);
+      return (j == i && jj == 0) ? tile_ref(Udi, T, kl, 0, 2) : tile_ref(rowj + (long long)(i + jj) * T, ld, kl);
+    };
+    if (j == i) gemm_nt<true>(acc, u.nt - i, uA, uB, mlim, nlim, pipe);
+    else gemm_nt<false>(acc, u.nt - i, uA, uB, mlim, nlim, pipe);
+  }
+  if (P.keep_kinv) acc_store(acc, P.arena + u.m_off + (long long)i * T * ld + (long long)j * T, ld);
+  const double dyd = (double)P.dy;
+#pragma unroll
+  for (int m = 0; m < MB; ++m)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      acc.c[m][n][0] *= -dyd;
+      acc.c[m][n][1] *= -dyd;
+    }
+  // Saved-K values of this thread's fragments, fetched in two halves (block columns 0-3 / 4-7) so
+  // that the global-load latency hides behind the Alpha product and behind the first half of the
+  // epilogue instead of being paid once per block column.
   const double* Kst = P.arena + u.k_off + (long long)i * T * ld + (long long)j * T;
-  double2 kinA[4][MB], ksvA[4][MB], kinB[4][MB], ksvB[4][MB];
-  auto load_half = [&](int h, double2 (&kin)[4][MB], double2 (&ksv)[4][MB]) {
+  double2 ksvA[4][MB], ksvB[4][MB];
+  auto load_half = [&](int h, double2 (&ksv)[4][MB]) {
 #pragma unroll
     for (int nn = 0; nn < 4; ++nn)
 #pragma unroll
-      for (int m = 0; m < MB; ++m) {
-        const long long o = (long long)acc_row(m) * ld + acc_col(h * 4 + nn);
-        kin[nn][m] = *reinterpret_cast<const double2*>(Kt + o);
-        ksv[nn][m] = *reinterpret_cast<const double2*>(Kst + o);
-      }
+      for (int m = 0; m < MB; ++m)
+        ksv[nn][m] = *reinterpret_cast<const double2*>(Kst + (long long)acc_row(m) * ld + acc_col(h * 4 + nn));
   };
-  load_half(0, kinA, ksvA);
+  load_half(0, ksvA);
+  // G = Alpha_i Alpha_j^T - dy K^-1_ij, accumulated on top of the scaled K^-1 tile
   auto tA = [&](int c) { return tile_ref(ai + c * T, (long long)P.yr, min(NB8, (P.dy - c * T + 7) >> 3)); };
   auto tB = [&](int c) { return tile_ref(aj + c * T, (long long)P.yr, min(NB8, (P.dy - c * T + 7) >> 3)); };
   if (i == j) gemm_nt<true>(acc, P.nya, tA, tB, mlim, nlim, pipe);
@@ -536,8 +547,7 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
   __syncthreads();
   trace_mark(P, &sc.tcur, 71);
 
-  load_half(1, kinB, ksvB);
-  const double dyd = (double)P.dy;
+  load_half(1, ksvB);
   const double inv_s2 = 1.0 / P.cp.s2;
   // Raw sums; for the euclidean family they are scaled by the lengthscale factors at the end:
   //   t_d = G w'(r)/r (x_p - x_q)_d ;  rs = il2_d sum t_d ; cs = -il2_d sum t_d ; th[2+d] = -il3_d sum t_d (x_p-x_q)_d
@@ -557,7 +567,7 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
   bool mact[MB];
 #pragma unroll
   for (int m = 0; m < MB; ++m) mact[m] = acc_brow(m) < mlim;
-  auto epilogue_half = [&](int h, const double2 (&kinH)[4][MB], const double2 (&ksvH)[4][MB]) {
+  auto epilogue_half = [&](int h, const double2 (&ksvH)[4][MB]) {
 #pragma unroll
   for (int nn = 0; nn < 4; ++nn) {
     const int n = h * 4 + nn;
@@ -589,7 +599,7 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
         const int r = acc_row(m);
         const int p = i * T + r;
         double kv = (e == 0 ? ksvH[nn][m].x : ksvH[nn][m].y);
-        double G = acc.c[m][h * 4 + nn][e] - dyd * (e == 0 ? kinH[nn][m].x : kinH[nn][m].y);
+        double G = acc.c[m][h * 4 + nn][e];
         const bool inside = bact[m] && p < u.s && q < u.s;
         if (i == j && inside && q == p) {
           th[0] += 0.5 * G;
@@ -641,9 +651,9 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
     }
   }
   };
-  epilogue_half(0, kinA, ksvA);
+  epilogue_half(0, ksvA);
   trace_mark(P, &sc.tcur, 72);
-  epilogue_half(1, kinB, ksvB);
+  epilogue_half(1, ksvB);
   trace_mark(P, &sc.tcur, 73);
   th[1] *= inv_s2;
   if (DFN == DFN_EUCLIDEAN) {
@@ -821,8 +831,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_unit_fused(EvalParams P, double
       trace_mark(P, &sc.tcur, 5);
     }
     const int ntri = tri(nt);
-    for (int x = 0; x < ntri + nt * P.nya; ++x) {
-      lauum_tile(P, u, x, ntri, pipe);
+    for (int x = 0; x < nt * P.nya; ++x) {
+      alpha_tile(P, u, x, pipe);
       __syncthreads();
       trace_mark(P, &sc.tcur, 60);
     }

@@ -70,6 +70,7 @@ struct gprf_ctx {
   std::vector<unsigned char> explicit_mask, lpt, seen;
   bool use_explicit_mask = false, adj_dirty = true, blocks_from_device = false;
   int shard_rank = 0, shard_world = 1;
+  bool keep_kinv = false;          // store K^-1 tiles (gprf_set_keep_kinv)
   int fused_nt = 8;                // units of up to this many 64-point tiles take k_unit_fused
   unsigned long long* dTrace = nullptr;   // debug trace of the fused kernel (gprf_debug_trace)
   size_t capTrace = 0;
@@ -192,7 +193,7 @@ static void set_attrs() {
   set_attrs_t<1, 1>();
   cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
   cudaFuncSetAttribute(k_trtri, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
-  cudaFuncSetAttribute(k_lauum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
+  cudaFuncSetAttribute(k_alpha, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
 }
 
 #define DISPATCH_COV(h, CALL)                                  \
@@ -274,6 +275,12 @@ extern "C" int gprf_debug_trace(gprf_handle h, int n_ctas, unsigned long long* o
     CUDA_OK(cudaMemset(h->dTrace, 0, len * sizeof(unsigned long long)));
     h->capTrace = len;
   }
+  return GPRF_OK;
+}
+
+extern "C" int gprf_set_keep_kinv(gprf_handle h, int on) {
+  if (!h) return GPRF_ERR_ARG;
+  h->keep_kinv = on != 0;
   return GPRF_OK;
 }
 
@@ -798,7 +805,7 @@ static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, int nlist, int n
       for (int d = 1; d < ntmax; ++d) {
         LAUNCH(3, (k_trtri<<<dim3(ntmax - d, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, d)));
       }
-      LAUNCH(4, (k_lauum<<<dim3(ntri_max + ntmax * h->nya, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, ntri_max)));
+      LAUNCH(4, (k_alpha<<<dim3(ntmax * h->nya, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc)));
 #define CALL_GRAD(D, W) k_grad<D, W><<<dim3(ntri_max, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc)
       LAUNCH(5, DISPATCH_COV(h, CALL_GRAD));
     }
@@ -833,6 +840,7 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
   P.dy = h->dy;
   P.yr = h->yr;
   P.nya = h->nya;
+  P.keep_kinv = h->keep_kinv ? 1 : 0;
   P.cp = cp;
   P.trace = nullptr;        // set for the fused launches only (launch_units)
   P.trace_ctas = 0;
@@ -996,7 +1004,7 @@ extern "C" int gprf_set_profiling(gprf_handle h, int on) {
 
 extern "C" const char* gprf_family_name(int fam) {
   static const char* names[GPRF_N_FAMILIES] = {"prep", "potrf_diag", "potrf_panel", "trtri",
-                                               "lauum", "grad", "unit_finalize", "combine", "unit_fused"};
+                                               "alpha", "kinv_grad", "unit_finalize", "combine", "unit_fused"};
   return (fam >= 0 && fam < GPRF_N_FAMILIES) ? names[fam] : "";
 }
 

@@ -357,6 +357,10 @@ class GPRF(object):
         self._lib.gprf_last_timing(self._h, C.byref(ms), C.byref(n))
         return ms.value, n.value
 
+    def set_keep_kinv(self, on=True):
+        """Also store K^-1 of every unit (lower triangle of its working matrix, see gprf_debug_unit)."""
+        self._check(self._lib.gprf_set_keep_kinv(self._h, int(bool(on))))
+
     def set_fused_nt(self, nt):
         """Units of up to `nt` 64-point tiles use the fused one-CTA-per-unit kernel (0: never)."""
         self._check(self._lib.gprf_set_fused_nt(self._h, int(nt)))

@@ -153,6 +153,12 @@ int gprf_last_timing(gprf_handle h, float* ms, int* launches);
  * n_ctas * 512 * 2 values.  Tags: see scripts/trace_fused.py. */
 int gprf_debug_trace(gprf_handle h, int n_ctas, unsigned long long* out);
 
+/* K^-1 normally lives only in registers (it is turned into G = Alpha Alpha^T - dy K^-1
+ * in place).  With keep != 0 every evaluation also writes it to the lower triangle
+ * of the unit's working matrix, where gprf_debug_unit reads it (dpotri's result,
+ * gpy_linalg.py:150-171; needed by tests and by a train_predictor port). */
+int gprf_set_keep_kinv(gprf_handle h, int keep);
+
 /* Scheduling knob (no effect on results beyond fp64 summation order, which is
  * identical on both paths): units of up to `nt` 64-point tiles are evaluated by
  * the fused one-CTA-per-unit kernel, larger ones by the multi-launch tile

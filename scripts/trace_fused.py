@@ -6,7 +6,7 @@ Enables gprf_debug_trace, runs a few device-resident evaluations and prints the 
 events thread 0 of each traced CTA recorded.  Tags: 1 start, 2 prep done, 31 diag product done,
 32 diag tile in smem, 33 smem Cholesky+inverse done, 3 diag phase done, 41 panel product done,
 42 panel triangular multiply done, 40 panel task done, 4 panel phase done, 50/5 trtri task/phase,
-60/6 lauum task/phase, 70/7 grad task/phase, 8 finalize done.
+60/6 alpha task/phase, 70/7 kinv_grad task/phase (71 products done, 72/73 epilogue halves), 8 finalize done.
 """
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -36,7 +36,7 @@ tags = buf[:, :, 0].astype(np.int64)
 t = buf[:, :, 1].astype(np.int64)
 t0 = t[t > 0].min()
 NAMES = {1: "start", 2: "prep", 31: "dg.gemm", 32: "dg.S", 33: "dg.chol", 3: "DIAG", 41: "pn.gemm", 42: "pn.mul",
-         40: "pn.task", 4: "PANEL", 50: "tr.task", 5: "TRTRI", 60: "la.task", 6: "LAUUM", 71: "gr.gemm", 72: "gr.ep0", 73: "gr.ep1", 70: "gr.task", 7: "GRAD",
+         40: "pn.task", 4: "PANEL", 50: "tr.task", 5: "TRTRI", 60: "al.task", 6: "ALPHA", 71: "gr.gemm", 72: "gr.ep0", 73: "gr.ep1", 70: "gr.task", 7: "GRAD",
          8: "FIN"}
 print("# units %d; kernel span %.1f us" % (nct, (t.max() - t0) / 1e3))
 show = [0, 1, nct // 2, nct - 1] if len(sys.argv) < 3 else list(range(int(sys.argv[2])))

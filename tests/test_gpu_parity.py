@@ -74,7 +74,16 @@ def test_single_unit_stages(s):
     from gprf_b200 import _lib
     o, g = build_pair("euclid_se", [s], [], dy=7, seed=s)
     want = o.llgrad(grad_X=True, grad_cov=True)
+    # K^-1 normally stays in registers: without keep_kinv the lower triangle still holds L
+    got0 = g.llgrad(grad_X=True, grad_cov=True)
+    sp0 = ((s + 63) // 64) * 64
+    M0 = np.zeros((sp0 + 64, sp0))
+    g._lib.gprf_debug_unit(g._h, 0, None, None, None, _lib.ptr(M0), None, None)
+    Lref = np.linalg.cholesky(o.kernel(o.X[o.block_idxs[0]]))
+    assert np.abs(np.tril(M0[:s, :s]) - Lref).max() <= 1e-9 * np.abs(Lref).max(), "L (lower) wrong"
+    g.set_keep_kinv(True)
     got = g.llgrad(grad_X=True, grad_cov=True)
+    assert got0[0] == got[0] and np.array_equal(got0[1], got[1]) and np.array_equal(got0[2], got[2])
     sz, sp, yr = C.c_int(), C.c_int(), C.c_int()
     g._lib.gprf_debug_unit(g._h, 0, C.byref(sz), C.byref(sp), C.byref(yr), None, None, None)
     assert sz.value == s and sp.value == ((s + 63) // 64) * 64 and yr.value == 64
