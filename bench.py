@@ -326,6 +326,43 @@ class Runner(object):
 FUSED_NT = int(os.environ.get("GPRF_FUSED_NT", "8"))   # library default (include/gprf_b200.h)
 
 
+def lbfgs_full_run():
+    """BASELINE.json configs[1] end to end: the whole L-BFGS optimisation of the README configuration
+    through gprf_b200/gprfopt.py (py3 mirror of the reference driver, same scipy options), compared with
+    the run the reference logged for the same seed (tests/golden/gprf_trajectories_golden.json)."""
+    import tempfile
+    from gprf_b200 import gprfopt
+    from gprf_b200.synthetic import readme_dataset
+    name = "10000_10500_100_0.060000_0.020000_0.1000_50_l-bfgs-b_x_-1_0.0100_s0_gprf0"
+    gold = None
+    gpath = os.path.join(ROOT, "tests", "golden", "gprf_trajectories_golden.json")
+    if os.path.exists(gpath):
+        gold = [r for r in json.load(open(gpath))["runs"] if r["dir"] == name][0]["steps"]
+    sd = readme_dataset(ntrain=10000, nblocks=100, ntest=500, yd=DY, seed=0)
+    gp = sd.build_gprf(local_dist=0.1)
+    for _ in range(3):
+        gp.llgrad(grad_X=True)                       # warm the context outside the timed run
+    with tempfile.TemporaryDirectory() as d:
+        t0 = time.perf_counter()
+        log = gprfopt.do_optimization(d, gp, sd.X_obs, None, sd, save_steps=False)
+        wall = time.perf_counter() - t0
+    out = {"config": name, "evals": len(log), "wall_s": wall, "evals_per_s": len(log) / wall,
+           "final_objective": log[-1][2], "best_objective": max(l[2] for l in log),
+           "note": "scipy L-BFGS-B ftol 1e-6 maxiter 200 (gprfopt.py:418); host numpy in/out every evaluation, "
+                   "step_*.npy dumps off"}
+    if gold:
+        nsame = 0
+        for (st, _t, ll), g in zip(log, gold):
+            if abs(ll - g[1]) > 0.011:
+                break
+            nsame += 1
+        out["reference_log"] = {"evals": len(gold), "final_objective": gold[-1][1],
+                                "seconds_logged_by_reference": 650.03,
+                                "leading_evals_identical_to_2_decimals": nsame}
+    gp.close()
+    return out
+
+
 def roofline_from_profile(fam, sizes_local, dy, peak_tflops, peak_note):
     """Dominant kernel family of one evaluation.  Units of up to FUSED_NT tiles run the whole pipeline
     in k_unit_fused (algorithmic flops s^3 + 4 s^2 dy each); larger ones go through the per-family
@@ -438,6 +475,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--no-n200k", action="store_true", help="skip the extra n=200k measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-lbfgs", action="store_true", help="skip the full L-BFGS run of the README configuration")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -476,6 +514,8 @@ def main():
             "roofline": r["roofline"]}
     if "cpu_baseline" in r:
         line["cpu_baseline"] = r["cpu_baseline"]
+    if world == 1 and args.workload == "cfg2" and not args.no_lbfgs:
+        line["lbfgs_full_run"] = lbfgs_full_run()
     if not args.no_n200k and args.workload != "cfg5":
         k5 = max(2, min(args.steps, 5))
         r5 = measure(torch, dist, args, "cfg5", rank, world, local_rank, k5, 1, with_cpu=False)

@@ -18,10 +18,12 @@ import tarfile
 
 SRC = "/root/reference/gprf_results.tgz"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gprf_results_golden.json")
+OUT_TRAJ = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gprf_trajectories_golden.json")
 
 
 def main():
     runs = []
+    trajs = []
     with tarfile.open(SRC) as tf:
         for m in tf.getmembers():
             if not m.name.endswith("results.txt"):
@@ -49,7 +51,19 @@ def main():
                 rec["trueX_ll"] = float(true[0][2]) if true[0][2] != "-inf" else None
                 rec["trueX_xprior"] = float(true[0][5])
             runs.append(rec)
+            # full optimiser trajectory of the small runs and of the README configuration:
+            # (step, ll, mean distance to the true X, x_prior) per objective evaluation
+            if f[0] in ("2000", "5000") or (f[0] == "10000" and f[2] == "100"):
+                trajs.append({"dir": d, "ntrain": rec["ntrain"], "nblocks": rec["nblocks"],
+                              "local_dist": rec["local_dist"], "task": rec["task"], "init_seed": rec["init_seed"],
+                              "seed": rec["seed"],
+                              "steps": [[int(x[0]), float(x[2]), float(x[3]), float(x[4]), float(x[5])]
+                                        for x in steps]})
     runs.sort(key=lambda r: (r["ntrain"], r["nblocks"], r["local_dist"], r["task"], r["init_seed"]))
+    with open(OUT_TRAJ, "w") as fh:
+        json.dump({"source": "gprf_results.tgz (davmre/gprf): results.txt rows, columns step ll lscale_ratio mad xprior",
+                   "runs": trajs}, fh)
+    print("wrote %d trajectories to %s" % (len(trajs), OUT_TRAJ))
     with open(OUT, "w") as fh:
         json.dump({"source": "gprf_results.tgz (davmre/gprf)", "runs": runs}, fh, indent=1)
     print("wrote %d runs to %s" % (len(runs), OUT))
