@@ -53,6 +53,8 @@ _SIGNATURES = {
     "gprf_debug_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gprf_set_keep_kinv": (C.c_int, [C.c_void_p, C.c_int]),
     "gprf_set_fused_nt": (C.c_int, [C.c_void_p, C.c_int]),
+    "gprf_set_factor_reuse": (C.c_int, [C.c_void_p, C.c_int]),
+    "gprf_factor_reuse_stats": (C.c_int, [C.c_void_p, _ip, _llp]),
     "gprf_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gprf_family_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), _ip]),
     "gprf_family_name": (C.c_char_p, [C.c_int]),

@@ -37,8 +37,18 @@ constexpr int PART_TH = 384;
 struct UnitDesc {
   int s, ni, nt, sp;
   int a_start, b_start;       // offsets of the two blocks' rows in perm
-  int active, pad_;
+  int active;
+  // Factor reuse for edges (the Schur-complement form of the pair factorisation): the first
+  // `share` 64-point tiles of a pair unit lie entirely inside block i, whose rows come first
+  // (gprf.py:310-330), so the leading share x share tile square of L, U = L^-T, W/U_kk, the
+  // saved K tiles, the logdet partials and the first `share` column tiles of Z^T = (L^-1 Y)^T
+  // are bit-identical to those of block i's own unit (same operands, same summation order).
+  // The pair does not recompute them: it reads them from the parent's arena regions
+  // (p_*), and factors only the tiles that involve block j.  share = 0: self-contained unit.
+  int share;
+  int p_sp, p_nt;
   long long m_off, d_off, al_off, xs_off, part_off, ld_off, gx_off, k_off;
+  long long p_m_off, p_d_off, p_ld_off, p_k_off;
   double weight;
 };
 
@@ -54,6 +64,7 @@ struct EvalParams {
   int* nfail;
   int dx, dy, yr, nya;
   int keep_kinv;              // write K^-1 tiles back to M (debug / predictor); llgrad itself needs only G
+  int no_share;               // jitter retries: every unit factors all of its own tiles
   CovParams cp;
   unsigned long long* trace;  // debug: TRACE_SLOTS (tag, ns) pairs per fused CTA, or nullptr
   int trace_ctas;
@@ -90,6 +101,36 @@ __device__ __forceinline__ void tri_decode(int x, int& i, int& j) {
 __device__ __forceinline__ int ext8(int s, int t) {
   const int r = s - t * T;
   return r >= T ? NB8 : (r + 7) >> 3;
+}
+
+// Load a unit descriptor for a launch (jitter retries switch the factor reuse off).
+__device__ __forceinline__ UnitDesc load_unit(const EvalParams& P, int uid) {
+  UnitDesc u = P.units[uid];
+  if (P.no_share) u.share = 0;
+  return u;
+}
+
+// Tile (r, c) of a unit's working matrix: r < nt are point row tiles, r >= nt the augmented
+// Y^T / Z^T rows.  Tiles of the leading share x share square and the first `share` column tiles
+// of the augmented rows live in the parent block's matrix (see UnitDesc::share).
+__device__ __forceinline__ bool tile_shared(const UnitDesc& u, int r, int c) {
+  return c < u.share && (r < u.share || r >= u.nt);
+}
+__device__ __forceinline__ TileRef mtile(const EvalParams& P, const UnitDesc& u, int r, int c, int klim = NB8,
+                                         int atri = 0, int btri = 0) {
+  if (tile_shared(u, r, c)) {
+    const int rr = r < u.nt ? r : u.p_nt + (r - u.nt);
+    return tile_ref(P.arena + u.p_m_off + (long long)rr * T * u.p_sp + (long long)c * T, u.p_sp, klim, atri, btri);
+  }
+  return tile_ref(P.arena + u.m_off + (long long)r * T * u.sp + (long long)c * T, u.sp, klim, atri, btri);
+}
+// W_kk = L_kk^-1 and U_kk = W_kk^T of diagonal tile k
+__device__ __forceinline__ const double* dtile_w(const EvalParams& P, const UnitDesc& u, int k) {
+  return k < u.share ? P.arena + u.p_d_off + (long long)k * T * T : P.arena + u.d_off + (long long)k * T * T;
+}
+__device__ __forceinline__ const double* dtile_u(const EvalParams& P, const UnitDesc& u, int k) {
+  return k < u.share ? P.arena + u.p_d_off + (long long)(u.p_nt + k) * T * T
+                     : P.arena + u.d_off + (long long)(u.nt + k) * T * T;
 }
 
 // Small static scratch shared by every tile task (one instance per CTA).  Everything
@@ -159,7 +200,7 @@ __device__ __forceinline__ void prep_tile(const EvalParams& P, const UnitDesc& u
 // grid (nt_max, nlist), NTHREADS threads
 #ifndef GPRF_FUSED_ONLY
 __global__ void __launch_bounds__(NTHREADS) k_prep(EvalParams P) {
-  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  const UnitDesc u = load_unit(P, P.ulist[blockIdx.y]);
   if ((int)blockIdx.x >= u.nt) return;
   extern __shared__ __align__(16) double smem[];
   __shared__ TileScratch sc;
@@ -271,8 +312,8 @@ __device__ __forceinline__ void diag_tile(const EvalParams& P, int uid, const Un
 template <int DFN, int WFN>
 __global__ void __launch_bounds__(NTHREADS, 2) k_potrf_diag(EvalParams P, int k) {
   const int uid = P.ulist[blockIdx.y];
-  const UnitDesc u = P.units[uid];
-  if (k >= u.nt) return;
+  const UnitDesc u = load_unit(P, uid);
+  if (k >= u.nt || k < u.share) return;
   extern __shared__ __align__(16) double smem[];
   __shared__ TileScratch sc;
   diag_tile<DFN, WFN>(P, uid, u, k, smem, sc);
@@ -296,6 +337,7 @@ __device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& 
     it = u.nt + a;
     aug = true;
   }
+  if (k < u.share && (aug || it < u.share)) return;     // the parent block owns this tile
   double (*sxr)[4] = sc.xa;
   double (*sxc)[4] = sc.xb;
   const int tid = threadIdx.x;
@@ -313,8 +355,6 @@ __device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& 
   // block masks: rows of this tile (points of tile `it`, or outputs of Y^T), columns = points of tile k
   const int mlim = aug ? min(NB8, (P.dy - (it - u.nt) * T + 7) >> 3) : ext8(u.s, it);
   const int nlim = ext8(u.s, k);
-  const double* rowi = M + (long long)it * T * ld;
-  const double* rowk = M + (long long)k * T * ld;
   double* out = M + (long long)it * T * ld + k * T;
   double* Ks = P.arena + u.k_off + (long long)it * T * ld + k * T;    // saved K tile (it, k), non-aug only
   // acc = -C0 (covariance values K_ik, or the Y^T rows), evaluated while the first operand chunk
@@ -361,10 +401,10 @@ __device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& 
       }
     }
   };
-  auto tA = [&](int j) { return tile_ref(rowi + j * T, ld); };
-  auto tB = [&](int j) { return tile_ref(rowk + j * T, ld); };
+  auto tA = [&](int j) { return mtile(P, u, it, j); };
+  auto tB = [&](int j) { return mtile(P, u, k, j); };
   // W_kk arrives in the idle stage buffer while the last chunk is multiplied
-  const double* Wd = P.arena + u.d_off + (long long)k * T * T;
+  const double* Wd = dtile_w(P, u, k);
   const double* sW = gemm_nt<false>(acc, k, tA, tB, mlim, nlim, pipe, init, Wd, T);
   trace_mark(P, &sc.tcur, 41);
   // L_ik = (C0 - sum) W_kk^T = -(acc W_kk^T)
@@ -382,12 +422,12 @@ __device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& 
 template <int DFN, int WFN>
 __global__ void __launch_bounds__(NTHREADS, 2) k_potrf_panel(EvalParams P, int k) {
   const int uid = P.ulist[blockIdx.x];
-  const UnitDesc u = P.units[uid];
+  const UnitDesc u = load_unit(P, uid);
   if (k >= u.nt) return;
   extern __shared__ __align__(16) double smem[];
   __shared__ TileScratch sc;
   panel_tile<DFN, WFN>(P, u, k, blockIdx.y, smem, sc);
-  if (blockIdx.y == 0 && k + 1 < u.nt) {
+  if (blockIdx.y == 0 && k + 1 < u.nt && k + 1 >= u.share) {
     __threadfence();
     __syncthreads();
     diag_tile<DFN, WFN>(P, uid, u, k + 1, smem, sc);
@@ -399,20 +439,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_potrf_panel(EvalParams P, int k
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void trtri_tile(const EvalParams& P, const UnitDesc& u, int k, int d, double* pipe) {
   const int i = k + d;
-  if (i >= u.nt) return;
+  if (i >= u.nt || i < u.share) return;      // U_{k,i} with i < share is the parent block's
   double* M = P.arena + u.m_off;
   const long long ld = u.sp;
-  const double* Ud = P.arena + u.d_off + (long long)(u.nt + k) * T * T;
-  const double* rowk = M + (long long)k * T * ld;
-  const double* rowi = M + (long long)i * T * ld;
+  const double* Ud = dtile_u(P, u, k);
   Acc acc;
   acc_zero(acc);
   const int nlim = ext8(u.s, i);      // tile k < i is never the padded one
-  auto tA = [&](int jj) {
-    return jj == 0 ? tile_ref(Ud, T, NB8, 1, 0) : tile_ref(rowk + (long long)(k + jj) * T, ld);
-  };
-  auto tB = [&](int jj) { return tile_ref(rowi + (long long)(k + jj) * T, ld); };
-  const double* Wd = P.arena + u.d_off + (long long)i * T * T;
+  auto tA = [&](int jj) { return jj == 0 ? tile_ref(Ud, T, NB8, 1, 0) : mtile(P, u, k, k + jj); };
+  auto tB = [&](int jj) { return mtile(P, u, i, k + jj); };
+  const double* Wd = dtile_w(P, u, i);
   const double* sW = gemm_nt<false>(acc, d, tA, tB, NB8, nlim, pipe, NoHook(), Wd, T);
   Acc res;
   mul_acc_by_wt(res, acc, sW, -1.0, NB8, nlim);
@@ -422,7 +458,7 @@ __device__ __forceinline__ void trtri_tile(const EvalParams& P, const UnitDesc& 
 // grid (ntmax - d, nlist)
 #ifndef GPRF_FUSED_ONLY
 __global__ void __launch_bounds__(NTHREADS, 2) k_trtri(EvalParams P, int d) {
-  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  const UnitDesc u = load_unit(P, P.ulist[blockIdx.y]);
   extern __shared__ __align__(16) double smem[];
   trtri_tile(P, u, blockIdx.x, d, smem);
 }
@@ -436,11 +472,7 @@ __device__ __forceinline__ void alpha_tile(const EvalParams& P, const UnitDesc& 
   const int i = x / P.nya, a = x % P.nya;
   if (i >= u.nt) return;
   const int j = u.nt + a;
-  const double* M = P.arena + u.m_off;
-  const long long ld = u.sp;
-  const double* Udi = P.arena + u.d_off + (long long)(u.nt + i) * T * T;
-  const double* rowi = M + (long long)i * T * ld;
-  const double* rowj = M + (long long)j * T * ld;
+  const double* Udi = dtile_u(P, u, i);
   Acc acc;
   acc_zero(acc);
   const int mlim = ext8(u.s, i);
@@ -448,9 +480,9 @@ __device__ __forceinline__ void alpha_tile(const EvalParams& P, const UnitDesc& 
   // contraction over point tiles m = i + jj; U_ii is upper triangular
   auto tA = [&](int jj) {
     const int kl = ext8(u.s, i + jj);
-    return jj == 0 ? tile_ref(Udi, T, kl, 1, 0) : tile_ref(rowi + (long long)(i + jj) * T, ld, kl);
+    return jj == 0 ? tile_ref(Udi, T, kl, 1, 0) : mtile(P, u, i, i + jj, kl);
   };
-  auto tB = [&](int jj) { return tile_ref(rowj + (long long)(i + jj) * T, ld, ext8(u.s, i + jj)); };
+  auto tB = [&](int jj) { return mtile(P, u, j, i + jj, ext8(u.s, i + jj)); };
   gemm_nt<false>(acc, u.nt - i, tA, tB, mlim, nlim, pipe);
   double* Al = P.arena + u.al_off;
   acc_store(acc, Al + (long long)i * T * P.yr + (long long)a * T, P.yr);
@@ -459,7 +491,7 @@ __device__ __forceinline__ void alpha_tile(const EvalParams& P, const UnitDesc& 
 // grid (ntmax*nya, nlist)
 #ifndef GPRF_FUSED_ONLY
 __global__ void __launch_bounds__(NTHREADS, 2) k_alpha(EvalParams P) {
-  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  const UnitDesc u = load_unit(P, P.ulist[blockIdx.y]);
   extern __shared__ __align__(16) double smem[];
   alpha_tile(P, u, blockIdx.x, smem);
 }
@@ -485,7 +517,6 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
   double (*scol)[T][3] = sc.scol;
   double (*sth)[MAX_NCOV] = sc.sth;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double* M = P.arena + u.m_off;
   const long long ld = u.sp;
   const double* Al = P.arena + u.al_off;
   if (tid < T) {
@@ -503,16 +534,14 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
   const int mlim = ext8(u.s, i), nlim = ext8(u.s, j);
   // K^-1_ij: contraction over point tiles m = i + jj; U_ii is upper triangular
   {
-    const double* Udi = P.arena + u.d_off + (long long)(u.nt + i) * T * T;
-    const double* rowi = M + (long long)i * T * ld;
-    const double* rowj = M + (long long)j * T * ld;
+    const double* Udi = dtile_u(P, u, i);
     auto uA = [&](int jj) {
       const int kl = ext8(u.s, i + jj);
-      return jj == 0 ? tile_ref(Udi, T, kl, 1, 0) : tile_ref(rowi + (long long)(i + jj) * T, ld, kl);
+      return jj == 0 ? tile_ref(Udi, T, kl, 1, 0) : mtile(P, u, i, i + jj, kl);
     };
     auto uB = [&](int jj) {
       const int kl = ext8(u.s, i + jj);
-      return (j == i && jj == 0) ? tile_ref(Udi, T, kl, 0, 2) : tile_ref(rowj + (long long)(i + jj) * T, ld, kl);
+      return (j == i && jj == 0) ? tile_ref(Udi, T, kl, 0, 2) : mtile(P, u, j, i + jj, kl);
     };
     if (j == i) gemm_nt<true>(acc, u.nt - i, uA, uB, mlim, nlim, pipe);
     else gemm_nt<false>(acc, u.nt - i, uA, uB, mlim, nlim, pipe);
@@ -529,14 +558,16 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
   // Saved-K values of this thread's fragments, fetched in two halves (block columns 0-3 / 4-7) so
   // that the global-load latency hides behind the Alpha product and behind the first half of the
   // epilogue instead of being paid once per block column.
-  const double* Kst = P.arena + u.k_off + (long long)i * T * ld + (long long)j * T;
+  // saved K tile (i, j); tiles of the leading square were saved by the parent block
+  const long long kld = i < u.share ? u.p_sp : ld;
+  const double* Kst = (i < u.share ? P.arena + u.p_k_off : P.arena + u.k_off) + (long long)i * T * kld + (long long)j * T;
   double2 ksvA[4][MB], ksvB[4][MB];
   auto load_half = [&](int h, double2 (&ksv)[4][MB]) {
 #pragma unroll
     for (int nn = 0; nn < 4; ++nn)
 #pragma unroll
       for (int m = 0; m < MB; ++m)
-        ksv[nn][m] = *reinterpret_cast<const double2*>(Kst + (long long)acc_row(m) * ld + acc_col(h * 4 + nn));
+        ksv[nn][m] = *reinterpret_cast<const double2*>(Kst + (long long)acc_row(m) * kld + acc_col(h * 4 + nn));
   };
   load_half(0, ksvA);
   // G = Alpha_i Alpha_j^T - dy K^-1_ij, accumulated on top of the scaled K^-1 tile
@@ -701,7 +732,7 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
 // grid (ntri_max, nlist)
 template <int DFN, int WFN>
 __global__ void __launch_bounds__(NTHREADS, 2) k_grad(EvalParams P) {
-  const UnitDesc u = P.units[P.ulist[blockIdx.y]];
+  const UnitDesc u = load_unit(P, P.ulist[blockIdx.y]);
   extern __shared__ __align__(16) double smem[];
   __shared__ TileScratch sc;
   grad_tile<DFN, WFN>(P, u, blockIdx.x, smem, sc);
@@ -719,9 +750,20 @@ __device__ __forceinline__ void finalize_unit(const EvalParams& P, int uid, cons
   double q = 0.0;
   const long long tot = (long long)P.yr * u.sp;
   const double* Z = M + (long long)u.sp * u.sp;
-  for (long long e = tid; e < tot; e += NTHREADS) {
-    double z = Z[e];
-    q += z * z;
+  if (u.share == 0) {
+    for (long long e = tid; e < tot; e += NTHREADS) {
+      double z = Z[e];
+      q += z * z;
+    }
+  } else {
+    // same element order; the first share*64 columns of Z^T are the parent block's
+    const double* Zp = P.arena + u.p_m_off + (long long)u.p_sp * u.p_sp;
+    const int csh = u.share * T;
+    for (long long e = tid; e < tot; e += NTHREADS) {
+      const int r = (int)(e / u.sp), c = (int)(e % u.sp);
+      double z = c < csh ? Zp[(long long)r * u.p_sp + c] : Z[e];
+      q += z * z;
+    }
   }
   red[tid] = q;
   __syncthreads();
@@ -732,7 +774,8 @@ __device__ __forceinline__ void finalize_unit(const EvalParams& P, int uid, cons
   if (tid == 0) {
     double lsum = 0.0;
     const double* ldp = P.arena + u.ld_off;
-    for (int k = 0; k < u.nt; ++k) lsum += ldp[k];
+    const double* ldq = P.arena + u.p_ld_off;
+    for (int k = 0; k < u.nt; ++k) lsum += k < u.share ? ldq[k] : ldp[k];
     const double logdet = 2.0 * lsum;
     ll_u[uid] = -0.5 * red[0] - 0.5 * P.dy * logdet - 0.5 * P.dy * (double)u.s * 1.8378770664093454836;
   }
@@ -767,7 +810,7 @@ __device__ __forceinline__ void finalize_unit(const EvalParams& P, int uid, cons
 __global__ void __launch_bounds__(NTHREADS) k_unit_finalize(EvalParams P, double* ll_u, double* gth_u,
                                                           int want_grad) {
   const int uid = P.ulist[blockIdx.x];
-  const UnitDesc u = P.units[uid];
+  const UnitDesc u = load_unit(P, uid);
   __shared__ double red[NTHREADS];
   finalize_unit(P, uid, u, ll_u, gth_u, want_grad, red);
 }
@@ -794,7 +837,8 @@ template <int DFN, int WFN>
 __global__ void __launch_bounds__(NTHREADS, 2) k_unit_fused(EvalParams P, double* ll_u, double* gth_u,
                                                             int want_grad) {
   const int uid = P.ulist[blockIdx.x];
-  const UnitDesc u = P.units[uid];
+  UnitDesc u = P.units[uid];
+  u.share = 0;                 // the host gives fused units share = 0 (no cross-CTA ordering here)
   extern __shared__ __align__(16) double smem[];
   __shared__ TileScratch sc;
   double* pipe = smem;

@@ -71,6 +71,10 @@ struct gprf_ctx {
   bool use_explicit_mask = false, adj_dirty = true, blocks_from_device = false;
   int shard_rank = 0, shard_world = 1;
   bool keep_kinv = false;          // store K^-1 tiles (gprf_set_keep_kinv)
+  bool share_on = true;            // edges reuse block i's factor tiles (gprf_set_factor_reuse)
+  bool any_share = false;
+  int n_share_units = 0;
+  long long n_share_tiles = 0;     // potrf/trtri/forward-solve tile tasks not executed thanks to the reuse
   int fused_nt = 8;                // units of up to this many 64-point tiles take k_unit_fused
   unsigned long long* dTrace = nullptr;   // debug trace of the fused kernel (gprf_debug_trace)
   size_t capTrace = 0;
@@ -278,15 +282,39 @@ extern "C" int gprf_debug_trace(gprf_handle h, int n_ctas, unsigned long long* o
   return GPRF_OK;
 }
 
+static int rebuild_units(gprf_ctx* h, cudaStream_t st);
+// The factor-reuse plan depends on these switches: rebuild the unit descriptors.
+static int replan(gprf_ctx* h) {
+  if (!h->have_structure) return GPRF_OK;
+  CUDA_OK(cudaSetDevice(h->device));
+  int rc = rebuild_units(h, h->stream);
+  if (rc != GPRF_OK) return rc;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return GPRF_OK;
+}
+
 extern "C" int gprf_set_keep_kinv(gprf_handle h, int on) {
   if (!h) return GPRF_ERR_ARG;
   h->keep_kinv = on != 0;
-  return GPRF_OK;
+  return replan(h);
 }
 
 extern "C" int gprf_set_fused_nt(gprf_handle h, int nt) {
   if (!h || nt < 0) return GPRF_ERR_ARG;
   h->fused_nt = nt;
+  return replan(h);
+}
+
+extern "C" int gprf_set_factor_reuse(gprf_handle h, int on) {
+  if (!h) return GPRF_ERR_ARG;
+  h->share_on = on != 0;
+  return replan(h);
+}
+
+extern "C" int gprf_factor_reuse_stats(gprf_handle h, int* n_units, long long* n_tiles) {
+  if (!h) return GPRF_ERR_ARG;
+  if (n_units) *n_units = h->n_share_units;
+  if (n_tiles) *n_tiles = h->n_share_tiles;
   return GPRF_OK;
 }
 
@@ -360,26 +388,35 @@ static int rebuild_adjacency(gprf_ctx* h) {
   return GPRF_OK;
 }
 
-// Longest-processing-time sharding of the units over `world` ranks on the work model
-// W(s) = s^3 + 4 s^2 * 50 - the same rule as gprf_b200/dist.py::shard_units.
-static void lpt_mask(const std::vector<double>& sizes, int rank, int world, std::vector<unsigned char>& mask) {
+// Multi-GPU sharding of the units over `world` ranks - the same rule as
+// gprf_b200/dist.py::shard_units.  The unit of assignment is a GROUP: block i together with
+// every edge (i, j) whose rows start with block i (gprf.py:310-330), so that a pair always
+// finds its parent's factor on its own rank (UnitDesc::share).  Groups are placed by a
+// longest-processing-time greedy on the work model W(s) = s^3 + 4 s^2 * 50.
+static void lpt_mask(const std::vector<double>& sizes, int B, const int* edges, int rank, int world,
+                     std::vector<unsigned char>& mask) {
   const size_t U = sizes.size();
   mask.assign(U, 1);
   if (world <= 1) return;
-  std::vector<double> cost(U);
-  for (size_t u = 0; u < U; ++u) cost[u] = sizes[u] * sizes[u] * sizes[u] + 4.0 * 50.0 * sizes[u] * sizes[u];
-  std::vector<int> order(U);
-  for (size_t u = 0; u < U; ++u) order[u] = (int)u;
+  auto W = [](double s) { return s * s * s + 4.0 * 50.0 * s * s; };
+  std::vector<double> cost(B);
+  for (int b = 0; b < B; ++b) cost[b] = W(sizes[b]);
+  for (size_t u = B; u < U; ++u) cost[edges[2 * (u - B)]] += W(sizes[u]);
+  std::vector<int> order(B);
+  for (int b = 0; b < B; ++b) order[b] = b;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
   typedef std::pair<double, int> LR;
   std::priority_queue<LR, std::vector<LR>, std::greater<LR>> heap;
   for (int r = 0; r < world; ++r) heap.push(LR(0.0, r));
-  for (int u : order) {
+  std::vector<int> owner(B);
+  for (int b : order) {
     LR t = heap.top();
     heap.pop();
-    mask[u] = (t.second == rank) ? 1 : 0;
-    heap.push(LR(t.first + cost[u], t.second));
+    owner[b] = t.second;
+    heap.push(LR(t.first + cost[b], t.second));
   }
+  for (int b = 0; b < B; ++b) mask[b] = owner[b] == rank ? 1 : 0;
+  for (size_t u = B; u < U; ++u) mask[u] = owner[edges[2 * (u - B)]] == rank ? 1 : 0;
 }
 
 // Units from h->block_ptr_h + edges (+ mask / shard).  Uploads descriptors on `st` from pinned staging.
@@ -402,7 +439,7 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
     std::vector<double> sizes(U);
     for (int b = 0; b < B; ++b) sizes[b] = (double)(block_ptr[b + 1] - block_ptr[b]);
     for (int e = 0; e < E; ++e) sizes[B + e] = sizes[edges[2 * e]] + sizes[edges[2 * e + 1]];
-    lpt_mask(sizes, h->shard_rank, h->shard_world, h->lpt);
+    lpt_mask(sizes, B, edges, h->shard_rank, h->shard_world, h->lpt);
     mask = h->lpt.data();
   }
   h->units.assign(U, UnitDesc());
@@ -432,7 +469,9 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
     u.nt = (u.s + T - 1) / T;
     u.sp = u.nt * T;
     u.active = (!mask || mask[uix]) ? 1 : 0;
-    u.pad_ = 0;
+    u.share = 0;
+    u.p_sp = u.p_nt = 0;
+    u.p_m_off = u.p_d_off = u.p_ld_off = u.p_k_off = 0;
     if (u.active && u.s > 0) {
       const size_t sp = u.sp, nt = u.nt;
       u.m_off = off;   off += align16((sp + h->yr) * sp);
@@ -451,6 +490,34 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
   }
   std::stable_sort(h->all_list.begin(), h->all_list.end(),
                    [&](int a, int b) { return h->units[a].s > h->units[b].s; });
+  // Factor reuse (UnitDesc::share): a pair that takes the tiled schedule reads the tiles that lie
+  // entirely inside block i from block i's own unit when that unit is evaluated on this device.
+  // A fused parent is complete before the tiled launches start (launch_units); a tiled parent
+  // advances level by level in the same launches, one level ahead of every read.
+  h->any_share = false;
+  h->n_share_units = 0;
+  h->n_share_tiles = 0;
+  if (h->share_on && !h->keep_kinv) {
+    for (int e = 0; e < E; ++e) {
+      UnitDesc& u = h->units[B + e];
+      const UnitDesc& p = h->units[edges[2 * e]];
+      if (!u.active || u.s == 0 || u.nt <= h->fused_nt) continue;
+      if (!p.active || p.s == 0) continue;
+      const int m = u.ni / T;
+      if (m < 1) continue;
+      u.share = m;
+      u.p_sp = p.sp;
+      u.p_nt = p.nt;
+      u.p_m_off = p.m_off;
+      u.p_d_off = p.d_off;
+      u.p_ld_off = p.ld_off;
+      u.p_k_off = p.k_off;
+      h->any_share = true;
+      h->n_share_units++;
+      // diag + below-diagonal panel tiles + trtri tiles of the leading square, forward-solve tiles
+      h->n_share_tiles += (long long)m * (m + 1) / 2 + (long long)m * (m - 1) / 2 + (long long)m * h->nya;
+    }
+  }
 
   if (off > h->arena_cap || !h->arena) {
     CUDA_OK(cudaStreamSynchronize(st));
@@ -768,7 +835,9 @@ static int launch_units(gprf_ctx* h, const EvalParams& P, const int* list_host, 
     ntl = std::max(ntl, h->units[list_host[nlarge]].nt);
     ++nlarge;
   }
-  if (nlarge > 0) launches += launch_units_tiled(h, P, nlarge, ntl, want_grad, st);
+  // With factor reuse the blocks that take the fused kernel are parents of tiled pairs: they go first.
+  const bool fused_first = h->any_share && !P.no_share;
+  if (nlarge > 0 && !fused_first) launches += launch_units_tiled(h, P, nlarge, ntl, want_grad, st);
   const int CH = 1 << 20;
   for (int base = nlarge; base < nlist; base += CH) {
     const int cnt = std::min(CH, nlist - base);
@@ -779,6 +848,7 @@ static int launch_units(gprf_ctx* h, const EvalParams& P, const int* list_host, 
 #define CALL_FUSED(D, W) fused_launch<D, W>(Pc, h->dLLu, h->dGthU, want_grad ? 1 : 0, cnt, st)
     LAUNCH(8, DISPATCH_COV(h, CALL_FUSED));
   }
+  if (nlarge > 0 && fused_first) launches += launch_units_tiled(h, P, nlarge, ntl, want_grad, st);
   (void)ntmax;
   return launches;
 }
@@ -841,6 +911,7 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
   P.yr = h->yr;
   P.nya = h->nya;
   P.keep_kinv = h->keep_kinv ? 1 : 0;
+  P.no_share = 0;
   P.cp = cp;
   P.trace = nullptr;        // set for the fused launches only (launch_units)
   P.trace_ctas = 0;
@@ -869,6 +940,17 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
     if (!(cp.s2 + cp.nv > 0.0)) return GPRF_ERR_NONPOS_DIAG;
     info.resize(U);
     CUDA_OK(cudaMemcpy(info.data(), h->dInfo, (size_t)U * sizeof(int), cudaMemcpyDeviceToHost));
+    if (!P.no_share && h->any_share) {
+      // A pair that read its leading tiles from block i never ran their pivots: a failure of the
+      // parent inside the shared tiles is the pair's failure too (its own dpotrf would have
+      // stopped at the same pivot, gpy_linalg.py:81-83).
+      for (int e = 0; e < h->E; ++e) {
+        const UnitDesc& u = h->units[h->B + e];
+        const int pi = info[h->edges[2 * e]];
+        if (u.share > 0 && info[h->B + e] == 0 && pi != 0 && pi - 1 < u.share * T) info[h->B + e] = pi;
+      }
+    }
+    P.no_share = 1;            // retried units factor all of their own tiles
     std::vector<int> failed;
     int ntm = 0;
     for (int uix = 0; uix < U; ++uix) {

@@ -29,23 +29,36 @@ def unit_costs(block_ptr, edges):
     return s ** 3 + 4.0 * COST_DY * s ** 2
 
 
-def shard_units(block_ptr, edges, rank, world):
-    """uint8 mask over units (blocks, then edges): 1 = evaluated on ``rank``.
+def shard_owners(block_ptr, edges, world):
+    """Owner rank of every unit (blocks, then edges).
 
-    Longest-processing-time greedy on the work model; deterministic, so every
-    rank derives the same global assignment without communication.
+    The unit of assignment is a *group*: block i together with every edge (i, j) whose stacked
+    rows start with block i (gprf.py:310-330), so a pair always finds its parent block's factor
+    on its own rank (factor reuse, ``gprf_set_factor_reuse``).  Groups are placed by a
+    longest-processing-time greedy on the work model; deterministic, so every rank derives
+    the same global assignment without communication (same rule as ``lpt_mask`` in C++).
     """
     cost = unit_costs(block_ptr, edges)
-    owner = np.zeros(len(cost), dtype=np.int64)
+    B = len(block_ptr) - 1
+    e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    group = cost[:B].copy()
+    for k in range(len(e)):                       # sequential adds: same rounding as the C++ loop
+        group[e[k, 0]] += cost[B + k]
+    owner_b = np.zeros(B, dtype=np.int64)
     if world > 1:
-        order = np.argsort(-cost, kind="stable")
+        order = np.argsort(-group, kind="stable")
         heap = [(0.0, r) for r in range(world)]
         heapq.heapify(heap)
-        for u in order:
+        for b in order:
             load, r = heapq.heappop(heap)
-            owner[u] = r
-            heapq.heappush(heap, (load + cost[u], r))
-    return np.ascontiguousarray((owner == rank).astype(np.uint8))
+            owner_b[b] = r
+            heapq.heappush(heap, (load + group[b], r))
+    return np.concatenate([owner_b, owner_b[e[:, 0]]]) if len(e) else owner_b
+
+
+def shard_units(block_ptr, edges, rank, world):
+    """uint8 mask over units (blocks, then edges): 1 = evaluated on ``rank``."""
+    return np.ascontiguousarray((shard_owners(block_ptr, edges, world) == rank).astype(np.uint8))
 
 
 def pack(ll, gX, gC, n, dx):

@@ -365,6 +365,17 @@ class GPRF(object):
         """Units of up to `nt` 64-point tiles use the fused one-CTA-per-unit kernel (0: never)."""
         self._check(self._lib.gprf_set_fused_nt(self._h, int(nt)))
 
+    def set_factor_reuse(self, on=True):
+        """Pairs read block i's factor tiles instead of recomputing them (default on; bit-identical)."""
+        self._check(self._lib.gprf_set_factor_reuse(self._h, int(bool(on))))
+
+    def factor_reuse_stats(self):
+        """(pair units reusing their parent's factor, tile tasks saved) for the current structure."""
+        nu = C.c_int()
+        ntl = C.c_longlong()
+        self._check(self._lib.gprf_factor_reuse_stats(self._h, C.byref(nu), C.byref(ntl)))
+        return nu.value, ntl.value
+
     def set_profiling(self, on=True):
         self._lib.gprf_set_profiling(self._h, int(bool(on)))
 

@@ -165,6 +165,19 @@ int gprf_set_keep_kinv(gprf_handle h, int keep);
  * pipeline.  Default 8 (environment override GPRF_FUSED_NT); 0 disables fusion. */
 int gprf_set_fused_nt(gprf_handle h, int nt);
 
+/* Edge factorisations reuse block i's Cholesky factor (default on).  The pair unit
+ * of edge (i, j) stacks block i's rows first (gprf.py:310-330), so the leading
+ * floor(n_i / 64) tiles of its factor L, of U = L^-T, of the forward solve L^-1 Y and
+ * of the logdet are those of block i's own unit (gprf.py:299-308), bit for bit; a
+ * pair evaluated by the tile pipeline reads them from there and factors only the
+ * Schur complement (the tiles that involve block j).  Results are bit-identical
+ * with on = 0, where the reference's independent pdinv per unit
+ * (gpy_linalg.py:219-240) is executed literally.  Units that need jitter are
+ * re-factored on their own, as jitchol does (gpy_linalg.py:77-97).
+ * gprf_factor_reuse_stats: pair units that reuse, and tile tasks not executed. */
+int gprf_set_factor_reuse(gprf_handle h, int on);
+int gprf_factor_reuse_stats(gprf_handle h, int* n_units, long long* n_tiles);
+
 /* Optional per-kernel-family timing: when on, every launch is bracketed by CUDA
  * events on the launching stream; gprf_family_timing returns, for the last
  * evaluation, the summed device time (ms) and launch count of each family

@@ -154,6 +154,73 @@ def test_fused_and_tiled_paths_bit_identical(name):
         assert np.array_equal(res[nt][1], res[0][1]) and np.array_equal(res[nt][2], res[0][2])
 
 
+@pytest.mark.parametrize("name", sorted(COVS))
+def test_factor_reuse_bit_identical(name):
+    """Edges reuse block i's Cholesky factor (gprf_set_factor_reuse): the pair reads the tiles that
+    lie inside block i from block i's own unit and factors only the Schur complement.  Those tiles
+    are the same numbers, so the results must not change by a single bit - with the parent in
+    the tile pipeline (fused_nt 0), in the fused kernel (3: blocks fused, pairs tiled) and mixed."""
+    sizes = [200, 130, 64, 150, 70, 260, 128, 0, 63]
+    edges = [(1, 0), (2, 1), (3, 2), (5, 0), (5, 3), (4, 3), (6, 5), (6, 2), (7, 6), (8, 6), (6, 4)]
+    o, g = build_pair(name, sizes, edges)
+    kw = dict(grad_X=True, grad_cov=True)
+    want = o.llgrad(**kw)
+    for nt in (0, 2, 3, 4):
+        g.set_fused_nt(nt)
+        g.set_factor_reuse(False)
+        assert g.factor_reuse_stats() == (0, 0)
+        off = g.llgrad(**kw)
+        off_ll = g.llgrad()[0]
+        off_units = g.unit_results()[0]
+        g.set_factor_reuse(True)
+        nu, ntiles = g.factor_reuse_stats()
+        assert nu > 0 and ntiles > 0, (nt, nu, ntiles)
+        on = g.llgrad(**kw)
+        assert on[0] == off[0] and g.llgrad()[0] == off_ll, (nt, on[0], off[0])
+        assert np.array_equal(on[1], off[1]) and np.array_equal(on[2], off[2])
+        assert np.array_equal(g.unit_results()[0], off_units)
+        assert_parity(want, on, "%s fused_nt=%d" % (name, nt))
+    g.set_fused_nt(8)           # every pair fused: nothing to share
+    assert g.factor_reuse_stats() == (0, 0)
+    assert_parity(want, g.llgrad(**kw), name)
+
+
+def test_factor_reuse_with_jitter():
+    """A parent block that needs jitter (gpy_linalg.py:77-97): the pairs that read its tiles fail
+    with it and are re-factored on their own, like the reference's independent jitchol per unit."""
+    from gprf_b200 import GPRF
+    from oracle.gprf_oracle import OracleGPRF
+    cov, _ = COVS["euclid_se"]
+    rng = np.random.RandomState(11)
+    base = rng.rand(30, 2)
+    X = np.repeat(base, 8, axis=0) + 1e-9 * rng.randn(240, 2)     # 30 clusters of 8 near-duplicates
+    Y = rng.randn(240, 5)
+    # block 1 (rows 100..240) is well conditioned only if it avoids duplicates: take one per cluster
+    dup = np.arange(0, 100)                                       # 12.5 clusters: needs jitter
+    clean = np.arange(100, 240, 8)                                # one point per remaining cluster
+    X2 = np.concatenate([X, rng.rand(150, 2)])
+    Y2 = np.concatenate([Y, rng.randn(150, 5)])
+    blocks = [np.concatenate([clean, np.arange(240, 320)]), dup, np.arange(320, 390)]
+    edges = [(1, 0), (2, 1), (2, 0)]
+    s2 = cov.wfn_params[0]
+    nv = -2e-4 * s2
+    # keep the well-conditioned blocks PD under the negative nugget: spread points
+    o = OracleGPRF(X2, Y2, None, cov, nv, block_idxs=blocks, neighbors=edges)
+    g = GPRF(X2, Y2, None, prod_cov(cov), nv, block_idxs=blocks, neighbors=edges)
+    kw = dict(grad_X=True, grad_cov=True)
+    res = {}
+    for on in (False, True):
+        g.set_fused_nt(0)
+        g.set_factor_reuse(on)
+        res[on] = g.llgrad(**kw), g.unit_results()
+    (a, (la, ja)), (b, (lb, jb)) = res[False], res[True]
+    assert ja[1] > 0 and ja[3] > 0          # block 1 and the pair (1, 0), whose rows start with block 1
+    assert np.array_equal(ja, jb) and np.array_equal(la, lb)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    want = o.llgrad(**kw)
+    assert abs(b[0] - want[0]) <= 1e-6 * abs(want[0])
+
+
 def test_llgrad_nonlocal_all_pairs():
     o, g = build_pair("euclid_se", [30, 45, 20, 33], [(1, 0)])
     kw = dict(grad_X=True, grad_cov=True)

@@ -85,6 +85,9 @@ def test_shard_units_partitions_and_balances():
         assert np.array_equal(np.sum(masks, axis=0), np.ones(442))
         loads = [cost[m.astype(bool)].sum() for m in masks]
         assert max(loads) / (sum(loads) / world) < 1.05
+        # every pair sits on the rank of its parent block i (factor reuse needs it there)
+        for m in masks:
+            assert np.array_equal(m[100:], m[edges[:, 0]])
 
 
 def _gloo_worker(rank, world, port, q):
