@@ -324,6 +324,7 @@ class Runner(object):
 
 
 FUSED_NT = int(os.environ.get("GPRF_FUSED_NT", "8"))   # library default (include/gprf_b200.h)
+FUSED_MIXED_NT = int(os.environ.get("GPRF_FUSED_MIXED_NT", "4"))
 
 
 def lbfgs_full_run():
@@ -367,7 +368,11 @@ def roofline_from_profile(fam, sizes_local, dy, peak_tflops, peak_note):
     """Dominant kernel family of one evaluation.  Units of up to FUSED_NT tiles run the whole pipeline
     in k_unit_fused (algorithmic flops s^3 + 4 s^2 dy each); larger ones go through the per-family
     tile kernels, whose algorithmic flops are split as in FAMILY_FLOPS."""
-    fused = np.ceil(sizes_local / 64.0) <= FUSED_NT
+    nts = np.ceil(sizes_local / 64.0)
+    # library rule (include/gprf_b200.h, gprf_set_fused_nt): once some unit needs the tile pipeline,
+    # only units of up to min(FUSED_NT, 4) tiles stay in the fused kernel
+    thr = min(FUSED_NT, FUSED_MIXED_NT) if nts.size and nts.max() > FUSED_NT else FUSED_NT
+    fused = nts <= thr
     big = sizes_local[~fused]
     merged = {"potrf": [fam["potrf_diag"][0] + fam["potrf_panel"][0], fam["potrf_diag"][1] + fam["potrf_panel"][1]],
               "trtri": fam["trtri"], "alpha": fam["alpha"], "kinv_grad": fam["kinv_grad"],
@@ -380,7 +385,12 @@ def roofline_from_profile(fam, sizes_local, dy, peak_tflops, peak_note):
     else:
         flops = float(np.sum(FAMILY_FLOPS[name](big, dy)))
     achieved = flops / (ms * 1e-3) * 1e-12 if ms > 0 else 0.0
-    return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+    # every tile-pipeline family against the same peak (reference-algorithm flops, also with factor reuse on)
+    fam_frac = {}
+    for k in FAMILY_FLOPS:
+        if merged[k][0] > 0 and big.size:
+            fam_frac[k] = round(float(np.sum(FAMILY_FLOPS[k](big, dy))) / (merged[k][0] * 1e-3) * 1e-12 / peak_tflops, 4)
+    return {"bound": "tensor", "families_frac_of_peak": fam_frac, "kernel": name, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": achieved / peak_tflops, "traffic": None, "peak_source": peak_note,
             "launches_per_eval": nl, "ms_per_eval": ms,
             "families_ms": dict((k, round(v[0], 4)) for k, v in fam.items())}
@@ -454,6 +464,22 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
     roof = roofline_from_profile(fam, sizes_local, DY, peak, peak_note)
     roof["eval_tflops"] = flops_eval / (ms_per_step * 1e-3) * 1e-12
     roof["eval_frac_of_peak_all_gpus"] = roof["eval_tflops"] / (peak * world)
+    ar_ms = None
+    if world > 1:                        # the one collective of the path, timed alone (CUDA events)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(R.out)
+        e1.record()
+        e1.synchronize()
+        ta = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=R.dev)
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        ar_ms = ta.item()
+    roof["factor_reuse"] = dict(zip(("pair_units", "tile_tasks_saved"), R.g.factor_reuse_stats()))
+    if ar_ms is not None:
+        roof["allreduce_ms"] = ar_ms
+        roof["allreduce_bytes"] = int(R.out.numel() * 8)
     res = {"wl": wl, "reblock": R.reblock, "ms_per_step": ms_per_step, "value": 1e3 / ms_per_step, "launches": launches // steps,
            "clocks": clocks, "e2e": {"value": 1.0 / e2e_sec, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec * 1e3},

@@ -88,6 +88,12 @@ __device__ __forceinline__ long long unit_point(const UnitDesc& u, const long lo
   return p < u.ni ? perm[u.a_start + p] : perm[u.b_start + (p - u.ni)];
 }
 
+// The saved covariance tiles are written once (potrf) and read once (grad), a whole factorisation
+// apart: streaming (evict-first) accesses keep them from displacing the L / U tiles that every
+// level re-reads through L2.
+__device__ __forceinline__ void st_stream(double* p, double2 v) { __stcs(reinterpret_cast<double2*>(p), v); }
+__device__ __forceinline__ double2 ld_stream(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
+
 __device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
 
 __device__ __forceinline__ void tri_decode(int x, int& i, int& j) {
@@ -259,7 +265,7 @@ __device__ __forceinline__ void diag_tile(const EvalParams& P, int uid, const Un
           acc.c[m][n][e] = -kv;
         }
         if (rowact && n <= acc_brow(m))          // noise-free off-diagonal values are what grad re-reads
-          *reinterpret_cast<double2*>(Ks + (long long)r * ld + acc_col(n)) = make_double2(kvs[0], kvs[1]);
+          st_stream(Ks + (long long)r * ld + acc_col(n), make_double2(kvs[0], kvs[1]));
       }
     }
   };
@@ -394,7 +400,7 @@ __device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& 
           const bool act = rowact && n < nlim;
           const double c0 = (act && pin && k * T + c < u.s) ? v0 : 0.0;
           const double c1 = (act && pin && k * T + c + 1 < u.s) ? v1 : 0.0;
-          if (act) *reinterpret_cast<double2*>(Ks + (long long)r * ld + c) = make_double2(c0, c1);
+          if (act) st_stream(Ks + (long long)r * ld + c, make_double2(c0, c1));
           acc.c[m][n][0] = -c0;
           acc.c[m][n][1] = -c1;
         }
@@ -414,20 +420,24 @@ __device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& 
   acc_store(res, out, ld);
 }
 
-// grid (nlist, ntmax - k - 1 + nya): unit = blockIdx.x, task = blockIdx.y.  Look-ahead: the CTA
+// grid (nlist, ntmax - k - 1 + nya) task-major, or (ntmax - k - 1 + nya, nlist) unit-major: the
+// tasks of one unit share the B operand (row k), so unit-major order keeps it in L2 when the
+// launch is many waves long; task-major order starts every unit's long CTA first, which wins
+// when the launch is only a wave or two.  Look-ahead: the CTA
 // that produced L_{k+1,k} (task 0) goes straight on to the diagonal tile k+1 (its other operands
 // are older), so the serial 64x64 factorisation overlaps with the remaining panel tiles of this
 // launch instead of being a launch of its own with one CTA per unit (k_potrf_diag is launched
 // for k = 0 only).  Task-major grid order dispatches those long CTAs first.
 template <int DFN, int WFN>
-__global__ void __launch_bounds__(NTHREADS, 2) k_potrf_panel(EvalParams P, int k) {
-  const int uid = P.ulist[blockIdx.x];
+__global__ void __launch_bounds__(NTHREADS, 2) k_potrf_panel(EvalParams P, int k, int unit_major) {
+  const int uid = P.ulist[unit_major ? blockIdx.y : blockIdx.x];
+  const int task = unit_major ? blockIdx.x : blockIdx.y;
   const UnitDesc u = load_unit(P, uid);
   if (k >= u.nt) return;
   extern __shared__ __align__(16) double smem[];
   __shared__ TileScratch sc;
-  panel_tile<DFN, WFN>(P, u, k, blockIdx.y, smem, sc);
-  if (blockIdx.y == 0 && k + 1 < u.nt && k + 1 >= u.share) {
+  panel_tile<DFN, WFN>(P, u, k, task, smem, sc);
+  if (task == 0 && k + 1 < u.nt && k + 1 >= u.share) {
     __threadfence();
     __syncthreads();
     diag_tile<DFN, WFN>(P, uid, u, k + 1, smem, sc);
@@ -567,7 +577,7 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
     for (int nn = 0; nn < 4; ++nn)
 #pragma unroll
       for (int m = 0; m < MB; ++m)
-        ksv[nn][m] = *reinterpret_cast<const double2*>(Kst + (long long)acc_row(m) * kld + acc_col(h * 4 + nn));
+        ksv[nn][m] = ld_stream(Kst + (long long)acc_row(m) * kld + acc_col(h * 4 + nn));
   };
   load_half(0, ksvA);
   // G = Alpha_i Alpha_j^T - dy K^-1_ij, accumulated on top of the scaled K^-1 tile
@@ -759,10 +769,12 @@ __device__ __forceinline__ void finalize_unit(const EvalParams& P, int uid, cons
     // same element order; the first share*64 columns of Z^T are the parent block's
     const double* Zp = P.arena + u.p_m_off + (long long)u.p_sp * u.p_sp;
     const int csh = u.share * T;
+    int r = tid / u.sp, c = tid % u.sp;
     for (long long e = tid; e < tot; e += NTHREADS) {
-      const int r = (int)(e / u.sp), c = (int)(e % u.sp);
       double z = c < csh ? Zp[(long long)r * u.p_sp + c] : Z[e];
       q += z * z;
+      c += NTHREADS;
+      while (c >= u.sp) { c -= u.sp; ++r; }
     }
   }
   red[tid] = q;
@@ -837,8 +849,8 @@ template <int DFN, int WFN>
 __global__ void __launch_bounds__(NTHREADS, 2) k_unit_fused(EvalParams P, double* ll_u, double* gth_u,
                                                             int want_grad) {
   const int uid = P.ulist[blockIdx.x];
-  UnitDesc u = P.units[uid];
-  u.share = 0;                 // the host gives fused units share = 0 (no cross-CTA ordering here)
+  // A fused pair with share > 0 runs in a launch behind its parent block's (launch_units).
+  const UnitDesc u = load_unit(P, uid);
   extern __shared__ __align__(16) double smem[];
   __shared__ TileScratch sc;
   double* pipe = smem;
@@ -852,7 +864,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_unit_fused(EvalParams P, double
   phase_sync();
   trace_mark(P, &sc.tcur, 2);
   for (int k = 0; k < nt; ++k) {
-    diag_tile<DFN, WFN>(P, uid, u, k, pipe, sc);
+    if (k >= u.share) diag_tile<DFN, WFN>(P, uid, u, k, pipe, sc);
     phase_sync();
     trace_mark(P, &sc.tcur, 3);
     const int ntask = nt - k - 1 + P.nya;

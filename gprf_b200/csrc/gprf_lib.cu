@@ -73,9 +73,15 @@ struct gprf_ctx {
   bool keep_kinv = false;          // store K^-1 tiles (gprf_set_keep_kinv)
   bool share_on = true;            // edges reuse block i's factor tiles (gprf_set_factor_reuse)
   bool any_share = false;
+  int fused_share_min = -1;        // fused pairs reuse too once there are this many of them (-1: 8 per SM)
+  int n_fused_parents = 0;         // all_list = [tiled | fused parents of sharing pairs | other fused]
   int n_share_units = 0;
   long long n_share_tiles = 0;     // potrf/trtri/forward-solve tile tasks not executed thanks to the reuse
+  int n_sm = 148;
+  int panel_order = 0;             // 0 task-major (default: measured faster), 1 unit-major, -1 by launch size (GPRF_PANEL_ORDER)
   int fused_nt = 8;                // units of up to this many 64-point tiles take k_unit_fused
+  int fused_mixed_nt = 4;          // ... but only up to this many when larger units run the tile pipeline anyway
+  int fused_eff = 8;               // threshold in force for the current structure (rebuild_units)
   unsigned long long* dTrace = nullptr;   // debug trace of the fused kernel (gprf_debug_trace)
   size_t capTrace = 0;
 
@@ -256,6 +262,11 @@ extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, in
   CUDA_OK(cudaMemcpy(h->dY, Y, (size_t)n * dy * sizeof(double), cudaMemcpyHostToDevice));
   set_attrs();
   if (const char* e = getenv("GPRF_FUSED_NT")) h->fused_nt = atoi(e);
+  if (const char* e = getenv("GPRF_PANEL_ORDER")) h->panel_order = atoi(e);
+  if (const char* e = getenv("GPRF_FUSED_SHARE_MIN")) h->fused_share_min = atoi(e);
+  cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
+  if (const char* e = getenv("GPRF_FUSED_MIXED_NT")) h->fused_mixed_nt = atoi(e);
+  h->fused_mixed_nt = std::min(h->fused_mixed_nt, h->fused_nt);
   CUDA_OK(cudaGetLastError());
   return GPRF_OK;
 }
@@ -302,12 +313,15 @@ extern "C" int gprf_set_keep_kinv(gprf_handle h, int on) {
 extern "C" int gprf_set_fused_nt(gprf_handle h, int nt) {
   if (!h || nt < 0) return GPRF_ERR_ARG;
   h->fused_nt = nt;
+  h->fused_mixed_nt = std::min(nt, 4);
   return replan(h);
 }
 
 extern "C" int gprf_set_factor_reuse(gprf_handle h, int on) {
   if (!h) return GPRF_ERR_ARG;
   h->share_on = on != 0;
+  if (on == 2) h->fused_share_min = 1;        // fused pairs too, however few
+  else if (on == 1 && h->fused_share_min == 1) h->fused_share_min = -1;
   return replan(h);
 }
 
@@ -494,17 +508,34 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
   // entirely inside block i from block i's own unit when that unit is evaluated on this device.
   // A fused parent is complete before the tiled launches start (launch_units); a tiled parent
   // advances level by level in the same launches, one level ahead of every read.
+  // A fused unit occupies one CTA for its whole life: a handful of 5-8 tile units next to a tile
+  // pipeline that is running anyway is a ~2 ms latency-bound tail (n=200k: the 500-point blocks),
+  // while as extra tiles of the pipeline's launches they are nearly free.
+  h->fused_eff = (h->ntmax > h->fused_nt) ? std::min(h->fused_nt, h->fused_mixed_nt) : h->fused_nt;
   h->any_share = false;
   h->n_share_units = 0;
   h->n_share_tiles = 0;
+  h->n_fused_parents = 0;
   if (h->share_on && !h->keep_kinv) {
+    // Fused pairs can reuse as well, but only behind a launch of their own for the parent blocks;
+    // that extra dependent launch pays off once the pairs fill the GPU several times over.
+    const int fmin = h->fused_share_min >= 0 ? h->fused_share_min : 8 * h->n_sm;
+    auto candidate = [&](int e) {
+      const UnitDesc& u = h->units[B + e];
+      const UnitDesc& p = h->units[edges[2 * e]];
+      return u.active && u.s > 0 && p.active && p.s > 0 && u.ni / T >= 1;
+    };
+    int n_fused_cand = 0;
+    for (int e = 0; e < E; ++e)
+      if (candidate(e) && h->units[B + e].nt <= h->fused_eff) ++n_fused_cand;
+    const bool fused_share = n_fused_cand >= std::max(fmin, 1);
+    std::vector<unsigned char> is_parent(B, 0);
     for (int e = 0; e < E; ++e) {
       UnitDesc& u = h->units[B + e];
       const UnitDesc& p = h->units[edges[2 * e]];
-      if (!u.active || u.s == 0 || u.nt <= h->fused_nt) continue;
-      if (!p.active || p.s == 0) continue;
+      if (!candidate(e)) continue;
+      if (u.nt <= h->fused_eff && !fused_share) continue;
       const int m = u.ni / T;
-      if (m < 1) continue;
       u.share = m;
       u.p_sp = p.sp;
       u.p_nt = p.nt;
@@ -512,13 +543,19 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
       u.p_d_off = p.d_off;
       u.p_ld_off = p.ld_off;
       u.p_k_off = p.k_off;
+      is_parent[edges[2 * e]] = 1;
       h->any_share = true;
       h->n_share_units++;
       // diag + below-diagonal panel tiles + trtri tiles of the leading square, forward-solve tiles
       h->n_share_tiles += (long long)m * (m + 1) / 2 + (long long)m * (m - 1) / 2 + (long long)m * h->nya;
     }
+    // fused parents first among the fused units (the tiled prefix stays in front)
+    auto first_fused = std::find_if(h->all_list.begin(), h->all_list.end(),
+                                    [&](int uix) { return h->units[uix].nt <= h->fused_eff; });
+    auto mid = std::stable_partition(first_fused, h->all_list.end(),
+                                     [&](int uix) { return uix < B && is_parent[uix]; });
+    h->n_fused_parents = (int)(mid - first_fused);
   }
-
   if (off > h->arena_cap || !h->arena) {
     CUDA_OK(cudaStreamSynchronize(st));
     size_t acap = h->arena_cap;
@@ -826,29 +863,32 @@ extern "C" int gprf_get_blocks(gprf_handle h, long long* block_ptr, long long* p
 static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, int nlist, int ntmax, bool want_grad,
                               cudaStream_t st);
 
+static int launch_fused(gprf_ctx* h, const EvalParams& P, int base, int cnt, bool want_grad, cudaStream_t st) {
+  int launches = 0;
+  if (cnt <= 0) return 0;
+  EvalParams Pc = P;
+  Pc.ulist = P.ulist + base;
+  Pc.trace = h->dTrace;
+  Pc.trace_ctas = (int)(h->capTrace / (2 * TRACE_SLOTS));
+#define CALL_FUSED(D, W) fused_launch<D, W>(Pc, h->dLLu, h->dGthU, want_grad ? 1 : 0, cnt, st)
+  LAUNCH(8, DISPATCH_COV(h, CALL_FUSED));
+  return launches;
+}
+
+// `n_parents`: the fused units [nlarge, nlarge + n_parents) of the list are parents of pairs that
+// reuse their factor (main pass only): they are launched first, everything else after them.
 static int launch_units(gprf_ctx* h, const EvalParams& P, const int* list_host, int nlist, int ntmax,
-                        bool want_grad, cudaStream_t st) {
+                        bool want_grad, cudaStream_t st, int n_parents = 0) {
   int launches = 0;
   if (nlist == 0) return 0;
   int nlarge = 0, ntl = 0;
-  while (nlarge < nlist && h->units[list_host[nlarge]].nt > h->fused_nt) {
+  while (nlarge < nlist && h->units[list_host[nlarge]].nt > h->fused_eff) {
     ntl = std::max(ntl, h->units[list_host[nlarge]].nt);
     ++nlarge;
   }
-  // With factor reuse the blocks that take the fused kernel are parents of tiled pairs: they go first.
-  const bool fused_first = h->any_share && !P.no_share;
-  if (nlarge > 0 && !fused_first) launches += launch_units_tiled(h, P, nlarge, ntl, want_grad, st);
-  const int CH = 1 << 20;
-  for (int base = nlarge; base < nlist; base += CH) {
-    const int cnt = std::min(CH, nlist - base);
-    EvalParams Pc = P;
-    Pc.ulist = P.ulist + base;
-    Pc.trace = h->dTrace;
-    Pc.trace_ctas = (int)(h->capTrace / (2 * TRACE_SLOTS));
-#define CALL_FUSED(D, W) fused_launch<D, W>(Pc, h->dLLu, h->dGthU, want_grad ? 1 : 0, cnt, st)
-    LAUNCH(8, DISPATCH_COV(h, CALL_FUSED));
-  }
-  if (nlarge > 0 && fused_first) launches += launch_units_tiled(h, P, nlarge, ntl, want_grad, st);
+  launches += launch_fused(h, P, nlarge, n_parents, want_grad, st);
+  if (nlarge > 0) launches += launch_units_tiled(h, P, nlarge, ntl, want_grad, st);
+  launches += launch_fused(h, P, nlarge + n_parents, nlist - nlarge - n_parents, want_grad, st);
   (void)ntmax;
   return launches;
 }
@@ -868,7 +908,10 @@ static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, int nlist, int n
 #define CALL_DIAG(D, W) k_potrf_diag<D, W><<<dim3(1, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, k)
       if (k == 0) LAUNCH(1, DISPATCH_COV(h, CALL_DIAG));   // diag(k+1) rides in panel(k)
       const int gx = ntmax - k - 1 + h->nya;
-#define CALL_PANEL(D, W) k_potrf_panel<D, W><<<dim3(cnt, gx), NTHREADS, PIPE_BYTES, st>>>(Pc, k)
+      // unit-major once the launch is several waves long (see k_potrf_panel)
+      const int um = h->panel_order >= 0 ? h->panel_order : ((long long)cnt * gx >= 4LL * 2 * h->n_sm ? 1 : 0);
+#define CALL_PANEL(D, W) \
+  k_potrf_panel<D, W><<<um ? dim3(gx, cnt) : dim3(cnt, gx), NTHREADS, PIPE_BYTES, st>>>(Pc, k, um)
       LAUNCH(2, DISPATCH_COV(h, CALL_PANEL));
     }
     if (want_grad) {
@@ -927,7 +970,8 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
   CUDA_OK(cudaMemsetAsync(out_dev, 0, outlen * sizeof(double), st));
   const int nlist = (int)h->all_list.size();
   P.ulist = h->dListAll;
-  int launches = launch_units(h, P, h->all_list.data(), nlist, h->ntmax, want_grad, st);
+  int launches = launch_units(h, P, h->all_list.data(), nlist, h->ntmax, want_grad, st,
+                              h->any_share ? h->n_fused_parents : 0);
   P.ulist = h->dList;
   CUDA_OK(cudaGetLastError());
 

@@ -366,8 +366,9 @@ class GPRF(object):
         self._check(self._lib.gprf_set_fused_nt(self._h, int(nt)))
 
     def set_factor_reuse(self, on=True):
-        """Pairs read block i's factor tiles instead of recomputing them (default on; bit-identical)."""
-        self._check(self._lib.gprf_set_factor_reuse(self._h, int(bool(on))))
+        """Pairs read block i's factor tiles instead of recomputing them (default on; bit-identical).
+        ``on=2`` also lets fused pairs reuse when there are only a few of them (include/gprf_b200.h)."""
+        self._check(self._lib.gprf_set_factor_reuse(self._h, 2 if on == 2 else int(bool(on))))
 
     def factor_reuse_stats(self):
         """(pair units reusing their parent's factor, tile tasks saved) for the current structure."""

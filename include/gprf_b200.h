@@ -162,7 +162,10 @@ int gprf_set_keep_kinv(gprf_handle h, int keep);
 /* Scheduling knob (no effect on results beyond fp64 summation order, which is
  * identical on both paths): units of up to `nt` 64-point tiles are evaluated by
  * the fused one-CTA-per-unit kernel, larger ones by the multi-launch tile
- * pipeline.  Default 8 (environment override GPRF_FUSED_NT); 0 disables fusion. */
+ * pipeline.  Default 8 (environment override GPRF_FUSED_NT); 0 disables fusion.
+ * When some unit exceeds `nt` (so the tile pipeline runs anyway), only units of up
+ * to min(nt, 4) tiles stay fused (GPRF_FUSED_MIXED_NT): the rest ride along in the
+ * pipeline's launches instead of forming a latency-bound tail of their own. */
 int gprf_set_fused_nt(gprf_handle h, int nt);
 
 /* Edge factorisations reuse block i's Cholesky factor (default on).  The pair unit
@@ -174,6 +177,9 @@ int gprf_set_fused_nt(gprf_handle h, int nt);
  * with on = 0, where the reference's independent pdinv per unit
  * (gpy_linalg.py:219-240) is executed literally.  Units that need jitter are
  * re-factored on their own, as jitchol does (gpy_linalg.py:77-97).
+ * Pairs evaluated by the fused one-CTA-per-unit kernel reuse as well once there
+ * are at least 8 per SM of them (GPRF_FUSED_SHARE_MIN), because their parent blocks
+ * then need a launch of their own in front; on = 2 forces that for any count.
  * gprf_factor_reuse_stats: pair units that reuse, and tile tasks not executed. */
 int gprf_set_factor_reuse(gprf_handle h, int on);
 int gprf_factor_reuse_stats(gprf_handle h, int* n_units, long long* n_tiles);

@@ -180,9 +180,18 @@ def test_factor_reuse_bit_identical(name):
         assert np.array_equal(on[1], off[1]) and np.array_equal(on[2], off[2])
         assert np.array_equal(g.unit_results()[0], off_units)
         assert_parity(want, on, "%s fused_nt=%d" % (name, nt))
-    g.set_fused_nt(8)           # every pair fused: nothing to share
+    g.set_fused_nt(8)           # every pair fused: too few of them for a parents-first launch ...
     assert g.factor_reuse_stats() == (0, 0)
-    assert_parity(want, g.llgrad(**kw), name)
+    off = g.llgrad(**kw)
+    assert_parity(want, off, name)
+    g.set_factor_reuse(2)       # ... unless forced: blocks that are parents, then everything else
+    assert g.factor_reuse_stats()[0] > 0
+    on = g.llgrad(**kw)
+    assert on[0] == off[0] and np.array_equal(on[1], off[1]) and np.array_equal(on[2], off[2])
+    for nt in (2, 4):           # mixed: tiled pairs with fused parents, fused pairs with fused parents
+        g.set_fused_nt(nt)
+        on = g.llgrad(**kw)
+        assert on[0] == off[0] and np.array_equal(on[1], off[1]) and np.array_equal(on[2], off[2])
 
 
 def test_factor_reuse_with_jitter():
@@ -209,11 +218,14 @@ def test_factor_reuse_with_jitter():
     g = GPRF(X2, Y2, None, prod_cov(cov), nv, block_idxs=blocks, neighbors=edges)
     kw = dict(grad_X=True, grad_cov=True)
     res = {}
-    for on in (False, True):
-        g.set_fused_nt(0)
+    for on in (False, True, 2):
+        g.set_fused_nt(8 if on == 2 else 0)
         g.set_factor_reuse(on)
         res[on] = g.llgrad(**kw), g.unit_results()
     (a, (la, ja)), (b, (lb, jb)) = res[False], res[True]
+    (c, (lc, jc)) = res[2]
+    assert np.array_equal(ja, jc) and np.array_equal(la, lc)
+    assert a[0] == c[0] and np.array_equal(a[1], c[1]) and np.array_equal(a[2], c[2])
     assert ja[1] > 0 and ja[3] > 0          # block 1 and the pair (1, 0), whose rows start with block 1
     assert np.array_equal(ja, jb) and np.array_equal(la, lb)
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
