@@ -23,6 +23,10 @@ enum { DFN_EUCLIDEAN = 0, DFN_LLD = 1 };
 enum { WFN_SE = 0, WFN_MATERN32 = 1 };
 
 constexpr int MAX_DX = 3;
+// Coordinate record of one point as the tile kernels see it: x[0..2], 0, sin(lat), cos(lat)
+// (the last two only for dfn lld: per-point terms of the haversine formula, evaluated once per
+// point by prep instead of once per pair).
+constexpr int XD = 6;
 constexpr int MAX_NLS = 3;
 constexpr int MAX_NCOV = 5;
 
@@ -33,6 +37,7 @@ struct CovParams {
   double il3[MAX_NLS];  // 1 / l_t^3
   int dx;
   int nls;
+  int dfn;              // DFN_EUCLIDEAN / DFN_LLD (run-time copy for the untemplated kernels)
 };
 
 #define GPRF_EARTH_R 6371.0
@@ -96,22 +101,89 @@ __device__ __forceinline__ void weight_and_wr(double r2, double s2, double& w, d
   }
 }
 
+// sin and cos of x, branch free, for the bounded arguments of the great-circle distance (half
+// differences of latitudes / longitudes in radians, latitudes; |x| up to ~1e5 is safe).
+// libdevice's sincos / asin end in range-check branches and slow paths; with 16-32 pair
+// evaluations per thread back to back those serialise, and the lld kernels were bound by them
+// (cfg4: potrf_panel 7.7 ms against 1.4 ms for the transcendental-free trtri).  Cody-Waite
+// reduction by pi/2 in two parts (fdlibm's pio2_1 / pio2_1t: n * pio2_1 is exact), fdlibm's
+// __kernel_sin / __kernel_cos minimax polynomials on [-pi/4, pi/4], quadrant fix-up by selects.
+// Checked against numpy on 3e6 arguments: max error 1 ulp.
+__device__ __forceinline__ void sincos_bounded(double x, double& s, double& c) {
+  const double MAGIC = 6755399441055744.0;
+  const double kf = fma(x, 0.63661977236758134308, MAGIC);
+  const int q = __double2loint(kf);
+  const double n = kf - MAGIC;
+  double r = fma(n, -1.57079632673412561417e+00, x);
+  r = fma(n, -6.07710050650619224932e-11, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double sr = fma(r * z, ps, r);
+  const double cr = fma(z, fma(z, pc, -0.5), 1.0);
+  const bool sw = (q & 1) != 0;
+  const double s0 = sw ? cr : sr, c0 = sw ? sr : cr;
+  s = (q & 2) ? -s0 : s0;
+  c = ((q + 1) & 2) ? -c0 : c0;
+}
+
+// asin(x) for x in [0, 1], branch free: fdlibm's rational approximation R(t) = p(t)/q(t) on
+// t = x^2 (x < 1/2) or t = (1 - x)/2 with asin(x) = pi/2 - 2 asin(sqrt(t)) (x >= 1/2).
+// Max error 2 ulp against numpy on 2e6 arguments.  x > 1 gives NaN like asin.
+__device__ __forceinline__ double asin01(double x) {
+  const bool big = x >= 0.5;
+  const double t = big ? 0.5 * (1.0 - x) : x * x;
+  const double sq = big ? sqrt(t) : x;
+  double p = 3.47933107596021167570e-05;
+  p = fma(p, t, 7.91534994289814532176e-04);
+  p = fma(p, t, -4.00555345006794114027e-02);
+  p = fma(p, t, 2.01212532134862925881e-01);
+  p = fma(p, t, -3.25565818622400915405e-01);
+  p = fma(p, t, 1.66666666666666657415e-01);
+  p *= t;
+  double q = 7.70381505559019352791e-02;
+  q = fma(q, t, -6.88283971605453293030e-01);
+  q = fma(q, t, 2.02094576023350569471e+00);
+  q = fma(q, t, -2.40339491173441421878e+00);
+  q = fma(q, t, 1.0);
+  const double a = fma(sq, p / q, sq);
+  return big ? fma(-2.0, a, 1.57079632679489655800e+00) + 6.12323399573676603587e-17 : a;
+}
+
+// Per-point terms of a coordinate record (prep): rec[4] = sin(lat), rec[5] = cos(lat).
+__device__ __forceinline__ void point_terms(int dfn, double* rec) {
+  double s = 0.0, c = 0.0;
+  if (dfn == DFN_LLD) sincos_bounded(rec[1] * GPRF_DEG, s, c);
+  rec[4] = s;
+  rec[5] = c;
+}
+
 struct Haversine {
   double h, sp, cp, sl, cl, c1, c2, s1, s2;
 };
 
+// xp / xq are coordinate records (XD doubles, point_terms applied).
 __device__ __forceinline__ Haversine haversine_terms(const double* xp, const double* xq) {
   Haversine t;
-  double p1 = xp[1] * GPRF_DEG, p2 = xq[1] * GPRF_DEG;
-  sincos((p1 - p2) * 0.5, &t.sp, &t.cp);
-  sincos((xp[0] * GPRF_DEG - xq[0] * GPRF_DEG) * 0.5, &t.sl, &t.cl);
-  sincos(p1, &t.s1, &t.c1);
-  sincos(p2, &t.s2, &t.c2);
+  sincos_bounded((xp[1] * GPRF_DEG - xq[1] * GPRF_DEG) * 0.5, t.sp, t.cp);
+  sincos_bounded((xp[0] * GPRF_DEG - xq[0] * GPRF_DEG) * 0.5, t.sl, t.cl);
+  t.s1 = xp[4]; t.c1 = xp[5];
+  t.s2 = xq[4]; t.c2 = xq[5];
   t.h = t.sp * t.sp + t.c1 * t.c2 * t.sl * t.sl;
   return t;
 }
 
-// Noise-free covariance k(x_p, x_q).  xp / xq point at MAX_DX+1 doubles.
+// Noise-free covariance k(x_p, x_q).  xp / xq point at coordinate records (XD doubles).
 template <int DFN, int WFN>
 __device__ __forceinline__ double cov_value(const double* xp, const double* xq, const CovParams& cp) {
   double r2;
@@ -124,7 +196,7 @@ __device__ __forceinline__ double cov_value(const double* xp, const double* xq, 
     }
   } else {
     Haversine t = haversine_terms(xp, xq);
-    double d = 2.0 * GPRF_EARTH_R * asin(sqrt(t.h));
+    double d = 2.0 * GPRF_EARTH_R * asin01(sqrt(t.h));
     double dz = xp[2] - xq[2];
     r2 = d * d * cp.il2[0] + dz * dz * cp.il2[1];
   }
@@ -163,7 +235,7 @@ __device__ __forceinline__ void cov_grad(const double* xp, const double* xq, con
     }
   } else {
     Haversine t = haversine_terms(xp, xq);
-    double d = 2.0 * GPRF_EARTH_R * asin(sqrt(t.h));
+    double d = 2.0 * GPRF_EARTH_R * asin01(sqrt(t.h));
     double dz = xp[2] - xq[2];
     double r2 = d * d * cp.il2[0] + dz * dz * cp.il2[1];
     if (HAVE_K) {

@@ -142,8 +142,8 @@ __device__ __forceinline__ const double* dtile_u(const EvalParams& P, const Unit
 // Small static scratch shared by every tile task (one instance per CTA).  Everything
 // larger lives in the dynamic `pipe` region (PIPE_DOUBLES doubles).
 struct __align__(16) TileScratch {
-  double xa[T][4];            // coordinates of the row-tile points
-  double xb[T][4];            // coordinates of the column-tile points
+  double xa[T][XD];           // coordinates of the row-tile points
+  double xb[T][XD];           // coordinates of the column-tile points
   double scol[NW][T][3];      // grad: per-warp column sums
   double sth[NW][MAX_NCOV];   // grad: per-warp theta partials
   long long idx[T];           // prep: gathered point indices
@@ -172,9 +172,12 @@ __device__ __forceinline__ void prep_tile(const EvalParams& P, const UnitDesc& u
     long long idx = -1;
     if (p < u.s) idx = unit_point(u, P.perm, p);
     sidx[tid] = idx;
+    double rec[XD];
 #pragma unroll
-    for (int d = 0; d < MAX_DX + 1; ++d)
-      xs[(long long)p * 4 + d] = (idx >= 0 && d < P.dx) ? P.X[idx * P.dx + d] : 0.0;
+    for (int d = 0; d < MAX_DX + 1; ++d) rec[d] = (idx >= 0 && d < P.dx) ? P.X[idx * P.dx + d] : 0.0;
+    point_terms(P.cp.dfn, rec);
+#pragma unroll
+    for (int d = 0; d < XD; ++d) xs[(long long)p * XD + d] = rec[d];
   }
   __syncthreads();
   for (int a = 0; a < P.nya; ++a) {
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(NTHREADS) k_prep(EvalParams P) {
 template <int DFN, int WFN>
 __device__ __forceinline__ void diag_tile(const EvalParams& P, int uid, const UnitDesc& u, int k, double* pipe,
                                           TileScratch& sc) {
-  double (*sx)[4] = sc.xa;
+  double (*sx)[XD] = sc.xa;
   int& sfail = sc.fail;
   const int tid = threadIdx.x;
   double* M = P.arena + u.m_off;
@@ -228,7 +231,7 @@ __device__ __forceinline__ void diag_tile(const EvalParams& P, int uid, const Un
   const double* xs = P.arena + u.xs_off;
   if (tid < T) {
 #pragma unroll
-    for (int d = 0; d < 4; ++d) sx[tid][d] = xs[(long long)(k * T + tid) * 4 + d];
+    for (int d = 0; d < XD; ++d) sx[tid][d] = xs[(long long)(k * T + tid) * XD + d];
   }
   if (tid == 0) sfail = 0;
 
@@ -246,9 +249,9 @@ __device__ __forceinline__ void diag_tile(const EvalParams& P, int uid, const Un
       const int r = acc_row(m);
       const int p = k * T + r;
       const bool rowact = acc_brow(m) < e8;
-      double xr[4];
+      double xr[XD];
 #pragma unroll
-      for (int d = 0; d < 4; ++d) xr[d] = sx[r][d];
+      for (int d = 0; d < XD; ++d) xr[d] = sx[r][d];
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
         // evaluated unconditionally and masked by selects (see panel_tile)
@@ -344,17 +347,17 @@ __device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& 
     aug = true;
   }
   if (k < u.share && (aug || it < u.share)) return;     // the parent block owns this tile
-  double (*sxr)[4] = sc.xa;
-  double (*sxc)[4] = sc.xb;
+  double (*sxr)[XD] = sc.xa;
+  double (*sxc)[XD] = sc.xb;
   const int tid = threadIdx.x;
   double* M = P.arena + u.m_off;
   const long long ld = u.sp;
   if (!aug && tid < T) {
     const double* xs = P.arena + u.xs_off;
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      sxr[tid][d] = xs[(long long)(it * T + tid) * 4 + d];
-      sxc[tid][d] = xs[(long long)(k * T + tid) * 4 + d];
+    for (int d = 0; d < XD; ++d) {
+      sxr[tid][d] = xs[(long long)(it * T + tid) * XD + d];
+      sxc[tid][d] = xs[(long long)(k * T + tid) * XD + d];
     }
   }
   Acc acc;
@@ -389,9 +392,9 @@ __device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& 
         const int r = acc_row(m);
         const bool rowact = acc_brow(m) < mlim;
         const bool pin = it * T + r < u.s;
-        double xr[4];
+        double xr[XD];
 #pragma unroll
-        for (int d = 0; d < 4; ++d) xr[d] = sxr[r][d];
+        for (int d = 0; d < XD; ++d) xr[d] = sxr[r][d];
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
           const int c = acc_col(n);
@@ -522,8 +525,8 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
   if (x >= tri(u.nt)) return;
   int i, j;
   tri_decode(x, i, j);
-  double (*sxi)[4] = sc.xa;
-  double (*sxj)[4] = sc.xb;
+  double (*sxi)[XD] = sc.xa;
+  double (*sxj)[XD] = sc.xb;
   double (*scol)[T][3] = sc.scol;
   double (*sth)[MAX_NCOV] = sc.sth;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -532,9 +535,9 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
   if (tid < T) {
     const double* xs = P.arena + u.xs_off;
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      sxi[tid][d] = xs[(long long)(i * T + tid) * 4 + d];
-      sxj[tid][d] = xs[(long long)(j * T + tid) * 4 + d];
+    for (int d = 0; d < XD; ++d) {
+      sxi[tid][d] = xs[(long long)(i * T + tid) * XD + d];
+      sxj[tid][d] = xs[(long long)(j * T + tid) * XD + d];
     }
   }
   Acc acc;
@@ -989,11 +992,13 @@ __global__ void k_kernel_matrix(const double* X1, long long n1, const double* X2
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot;
        e += (long long)gridDim.x * blockDim.x) {
     const long long p = e / n2, q = e % n2;
-    double xp[4] = {0, 0, 0, 0}, xq[4] = {0, 0, 0, 0};
+    double xp[XD] = {0, 0, 0, 0, 0, 0}, xq[XD] = {0, 0, 0, 0, 0, 0};
     for (int d = 0; d < dx; ++d) {
       xp[d] = X1[p * dx + d];
       xq[d] = X2[q * dx + d];
     }
+    point_terms(DFN, xp);
+    point_terms(DFN, xq);
     double kv = cov_value<DFN, WFN>(xp, xq, cp);
     if (add_noise && p == q) kv += cp.nv;
     K[e] = kv;
@@ -1014,11 +1019,13 @@ __global__ void k_block_maxk(const double* X, int dx, const long long* perm, con
   double best = -1.0;   // np.max over an empty block pair is never taken (reference would raise)
   for (long long e = threadIdx.x; e < ni * nj; e += blockDim.x) {
     const long long p = perm[ai + e / nj], q = perm[aj + e % nj];
-    double xp[4] = {0, 0, 0, 0}, xq[4] = {0, 0, 0, 0};
+    double xp[XD] = {0, 0, 0, 0, 0, 0}, xq[XD] = {0, 0, 0, 0, 0, 0};
     for (int d = 0; d < dx; ++d) {
       xp[d] = X[p * dx + d];
       xq[d] = X[q * dx + d];
     }
+    point_terms(DFN, xp);
+    point_terms(DFN, xq);
     double kv = fabs(cov_value<DFN, WFN>(xp, xq, cp)) / cp.s2;
     best = fmax(best, kv);
   }

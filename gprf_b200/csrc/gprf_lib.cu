@@ -166,6 +166,7 @@ static int make_cov(const gprf_ctx* h, const double* theta, int ncov, CovParams*
   cp->s2 = theta[1];
   cp->dx = h->dx;
   cp->nls = h->nls;
+  cp->dfn = h->dfn;
   for (int t = 0; t < MAX_NLS; ++t) {
     if (t < h->nls) {
       double l = theta[2 + t];
@@ -491,7 +492,7 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
       u.m_off = off;   off += align16((sp + h->yr) * sp);
       u.d_off = off;   off += align16(2 * nt * T * T);
       u.al_off = off;  off += align16(sp * h->yr);
-      u.xs_off = off;  off += align16(sp * 4);
+      u.xs_off = off;  off += align16(sp * XD);
       u.part_off = off; off += align16((nt * (nt + 1) / 2) * PART_STRIDE);
       u.ld_off = off;  off += align16(nt);
       u.gx_off = off;  off += align16(sp * 3);

@@ -14,7 +14,13 @@ out = torch.zeros(1 + 5 + n * dx, dtype=torch.float64, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for world in worlds:
     g = GPRF(wl["X"], wl["Y"], wl["block_fn"], wl["cov"], wl["noise_var"], block_idxs=wl["block_idxs"],
-             neighbors=wl["neighbors"], device=0, unit_shard=(0, world) if world > 1 else None)
+             neighbors=wl["neighbors"], device=0, neighbor_threshold=wl.get("threshold", 1e-3),
+             unit_shard=(0, world) if world > 1 else None)
+    if wl["neighbors"] is None:
+        wl["neighbors"] = list(g.neighbors)
+    if os.environ.get("REUSE"):
+        g.set_factor_reuse(int(os.environ["REUSE"]))
+    print("blocks %d edges %d reuse %s" % (g.n_blocks, len(g.neighbors), g.factor_reuse_stats()), flush=True)
     ts = []
     for it in range(5):
         if it == 3:
