@@ -530,6 +530,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version
+    # banner, nvcc, library chatter) is sent to stderr for the rest of the run
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -573,7 +579,8 @@ def main():
                          "ms_per_step": r5["ms_per_step"], "steps": k5, "e2e": r5["e2e"], "roofline": r5["roofline"],
                          "clocks": r5["clocks"], "scaling": "strong"}
     if rank == 0:
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
