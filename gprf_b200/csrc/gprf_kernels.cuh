@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(NTHREADS) k_unit_finalize(EvalParams P, double
 // Dependent phases are separated by __threadfence() + __syncthreads() (operands are
 // re-read through L2 by cp.async.cg), independent tasks by __syncthreads() only.
 // ---------------------------------------------------------------------------
-constexpr size_t FUSED_SMEM_BYTES = PIPE_DOUBLES * sizeof(double);
+constexpr size_t FUSED_SMEM_BYTES = PIPE_ALLOC_DOUBLES * sizeof(double);
 
 __device__ __forceinline__ void phase_sync() {
   __threadfence();

@@ -180,7 +180,7 @@ static int make_cov(const gprf_ctx* h, const double* theta, int ncov, CovParams*
   return GPRF_OK;
 }
 
-static const size_t PIPE_BYTES = PIPE_DOUBLES * sizeof(double);
+static const size_t PIPE_BYTES = PIPE_ALLOC_DOUBLES * sizeof(double);
 
 // k_unit_fused is instantiated in its own translation units (gprf_fused.cu, one per covariance
 // family, compiled in parallel by build.sh); these are their host-side launchers.

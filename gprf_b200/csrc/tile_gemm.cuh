@@ -56,6 +56,19 @@ constexpr int MB = NB8 / NW;     // block rows per warp
 constexpr int NTHREADS = NW * 32;
 constexpr int STAGE_DOUBLES = T * SLD;               // one operand, one stage
 constexpr int PIPE_DOUBLES = 4 * STAGE_DOUBLES;      // A,B x 2 stages
+// Operand staging.  0 (default): per-thread 16-byte cp.async (LDGSTS), double buffered.
+// 1 (-DGPRF_TMA=1): TMA bulk copies (cp.async.bulk, SASS UBLKCP) issued by one warp, one
+// 256-byte row per copy into the padded stage rows, completion signalled on an mbarrier per
+// stage (complete_tx) that every warp waits on, one __syncthreads per chunk instead of two.
+// Correct (all GPU parity tests pass) but measured SLOWER on B200: the row-major working
+// matrices allow only 256-byte copies (128 per stage), and at that granularity the copy
+// engine's per-operation cost dominates - n=200k 8-rank shard 11.6 -> 19.8 ms/eval, README
+// config 0.92 -> 1.28 ms.  TMA would need the tiles stored in HBM as contiguous stage images
+// (one 20 KB copy per operand chunk); see DESIGN.md section 5.
+#ifndef GPRF_TMA
+#define GPRF_TMA 0
+#endif
+constexpr int PIPE_ALLOC_DOUBLES = PIPE_DOUBLES + 8; // + 3 mbarriers (stage 0, stage 1, tail tile)
 constexpr int WLD = T + 8;       // stride of a fully staged 64x64 operand (72)
 constexpr int SQLD = T + 1;      // stride of the scalar potf2 scratch tile
 
@@ -94,6 +107,35 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;\n" ::"r"(count), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;\n" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // One source tile of a product and its block mask.
@@ -201,6 +243,26 @@ struct NoHook {
   __device__ __forceinline__ void operator()() const {}
 };
 
+#if GPRF_TMA
+// Producer side (warp 0 only): one stage = the first arows / brows rows of an A and a B chunk.
+__device__ __forceinline__ void tma_issue_chunk(double* dst, const double* pa, long long lda, const double* pb,
+                                                long long ldb, int arows, int brows, uint64_t* bar) {
+  const int lane = threadIdx.x;
+  if (lane == 0) mbar_expect_tx(bar, (uint32_t)(arows + brows) * (KC * 8));
+  __syncwarp();
+  for (int r = lane; r < arows; r += 32) bulk_g2s(dst + r * SLD, pa + (long long)r * lda, KC * 8, bar);
+  double* dB = dst + STAGE_DOUBLES;
+  for (int r = lane; r < brows; r += 32) bulk_g2s(dB + r * SLD, pb + (long long)r * ldb, KC * 8, bar);
+}
+// full 64x64 row-major tile -> stride WLD
+__device__ __forceinline__ void tma_issue_full(double* dst, const double* src, long long ld, uint64_t* bar) {
+  const int lane = threadIdx.x;
+  if (lane == 0) mbar_expect_tx(bar, (uint32_t)(T * T * 8));
+  __syncwarp();
+  for (int r = lane; r < T; r += 32) bulk_g2s(dst + r * WLD, src + (long long)r * ld, T * 8, bar);
+}
+#endif
+
 // acc += sum_{j=0}^{nk-1} A_j * B_j^T.  tileA(j) / tileB(j) return TileRefs (klim is taken
 // from A's ref and must agree with B's).  `pipe` = PIPE_DOUBLES of smem.
 // Ends with a __syncthreads(): `pipe` may be reused by the caller afterwards.
@@ -213,6 +275,72 @@ struct NoHook {
 //   tailW      a full 64x64 row-major tile (leading dimension tail_ld) fetched into the idle
 //              stage buffer while the last chunk is multiplied; the function returns its
 //              address in shared memory (stride WLD), ready to use.
+#if GPRF_TMA
+template <bool CLOW, class FA, class FB, class Hook = NoHook>
+__device__ __forceinline__ const double* gemm_nt(Acc& acc, int nk, FA tileA, FB tileB, int mlim, int nlim,
+                                                 double* pipe, Hook overlap = Hook(),
+                                                 const double* tailW = nullptr, long long tail_ld = T) {
+  constexpr int CPT = T / KC;        // chunks per tile
+  constexpr int BPC = KC / 8;        // 8-blocks per chunk
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pipe + PIPE_DOUBLES);
+  const bool prod = threadIdx.x < 32;          // warp 0 issues the bulk copies
+  // Arm the barriers for this product: every phase of an earlier product has completed (all of
+  // its copies were waited for), so the objects are simply re-initialised and parities restart
+  // at 0.  The __syncthreads also orders everyone's generic accesses to `pipe` before the
+  // async-proxy writes that follow.
+  if (threadIdx.x == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    mbar_init(bars + 2, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (prod) fence_proxy_async();
+  if (nk <= 0 || mlim <= 0 || nlim <= 0) {
+    if (tailW && prod) tma_issue_full(pipe, tailW, tail_ld, bars + 2);
+    overlap();
+    if (tailW) {
+      mbar_wait(bars + 2, 0);
+      __syncthreads();
+    }
+    return pipe;
+  }
+  const int arows = mlim * 8, brows = nlim * 8;
+  int j = 0, h = 0;
+  TileRef a = tileA(0), b = tileB(0);
+  if (prod) tma_issue_chunk(pipe, a.p, a.ld, b.p, b.ld, arows, brows, bars + 0);
+  overlap();
+  int cur = 0;
+  uint32_t par0 = 0, par1 = 0;
+  const double* wsm = pipe;
+  while (true) {
+    int jn = j, hn = h + 1;
+    if (hn == CPT || hn * BPC >= a.klim) { hn = 0; ++jn; }
+    const bool more = jn < nk;
+    TileRef an = a, bn = b;
+    if (more) {
+      if (jn != j) { an = tileA(jn); bn = tileB(jn); }
+      if (prod)
+        tma_issue_chunk(pipe + (cur ^ 1) * 2 * STAGE_DOUBLES, an.p + hn * KC, an.ld, bn.p + hn * KC, bn.ld, arows,
+                        brows, bars + (cur ^ 1));
+    } else if (tailW) {
+      double* nxt = pipe + (cur ^ 1) * 2 * STAGE_DOUBLES;
+      if (prod) tma_issue_full(nxt, tailW, tail_ld, bars + 2);
+      wsm = nxt;
+    }
+    if (cur) { mbar_wait(bars + 1, par1); par1 ^= 1; }
+    else { mbar_wait(bars + 0, par0); par0 ^= 1; }
+    const double* cs = pipe + cur * 2 * STAGE_DOUBLES;
+    mma_chunk<CLOW>(acc, cs, cs + STAGE_DOUBLES, h * BPC, mlim, nlim, a.klim, a.atri, b.btri);
+    if (!more && tailW) mbar_wait(bars + 2, 0);
+    __syncthreads();                 // stage `cur` is free again (next-but-one issue overwrites it)
+    if (!more) break;
+    j = jn; h = hn; a = an; b = bn;
+    cur ^= 1;
+  }
+  return wsm;
+}
+#else
 template <bool CLOW, class FA, class FB, class Hook = NoHook>
 __device__ __forceinline__ const double* gemm_nt(Acc& acc, int nk, FA tileA, FB tileB, int mlim, int nlim,
                                                  double* pipe, Hook overlap = Hook(),
@@ -272,6 +400,8 @@ __device__ __forceinline__ const double* gemm_nt(Acc& acc, int nk, FA tileA, FB 
   }
   return wsm;
 }
+
+#endif  // GPRF_TMA
 
 // Stage a full 64x64 row-major operand (ld) into smem with stride WLD (T * WLD doubles, which
 // fit in one pipeline stage: static_assert below).  _async: issue + commit only.
