@@ -486,6 +486,15 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
     else:
         sizes_local = sizes
     roof = roofline_from_profile(fam, sizes_local, DY, peak, peak_note)
+    try:        # DRAM bytes of the dominant kernel's launch, recorded from an ncu --set full capture (1 GPU)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f).get(wl_name, {}).get(roof["kernel"])
+        if ent and world == 1:
+            roof["traffic"] = ent["bytes"]
+            roof["traffic_unit"] = "bytes per launch (dram read + write)"
+            roof["traffic_source"] = ent["source"]
+    except (IOError, OSError, ValueError):
+        pass
     roof["eval_tflops"] = flops_eval / (ms_per_step * 1e-3) * 1e-12
     roof["eval_frac_of_peak_all_gpus"] = roof["eval_tflops"] / (peak * world)
     ar_ms = None
