@@ -411,6 +411,89 @@ class GPRF(object):
         return self.gaussian_llgrad(np.vstack([self.X[ii], self.X[jj]]),
                                     np.vstack([self.Y[ii], self.Y[jj]]), **kwargs)
 
+    # -- prediction (gprf.py:593-672) ---------------------------------------------
+    def block_precisions(self, Y=None):
+        """Per block: (K_b + nv I)^-1 and Alpha_b = K_b^-1 Y_b, computed by the device pipeline
+        (a local-GP evaluation with the K^-1 tiles kept: jitchol -> triangular inverse -> U U^T,
+        the dpotri route of gpy_linalg.py:219-240) and read back once."""
+        Yc = self.Y if Y is None else Y
+        blocks = self.block_idxs
+        sub = GPRF(np.ascontiguousarray(self.X, dtype=np.float64), np.ascontiguousarray(Yc, dtype=np.float64), None,
+                   self.cov, self.noise_var, block_idxs=blocks, neighbors=[], device=self.device)
+        try:
+            sub.set_keep_kinv(True)
+            sub.llgrad(grad_X=True)
+            Kinvs, Alphas = [], []
+            dy = sub._Yc.shape[1]
+            for b, idx in enumerate(blocks):
+                s = len(idx)
+                if s == 0:
+                    Kinvs.append(np.zeros((0, 0)))
+                    Alphas.append(np.zeros((0, dy)))
+                    continue
+                sz, sp, yr = C.c_int(), C.c_int(), C.c_int()
+                sub._check(sub._lib.gprf_debug_unit(sub._h, b, C.byref(sz), C.byref(sp), C.byref(yr), None, None, None))
+                M = np.empty((sp.value + yr.value, sp.value))
+                Al = np.empty((sp.value, yr.value))
+                sub._check(sub._lib.gprf_debug_unit(sub._h, b, None, None, None, _lib.ptr(M), _lib.ptr(Al), None))
+                L = np.tril(M[:s, :s])
+                Kinvs.append(L + np.tril(L, -1).T)
+                Alphas.append(np.array(Al[:s, :dy]))
+        finally:
+            sub.close()
+        return Kinvs, Alphas
+
+    def train_predictor(self, test_cov=None, Y=None):
+        """gprf.py:593-672: returns ``predict(Xstar, test_noise_var=0.0, local=False) -> (mean, cov)``,
+        the Bayesian-committee fusion of the GP predictions of the test points' block and its
+        neighbour blocks.  The O(b^3) part (per-block inverses and Alpha) runs on the GPU; the
+        fusion itself is a handful of ntest x ntest host operations per source block, with the
+        cross-covariances evaluated by the device kernel-matrix entry (gprf_kernel_matrix)."""
+        Yc = self.Y if Y is None else Y
+        block_Kinvs, block_Alphas = self.block_precisions(Y)
+        if test_cov is None:
+            kern_gp, own = self, False
+        else:                                   # the reference builds a dummy VectorTree for test_cov (:602-605)
+            dummy = np.zeros((1, np.asarray(self.X).shape[1]))
+            kern_gp = GPRF(dummy, np.zeros((1, 1)), None, test_cov, 0.0, block_idxs=[np.arange(1)], neighbors=[],
+                           device=self.device)
+            own = True
+        gp = self
+        dy = np.asarray(Yc).shape[1]
+
+        def kernel_fn(A, B):
+            return kern_gp.kernel(A, B)         # X2 given: cross kernel without noise (gprf.py:341-342)
+
+        def predict(Xstar, test_noise_var=0.0, local=False):
+            Xstar = np.ascontiguousarray(Xstar, dtype=np.float64)
+            prior_cov = kernel_fn(Xstar, Xstar) + np.eye(Xstar.shape[0]) * test_noise_var
+            prior_prec = np.linalg.inv(prior_cov)
+            prior_mean = np.zeros((Xstar.shape[0], dy))
+            source_blocks = set()
+            for i, idxs in enumerate(gp.block_fn(Xstar)):
+                if len(idxs) == 0:
+                    continue
+                source_blocks.add(i)
+                for j in gp.neighbor_dict[i]:
+                    source_blocks.add(j)
+            blocks = gp.block_idxs
+            Xall = np.asarray(gp.X)
+            for i in sorted(source_blocks):
+                Kstar = kernel_fn(Xstar, Xall[blocks[i]])
+                Kss = kernel_fn(Xstar, Xstar)
+                if test_noise_var > 0:
+                    Kss = Kss + np.eye(Kss.shape[0]) * gp.noise_var       # gprf.py:653-655
+                mean = np.dot(Kstar, block_Alphas[i])
+                cov = Kss - np.dot(Kstar, np.dot(block_Kinvs[i], Kstar.T))
+                prec = np.linalg.inv(cov)
+                prior_mean += np.dot(prec, mean)
+                prior_prec += prec - np.linalg.inv(Kss)
+            final_cov = np.linalg.inv(prior_prec)
+            return np.dot(final_cov, prior_mean), final_cov
+
+        predict._kernel_owner = kern_gp if own else None     # keeps the helper handle alive
+        return predict
+
     # -- kernel wrappers (gprf.py:333-375) --------------------------------------
     def kernel(self, X, X2=None):
         X1 = np.ascontiguousarray(X, dtype=np.float64)

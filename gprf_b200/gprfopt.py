@@ -7,8 +7,9 @@ Mirrors the reference's experiment driver for the GPRF objective (SURVEY.md sect
                                          update_X / update_covs -> llgrad -> + x_prior / cov_prior,
                                          log-theta chain rule, ``log.txt`` and ``step_%05d_X.npy``
   analyze_run       gprfopt.py:453-515   ``results.txt``: step time ll lscale_ratio mad xprior ... and
-                                         the final ``trueX`` line (prediction columns are written as 0,
-                                         exactly what the reference writes without --analyze_full)
+                                         the final ``trueX`` line; prediction columns (SMSE / MSLL of
+                                         gprfopt.py:121-170 through GPRF.train_predictor) with
+                                         predict=True, else 0 as without --analyze_full
   do_run            gprfopt.py:525-580   task = x | cov | xcov initialisation
   build_run_name    gprfopt.py:583-597   directory naming of a run
 
@@ -134,10 +135,22 @@ def mean_distance(sdata, x):
     return float(np.mean(np.linalg.norm(x.reshape(sdata.SX.shape) - sdata.SX, axis=1)))
 
 
-def analyze_run(d, sdata, local_dist=1.0, build_gprf=None):
-    """gprfopt.py:453-515 without --analyze_full (prediction columns are 0).  Returns the rows."""
+def analyze_run(d, sdata, local_dist=1.0, build_gprf=None, predict=False, predict_kwargs=None):
+    """gprfopt.py:453-515.  ``predict`` (the reference's --analyze_full) fills the six prediction
+    columns smse_local smse msll_local_block msll_block msll_local_diag msll_diag through
+    ``sdata.prediction_error`` (gprfopt.py:121-170); without it they are 0 as in the shipped logs.
+    Returns the rows."""
     steps, times, lls = load_log(d)
     rows = []
+    pk = predict_kwargs or {}
+
+    def pred_cols(X, FC):
+        if not predict:
+            return (0., 0., 0., 0., 0., 0.)
+        sl, bl, dl = sdata.prediction_error(X=X, cov=FC, local_dist=1.0, **pk)
+        s, b, dg = sdata.prediction_error(X=X, cov=FC, local_dist=local_dist, **pk) if local_dist < 1.0 else (sl, bl, dl)
+        return (sl, s, bl, b, dl, dg)
+
     with open(os.path.join(d, "results.txt"), "w") as res:
         for i, step in enumerate(steps):
             try:
@@ -151,9 +164,10 @@ def analyze_run(d, sdata, local_dist=1.0, build_gprf=None):
             mad = mean_distance(sdata, X.flatten())
             c1 = FC[0, 2] / sdata.cov.dfn_params[0] if FC is not None else 0.0      # lscale_error, :90-93
             xp = sdata.x_prior(X.flatten())[0]
-            rows.append((int(step), times[i], lls[i], c1, mad, xp))
+            pc = pred_cols(X, FC)
+            rows.append((int(step), times[i], lls[i], c1, mad, xp) + (pc if predict else ()))
             res.write("%d %.2f %.2f %.8f %.8f %.8f %.4f %.4f %.4f %.4f %.4f %.4f\n"
-                      % (step, times[i], lls[i], c1, mad, xp, 0., 0., 0., 0., 0., 0.))
+                      % ((step, times[i], lls[i], c1, mad, xp) + pc))
         ll1 = -np.inf
         if build_gprf is not None:
             g = build_gprf(X=sdata.SX, local_dist=local_dist)
@@ -163,7 +177,7 @@ def analyze_run(d, sdata, local_dist=1.0, build_gprf=None):
             except Exception:      # the reference swallows any failure here (gprfopt.py:507-511)
                 pass
         res.write("trueX inf %.2f %.4f %.4f %.4f %.4f %.4f %.4f %.4f %.4f %.4f\n"
-                  % (ll1, 0.0, 0.0, sdata.x_prior(sdata.SX.flatten())[0], 0., 0., 0., 0., 0., 0.))
+                  % ((ll1, 0.0, 0.0, sdata.x_prior(sdata.SX.flatten())[0]) + pred_cols(sdata.SX, None)))
     return rows
 
 

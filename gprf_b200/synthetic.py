@@ -81,6 +81,44 @@ class SampledData(object):
         return cls(X, self.SY, self.reblock, cov, noise_var, neighbor_threshold=local_dist,
                    block_idxs=self.block_idxs, neighbors=self.neighbors if local_dist < 1.0 else [], **extra)
 
+
+    def prediction_error(self, X=None, cov=None, local_dist=1.0, cls=GPRF, **extra):
+        """gprfopt.py:121-170: (smse, msll_block, msll_block_diag) of the BCM predictions on the
+        held-out points, block by block of the test set."""
+        import scipy.stats
+        gprf = self.build_gprf(X=X, cov=cov, local_dist=local_dist, cls=cls, **extra)
+        p = gprf.train_predictor()
+        test_blocks = self.reblock(self.Xtest)
+
+        def gaussian_ll(Y, M, Cm):
+            ntest, yd = Y.shape
+            P = np.linalg.inv(Cm)
+            R = Y - M
+            ll = -.5 * np.sum(P * np.dot(R, R.T))
+            ll -= .5 * yd * np.linalg.slogdet(Cm)[1]
+            ll -= .5 * yd * ntest * np.log(2 * np.pi)
+            return ll
+
+        ll_block = ll_block_diag = se_block = 0.0
+        for idxs in test_blocks:
+            if len(idxs) == 0:              # (the reference would invert a 0x0 matrix here: harmless no-op)
+                continue
+            Xt, Yt = self.Xtest[idxs], self.Ytest[idxs]
+            PM, PC = p(Xt, test_noise_var=self.noise_var)
+            ll_block += gaussian_ll(Yt, PM, PC)
+            ll_block_diag += gaussian_ll(Yt, PM, np.diag(np.diag(PC)))
+            se_block += np.sum((Yt - PM) ** 2)
+        ntest, yd = self.Ytest.shape
+        Ymean = np.mean(self.SY, axis=0)
+        smse = se_block / np.sum((self.Ytest - Ymean) ** 2)
+        Ystd = np.std(self.SY, axis=0)
+        ll_baseline = np.sum([np.sum(scipy.stats.norm(loc=Ymean[i], scale=Ystd[i]).logpdf(self.Ytest[:, i]))
+                              for i in range(yd)])
+        mll_baseline = ll_baseline / (ntest * yd)
+        if hasattr(gprf, "close"):
+            gprf.close()
+        return smse, ll_block / (ntest * yd) - mll_baseline, ll_block_diag / (ntest * yd) - mll_baseline
+
     def x_prior(self, xx):
         resid = xx - self.X_obs.ravel()
         ll = -.5 * np.sum((resid / self.obs_std) ** 2) - .5 * len(xx) * np.log(2 * np.pi * self.obs_std ** 2)

@@ -65,6 +65,37 @@ class SampledData(object):
                    neighbor_threshold=local_dist, block_idxs=self.block_idxs,
                    neighbors=self.neighbors if local_dist < 1.0 else [], **extra)
 
+    def prediction_error(self, X=None, cov=None, local_dist=1.0):
+        """gprfopt.py:121-170 restated: (smse, msll_block, msll_block_diag)."""
+        import scipy.stats
+        assert cov is None, "the oracle restatement covers the task=x use (cov fixed at its true value)"
+        gprf = self.build_gprf(X=X, local_dist=local_dist)
+        p = gprf.train_predictor()
+        test_blocks = self.reblock(self.Xtest)
+
+        def gaussian_ll(Y, M, Cm):
+            ntest, yd = Y.shape
+            R = Y - M
+            ll = -.5 * np.sum(np.linalg.inv(Cm) * np.dot(R, R.T))
+            ll -= .5 * yd * np.linalg.slogdet(Cm)[1]
+            return ll - .5 * yd * ntest * np.log(2 * np.pi)
+
+        ll_block = ll_block_diag = se_block = 0.0
+        for idxs in test_blocks:
+            if len(idxs) == 0:
+                continue
+            Xt, Yt = self.Xtest[idxs], self.Ytest[idxs]
+            PM, PC = p(Xt, test_noise_var=self.noise_var)
+            ll_block += gaussian_ll(Yt, PM, PC)
+            ll_block_diag += gaussian_ll(Yt, PM, np.diag(np.diag(PC)))
+            se_block += np.sum((Yt - PM) ** 2)
+        ntest, yd = self.Ytest.shape
+        Ymean, Ystd = np.mean(self.SY, axis=0), np.std(self.SY, axis=0)
+        smse = se_block / np.sum((self.Ytest - Ymean) ** 2)
+        mll_baseline = sum(np.sum(scipy.stats.norm(loc=Ymean[i], scale=Ystd[i]).logpdf(self.Ytest[:, i]))
+                           for i in range(yd)) / (ntest * yd)
+        return smse, ll_block / (ntest * yd) - mll_baseline, ll_block_diag / (ntest * yd) - mll_baseline
+
     def x_prior(self, xx):
         flat = self.X_obs.flatten()
         r = (xx - flat) / self.obs_std
