@@ -47,8 +47,14 @@ struct UnitDesc {
   // (p_*), and factors only the tiles that involve block j.  share = 0: self-contained unit.
   int share;
   int p_sp, p_nt;
-  long long m_off, d_off, al_off, xs_off, part_off, ld_off, gx_off, k_off;
-  long long p_m_off, p_d_off, p_ld_off, p_k_off;
+  // The same holds for the leading partial sums of the two U-products: with the contraction
+  // index m ascending, sum_{m < share} U_im U_jm^T (tiles i, j < share) and sum_{m < share} U_im Z_m
+  // are the first terms of block i's own K^-1_ij / Alpha_i.  A parent with pstore > 0 stores those
+  // partial accumulators (kp_off: sp x sp, ap_off: sp x yr) when its contraction passes m = pstore;
+  // its pairs start from them instead of from zero (p_kp_off / p_ap_off).
+  int pstore, pad_;
+  long long m_off, d_off, al_off, xs_off, part_off, ld_off, gx_off, k_off, kp_off, ap_off;
+  long long p_m_off, p_d_off, p_ld_off, p_k_off, p_kp_off, p_ap_off;
   double weight;
 };
 
@@ -486,16 +492,37 @@ __device__ __forceinline__ void alpha_tile(const EvalParams& P, const UnitDesc& 
   const int j = u.nt + a;
   const double* Udi = dtile_u(P, u, i);
   Acc acc;
-  acc_zero(acc);
   const int mlim = ext8(u.s, i);
   const int nlim = min(NB8, (P.dy - a * T + 7) >> 3);
-  // contraction over point tiles m = i + jj; U_ii is upper triangular
+  // contraction over point tiles m = i + jj (ascending); U_ii is upper triangular.
+  // jj0: terms already contained in the parent's stored partial sum (UnitDesc::pstore).
+  const int jj0 = i < u.share ? u.share - i : 0;
   auto tA = [&](int jj) {
     const int kl = ext8(u.s, i + jj);
     return jj == 0 ? tile_ref(Udi, T, kl, 1, 0) : mtile(P, u, i, i + jj, kl);
   };
   auto tB = [&](int jj) { return mtile(P, u, j, i + jj, ext8(u.s, i + jj)); };
-  gemm_nt<false>(acc, u.nt - i, tA, tB, mlim, nlim, pipe);
+  if (jj0 > 0) {
+    const double* src = P.arena + u.p_ap_off + (long long)i * T * P.yr + (long long)a * T;
+    auto tA0 = [&](int jj) { return tA(jj + jj0); };
+    auto tB0 = [&](int jj) { return tB(jj + jj0); };
+    auto init = [&]() { acc_load(acc, src, P.yr); };
+    gemm_nt<false>(acc, u.nt - i - jj0, tA0, tB0, mlim, nlim, pipe, init);
+  } else if (i < u.pstore && u.pstore < u.nt) {
+    // parent: stop at m = pstore, store the partial sum for the pairs, go on
+    acc_zero(acc);
+    const int n1 = u.pstore - i;
+    gemm_nt<false>(acc, n1, tA, tB, mlim, nlim, pipe);
+    acc_store(acc, P.arena + u.ap_off + (long long)i * T * P.yr + (long long)a * T, P.yr);
+    auto tA1 = [&](int jj) { return tA(jj + n1); };
+    auto tB1 = [&](int jj) { return tB(jj + n1); };
+    gemm_nt<false>(acc, u.nt - i - n1, tA1, tB1, mlim, nlim, pipe);
+  } else {
+    acc_zero(acc);
+    gemm_nt<false>(acc, u.nt - i, tA, tB, mlim, nlim, pipe);
+    if (i < u.pstore)        // pstore == nt: the complete sum is the partial sum
+      acc_store(acc, P.arena + u.ap_off + (long long)i * T * P.yr + (long long)a * T, P.yr);
+  }
   double* Al = P.arena + u.al_off;
   acc_store(acc, Al + (long long)i * T * P.yr + (long long)a * T, P.yr);
 }
@@ -540,11 +567,11 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
     }
   }
   Acc acc;
-  acc_zero(acc);
   const double* ai = Al + (long long)i * T * P.yr;
   const double* aj = Al + (long long)j * T * P.yr;
   const int mlim = ext8(u.s, i), nlim = ext8(u.s, j);
-  // K^-1_ij: contraction over point tiles m = i + jj; U_ii is upper triangular
+  // K^-1_ij: contraction over point tiles m = i + jj (ascending); U_ii is upper triangular.
+  // Pairs start from the parent's stored partial sum over m < share (UnitDesc::pstore).
   {
     const double* Udi = dtile_u(P, u, i);
     auto uA = [&](int jj) {
@@ -555,8 +582,28 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
       const int kl = ext8(u.s, i + jj);
       return (j == i && jj == 0) ? tile_ref(Udi, T, kl, 0, 2) : mtile(P, u, j, i + jj, kl);
     };
-    if (j == i) gemm_nt<true>(acc, u.nt - i, uA, uB, mlim, nlim, pipe);
-    else gemm_nt<false>(acc, u.nt - i, uA, uB, mlim, nlim, pipe);
+    auto run = [&](int nk, int off, bool load) {
+      auto a2 = [&](int jj) { return uA(jj + off); };
+      auto b2 = [&](int jj) { return uB(jj + off); };
+      const double* src = P.arena + u.p_kp_off + (long long)i * T * u.p_sp + (long long)j * T;
+      auto init = [&]() { if (load) acc_load(acc, src, u.p_sp); };
+      if (j == i) gemm_nt<true>(acc, nk, a2, b2, mlim, nlim, pipe, init);
+      else gemm_nt<false>(acc, nk, a2, b2, mlim, nlim, pipe, init);
+    };
+    double* kp = P.arena + u.kp_off + (long long)i * T * ld + (long long)j * T;
+    const int jj0 = i < u.share ? u.share - i : 0;
+    if (jj0 > 0) {
+      run(u.nt - i - jj0, jj0, true);
+    } else if (i < u.pstore && u.pstore < u.nt) {
+      acc_zero(acc);
+      run(u.pstore - i, 0, false);
+      acc_store(acc, kp, ld);
+      run(u.nt - u.pstore, u.pstore - i, false);
+    } else {
+      acc_zero(acc);
+      run(u.nt - i, 0, false);
+      if (i < u.pstore) acc_store(acc, kp, ld);
+    }
   }
   if (P.keep_kinv) acc_store(acc, P.arena + u.m_off + (long long)i * T * ld + (long long)j * T, ld);
   const double dyd = (double)P.dy;

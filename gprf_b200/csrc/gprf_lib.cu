@@ -74,7 +74,8 @@ struct gprf_ctx {
   bool share_on = true;            // edges reuse block i's factor tiles (gprf_set_factor_reuse)
   bool any_share = false;
   int fused_share_min = -1;        // fused pairs reuse too once there are this many of them (-1: 8 per SM)
-  int n_fused_parents = 0;         // all_list = [tiled | fused parents of sharing pairs | other fused]
+  int n_fused_parents = 0;         // all_list = [tiled parents | other tiled | fused parents | other fused]
+  int n_tiled_parents = 0;
   int n_share_units = 0;
   long long n_share_tiles = 0;     // potrf/trtri/forward-solve tile tasks not executed thanks to the reuse
   int n_sm = 148;
@@ -485,8 +486,10 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
     u.sp = u.nt * T;
     u.active = (!mask || mask[uix]) ? 1 : 0;
     u.share = 0;
+    u.pstore = u.pad_ = 0;
     u.p_sp = u.p_nt = 0;
-    u.p_m_off = u.p_d_off = u.p_ld_off = u.p_k_off = 0;
+    u.p_m_off = u.p_d_off = u.p_ld_off = u.p_k_off = u.p_kp_off = u.p_ap_off = 0;
+    u.kp_off = u.ap_off = 0;
     if (u.active && u.s > 0) {
       const size_t sp = u.sp, nt = u.nt;
       u.m_off = off;   off += align16((sp + h->yr) * sp);
@@ -497,6 +500,11 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
       u.ld_off = off;  off += align16(nt);
       u.gx_off = off;  off += align16(sp * 3);
       u.k_off = off;   off += align16(sp * sp);
+      if (uix < B && h->share_on && !h->keep_kinv && h->deg[bi] > 0 && u.ni >= T) {
+        // room for the partial U-products this block's pairs may start from (UnitDesc::pstore)
+        u.kp_off = off;  off += align16(sp * sp);
+        u.ap_off = off;  off += align16(sp * h->yr);
+      }
       h->all_list.push_back(uix);
       h->ntmax = std::max(h->ntmax, u.nt);
     } else {
@@ -517,6 +525,7 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
   h->n_share_units = 0;
   h->n_share_tiles = 0;
   h->n_fused_parents = 0;
+  h->n_tiled_parents = 0;
   if (h->share_on && !h->keep_kinv) {
     // Fused pairs can reuse as well, but only behind a launch of their own for the parent blocks;
     // that extra dependent launch pays off once the pairs fill the GPU several times over.
@@ -533,7 +542,7 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
     std::vector<unsigned char> is_parent(B, 0);
     for (int e = 0; e < E; ++e) {
       UnitDesc& u = h->units[B + e];
-      const UnitDesc& p = h->units[edges[2 * e]];
+      UnitDesc& p = h->units[edges[2 * e]];
       if (!candidate(e)) continue;
       if (u.nt <= h->fused_eff && !fused_share) continue;
       const int m = u.ni / T;
@@ -544,6 +553,9 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
       u.p_d_off = p.d_off;
       u.p_ld_off = p.ld_off;
       u.p_k_off = p.k_off;
+      u.p_kp_off = p.kp_off;
+      u.p_ap_off = p.ap_off;
+      h->units[edges[2 * e]].pstore = m;          // same m for every pair of this parent
       is_parent[edges[2 * e]] = 1;
       h->any_share = true;
       h->n_share_units++;
@@ -556,6 +568,11 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
     auto mid = std::stable_partition(first_fused, h->all_list.end(),
                                      [&](int uix) { return uix < B && is_parent[uix]; });
     h->n_fused_parents = (int)(mid - first_fused);
+    // tiled parents: the alpha / K^-1 launches run them first (their pairs start from the partial
+    // sums they store); kept at the FRONT of the tiled prefix of the list
+    auto tmid = std::stable_partition(h->all_list.begin(), first_fused,
+                                      [&](int uix) { return uix < B && is_parent[uix]; });
+    h->n_tiled_parents = (int)(tmid - h->all_list.begin());
   }
   if (off > h->arena_cap || !h->arena) {
     CUDA_OK(cudaStreamSynchronize(st));
@@ -861,8 +878,8 @@ extern "C" int gprf_get_blocks(gprf_handle h, long long* block_ptr, long long* p
 // Units of up to h->fused_nt tiles go through k_unit_fused (one CTA per unit, one launch);
 // larger ones through the multi-launch tile pipeline.  `nt_of(i)` = tile count of list entry i
 // (lists are sorted largest first, so the large units form a prefix).
-static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, int nlist, int ntmax, bool want_grad,
-                              cudaStream_t st);
+static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, const int* list_host, int nlist, int ntmax,
+                              bool want_grad, cudaStream_t st, int n_parents);
 
 static int launch_fused(gprf_ctx* h, const EvalParams& P, int base, int cnt, bool want_grad, cudaStream_t st) {
   int launches = 0;
@@ -879,7 +896,7 @@ static int launch_fused(gprf_ctx* h, const EvalParams& P, int base, int cnt, boo
 // `n_parents`: the fused units [nlarge, nlarge + n_parents) of the list are parents of pairs that
 // reuse their factor (main pass only): they are launched first, everything else after them.
 static int launch_units(gprf_ctx* h, const EvalParams& P, const int* list_host, int nlist, int ntmax,
-                        bool want_grad, cudaStream_t st, int n_parents = 0) {
+                        bool want_grad, cudaStream_t st, int n_parents = 0, int n_tiled_parents = 0) {
   int launches = 0;
   if (nlist == 0) return 0;
   int nlarge = 0, ntl = 0;
@@ -888,17 +905,19 @@ static int launch_units(gprf_ctx* h, const EvalParams& P, const int* list_host, 
     ++nlarge;
   }
   launches += launch_fused(h, P, nlarge, n_parents, want_grad, st);
-  if (nlarge > 0) launches += launch_units_tiled(h, P, nlarge, ntl, want_grad, st);
+  if (nlarge > 0)
+    launches += launch_units_tiled(h, P, list_host, nlarge, ntl, want_grad, st, n_tiled_parents);
   launches += launch_fused(h, P, nlarge + n_parents, nlist - nlarge - n_parents, want_grad, st);
   (void)ntmax;
   return launches;
 }
 
-static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, int nlist, int ntmax, bool want_grad,
-                              cudaStream_t st) {
+// `n_parents`: the first n_parents units of the list store partial U-products that other units of
+// the list start from (UnitDesc::pstore): their alpha / K^-1 launches go first.
+static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, const int* list_host, int nlist, int ntmax,
+                              bool want_grad, cudaStream_t st, int n_parents) {
   int launches = 0;
   if (nlist == 0) return 0;
-  const int ntri_max = ntmax * (ntmax + 1) / 2;
   const int CH = 32768;   // gridDim.y limit is 65535
   for (int base = 0; base < nlist; base += CH) {
     const int cnt = std::min(CH, nlist - base);
@@ -919,9 +938,18 @@ static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, int nlist, int n
       for (int d = 1; d < ntmax; ++d) {
         LAUNCH(3, (k_trtri<<<dim3(ntmax - d, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc, d)));
       }
-      LAUNCH(4, (k_alpha<<<dim3(ntmax * h->nya, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc)));
-#define CALL_GRAD(D, W) k_grad<D, W><<<dim3(ntri_max, cnt), NTHREADS, PIPE_BYTES, st>>>(Pc)
-      LAUNCH(5, DISPATCH_COV(h, CALL_GRAD));
+      const int npc = std::max(0, std::min(n_parents - base, cnt));
+      for (int part = 0; part < 2; ++part) {
+        const int c0 = part == 0 ? 0 : npc, c1 = part == 0 ? npc : cnt;
+        if (c1 <= c0) continue;
+        EvalParams Pp = Pc;
+        Pp.ulist = Pc.ulist + c0;
+        int ntp = 0;                        // parents are blocks: far fewer tiles than ntmax
+        for (int q = c0; q < c1; ++q) ntp = std::max(ntp, h->units[list_host[base + q]].nt);
+        LAUNCH(4, (k_alpha<<<dim3(ntp * h->nya, c1 - c0), NTHREADS, PIPE_BYTES, st>>>(Pp)));
+#define CALL_GRAD(D, W) k_grad<D, W><<<dim3(ntp * (ntp + 1) / 2, c1 - c0), NTHREADS, PIPE_BYTES, st>>>(Pp)
+        LAUNCH(5, DISPATCH_COV(h, CALL_GRAD));
+      }
     }
     LAUNCH(6, (k_unit_finalize<<<cnt, NTHREADS, 0, st>>>(Pc, h->dLLu, h->dGthU, want_grad ? 1 : 0)));
   }
@@ -972,7 +1000,7 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
   const int nlist = (int)h->all_list.size();
   P.ulist = h->dListAll;
   int launches = launch_units(h, P, h->all_list.data(), nlist, h->ntmax, want_grad, st,
-                              h->any_share ? h->n_fused_parents : 0);
+                              h->any_share ? h->n_fused_parents : 0, h->any_share ? h->n_tiled_parents : 0);
   P.ulist = h->dList;
   CUDA_OK(cudaGetLastError());
 

@@ -474,4 +474,16 @@ __device__ __forceinline__ void acc_store(const Acc& a, double* dst, long long l
     }
 }
 
+// Load an accumulator tile stored by acc_store.
+__device__ __forceinline__ void acc_load(Acc& a, const double* src, long long ld) {
+#pragma unroll
+  for (int m = 0; m < MB; ++m)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const double2 v = *reinterpret_cast<const double2*>(src + (long long)acc_row(m) * ld + acc_col(n));
+      a.c[m][n][0] = v.x;
+      a.c[m][n][1] = v.y;
+    }
+}
+
 }  // namespace gprf
