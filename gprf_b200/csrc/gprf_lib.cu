@@ -98,8 +98,14 @@ struct gprf_ctx {
 
   double* arena = nullptr;
   size_t arena_cap = 0;            // doubles
+  // per-evaluation scratch, one allocation so that one memset clears it:
+  // [ll per unit | jitter per unit | info per unit | nfail]
+  void* dScratch = nullptr;
+  size_t scratch_bytes = 0;
   double *dLLu = nullptr, *dGthU = nullptr, *dJitter = nullptr;
   int *dInfo = nullptr, *dNfail = nullptr;
+  int* hNfail = nullptr;           // pinned
+  bool units_built = false;        // descriptors on the device match block_ptr_h / edges / switches
   std::vector<double> jitter;
   std::vector<int> tries;
 
@@ -260,7 +266,7 @@ extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, in
   CUDA_OK(cudaMalloc((void**)&h->dOut, outlen * sizeof(double)));
   CUDA_OK(cudaMallocHost((void**)&h->hX, (size_t)n * dx * sizeof(double)));
   CUDA_OK(cudaMallocHost((void**)&h->hOut, outlen * sizeof(double)));
-  CUDA_OK(cudaMalloc((void**)&h->dNfail, sizeof(int)));
+  CUDA_OK(cudaMallocHost((void**)&h->hNfail, sizeof(int)));
   CUDA_OK(cudaMemcpy(h->dY, Y, (size_t)n * dy * sizeof(double), cudaMemcpyHostToDevice));
   set_attrs();
   if (const char* e = getenv("GPRF_FUSED_NT")) h->fused_nt = atoi(e);
@@ -341,8 +347,8 @@ extern "C" int gprf_destroy(gprf_handle h) {
   cudaFreeHost(h->hX); cudaFreeHost(h->hOut);
   cudaFree(h->dUnits); cudaFree(h->dList); cudaFree(h->dListAll); cudaFree(h->dPerm); cudaFree(h->dBlockPtr);
   cudaFree(h->dPosBlock); cudaFree(h->dAdjPtr); cudaFree(h->dAdjEdge); cudaFree(h->dAdjSide);
-  cudaFree(h->arena); cudaFree(h->dLLu); cudaFree(h->dGthU); cudaFree(h->dJitter);
-  cudaFree(h->dInfo); cudaFree(h->dNfail);
+  cudaFree(h->arena); cudaFree(h->dScratch); cudaFree(h->dGthU);
+  if (h->hNfail) cudaFreeHost(h->hNfail);
   cudaFree(h->dPartA); cudaFree(h->dPartB); cudaFree(h->dPartC); cudaFree(h->dPartChild);
   cudaFree(h->dOwner); cudaFree(h->dIota); cudaFree(h->dIdxSorted); cudaFree(h->dCub);
   if (h->hUnits) cudaFreeHost(h->hUnits);
@@ -582,20 +588,22 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
   }
   if ((size_t)U > h->capUnits || !h->dUnits) {
     CUDA_OK(cudaStreamSynchronize(st));
-    cudaFree(h->dUnits); cudaFree(h->dList); cudaFree(h->dListAll); cudaFree(h->dLLu); cudaFree(h->dGthU);
-    cudaFree(h->dJitter); cudaFree(h->dInfo);
+    cudaFree(h->dUnits); cudaFree(h->dList); cudaFree(h->dListAll); cudaFree(h->dScratch); cudaFree(h->dGthU);
     if (h->hUnits) cudaFreeHost(h->hUnits);
     if (h->hList) cudaFreeHost(h->hList);
-    h->dUnits = nullptr; h->dList = nullptr; h->dListAll = nullptr; h->dLLu = nullptr; h->dGthU = nullptr;
-    h->dJitter = nullptr; h->dInfo = nullptr; h->hUnits = nullptr; h->hList = nullptr;
+    h->dUnits = nullptr; h->dList = nullptr; h->dListAll = nullptr; h->dScratch = nullptr; h->dGthU = nullptr;
+    h->hUnits = nullptr; h->hList = nullptr;
     size_t cu = (size_t)U + U / 4 + 16;
     CUDA_OK(cudaMalloc((void**)&h->dUnits, cu * sizeof(UnitDesc)));
     CUDA_OK(cudaMalloc((void**)&h->dList, cu * sizeof(int)));
     CUDA_OK(cudaMalloc((void**)&h->dListAll, cu * sizeof(int)));
-    CUDA_OK(cudaMalloc((void**)&h->dLLu, cu * sizeof(double)));
+    h->scratch_bytes = cu * (2 * sizeof(double) + sizeof(int)) + 16;
+    CUDA_OK(cudaMalloc(&h->dScratch, h->scratch_bytes));
+    h->dLLu = (double*)h->dScratch;
+    h->dJitter = h->dLLu + cu;
+    h->dInfo = (int*)(h->dJitter + cu);
+    h->dNfail = h->dInfo + cu;
     CUDA_OK(cudaMalloc((void**)&h->dGthU, cu * MAX_NCOV * sizeof(double)));
-    CUDA_OK(cudaMalloc((void**)&h->dJitter, cu * sizeof(double)));
-    CUDA_OK(cudaMalloc((void**)&h->dInfo, cu * sizeof(int)));
     CUDA_OK(cudaMallocHost((void**)&h->hUnits, cu * sizeof(UnitDesc)));
     CUDA_OK(cudaMallocHost((void**)&h->hList, cu * sizeof(int)));
     h->capUnits = cu;
@@ -611,6 +619,7 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
   h->jitter.assign(U, 0.0);
   h->tries.assign(U, 0);
   h->have_structure = true;
+  h->units_built = true;
   return GPRF_OK;
 }
 
@@ -647,6 +656,7 @@ static int store_blocks_host(gprf_ctx* h, int B, const long long* block_ptr, con
   }
   CUDA_OK(cudaMemcpy(h->dBlockPtr, block_ptr, (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice));
   h->blocks_from_device = false;
+  h->units_built = false;
   return GPRF_OK;
 }
 
@@ -661,6 +671,7 @@ extern "C" int gprf_set_edges(gprf_handle h, int E, const int* edges, int shard_
   h->use_explicit_mask = false;
   h->adj_dirty = true;
   h->have_structure = false;
+  h->units_built = false;
   if ((int)h->block_ptr_h.size() == h->B + 1 && h->B > 0) {
     int rc = rebuild_units(h, h->stream);
     if (rc != GPRF_OK) return rc;
@@ -785,7 +796,8 @@ static int reblock_device(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
     CUDA_OK(cudaMalloc(&h->dCub, need + 256));
     h->capCub = need + 256;
   }
-  const int tb = 256;
+  // small CTAs: at n = 10^4 a 256-thread CTA per 256 points would light up only 40 of the 148 SMs
+  const int tb = n >= 256LL * 4 * h->n_sm ? 256 : 64;
   const unsigned gb = (unsigned)((n + tb - 1) / tb);
   if (h->part_kind == 1) {
     const size_t sm = (size_t)B * (h->dx + 1) * sizeof(double);
@@ -824,12 +836,20 @@ static int reblock_device(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
   }
   CUDA_OK(cudaMemcpyAsync(h->hBlockPtr, h->dBlockPtr, ((size_t)B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
+  h->part_launches = 5;
+  // Unit descriptors depend on the block SIZES only (which points sit in a block is in dPerm,
+  // already rewritten on the device): late in an optimisation few points change block, and then
+  // nothing has to be rebuilt or uploaded.
+  if (h->units_built && h->blocks_from_device && B == h->B && h->plen == n && (int)h->block_ptr_h.size() == B + 1 &&
+      memcmp(h->block_ptr_h.data(), h->hBlockPtr, ((size_t)B + 1) * sizeof(long long)) == 0) {
+    h->have_structure = true;
+    return GPRF_OK;
+  }
   if (B != h->B) h->adj_dirty = true;
   h->B = B;
   h->plen = n;
   h->block_ptr_h.assign(h->hBlockPtr, h->hBlockPtr + B + 1);
   h->blocks_from_device = true;
-  h->part_launches = 5;
   return rebuild_units(h, st);
 }
 
@@ -956,8 +976,9 @@ static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, const int* list_
   return launches;
 }
 
+// On return the stream has drained: out_dev (and host_out, a pinned buffer, when given) hold the results.
 static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int ncov, int grad_X, int grad_cov,
-                    double* out_dev, cudaStream_t st, int* failed_unit) {
+                    double* out_dev, cudaStream_t st, int* failed_unit, double* host_out = nullptr) {
   if (failed_unit) *failed_unit = -1;
   if (!h->have_structure) return GPRF_ERR_NO_STRUCTURE;
   CovParams cp;
@@ -991,10 +1012,7 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
   std::fill(h->jitter.begin(), h->jitter.end(), 0.0);
   std::fill(h->tries.begin(), h->tries.end(), 0);
   CUDA_OK(cudaEventRecord(h->ev0, st));
-  CUDA_OK(cudaMemsetAsync(h->dJitter, 0, (size_t)U * sizeof(double), st));
-  CUDA_OK(cudaMemsetAsync(h->dInfo, 0, (size_t)U * sizeof(int), st));
-  CUDA_OK(cudaMemsetAsync(h->dNfail, 0, sizeof(int), st));
-  CUDA_OK(cudaMemsetAsync(h->dLLu, 0, (size_t)U * sizeof(double), st));
+  CUDA_OK(cudaMemsetAsync(h->dScratch, 0, h->scratch_bytes, st));
   const size_t outlen = 1 + MAX_NCOV + (grad_X ? (size_t)h->n * h->dx : 0);
   CUDA_OK(cudaMemsetAsync(out_dev, 0, outlen * sizeof(double), st));
   const int nlist = (int)h->all_list.size();
@@ -1004,10 +1022,40 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
   P.ulist = h->dList;
   CUDA_OK(cudaGetLastError());
 
+  // weighted sums over the units (gprf.py:245-291) and, for the host-buffer entries, the D2H copy
+  auto combine = [&]() -> int {
+    LAUNCH(7, (k_combine_scalars<<<1, 256, 0, st>>>(h->dUnits, U, h->dLLu, h->dGthU, grad_cov ? 1 : 0, out_dev)));
+    if (grad_X && h->plen > 0) {
+      CombineParams C;
+      C.units = h->dUnits;
+      C.arena = h->arena;
+      C.perm = h->dPerm;
+      C.pos_block = h->dPosBlock;
+      C.block_ptr = h->dBlockPtr;
+      C.adj_ptr = h->dAdjPtr;
+      C.adj_edge = h->dAdjEdge;
+      C.adj_side = h->dAdjSide;
+      C.B = h->B;
+      C.dx = h->dx;
+      C.plen = h->plen;
+      const int tb = 64;
+      LAUNCH(7, (k_combine_gradx<<<(unsigned)((h->plen + tb - 1) / tb), tb, 0, st>>>(C, out_dev + 1 + MAX_NCOV)));
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(h->ev1, st));
+    if (host_out) CUDA_OK(cudaMemcpyAsync(host_out, out_dev, outlen * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return GPRF_OK;
+  };
+  // The combination is enqueued before the Cholesky status is known (one host round trip per
+  // evaluation instead of two); in the rare case of a failed unit it is simply redone below.
+  rc = combine();
+  if (rc != GPRF_OK) return rc;
+
   // jitter rule (gpy_linalg.py:77-97): host-driven retry of the failed units only
-  int nfail = 0;
-  CUDA_OK(cudaMemcpyAsync(&nfail, h->dNfail, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(h->hNfail, h->dNfail, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
+  int nfail = *h->hNfail;
+  const bool any_retry = nfail > 0;
   std::vector<int> info;
   while (nfail > 0) {
     if (!(cp.s2 + cp.nv > 0.0)) return GPRF_ERR_NONPOS_DIAG;
@@ -1048,29 +1096,15 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
     CUDA_OK(cudaMemcpyAsync(h->dList, failed.data(), failed.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     launches += launch_units(h, P, failed.data(), (int)failed.size(), ntm, want_grad, st);
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaMemcpyAsync(&nfail, h->dNfail, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(h->hNfail, h->dNfail, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    nfail = *h->hNfail;
+  }
+  if (any_retry) {
+    rc = combine();
+    if (rc != GPRF_OK) return rc;
     CUDA_OK(cudaStreamSynchronize(st));
   }
-
-  LAUNCH(7, (k_combine_scalars<<<1, 256, 0, st>>>(h->dUnits, U, h->dLLu, h->dGthU, grad_cov ? 1 : 0, out_dev)));
-  if (grad_X && h->plen > 0) {
-    CombineParams C;
-    C.units = h->dUnits;
-    C.arena = h->arena;
-    C.perm = h->dPerm;
-    C.pos_block = h->dPosBlock;
-    C.block_ptr = h->dBlockPtr;
-    C.adj_ptr = h->dAdjPtr;
-    C.adj_edge = h->dAdjEdge;
-    C.adj_side = h->dAdjSide;
-    C.B = h->B;
-    C.dx = h->dx;
-    C.plen = h->plen;
-    const int tb = 256;
-    LAUNCH(7, (k_combine_gradx<<<(unsigned)((h->plen + tb - 1) / tb), tb, 0, st>>>(C, out_dev + 1 + MAX_NCOV)));
-  }
-  CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaEventRecord(h->ev1, st));
   h->last_launches = launches;
   return GPRF_OK;
 }
@@ -1082,7 +1116,6 @@ extern "C" int gprf_llgrad_device(gprf_handle h, const double* X_dev, const doub
   cudaStream_t st = (cudaStream_t)stream;
   int rc = run_eval(h, X_dev, theta, ncov, grad_X, grad_cov, out_dev, st, failed_unit);
   if (rc != GPRF_OK) return rc;
-  CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   if (h->profile) h->prof_resolve();
   return GPRF_OK;
@@ -1096,11 +1129,8 @@ extern "C" int gprf_llgrad(gprf_handle h, const double* X, const double* theta, 
   const size_t xb = (size_t)h->n * h->dx * sizeof(double);
   memcpy(h->hX, X, xb);
   CUDA_OK(cudaMemcpyAsync(h->dX, h->hX, xb, cudaMemcpyHostToDevice, h->stream));
-  int rc = run_eval(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, failed_unit);
+  int rc = run_eval(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, failed_unit, h->hOut);
   if (rc != GPRF_OK) return rc;
-  const size_t outlen = 1 + MAX_NCOV + (grad_X ? (size_t)h->n * h->dx : 0);
-  CUDA_OK(cudaMemcpyAsync(h->hOut, h->dOut, outlen * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   if (h->profile) h->prof_resolve();
   *ll = h->hOut[0];
@@ -1121,11 +1151,8 @@ extern "C" int gprf_llgrad_reblock(gprf_handle h, const double* X, const double*
   h->have_structure = false;
   int rc = reblock_device(h, h->dX, h->stream);
   if (rc != GPRF_OK) return rc;
-  rc = run_eval(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, failed_unit);
+  rc = run_eval(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, failed_unit, h->hOut);
   if (rc != GPRF_OK) return rc;
-  const size_t outlen = 1 + MAX_NCOV + (grad_X ? (size_t)h->n * h->dx : 0);
-  CUDA_OK(cudaMemcpyAsync(h->hOut, h->dOut, outlen * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   if (h->profile) h->prof_resolve();
   h->last_launches += h->part_launches;

@@ -55,17 +55,28 @@ __global__ void k_assign_grid(const double* X, long long n, int dx, const double
   for (int i = 1; i < dx; ++i) a = __dadd_rn(a, __dmul_rn(x[i], x[i]));
   int best = 0;
   double bestd = 0.0;
-  for (int b = 0; b < B; ++b) {
-    const double dot = dot_rounded<MODE>(x, sc + b * dx, dx);
-    const double t = __dadd_rn(__dsub_rn(a, 2.0 * dot), sc[B * dx + b]);
-    const double dist = __dsqrt_rn(t);
-    if (dist != dist) {          // np.argmin: the first NaN is the minimum
-      best = b;
-      break;
+  bool done = false;
+  // four independent (correctly rounded) distances at a time, then numpy's sequential argmin rule
+  for (int b0 = 0; b0 < B && !done; b0 += 4) {
+    double dist[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = min(b0 + u, B - 1);
+      const double dot = dot_rounded<MODE>(x, sc + b * dx, dx);
+      const double t = __dadd_rn(__dsub_rn(a, 2.0 * dot), sc[B * dx + b]);
+      dist[u] = __dsqrt_rn(t);
     }
-    if (b == 0 || dist < bestd) {
-      best = b;
-      bestd = dist;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = b0 + u;
+      if (b >= B || done) continue;
+      if (dist[u] != dist[u]) {      // np.argmin: the first NaN is the minimum
+        best = b;
+        done = true;
+      } else if (b == 0 || dist[u] < bestd) {
+        best = b;
+        bestd = dist[u];
+      }
     }
   }
   owner[p] = best;
