@@ -367,11 +367,15 @@ def lbfgs_full_run():
     gp = sd.build_gprf(local_dist=0.1)
     for _ in range(3):
         gp.llgrad(grad_X=True)                       # warm the context outside the timed run
-    with tempfile.TemporaryDirectory() as d:
-        t0 = time.perf_counter()
-        log = gprfopt.do_optimization(d, gp, sd.X_obs, None, sd, save_steps=False)
-        wall = time.perf_counter() - t0
-    out = {"config": name, "evals": len(log), "wall_s": wall, "evals_per_s": len(log) / wall,
+    walls = []
+    for _ in range(2):          # the same deterministic run twice: host jitter (scipy's L-BFGS core is ~half of it)
+        gp.update_X(sd.X_obs)
+        with tempfile.TemporaryDirectory() as d:
+            t0 = time.perf_counter()
+            log = gprfopt.do_optimization(d, gp, sd.X_obs, None, sd, save_steps=False)
+            walls.append(time.perf_counter() - t0)
+    wall = min(walls)
+    out = {"config": name, "evals": len(log), "wall_s": wall, "wall_s_runs": walls, "evals_per_s": len(log) / wall,
            "final_objective": log[-1][2], "best_objective": max(l[2] for l in log),
            "note": "scipy L-BFGS-B ftol 1e-6 maxiter 200 (gprfopt.py:418); host numpy in/out every evaluation, "
                    "step_*.npy dumps off"}
