@@ -376,6 +376,62 @@ def test_large_units_property():
     assert abs(np.dot(w, lls) - g.llgrad()[0]) <= 1e-12 * abs(g.llgrad()[0])
 
 
+def test_n200k_full_size_properties():
+    """BASELINE configs[4] at full size (n = 200000, 400 blocks, 1482 edges), where the oracle takes
+    minutes: size-independent properties instead.  (i) the objective is the weighted sum of the
+    per-unit values (gprf.py:253-254); (ii) the edge factor reuse changes no bit of ll / gradX;
+    (iii) the same holds for every rank's shard of an 8-way split, whose partial results add up
+    to the full result; (iv) a handful of units against the oracle."""
+    import bench
+    from gprf_b200 import GPRF
+    from oracle.gprf_oracle import OracleGPRF
+    from oracle.kernels import GPCov as OCov
+    wl = bench.make_workload("cfg5")
+    kw = dict(block_idxs=wl["block_idxs"], neighbors=wl["neighbors"])
+    g = GPRF(wl["X"], wl["Y"], wl["block_fn"], wl["cov"], wl["noise_var"], **kw)
+    ll, gX, _ = g.llgrad(grad_X=True)
+    assert g.factor_reuse_stats()[0] == len(wl["neighbors"])
+    lls, jit = g.unit_results()
+    assert np.all(jit == 0)
+    B = g.n_blocks
+    deg = np.zeros(B)
+    for i, j in wl["neighbors"]:
+        deg[i] += 1
+        deg[j] += 1
+    assert abs(np.dot(1 - deg, lls[:B]) + lls[B:].sum() - ll) <= 1e-11 * abs(ll)
+    g.set_factor_reuse(False)
+    ll0, gX0, _ = g.llgrad(grad_X=True)
+    assert ll0 == ll and np.array_equal(gX0, gX)
+    assert np.array_equal(g.unit_results()[0], lls)
+    g.close()
+    # shards: rank 0 and rank 7 of 8 evaluate disjoint unit sets; all 8 add up (two of them checked bitwise
+    # against their own no-reuse evaluation, the sum against the full result)
+    tot_ll, tot_g = 0.0, np.zeros_like(gX)
+    for rank in range(8):
+        gs = GPRF(wl["X"], wl["Y"], wl["block_fn"], wl["cov"], wl["noise_var"], unit_shard=(rank, 8), **kw)
+        a = gs.llgrad(grad_X=True)
+        if rank in (0, 7):
+            assert gs.factor_reuse_stats()[0] > 150
+            gs.set_factor_reuse(False)
+            b = gs.llgrad(grad_X=True)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1])
+        tot_ll += a[0]
+        tot_g += a[1]
+        gs.close()
+    assert abs(tot_ll - ll) <= 1e-11 * abs(ll)
+    assert np.abs(tot_g - gX).max() <= 1e-11 * np.abs(gX).max()
+    # spot check against the oracle: two blocks and one pair
+    c = wl["cov"]
+    o = OracleGPRF(wl["X"], wl["Y"], None, OCov(c.wfn_params, c.dfn_params, c.dfn_str, c.wfn_str), wl["noise_var"],
+                   **kw)
+    for b in (0, 217):
+        want = o.llgrad_unary(b)[0]
+        assert abs(lls[b] - want) <= LL_RTOL * abs(want)
+    e = 700
+    want = o.llgrad_joint(*wl["neighbors"][e])[0]
+    assert abs(lls[B + e] - want) <= LL_RTOL * abs(want)
+
+
 def test_device_partitioner_grid_bit_exact():
     """K8 on the device: block membership after update_X equals the host numpy partition,
     including points on cell boundaries (ties) and outside the unit square."""
