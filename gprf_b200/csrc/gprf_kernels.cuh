@@ -313,11 +313,15 @@ __device__ __forceinline__ void diag_tile(const EvalParams& P, int uid, const Un
     Ud[e] = S2[r * WLD + c];
     Wd[e] = S2[c * WLD + r];
   }
-  if (tid < T) Wsm[tid] = log(S[tid * WLD + tid]);
+  if (tid < T) {                        // log-determinant partial: 2 warps, shuffle tree, fixed order
+    double lv = log(S[tid * WLD + tid]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
+    if ((tid & 31) == 0) Wsm[tid >> 5] = lv;
+  }
   __syncthreads();
   if (tid == 0) {
-    double lsum = 0.0;
-    for (int r = 0; r < T; ++r) lsum += Wsm[r];
+    const double lsum = Wsm[0] + Wsm[1];
     (P.arena + u.ld_off)[k] = lsum;
     if (sfail != 0 && atomicCAS(&P.info[uid], 0, sfail) == 0) atomicAdd(P.nfail, 1);
   }
@@ -427,6 +431,26 @@ __device__ __forceinline__ void panel_tile(const EvalParams& P, const UnitDesc& 
   mul_acc_by_wt(res, acc, sW, -1.0, mlim, nlim);
   trace_mark(P, &sc.tcur, 42);
   acc_store(res, out, ld);
+  if (aug) {
+    // ||Z||^2 of this (output tile, point tile) pair, for the quadratic term of gprf.py:542-544:
+    // reduced here, where Z is in registers, in a fixed order (lanes, then warps)
+    double q = 0.0;
+#pragma unroll
+    for (int m = 0; m < MB; ++m)
+#pragma unroll
+      for (int n = 0; n < 8; ++n) q += res.c[m][n][0] * res.c[m][n][0] + res.c[m][n][1] * res.c[m][n][1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    double* red = &sc.sth[0][0];
+    if ((tid & 31) == 0) red[tid >> 5] = q;
+    __syncthreads();
+    if (tid == 0) {
+      double t = red[0];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) t += red[w];
+      (P.arena + u.ld_off)[u.nt + k * P.nya + (it - u.nt)] = t;
+    }
+  }
 }
 
 // grid (nlist, ntmax - k - 1 + nya) task-major, or (ntmax - k - 1 + nya, nlist) unit-major: the
@@ -804,41 +828,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_grad(EvalParams P) {
 __device__ __forceinline__ void finalize_unit(const EvalParams& P, int uid, const UnitDesc& u, double* ll_u,
                                               double* gth_u, int want_grad, double* red) {
   const int tid = threadIdx.x;
-  const double* M = P.arena + u.m_off;
-  // quadratic term ||Z||^2 over the augmented rows
-  double q = 0.0;
-  const long long tot = (long long)P.yr * u.sp;
-  const double* Z = M + (long long)u.sp * u.sp;
-  if (u.share == 0) {
-    for (long long e = tid; e < tot; e += NTHREADS) {
-      double z = Z[e];
-      q += z * z;
-    }
-  } else {
-    // same element order; the first share*64 columns of Z^T are the parent block's
-    const double* Zp = P.arena + u.p_m_off + (long long)u.p_sp * u.p_sp;
-    const int csh = u.share * T;
-    int r = tid / u.sp, c = tid % u.sp;
-    for (long long e = tid; e < tot; e += NTHREADS) {
-      double z = c < csh ? Zp[(long long)r * u.p_sp + c] : Z[e];
-      q += z * z;
-      c += NTHREADS;
-      while (c >= u.sp) { c -= u.sp; ++r; }
-    }
-  }
-  red[tid] = q;
-  __syncthreads();
-  for (int o = NTHREADS / 2; o > 0; o >>= 1) {
-    if (tid < o) red[tid] += red[tid + o];
-    __syncthreads();
-  }
+  // quadratic term ||Z||^2: partial sums left by the forward-solve tasks (panel_tile), one per
+  // (point tile k, output tile a); those of the first `share` point tiles are the parent's
   if (tid == 0) {
     double lsum = 0.0;
     const double* ldp = P.arena + u.ld_off;
     const double* ldq = P.arena + u.p_ld_off;
     for (int k = 0; k < u.nt; ++k) lsum += k < u.share ? ldq[k] : ldp[k];
+    double q = 0.0;
+    for (int k = 0; k < u.nt; ++k)
+      for (int a = 0; a < P.nya; ++a)
+        q += k < u.share ? ldq[u.p_nt + k * P.nya + a] : ldp[u.nt + k * P.nya + a];
     const double logdet = 2.0 * lsum;
-    ll_u[uid] = -0.5 * red[0] - 0.5 * P.dy * logdet - 0.5 * P.dy * (double)u.s * 1.8378770664093454836;
+    ll_u[uid] = -0.5 * q - 0.5 * P.dy * logdet - 0.5 * P.dy * (double)u.s * 1.8378770664093454836;
   }
   if (!want_grad) return;
   const double* part = P.arena + u.part_off;

@@ -503,7 +503,7 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
       u.al_off = off;  off += align16(sp * h->yr);
       u.xs_off = off;  off += align16(sp * XD);
       u.part_off = off; off += align16((nt * (nt + 1) / 2) * PART_STRIDE);
-      u.ld_off = off;  off += align16(nt);
+      u.ld_off = off;  off += align16(nt * (1 + h->nya));   // logdet partials, then ||Z||^2 partials
       u.gx_off = off;  off += align16(sp * 3);
       u.k_off = off;   off += align16(sp * sp);
       if (uix < B && h->share_on && !h->keep_kinv && h->deg[bi] > 0 && u.ni >= T) {
