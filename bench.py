@@ -328,9 +328,17 @@ class Runner(object):
         return self.outh[0].item()
 
     def e2e_bytes(self):
+        """Bytes that cross PCIe in one e2e step.  With the on-device partitioner: X down; the block
+        bounds (to size the units), the Cholesky status word and [ll, grad theta, gradX] up.  Unit
+        descriptors go down again only when some block changed size (not the case for a repeated X).
+        Without it the host-computed block lists and descriptors are uploaded every step."""
         nb, ne = len(self.wl["block_idxs"]), len(self.wl["neighbors"])
-        h2d = self.n * self.dx * 8 + self.n * 8 + self.n * 4 + (nb + 1) * 12 + ne * 8 * 2 + ne * 8 + (nb + ne) * 104
+        h2d = self.n * self.dx * 8
         d2h = (1 + 5 + self.n * self.dx) * 8 + 4
+        if self.g._device_part is not None:
+            d2h += (nb + 1) * 8
+        else:
+            h2d += self.n * 8 + self.n * 4 + (nb + 1) * 16 + (nb + ne) * (176 + 4)
         return h2d, d2h
 
     def family_profile(self, reps=3):
