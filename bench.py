@@ -355,8 +355,8 @@ class Runner(object):
         return acc
 
 
-FUSED_NT = int(os.environ.get("GPRF_FUSED_NT", "8"))   # library default (include/gprf_b200.h)
-FUSED_MIXED_NT = int(os.environ.get("GPRF_FUSED_MIXED_NT", "4"))
+FUSED_NT = int(os.environ.get("GPRF_FUSED_NT", "0"))   # library default (include/gprf_b200.h): tile pipeline only
+FUSED_MIXED_NT = int(os.environ.get("GPRF_FUSED_MIXED_NT", str(min(FUSED_NT, 4))))
 
 
 def lbfgs_full_run():

@@ -80,9 +80,12 @@ struct gprf_ctx {
   long long n_share_tiles = 0;     // potrf/trtri/forward-solve tile tasks not executed thanks to the reuse
   int n_sm = 148;
   int panel_order = 0;             // 0 task-major (default: measured faster), 1 unit-major, -1 by launch size (GPRF_PANEL_ORDER)
-  int fused_nt = 8;                // units of up to this many 64-point tiles take k_unit_fused
-  int fused_mixed_nt = 4;          // ... but only up to this many when larger units run the tile pipeline anyway
-  int fused_eff = 8;               // threshold in force for the current structure (rebuild_units)
+  // Units of up to fused_nt 64-point tiles take k_unit_fused (one CTA per unit).  Default 0: every
+  // unit runs the tile pipeline, which is the faster schedule on B200 for every workload measured
+  // (README config 0.853 vs 0.904 ms, 8-rank shard of it 0.469 vs 0.611, cfg4 16.9 vs 18.6 ms).
+  int fused_nt = 0;
+  int fused_mixed_nt = 0;          // ... but only up to this many when larger units run the tile pipeline anyway
+  int fused_eff = 0;               // threshold in force for the current structure (rebuild_units)
   unsigned long long* dTrace = nullptr;   // debug trace of the fused kernel (gprf_debug_trace)
   size_t capTrace = 0;
 
@@ -269,7 +272,10 @@ extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, in
   CUDA_OK(cudaMallocHost((void**)&h->hNfail, sizeof(int)));
   CUDA_OK(cudaMemcpy(h->dY, Y, (size_t)n * dy * sizeof(double), cudaMemcpyHostToDevice));
   set_attrs();
-  if (const char* e = getenv("GPRF_FUSED_NT")) h->fused_nt = atoi(e);
+  if (const char* e = getenv("GPRF_FUSED_NT")) {
+    h->fused_nt = atoi(e);
+    h->fused_mixed_nt = std::min(h->fused_nt, 4);
+  }
   if (const char* e = getenv("GPRF_PANEL_ORDER")) h->panel_order = atoi(e);
   if (const char* e = getenv("GPRF_FUSED_SHARE_MIN")) h->fused_share_min = atoi(e);
   cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);

@@ -159,13 +159,13 @@ int gprf_debug_trace(gprf_handle h, int n_ctas, unsigned long long* out);
  * gpy_linalg.py:150-171; needed by tests and by a train_predictor port). */
 int gprf_set_keep_kinv(gprf_handle h, int keep);
 
-/* Scheduling knob (no effect on results beyond fp64 summation order, which is
- * identical on both paths): units of up to `nt` 64-point tiles are evaluated by
- * the fused one-CTA-per-unit kernel, larger ones by the multi-launch tile
- * pipeline.  Default 8 (environment override GPRF_FUSED_NT); 0 disables fusion.
- * When some unit exceeds `nt` (so the tile pipeline runs anyway), only units of up
- * to min(nt, 4) tiles stay fused (GPRF_FUSED_MIXED_NT): the rest ride along in the
- * pipeline's launches instead of forming a latency-bound tail of their own. */
+/* Scheduling knob (no effect on results: both schedules run the same tile tasks in the
+ * same arithmetic order and agree bit for bit): units of up to `nt` 64-point tiles
+ * are evaluated by the fused one-CTA-per-unit kernel, larger ones by the multi-launch
+ * tile pipeline.  Default 0 = tile pipeline for every unit, the faster schedule on
+ * B200 for every workload measured; environment override
+ * GPRF_FUSED_NT.  When some unit exceeds `nt` (so the tile pipeline runs anyway), only
+ * units of up to min(nt, 4) tiles stay fused (GPRF_FUSED_MIXED_NT). */
 int gprf_set_fused_nt(gprf_handle h, int nt);
 
 /* Edge factorisations reuse block i's Cholesky factor (default on).  The pair unit

@@ -20,6 +20,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 wl = bench.make_workload(name)
 R = bench.Runner(torch, None, wl, 0, 1, 0)
 g = R.g
+g.set_fused_nt(8)            # the fused kernel is no longer the default schedule
 sizes = bench.unit_sizes(wl["block_idxs"], wl["neighbors"])
 order = np.argsort(-sizes, kind="stable")
 nct = len(sizes)
