@@ -64,13 +64,14 @@ __device__ __forceinline__ void smem_potrf_trtri(double* S, double* S2, double* 
       double a[8], w[8];
       const int r = lane & 7;
       const double* src = S + (8 * J + r) * ld + 8 * J;
+      if (lane < 8) {
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        double2 t = *reinterpret_cast<const double2*>(src + 2 * v);
-        a[2 * v] = t.x;
-        a[2 * v + 1] = t.y;
-      }
-      if (lane >= 8) {
+        for (int v = 0; v < 4; ++v) {
+          double2 t = *reinterpret_cast<const double2*>(src + 2 * v);
+          a[2 * v] = t.x;
+          a[2 * v + 1] = t.y;
+        }
+      } else {                            // idle lanes carry an identity block through the shuffles
 #pragma unroll
         for (int v = 0; v < 8; ++v) a[v] = (v == r) ? 1.0 : 0.0;
       }
