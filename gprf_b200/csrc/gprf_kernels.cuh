@@ -52,7 +52,7 @@ struct UnitDesc {
   // are the first terms of block i's own K^-1_ij / Alpha_i.  A parent with pstore > 0 stores those
   // partial accumulators (kp_off: sp x sp, ap_off: sp x yr) when its contraction passes m = pstore;
   // its pairs start from them instead of from zero (p_kp_off / p_ap_off).
-  int pstore, pad_;
+  int pstore, pshare;          // pshare: leading tiles whose partial sums the parent stored (0 or share)
   long long m_off, d_off, al_off, xs_off, part_off, ld_off, gx_off, k_off, kp_off, ap_off;
   long long p_m_off, p_d_off, p_ld_off, p_k_off, p_kp_off, p_ap_off;
   double weight;
@@ -118,7 +118,7 @@ __device__ __forceinline__ int ext8(int s, int t) {
 // Load a unit descriptor for a launch (jitter retries switch the factor reuse off).
 __device__ __forceinline__ UnitDesc load_unit(const EvalParams& P, int uid) {
   UnitDesc u = P.units[uid];
-  if (P.no_share) u.share = 0;
+  if (P.no_share) u.share = u.pshare = 0;
   return u;
 }
 
@@ -520,7 +520,7 @@ __device__ __forceinline__ void alpha_tile(const EvalParams& P, const UnitDesc& 
   const int nlim = min(NB8, (P.dy - a * T + 7) >> 3);
   // contraction over point tiles m = i + jj (ascending); U_ii is upper triangular.
   // jj0: terms already contained in the parent's stored partial sum (UnitDesc::pstore).
-  const int jj0 = i < u.share ? u.share - i : 0;
+  const int jj0 = i < u.pshare ? u.pshare - i : 0;
   auto tA = [&](int jj) {
     const int kl = ext8(u.s, i + jj);
     return jj == 0 ? tile_ref(Udi, T, kl, 1, 0) : mtile(P, u, i, i + jj, kl);
@@ -615,7 +615,7 @@ __device__ __forceinline__ void grad_tile(const EvalParams& P, const UnitDesc& u
       else gemm_nt<false>(acc, nk, a2, b2, mlim, nlim, pipe, init);
     };
     double* kp = P.arena + u.kp_off + (long long)i * T * ld + (long long)j * T;
-    const int jj0 = i < u.share ? u.share - i : 0;
+    const int jj0 = i < u.pshare ? u.pshare - i : 0;
     if (jj0 > 0) {
       run(u.nt - i - jj0, jj0, true);
     } else if (i < u.pstore && u.pstore < u.nt) {

@@ -498,7 +498,7 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
     u.sp = u.nt * T;
     u.active = (!mask || mask[uix]) ? 1 : 0;
     u.share = 0;
-    u.pstore = u.pad_ = 0;
+    u.pstore = u.pshare = 0;
     u.p_sp = u.p_nt = 0;
     u.p_m_off = u.p_d_off = u.p_ld_off = u.p_k_off = u.p_kp_off = u.p_ap_off = 0;
     u.kp_off = u.ap_off = 0;
@@ -565,10 +565,18 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
       u.p_d_off = p.d_off;
       u.p_ld_off = p.ld_off;
       u.p_k_off = p.k_off;
-      u.p_kp_off = p.kp_off;
-      u.p_ap_off = p.ap_off;
-      h->units[edges[2 * e]].pstore = m;          // same m for every pair of this parent
-      is_parent[edges[2 * e]] = 1;
+      // The partial U-products need the parents' alpha / K^-1 launches in front of everybody
+      // else's: worth it from two shared tiles on (README config, one shared tile of four: the two
+      // extra dependent launches cost 35 us of a 0.85 ms step and save 5 % of one family).
+      if (m >= 2 && p.kp_off != 0) {
+        u.pshare = m;
+        u.p_kp_off = p.kp_off;
+        u.p_ap_off = p.ap_off;
+        p.pstore = m;                             // same m for every pair of this parent
+        is_parent[edges[2 * e]] = 2;
+      } else if (is_parent[edges[2 * e]] == 0) {
+        is_parent[edges[2 * e]] = 1;
+      }
       h->any_share = true;
       h->n_share_units++;
       // diag + below-diagonal panel tiles + trtri tiles of the leading square, forward-solve tiles
@@ -583,7 +591,7 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
     // tiled parents: the alpha / K^-1 launches run them first (their pairs start from the partial
     // sums they store); kept at the FRONT of the tiled prefix of the list
     auto tmid = std::stable_partition(h->all_list.begin(), first_fused,
-                                      [&](int uix) { return uix < B && is_parent[uix]; });
+                                      [&](int uix) { return uix < B && is_parent[uix] == 2; });
     h->n_tiled_parents = (int)(tmid - h->all_list.begin());
   }
   if (off > h->arena_cap || !h->arena) {
