@@ -160,3 +160,23 @@ def test_product_synthetic_matches_oracle_bitwise():
     assert all(np.array_equal(x, y) for x, y in zip(a.block_idxs, b.block_idxs))
     xx = a.SX.flatten()
     assert a.x_prior(xx)[0] == b.x_prior(xx)[0]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints exactly one JSON line with the contract's keys (the CPU arm
+    needs no GPU; cfg1 is BASELINE configs[0], the reference's own CPU-runnable case)."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["value"] > 0 and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "n=2000" in d["config"]["workload"]
