@@ -530,7 +530,11 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
                                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec * 1e3},
            "roofline": roof, "flops_per_eval": flops_eval}
     if with_cpu and rank == 0 and world == 1:
-        res["cpu_baseline"] = cpu_baseline(wl)
+        try:
+            res["cpu_baseline"] = cpu_baseline(wl)
+        except Exception as exc:        # noqa: BLE001  (a broken host pool must not cost the GPU line)
+            res["cpu_baseline"] = {"value": None, "unit": "evals/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": "failed: %s: %s" % (type(exc).__name__, exc)}
     R.g.close()
     del R
     torch.cuda.empty_cache()
