@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgprf_b200.so")
 MAX_NCOV = 5
-N_FAMILIES = 9
+N_FAMILIES = 13
 
 OK, ERR_NOT_PD, ERR_NONPOS_DIAG, ERR_ARG, ERR_CUDA, ERR_NO_STRUCTURE = range(6)
 
@@ -58,6 +58,11 @@ _SIGNATURES = {
     "gprf_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "gprf_family_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), _ip]),
     "gprf_family_name": (C.c_char_p, [C.c_int]),
+    "gprf_set_resident": (C.c_int, [C.c_void_p, C.c_int]),
+    "gprf_resident_stats": (C.c_int, [C.c_void_p, _llp, _llp, _ip]),
+    "gprf_resident_layout": (C.c_int, [_llp, C.c_int]),
+    "gprf_set_resident_debug": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "gprf_get_resident_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 EXPORTS = sorted(_SIGNATURES)

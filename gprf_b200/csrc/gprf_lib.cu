@@ -14,6 +14,7 @@
 #include "../../include/gprf_b200.h"
 #include "gprf_kernels.cuh"
 #include "partition.cuh"
+#include "resident.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <queue>
 
@@ -112,6 +113,28 @@ struct gprf_ctx {
   std::vector<double> jitter;
   std::vector<int> tries;
 
+  // resident (shared-memory) unit path, resident.cuh
+  bool res_enable = true;
+  bool dev_blocks_valid = false;   // dPerm / dPosBlock / dBlockPtr describe the current blocks
+  bool host_blocks_stale = false;  // ... and are newer than block_ptr_h / the unit descriptors
+  cudaStream_t blocks_stream = nullptr;   // stream the device-held blocks were last written on
+  bool res_static_dirty = true;    // edges / degrees / unit mask have to be uploaded again
+  bool last_resident = false;      // the last evaluation ran on the resident path
+  long long res_evals = 0, res_fallbacks = 0;
+  int res_last_status = 0;
+  double* dResExports = nullptr;
+  double* dResScratch = nullptr;
+  double *dResLL = nullptr, *dResGth = nullptr, *dResGx = nullptr;
+  int *dResInfo = nullptr, *dResOrderB = nullptr, *dResOrderP = nullptr, *dResCounts = nullptr;
+  int *dResEdges = nullptr, *dResDeg = nullptr;
+  unsigned char* dResActive = nullptr;
+  bool res_have_mask = false;
+  size_t capResExp = 0, capResScr = 0, capResU = 0, capResB = 0, capResE = 0, capResAct = 0;
+  int* hResStatus = nullptr;       // pinned: [status]
+  double* dResDbg = nullptr;
+  int res_dbg_unit = -1, res_dbg_phase = -1;
+  std::vector<unsigned char> res_mask;
+
   // optional per-kernel-family timing (CUDA events around every launch)
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -200,8 +223,16 @@ template <int DFN, int WFN>
 void fused_launch(const EvalParams& P, double* ll_u, double* gth_u, int want_grad, int nunits, cudaStream_t st);
 }
 
+namespace gprf {
+namespace res {
+template <int DFN, int WFN> int resident_set_attr();
+template <int DFN, int WFN> void resident_launch(const ResParams& P, int grid, cudaStream_t st);
+}
+}
+
 template <int DFN, int WFN>
 static void set_attrs_t() {
+  res::resident_set_attr<DFN, WFN>();
   cudaFuncSetAttribute(k_potrf_diag<DFN, WFN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
   cudaFuncSetAttribute(k_potrf_panel<DFN, WFN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
   cudaFuncSetAttribute(k_grad<DFN, WFN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_BYTES);
@@ -277,6 +308,8 @@ extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, in
     h->fused_mixed_nt = std::min(h->fused_nt, 4);
   }
   if (const char* e = getenv("GPRF_PANEL_ORDER")) h->panel_order = atoi(e);
+  if (const char* e = getenv("GPRF_RESIDENT")) h->res_enable = atoi(e) != 0;
+  CUDA_OK(cudaMallocHost((void**)&h->hResStatus, 4 * sizeof(int)));
   if (const char* e = getenv("GPRF_FUSED_SHARE_MIN")) h->fused_share_min = atoi(e);
   cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
   if (const char* e = getenv("GPRF_FUSED_MIXED_NT")) h->fused_mixed_nt = atoi(e);
@@ -357,6 +390,10 @@ extern "C" int gprf_destroy(gprf_handle h) {
   if (h->hNfail) cudaFreeHost(h->hNfail);
   cudaFree(h->dPartA); cudaFree(h->dPartB); cudaFree(h->dPartC); cudaFree(h->dPartChild);
   cudaFree(h->dOwner); cudaFree(h->dIota); cudaFree(h->dIdxSorted); cudaFree(h->dCub);
+  cudaFree(h->dResExports); cudaFree(h->dResScratch); cudaFree(h->dResLL); cudaFree(h->dResGth); cudaFree(h->dResGx);
+  cudaFree(h->dResInfo); cudaFree(h->dResOrderB); cudaFree(h->dResOrderP); cudaFree(h->dResCounts);
+  cudaFree(h->dResEdges); cudaFree(h->dResDeg); cudaFree(h->dResActive); cudaFree(h->dResDbg);
+  if (h->hResStatus) cudaFreeHost(h->hResStatus);
   if (h->hUnits) cudaFreeHost(h->hUnits);
   if (h->hList) cudaFreeHost(h->hList);
   if (h->hBlockPtr) cudaFreeHost(h->hBlockPtr);
@@ -413,6 +450,7 @@ static int rebuild_adjacency(gprf_ctx* h) {
     CUDA_OK(cudaMemcpy(h->dAdjSide, adj_side.data(), (size_t)2 * E * sizeof(int), cudaMemcpyHostToDevice));
   }
   h->adj_dirty = false;
+  h->res_static_dirty = true;
   return GPRF_OK;
 }
 
@@ -447,6 +485,30 @@ static void lpt_mask(const std::vector<double>& sizes, int B, const int* edges, 
   for (size_t u = B; u < U; ++u) mask[u] = owner[edges[2 * (u - B)]] == rank ? 1 : 0;
 }
 
+// The resident path (resident.cuh) is tried when the structure is of the small-unit kind: blocks of
+// ~100 points (at most 128 each, checked on the device per evaluation).  The test is a function of
+// static quantities only, so that every rank of a sharded job takes the same decision.
+static bool res_eligible(const gprf_ctx* h) {
+  if (!h->res_enable || h->keep_kinv || h->dy > 8 * res::RNYB || h->B < 1) return false;
+  if ((size_t)(h->B + h->E) * sizeof(int) > 160 * 1024) return false;     // plan kernel's shared arrays
+  return (double)h->n / (double)h->B <= 112.0;
+}
+
+// Unit sizes the multi-GPU split works on.  With the resident path the split must not depend on the
+// per-evaluation block sizes (they never reach the host): nominal sizes, every block alike.
+static void shard_sizes(const gprf_ctx* h, std::vector<double>& sizes) {
+  const int B = h->B, E = h->E;
+  sizes.assign((size_t)B + E, 0.0);
+  if (res_eligible(h)) {
+    for (int b = 0; b < B; ++b) sizes[b] = 100.0;
+    for (int e = 0; e < E; ++e) sizes[B + e] = 200.0;
+    return;
+  }
+  const long long* block_ptr = h->block_ptr_h.data();
+  for (int b = 0; b < B; ++b) sizes[b] = (double)(block_ptr[b + 1] - block_ptr[b]);
+  for (int e = 0; e < E; ++e) sizes[B + e] = sizes[h->edges[2 * e]] + sizes[h->edges[2 * e + 1]];
+}
+
 // Units from h->block_ptr_h + edges (+ mask / shard).  Uploads descriptors on `st` from pinned staging.
 static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
   const int B = h->B;
@@ -464,9 +526,8 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
     if ((int)h->explicit_mask.size() != U) return GPRF_ERR_ARG;
     mask = h->explicit_mask.data();
   } else if (h->shard_world > 1) {
-    std::vector<double> sizes(U);
-    for (int b = 0; b < B; ++b) sizes[b] = (double)(block_ptr[b + 1] - block_ptr[b]);
-    for (int e = 0; e < E; ++e) sizes[B + e] = sizes[edges[2 * e]] + sizes[edges[2 * e + 1]];
+    std::vector<double> sizes;
+    shard_sizes(h, sizes);
     lpt_mask(sizes, B, edges, h->shard_rank, h->shard_world, h->lpt);
     mask = h->lpt.data();
   }
@@ -671,6 +732,8 @@ static int store_blocks_host(gprf_ctx* h, int B, const long long* block_ptr, con
   CUDA_OK(cudaMemcpy(h->dBlockPtr, block_ptr, (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice));
   h->blocks_from_device = false;
   h->units_built = false;
+  h->dev_blocks_valid = true;
+  h->host_blocks_stale = false;
   return GPRF_OK;
 }
 
@@ -782,8 +845,9 @@ extern "C" int gprf_set_tree_partitioner(gprf_handle h, int n_nodes, const doubl
 }
 
 // Block membership of X_dev on the device: assignment kernel, stable radix sort, bounds.
-// Leaves perm / pos_block / block_ptr on the device, block_ptr on the host, and rebuilds the units.
-static int reblock_device(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
+// Leaves perm / pos_block / block_ptr on the device.  Nothing is read back: the resident path never
+// needs the block sizes on the host; reblock_finish() fetches them for the tile pipeline.
+static int reblock_launch(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
   if (h->part_kind == 0) {
     h->err = "no device partitioner set";
     return GPRF_ERR_ARG;
@@ -842,6 +906,24 @@ static int reblock_device(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
   k_block_bounds<<<(unsigned)((nthr + tb - 1) / tb), tb, 0, st>>>(h->dPosBlock, h->dIdxSorted, n, B, h->dBlockPtr,
                                                                     h->dPerm);
   CUDA_OK(cudaGetLastError());
+  h->part_launches = 5;
+  if (B != h->B) {
+    h->adj_dirty = true;
+    h->units_built = false;
+  }
+  h->B = B;
+  h->plen = n;
+  h->dev_blocks_valid = true;
+  h->host_blocks_stale = true;
+  h->have_structure = false;
+  h->blocks_stream = st;
+  return GPRF_OK;
+}
+
+// Bring the host view (block_ptr_h, unit descriptors of the tile pipeline) up to date with the
+// device-held blocks: one D2H copy + synchronisation, descriptors rebuilt only when a size changed.
+static int reblock_finish(gprf_ctx* h, cudaStream_t st) {
+  const int B = h->B;
   if (!h->hBlockPtr || h->capHB < (size_t)B + 1) {
     if (h->hBlockPtr) cudaFreeHost(h->hBlockPtr);
     h->hBlockPtr = nullptr;
@@ -850,27 +932,38 @@ static int reblock_device(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
   }
   CUDA_OK(cudaMemcpyAsync(h->hBlockPtr, h->dBlockPtr, ((size_t)B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
-  h->part_launches = 5;
+  h->host_blocks_stale = false;
   // Unit descriptors depend on the block SIZES only (which points sit in a block is in dPerm,
   // already rewritten on the device): late in an optimisation few points change block, and then
   // nothing has to be rebuilt or uploaded.
-  if (h->units_built && h->blocks_from_device && B == h->B && h->plen == n && (int)h->block_ptr_h.size() == B + 1 &&
+  if (h->units_built && h->blocks_from_device && (int)h->block_ptr_h.size() == B + 1 &&
       memcmp(h->block_ptr_h.data(), h->hBlockPtr, ((size_t)B + 1) * sizeof(long long)) == 0) {
     h->have_structure = true;
     return GPRF_OK;
   }
-  if (B != h->B) h->adj_dirty = true;
-  h->B = B;
-  h->plen = n;
   h->block_ptr_h.assign(h->hBlockPtr, h->hBlockPtr + B + 1);
   h->blocks_from_device = true;
   return rebuild_units(h, st);
+}
+
+static int reblock_device(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
+  int rc = reblock_launch(h, X_dev, st);
+  if (rc != GPRF_OK) return rc;
+  return reblock_finish(h, st);
+}
+
+// Host view needed (tile pipeline, gprf_get_blocks) while the blocks live on the device only.
+static int ensure_host_blocks(gprf_ctx* h, cudaStream_t st) {
+  if (h->host_blocks_stale) return reblock_finish(h, st);
+  if (!h->units_built && (int)h->block_ptr_h.size() == h->B + 1) return rebuild_units(h, st);
+  return GPRF_OK;
 }
 
 extern "C" int gprf_reblock_device(gprf_handle h, const double* X_dev, void* stream) {
   if (!h || !X_dev) return GPRF_ERR_ARG;
   CUDA_OK(cudaSetDevice(h->device));
   h->have_structure = false;
+  if (res_eligible(h)) return reblock_launch(h, X_dev, (cudaStream_t)stream);   // host view on demand
   return reblock_device(h, X_dev, (cudaStream_t)stream);
 }
 
@@ -881,7 +974,7 @@ extern "C" int gprf_reblock(gprf_handle h, const double* X) {
   const size_t xb = (size_t)h->n * h->dx * sizeof(double);
   memcpy(h->hX, X, xb);
   CUDA_OK(cudaMemcpyAsync(h->dX, h->hX, xb, cudaMemcpyHostToDevice, h->stream));
-  int rc = reblock_device(h, h->dX, h->stream);
+  int rc = res_eligible(h) ? reblock_launch(h, h->dX, h->stream) : reblock_device(h, h->dX, h->stream);
   if (rc != GPRF_OK) return rc;
   CUDA_OK(cudaStreamSynchronize(h->stream));
   return GPRF_OK;
@@ -889,6 +982,11 @@ extern "C" int gprf_reblock(gprf_handle h, const double* X) {
 
 extern "C" int gprf_block_count(gprf_handle h, int* n_blocks, long long* plen) {
   if (!h) return GPRF_ERR_ARG;
+  if (h->host_blocks_stale) {
+    CUDA_OK(cudaSetDevice(h->device));
+    int rc = ensure_host_blocks(h, h->blocks_stream);
+    if (rc != GPRF_OK) return rc;
+  }
   if ((int)h->block_ptr_h.size() != h->B + 1) return GPRF_ERR_NO_STRUCTURE;
   if (n_blocks) *n_blocks = h->B;
   if (plen) *plen = h->plen;
@@ -897,8 +995,13 @@ extern "C" int gprf_block_count(gprf_handle h, int* n_blocks, long long* plen) {
 
 extern "C" int gprf_get_blocks(gprf_handle h, long long* block_ptr, long long* perm) {
   if (!h) return GPRF_ERR_ARG;
-  if ((int)h->block_ptr_h.size() != h->B + 1) return GPRF_ERR_NO_STRUCTURE;
   CUDA_OK(cudaSetDevice(h->device));
+  if (h->host_blocks_stale) {
+    int rc = ensure_host_blocks(h, h->blocks_stream);
+    if (rc != GPRF_OK) return rc;
+  }
+  if ((int)h->block_ptr_h.size() != h->B + 1) return GPRF_ERR_NO_STRUCTURE;
+  if (h->blocks_stream) CUDA_OK(cudaStreamSynchronize(h->blocks_stream));
   if (block_ptr) memcpy(block_ptr, h->block_ptr_h.data(), (size_t)(h->B + 1) * sizeof(long long));
   if (perm && h->plen > 0) {
     CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -988,6 +1091,190 @@ static int launch_units_tiled(gprf_ctx* h, const EvalParams& P, const int* list_
     LAUNCH(6, (k_unit_finalize<<<cnt, NTHREADS, 0, st>>>(Pc, h->dLLu, h->dGthU, want_grad ? 1 : 0)));
   }
   return launches;
+}
+
+// ---------------------------------------------------------------------------
+// Resident path (resident.cuh): plan -> block units -> pair units -> combine, 4 launches, nothing
+// read back before the end of the evaluation.  The caller copies out / the status word and
+// synchronises once; a non-zero status sends the evaluation through the tile pipeline.
+// ---------------------------------------------------------------------------
+static int res_sync_static(gprf_ctx* h) {
+  if (h->adj_dirty) {
+    int rc = rebuild_adjacency(h);
+    if (rc != GPRF_OK) return rc;
+  }
+  if (!h->res_static_dirty) return GPRF_OK;
+  const int B = h->B, E = h->E, U = B + E;
+  CUDA_OK(ensure(&h->dResEdges, &h->capResE, (size_t)2 * E + 2));
+  CUDA_OK(ensure(&h->dResDeg, &h->capResB, (size_t)B + 1));
+  if (E > 0)
+    CUDA_OK(cudaMemcpy(h->dResEdges, h->edges.data(), (size_t)2 * E * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(h->dResDeg, h->deg.data(), (size_t)B * sizeof(int), cudaMemcpyHostToDevice));
+  h->res_have_mask = false;
+  if (h->use_explicit_mask) {
+    if ((int)h->explicit_mask.size() != U) return GPRF_ERR_ARG;
+    h->res_mask = h->explicit_mask;
+    h->res_have_mask = true;
+  } else if (h->shard_world > 1) {
+    std::vector<double> sizes;
+    shard_sizes(h, sizes);
+    lpt_mask(sizes, B, h->edges.data(), h->shard_rank, h->shard_world, h->res_mask);
+    h->res_have_mask = true;
+  }
+  if (h->res_have_mask) {
+    CUDA_OK(ensure(&h->dResActive, &h->capResAct, (size_t)U + 1));
+    CUDA_OK(cudaMemcpy(h->dResActive, h->res_mask.data(), (size_t)U, cudaMemcpyHostToDevice));
+  }
+  h->res_static_dirty = false;
+  return GPRF_OK;
+}
+
+static int res_alloc(gprf_ctx* h, int grid) {
+  const size_t B = (size_t)h->B, U = (size_t)h->B + h->E;
+  CUDA_OK(ensure(&h->dResExports, &h->capResExp, B * (size_t)res::EXP_STRIDE));
+  CUDA_OK(ensure(&h->dResScratch, &h->capResScr, (size_t)grid * (size_t)res::SCR_STRIDE));
+  if (U > h->capResU || !h->dResLL) {
+    cudaFree(h->dResLL); cudaFree(h->dResGth); cudaFree(h->dResGx); cudaFree(h->dResInfo);
+    cudaFree(h->dResOrderB); cudaFree(h->dResOrderP); cudaFree(h->dResCounts);
+    h->dResLL = h->dResGth = h->dResGx = nullptr;
+    h->dResInfo = h->dResOrderB = h->dResOrderP = h->dResCounts = nullptr;
+    const size_t cu = U + U / 4 + 16;
+    CUDA_OK(cudaMalloc((void**)&h->dResLL, cu * sizeof(double)));
+    CUDA_OK(cudaMalloc((void**)&h->dResGth, cu * MAX_NCOV * sizeof(double)));
+    CUDA_OK(cudaMalloc((void**)&h->dResGx, cu * res::GX_STRIDE * sizeof(double)));
+    CUDA_OK(cudaMalloc((void**)&h->dResInfo, cu * sizeof(int)));
+    CUDA_OK(cudaMalloc((void**)&h->dResOrderB, cu * sizeof(int)));
+    CUDA_OK(cudaMalloc((void**)&h->dResOrderP, cu * sizeof(int)));
+    CUDA_OK(cudaMalloc((void**)&h->dResCounts, 8 * sizeof(int)));
+    CUDA_OK(cudaMemset(h->dResLL, 0, cu * sizeof(double)));
+    CUDA_OK(cudaMemset(h->dResGth, 0, cu * MAX_NCOV * sizeof(double)));
+    CUDA_OK(cudaMemset(h->dResGx, 0, cu * res::GX_STRIDE * sizeof(double)));
+    h->capResU = cu;
+  }
+  if (!h->dResDbg) CUDA_OK(cudaMalloc((void**)&h->dResDbg, 2 * 128 * 128 * sizeof(double)));
+  return GPRF_OK;
+}
+
+// Enqueue one evaluation on the resident path.  out_dev = [ll, grad theta (5), gradX (n dx)].
+static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, int grad_X, int grad_cov,
+                        double* out_dev, cudaStream_t st, int* launches_out) {
+  int rc = res_sync_static(h);
+  if (rc != GPRF_OK) return rc;
+  const int B = h->B, E = h->E;
+  const int grid_b = std::max(1, std::min(B, h->n_sm));
+  const int grid_p = std::max(1, std::min(E, h->n_sm));
+  rc = res_alloc(h, std::max(grid_b, grid_p));
+  if (rc != GPRF_OK) return rc;
+  int launches = 0;
+  const size_t outlen = 1 + MAX_NCOV + (grad_X ? (size_t)h->n * h->dx : 0);
+  CUDA_OK(cudaMemsetAsync(out_dev, 0, outlen * sizeof(double), st));
+  res::PlanParams Q;
+  Q.block_ptr = h->dBlockPtr;
+  Q.edges = h->dResEdges;
+  Q.active = h->res_have_mask ? h->dResActive : nullptr;
+  Q.B = B;
+  Q.E = E;
+  Q.order_blocks = h->dResOrderB;
+  Q.order_pairs = h->dResOrderP;
+  Q.counts = h->dResCounts;
+  Q.status = h->dResCounts + 4;
+  Q.info = h->dResInfo;
+  const size_t plan_sm = (size_t)(B + E) * sizeof(int);
+  if (plan_sm > 48 * 1024)
+    cudaFuncSetAttribute(res::k_res_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_sm);
+  LAUNCH(9, (res::k_res_plan<<<1, 512, plan_sm, st>>>(Q)));
+  res::ResParams P;
+  P.X = X_dev;
+  P.Y = h->dY;
+  P.perm = h->dPerm;
+  P.block_ptr = h->dBlockPtr;
+  P.edges = h->dResEdges;
+  P.B = B;
+  P.dx = h->dx;
+  P.dy = h->dy;
+  P.nyb = (h->dy + 7) / 8;
+  P.want_grad = (grad_X || grad_cov) ? 1 : 0;
+  P.cp = cp;
+  P.exports = h->dResExports;
+  P.scratch = h->dResScratch;
+  P.ll_u = h->dResLL;
+  P.gth_u = h->dResGth;
+  P.gx_u = h->dResGx;
+  P.info = h->dResInfo;
+  P.status = h->dResCounts + 4;
+  P.dbg_unit = h->res_dbg_unit;
+  P.dbg_phase = h->res_dbg_phase;
+  P.dbg_out = h->dResDbg;
+  P.order = h->dResOrderB;
+  P.n_order = h->dResCounts + 0;
+  P.counter = h->dResCounts + 2;
+#define CALL_RESB(D, W) res::resident_launch<D, W>(P, grid_b, st)
+  LAUNCH(10, DISPATCH_COV(h, CALL_RESB));
+  if (E > 0) {
+    P.order = h->dResOrderP;
+    P.n_order = h->dResCounts + 1;
+    P.counter = h->dResCounts + 3;
+#define CALL_RESP(D, W) res::resident_launch<D, W>(P, grid_p, st)
+    LAUNCH(11, DISPATCH_COV(h, CALL_RESP));
+  }
+  res::ResCombine C;
+  C.perm = h->dPerm;
+  C.pos_block = h->dPosBlock;
+  C.block_ptr = h->dBlockPtr;
+  C.adj_ptr = h->dAdjPtr;
+  C.adj_edge = h->dAdjEdge;
+  C.adj_side = h->dAdjSide;
+  C.edges = h->dResEdges;
+  C.deg = h->dResDeg;
+  C.active = h->res_have_mask ? h->dResActive : nullptr;
+  C.ll_u = h->dResLL;
+  C.gth_u = h->dResGth;
+  C.gx_u = h->dResGx;
+  C.status = h->dResCounts + 4;
+  C.B = B;
+  C.E = E;
+  C.dx = h->dx;
+  C.plen = h->plen;
+  const unsigned gc = 1 + (grad_X ? (unsigned)((h->plen + 255) / 256) : 0);
+  LAUNCH(12, (res::k_res_combine<<<gc, 256, 0, st>>>(C, out_dev, grad_X ? 1 : 0, grad_cov ? 1 : 0, nullptr)));
+  CUDA_OK(cudaGetLastError());
+  if (launches_out) *launches_out = launches;
+  return GPRF_OK;
+}
+
+// Try the resident path for one evaluation.  Returns GPRF_OK with *done = 1 when the results are in
+// out_dev / host_out; *done = 0 means "run the tile pipeline" (not eligible, a unit did not fit, or
+// a pivot failed and the jitter rule has to be applied).
+static int try_resident(gprf_ctx* h, const double* X_dev, const double* theta, int ncov, int grad_X, int grad_cov,
+                        double* out_dev, cudaStream_t st, double* host_out, int* done) {
+  *done = 0;
+  h->last_resident = false;
+  if (!res_eligible(h) || !h->dev_blocks_valid || h->plen <= 0) return GPRF_OK;
+  CovParams cp;
+  int rc = make_cov(h, theta, ncov, &cp);
+  if (rc != GPRF_OK) {
+    h->err = "theta must have 2 + (number of lengthscales) entries";
+    return rc;
+  }
+  int launches = 0;
+  CUDA_OK(cudaEventRecord(h->ev0, st));
+  rc = run_resident(h, X_dev, cp, grad_X, grad_cov, out_dev, st, &launches);
+  if (rc != GPRF_OK) return rc;
+  CUDA_OK(cudaEventRecord(h->ev1, st));
+  const size_t outlen = 1 + MAX_NCOV + (grad_X ? (size_t)h->n * h->dx : 0);
+  if (host_out) CUDA_OK(cudaMemcpyAsync(host_out, out_dev, outlen * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(h->hResStatus, h->dResCounts + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  h->res_evals++;
+  h->res_last_status = h->hResStatus[0];
+  if (h->hResStatus[0] != 0) {
+    h->res_fallbacks++;
+    return GPRF_OK;
+  }
+  h->last_launches = launches;
+  h->last_resident = true;
+  *done = 1;
+  return GPRF_OK;
 }
 
 // On return the stream has drained: out_dev (and host_out, a pinned buffer, when given) hold the results.
@@ -1128,8 +1415,16 @@ extern "C" int gprf_llgrad_device(gprf_handle h, const double* X_dev, const doub
   if (!h || !X_dev || !theta || !out_dev) return GPRF_ERR_ARG;
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = run_eval(h, X_dev, theta, ncov, grad_X, grad_cov, out_dev, st, failed_unit);
+  if (failed_unit) *failed_unit = -1;
+  int done = 0;
+  int rc = try_resident(h, X_dev, theta, ncov, grad_X, grad_cov, out_dev, st, nullptr, &done);
   if (rc != GPRF_OK) return rc;
+  if (!done) {
+    rc = ensure_host_blocks(h, st);
+    if (rc != GPRF_OK) return rc;
+    rc = run_eval(h, X_dev, theta, ncov, grad_X, grad_cov, out_dev, st, failed_unit);
+    if (rc != GPRF_OK) return rc;
+  }
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   if (h->profile) h->prof_resolve();
   return GPRF_OK;
@@ -1143,8 +1438,16 @@ extern "C" int gprf_llgrad(gprf_handle h, const double* X, const double* theta, 
   const size_t xb = (size_t)h->n * h->dx * sizeof(double);
   memcpy(h->hX, X, xb);
   CUDA_OK(cudaMemcpyAsync(h->dX, h->hX, xb, cudaMemcpyHostToDevice, h->stream));
-  int rc = run_eval(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, failed_unit, h->hOut);
+  if (failed_unit) *failed_unit = -1;
+  int done = 0;
+  int rc = try_resident(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, h->hOut, &done);
   if (rc != GPRF_OK) return rc;
+  if (!done) {
+    rc = ensure_host_blocks(h, h->stream);
+    if (rc != GPRF_OK) return rc;
+    rc = run_eval(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, failed_unit, h->hOut);
+    if (rc != GPRF_OK) return rc;
+  }
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   if (h->profile) h->prof_resolve();
   *ll = h->hOut[0];
@@ -1163,10 +1466,18 @@ extern "C" int gprf_llgrad_reblock(gprf_handle h, const double* X, const double*
   memcpy(h->hX, X, xb);
   CUDA_OK(cudaMemcpyAsync(h->dX, h->hX, xb, cudaMemcpyHostToDevice, h->stream));
   h->have_structure = false;
-  int rc = reblock_device(h, h->dX, h->stream);
+  if (failed_unit) *failed_unit = -1;
+  int rc = reblock_launch(h, h->dX, h->stream);
   if (rc != GPRF_OK) return rc;
-  rc = run_eval(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, failed_unit, h->hOut);
+  int done = 0;
+  rc = try_resident(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, h->hOut, &done);
   if (rc != GPRF_OK) return rc;
+  if (!done) {
+    rc = reblock_finish(h, h->stream);
+    if (rc != GPRF_OK) return rc;
+    rc = run_eval(h, h->dX, theta, ncov, grad_X, grad_cov, h->dOut, h->stream, failed_unit, h->hOut);
+    if (rc != GPRF_OK) return rc;
+  }
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   if (h->profile) h->prof_resolve();
   h->last_launches += h->part_launches;
@@ -1178,10 +1489,75 @@ extern "C" int gprf_llgrad_reblock(gprf_handle h, const double* X, const double*
 }
 
 extern "C" int gprf_unit_results(gprf_handle h, double* ll_units, double* jitter_units) {
-  if (!h || !h->have_structure) return GPRF_ERR_NO_STRUCTURE;
+  if (!h || (!h->have_structure && !h->last_resident)) return GPRF_ERR_NO_STRUCTURE;
   CUDA_OK(cudaSetDevice(h->device));
+  if (h->last_resident) {
+    const size_t U = (size_t)h->B + h->E;
+    if (ll_units) CUDA_OK(cudaMemcpy(ll_units, h->dResLL, U * sizeof(double), cudaMemcpyDeviceToHost));
+    if (jitter_units) memset(jitter_units, 0, U * sizeof(double));
+    return GPRF_OK;
+  }
   if (ll_units) CUDA_OK(cudaMemcpy(ll_units, h->dLLu, (size_t)h->U * sizeof(double), cudaMemcpyDeviceToHost));
   if (jitter_units) memcpy(jitter_units, h->jitter.data(), (size_t)h->U * sizeof(double));
+  return GPRF_OK;
+}
+
+// ---- resident path: switches, statistics, debug ------------------------------------------------
+extern "C" int gprf_set_resident(gprf_handle h, int on) {
+  if (!h) return GPRF_ERR_ARG;
+  h->res_enable = on != 0;
+  h->res_static_dirty = true;
+  h->units_built = false;          // the multi-GPU split depends on it (shard_sizes)
+  if ((int)h->block_ptr_h.size() == h->B + 1 && h->B > 0 && !h->host_blocks_stale) return replan(h);
+  return GPRF_OK;
+}
+
+extern "C" int gprf_resident_stats(gprf_handle h, long long* evals, long long* fallbacks, int* last_status) {
+  if (!h) return GPRF_ERR_ARG;
+  if (evals) *evals = h->res_evals;
+  if (fallbacks) *fallbacks = h->res_fallbacks;
+  if (last_status) *last_status = h->res_last_status;
+  return GPRF_OK;
+}
+
+extern "C" int gprf_resident_layout(long long* out, int n) {
+  const long long v[] = {res::RMAXB, res::RNYB, res::RBLK, res::EXP_W, res::EXP_KINV, res::EXP_ZY, res::EXP_AROW,
+                         res::EXP_SCAL, res::EXP_STRIDE, res::GX_STRIDE, res::R_MAT_BLOCKS};
+  const int m = (int)(sizeof(v) / sizeof(v[0]));
+  if (!out || n < m) return m;
+  for (int i = 0; i < m; ++i) out[i] = v[i];
+  return m;
+}
+
+extern "C" int gprf_set_resident_debug(gprf_handle h, int unit, int phase) {
+  if (!h) return GPRF_ERR_ARG;
+  h->res_dbg_unit = unit;
+  h->res_dbg_phase = phase;
+  return GPRF_OK;
+}
+
+// out_dump: 2 x 128 x 128 doubles (R1, R2 of the unit / phase selected with gprf_set_resident_debug);
+// out_export: EXP_STRIDE doubles, the raw export record of `block`; out_unit: ll, grad theta (5),
+// gradX rows (GX_STRIDE) of unit `unit`.  Any pointer may be NULL.
+extern "C" int gprf_get_resident_debug(gprf_handle h, double* out_dump, int block, double* out_export, int unit,
+                                       double* out_unit) {
+  if (!h || !h->dResLL) return GPRF_ERR_NO_STRUCTURE;
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  if (out_dump) CUDA_OK(cudaMemcpy(out_dump, h->dResDbg, 2 * 128 * 128 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_export) {
+    if (block < 0 || block >= h->B) return GPRF_ERR_ARG;
+    CUDA_OK(cudaMemcpy(out_export, h->dResExports + (size_t)block * res::EXP_STRIDE, res::EXP_STRIDE * sizeof(double),
+                       cudaMemcpyDeviceToHost));
+  }
+  if (out_unit) {
+    if (unit < 0 || unit >= h->B + h->E) return GPRF_ERR_ARG;
+    CUDA_OK(cudaMemcpy(out_unit, h->dResLL + unit, sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(out_unit + 1, h->dResGth + (size_t)unit * MAX_NCOV, MAX_NCOV * sizeof(double),
+                       cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(out_unit + 1 + MAX_NCOV, h->dResGx + (size_t)unit * res::GX_STRIDE,
+                       res::GX_STRIDE * sizeof(double), cudaMemcpyDeviceToHost));
+  }
   return GPRF_OK;
 }
 
@@ -1200,7 +1576,8 @@ extern "C" int gprf_set_profiling(gprf_handle h, int on) {
 
 extern "C" const char* gprf_family_name(int fam) {
   static const char* names[GPRF_N_FAMILIES] = {"prep", "potrf_diag", "potrf_panel", "trtri",
-                                               "alpha", "kinv_grad", "unit_finalize", "combine", "unit_fused"};
+                                               "alpha", "kinv_grad", "unit_finalize", "combine", "unit_fused",
+                                               "res_plan", "res_blocks", "res_pairs", "res_combine"};
   return (fam >= 0 && fam < GPRF_N_FAMILIES) ? names[fam] : "";
 }
 

@@ -1,0 +1,956 @@
+// Resident unit kernel: one CTA evaluates one unit (a block, or an edge's pair of blocks) of the
+// GPRF objective (gprf.py:206-330, 496-591) entirely out of shared memory.
+//
+// The tile pipeline of gprf_kernels.cuh keeps every unit's working matrix in HBM/L2 and runs one
+// launch per dependency level; for the README configuration (442 units of 100-250 points) that
+// is a chain of ~25 latency-bound launches.  Here a unit never leaves the SM:
+//
+//   block unit b      K_bb -> L_b -> W_b = L_b^-1 (in place), Z_b = W_b Y_b, alpha_b = W_b^T Z_b,
+//                     K_bb^-1 = W_b^T W_b, G = alpha alpha^T - dy K^-1 contracted with dK in
+//                     registers; W_b, Z_b, alpha_b, K_bb^-1, logdet_b and |Z_b|^2 are exported.
+//   pair unit (i, j)  the edge factorisation REUSES block i's factor and factors only the Schur
+//                     complement of block j (rows of i come first, gprf.py:310-330):
+//                       L_ji = K_ji W_i^T                 S = K_jj + nv I - L_ji L_ji^T
+//                       L_S = chol(S), W_S = L_S^-1       Z_j = W_S (Y_j - L_ji Z_i)
+//                       V = -W_S L_ji W_i                 (L^-1 of the pair = [[W_i, 0], [V, W_S]])
+//                       alpha = [alpha_i + V^T Z_j ; W_S^T Z_j]
+//                       K^-1 = [[K_ii^-1 + V^T V, .], [W_S^T V, W_S^T W_S]]
+//                     (checked against the oracle on the CPU in tests/test_schur_model.py).
+//
+// Storage: matrices are kept as packed 8x8 blocks (the DMMA m8n8k4 fragment), 512 contiguous
+// bytes each, with an in-block swizzle that makes BOTH the row-major fragment load (LDS.128) and
+// the transposed fragment load (2 x LDS.64) bank-conflict free, so that every product on the
+// path reads its operands where they already are:
+//   R1  bb x ab blocks   L_ji -> T = L_ji W_i -> V         (pair units only)
+//   R2  lower triangle of bb x bb blocks   S -> L_S -> W_S
+//   XS  coordinate records of the unit's points, RING  3 x 8 KB staging ring
+// Operands that live in HBM/L2 (the parent block's exports, this CTA's own Z / alpha scratch)
+// are streamed through RING by TMA bulk copies (cp.async.bulk + mbarrier complete_tx).
+// Padding rows/columns (sizes are rounded up to 8 separately for block i and block j) form an
+// identity block, as in the tile pipeline.
+//
+// Limits: every block of the unit has at most 8*RMAXB = 128 points, bb*ab + tri(bb) <= R_MAT_BLOCKS
+// and dy <= 64.  Units outside them, and evaluations in which a pivot fails (the jitter rule of
+// gpy_linalg.py:77-97), are reported in the status word and re-run through the tile pipeline.
+#pragma once
+#include "covfn.cuh"
+#include "tile_gemm.cuh"
+#include "smem_chol.cuh"
+
+namespace gprf {
+namespace res {
+
+constexpr int RMAXB = 16;                 // 8x8 blocks per side of one block of points
+constexpr int RNYB = 8;                   // y blocks per row in the exported layouts (dy <= 64)
+constexpr int RNW = 16;                   // warps per CTA
+constexpr int RNT = RNW * 32;
+constexpr int RBLK = 64;                  // doubles per 8x8 block
+constexpr int RSTAGE_BLK = 16;            // blocks per ring stage (8 KB)
+constexpr int RSTAGES = 3;
+constexpr int R_XS_DOUBLES = 2 * RMAXB * 8 * XD;
+constexpr int R_RING_DOUBLES = RSTAGES * RSTAGE_BLK * RBLK;
+constexpr int R_MISC_DOUBLES = 320;
+constexpr int R_SMEM_BYTES = 232448;      // 227 KB, the sm_100 per-CTA maximum
+constexpr int R_MAT_BLOCKS = (R_SMEM_BYTES / 8 - R_XS_DOUBLES - R_RING_DOUBLES - R_MISC_DOUBLES) / RBLK;
+
+constexpr int RTRI = RMAXB * (RMAXB + 1) / 2;          // 136
+// per-block export (doubles)
+constexpr long long EXP_W = 0;
+constexpr long long EXP_KINV = (long long)RTRI * RBLK;
+constexpr long long EXP_ZY = 2LL * RTRI * RBLK;                     // (yb * RMAXB + k)
+constexpr long long EXP_AROW = EXP_ZY + (long long)RNYB * RMAXB * RBLK;     // (k * RNYB + yb)
+constexpr long long EXP_SCAL = EXP_AROW + (long long)RMAXB * RNYB * RBLK;   // logdet, |Z|^2
+constexpr long long EXP_STRIDE = EXP_SCAL + 16;
+// per-CTA scratch (doubles)
+constexpr long long SCR_ZY = 0;
+constexpr long long SCR_AROW = (long long)RNYB * RMAXB * RBLK;              // 2*RMAXB rows
+constexpr long long SCR_COLP = SCR_AROW + 2LL * RMAXB * RNYB * RBLK;
+constexpr int COLP = 24;
+constexpr long long SCR_STRIDE = SCR_COLP + (long long)(2 * RMAXB) * (2 * RMAXB + 1) / 2 * COLP;
+constexpr int GX_STRIDE = 2 * RMAXB * 8 * 3;           // per-unit gradX rows (padded local order)
+
+enum { ST_OVERFLOW = 1, ST_NOTPD = 2 };
+
+__host__ __device__ __forceinline__ int rtri(int i) { return i * (i + 1) / 2; }
+__host__ __device__ __forceinline__ bool res_fits(int ab, int bb) {
+  return ab <= RMAXB && bb <= RMAXB && bb * ab + rtri(bb) <= R_MAT_BLOCKS;
+}
+
+struct ResParams {
+  const double* X;              // n x dx
+  const double* Y;              // n x dy
+  const long long* perm;
+  const long long* block_ptr;   // B + 1
+  const int* edges;             // 2 E
+  const int* order;             // units of this launch (block id, or B + edge id)
+  const int* n_order;           // their number (device: written by k_res_plan)
+  int* counter;                 // dynamic queue head
+  int B, dx, dy, nyb;
+  int want_grad;
+  CovParams cp;
+  double* exports;              // B x EXP_STRIDE
+  double* scratch;              // gridDim.x x SCR_STRIDE
+  double* ll_u;                 // per unit
+  double* gth_u;                // per unit x MAX_NCOV
+  double* gx_u;                 // per unit x GX_STRIDE
+  int* info;                    // per unit: 1 + first failing local row
+  int* status;
+  int dbg_unit, dbg_phase;      // debug dump of R1 / R2 after a phase (-1: off)
+  double* dbg_out;              // 2 x (128 x 128) doubles
+};
+
+// ---- swizzled 8x8 block ---------------------------------------------------------------------
+// element (r, c) lives at  8 * (r ^ ((r >> 1) & 1)) + (c ^ (r & 4)).
+__host__ __device__ __forceinline__ int sw_off(int r, int c) { return ((r ^ ((r >> 1) & 1)) << 3) + (c ^ (r & 4)); }
+
+struct Lane {
+  int w, lane, g, q;
+  int on, ot0, ot1;             // offsets of the row-major / transposed fragment elements
+};
+__device__ __forceinline__ Lane make_lane() {
+  Lane L;
+  L.w = threadIdx.x >> 5;
+  L.lane = threadIdx.x & 31;
+  L.g = L.lane >> 2;
+  L.q = L.lane & 3;
+  L.on = sw_off(L.g, 2 * L.q);
+  L.ot0 = sw_off(2 * L.q, L.g);
+  L.ot1 = sw_off(2 * L.q + 1, L.g);
+  return L;
+}
+// row-major fragment: (M[g][2q], M[g][2q+1])  - A operand of C = A B^T, B operand given as [n][k],
+// and the accumulator layout
+__device__ __forceinline__ double2 ldn(const double* blk, const Lane& L) {
+  return *reinterpret_cast<const double2*>(blk + L.on);
+}
+// transposed fragment: (M[2q][g], M[2q+1][g]) - operand given as [k][m] / [k][n]
+__device__ __forceinline__ double2 ldt(const double* blk, const Lane& L) {
+  return make_double2(blk[L.ot0], blk[L.ot1]);
+}
+__device__ __forceinline__ void stn(double* blk, const Lane& L, double2 v) {
+  *reinterpret_cast<double2*>(blk + L.on) = v;
+}
+__device__ __forceinline__ void mma2(double2& c, double2 a, double2 b) {
+  dmma884(c.x, c.y, a.x, b.x);
+  dmma884(c.x, c.y, a.y, b.y);
+}
+__device__ __forceinline__ double2 neg2(double2 v) { return make_double2(-v.x, -v.y); }
+
+// ---- staging ring ------------------------------------------------------------------------------
+struct Ring {
+  double* buf;
+  uint64_t* bar;
+  unsigned par;                 // bit s: parity the next wait on stage s expects
+};
+__device__ __forceinline__ void ring_issue(const Ring& R, int stage, const double* src, int nblk) {
+  fence_proxy_async();
+  const uint32_t bytes = (uint32_t)nblk * RBLK * 8;
+  mbar_expect_tx(R.bar + stage, bytes);
+  bulk_g2s(R.buf + stage * RSTAGE_BLK * RBLK, src, bytes, R.bar + stage);
+}
+__device__ __forceinline__ void ring_wait(Ring& R, int stage) {
+  mbar_wait(R.bar + stage, (R.par >> stage) & 1u);
+  R.par ^= 1u << stage;
+}
+
+// Stream `nrows` rows of blocks (row r has rowlen(r) <= RSTAGE_BLK blocks, rows contiguous in
+// `src`) through NS stages of the ring; body(r, rowptr) is executed by every thread for every
+// row, in order.  All threads of the CTA must call it (it synchronises the CTA once per stage).
+template <int NS, class RowLen, class Body>
+__device__ __forceinline__ void stream_rows(Ring& R, const double* src, int nrows, RowLen rowlen, Body body) {
+  auto next = [&](int r0, int& nb) {
+    int r = r0;
+    nb = 0;
+    while (r < nrows && nb + rowlen(r) <= RSTAGE_BLK) {
+      nb += rowlen(r);
+      ++r;
+    }
+    return r;
+  };
+  __syncthreads();              // earlier users of the ring (any proxy) are done
+  int ir = 0, issued = 0;
+  long long ipos = 0;
+  auto issue_one = [&]() {
+    if (ir < nrows) {
+      int nb;
+      const int r1 = next(ir, nb);
+      if (threadIdx.x == 0) ring_issue(R, issued % NS, src + ipos * RBLK, nb);
+      ir = r1;
+      ipos += nb;
+      ++issued;
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < NS - 1; ++s) issue_one();
+  int r = 0, consumed = 0;
+  while (r < nrows) {
+    int nb;
+    const int r1 = next(r, nb);
+    issue_one();                // into the stage consumed one iteration ago (CTA-synchronised since)
+    const int st = consumed % NS;
+    ring_wait(R, st);
+    const double* p = R.buf + st * RSTAGE_BLK * RBLK;
+    for (int rr = r; rr < r1; ++rr) {
+      body(rr, p);
+      p += rowlen(rr) * RBLK;
+    }
+    __syncthreads();
+    r = r1;
+    ++consumed;
+  }
+}
+
+// ---- per-unit geometry ---------------------------------------------------------------------------
+struct Unit {
+  int uid, bi, bj;              // bi < 0: block unit
+  int a, b, ab, bb;             // points / 8-blocks of the i part (0 for block units) and the j part
+  long long ia, ja;             // offsets of the two blocks in perm
+};
+
+// coordinates of local row t (i part: [0, 8 ab), j part: [8 ab, 8 ab + 8 bb))
+__device__ __forceinline__ const double* xs_row(const double* XS, int t) { return XS + t * XD; }
+
+// ---------------------------------------------------------------------------------------------------
+template <int DFN, int WFN>
+__device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, double* smem, Ring& ring,
+                                         double* scratch) {
+  const Lane L = make_lane();
+  const int tid = threadIdx.x;
+  const int w = L.w;
+  const int a = u.a, b = u.b, ab = u.ab, bb = u.bb;
+  const int nr = ab + bb;                          // block rows of the whole unit
+  const bool pair = ab > 0;
+  const bool is_export = u.bi < 0;                 // block units export for their pairs
+  double* XS = smem;
+  double* RING = XS + R_XS_DOUBLES;
+  double* MISC = RING + R_RING_DOUBLES;
+  double* R2 = MISC + R_MISC_DOUBLES;
+  double* R1 = R2 + rtri(bb) * RBLK;
+  int* s_fail = reinterpret_cast<int*>(MISC + 4) + 1;
+  double* s_q = MISC + 8;                          // [RNW]
+  double* s_th = MISC + 24;                        // [RNW][MAX_NCOV]
+  double* s_ld = MISC + 104;                       // [RNW]
+  int* IDX = reinterpret_cast<int*>(MISC + 120);   // [2 * RMAXB * 8] global point index or -1
+  double* WD = RING;                               // diagonal-block inverses during the factorisation
+  double* RB = RING + 2 * RSTAGE_BLK * RBLK;       // stage 2: work buffer of the Y part
+  const double* pexp = pair ? P.exports + (long long)u.bi * EXP_STRIDE : nullptr;
+  double* oexp = is_export ? P.exports + (long long)u.bj * EXP_STRIDE : nullptr;
+  double* Zy = is_export ? oexp + EXP_ZY : scratch + SCR_ZY;
+  double* Arow = is_export ? oexp + EXP_AROW : scratch + SCR_AROW;
+  double* colp = scratch + SCR_COLP;
+  double* gx = P.gx_u + (long long)u.uid * GX_STRIDE;
+  const CovParams& cp = P.cp;
+
+  auto dbg_dump = [&](int phase) {
+    if (P.dbg_unit != u.uid || P.dbg_phase != phase) return;
+    __syncthreads();
+    for (int e = tid; e < 128 * 128; e += RNT) {
+      const int r = e >> 7, c = e & 127;
+      double v1 = 0.0, v2 = 0.0;
+      if (pair && r < bb * 8 && c < ab * 8) v1 = R1[((r >> 3) * ab + (c >> 3)) * RBLK + sw_off(r & 7, c & 7)];
+      if (r < bb * 8 && c <= (r | 7) && c < bb * 8 && (c >> 3) <= (r >> 3))
+        v2 = R2[(rtri(r >> 3) + (c >> 3)) * RBLK + sw_off(r & 7, c & 7)];
+      P.dbg_out[e] = v1;
+      P.dbg_out[128 * 128 + e] = v2;
+    }
+    __syncthreads();
+  };
+
+  // ---- P0: gather coordinates --------------------------------------------------------------------
+  if (tid == 0) *s_fail = 0;
+  for (int t = tid; t < nr * 8; t += RNT) {
+    long long idx = -1;
+    if (t < ab * 8) {
+      if (t < a) idx = P.perm[u.ia + t];
+    } else if (t - ab * 8 < b) {
+      idx = P.perm[u.ja + (t - ab * 8)];
+    }
+    IDX[t] = (int)idx;
+    double rec[XD];
+#pragma unroll
+    for (int d = 0; d < MAX_DX + 1; ++d) rec[d] = (idx >= 0 && d < P.dx) ? P.X[idx * P.dx + d] : 0.0;
+    point_terms(DFN, rec);
+#pragma unroll
+    for (int d = 0; d < XD; ++d) XS[t * XD + d] = rec[d];
+  }
+  __syncthreads();
+
+  // covariance fragment of block (rb, cb) in local block coordinates: rows 8 rb + g, cols 8 cb + 2q, +1
+  auto cov_frag = [&](int rb, int cb, bool with_diag) {
+    const int tr = rb * 8 + L.g;
+    const int tc = cb * 8 + 2 * L.q;
+    const bool rv = IDX[tr] >= 0;
+    const double* xr = xs_row(XS, tr);
+    double v0 = cov_value<DFN, WFN>(xr, xs_row(XS, tc), cp);
+    double v1 = cov_value<DFN, WFN>(xr, xs_row(XS, tc + 1), cp);
+    v0 = (rv && IDX[tc] >= 0) ? v0 : 0.0;
+    v1 = (rv && IDX[tc + 1] >= 0) ? v1 : 0.0;
+    if (with_diag) {
+      if (tr == tc) v0 = rv ? cp.s2 + cp.nv : 1.0;
+      if (tr == tc + 1) v1 = rv ? cp.s2 + cp.nv : 1.0;
+    }
+    return make_double2(v0, v1);
+  };
+
+  // ---- P1: L_ji = K_ji W_i^T  (row w of L_ji per warp; W_i streamed row by row) -----------------------
+  if (pair) {
+    double2 kf[RMAXB];
+    if (w < bb) {
+#pragma unroll
+      for (int k = 0; k < RMAXB; ++k) kf[k] = (k < ab) ? cov_frag(ab + w, k, false) : make_double2(0.0, 0.0);
+    }
+    stream_rows<RSTAGES>(ring, pexp + EXP_W, ab, [](int r) { return r + 1; }, [&](int c, const double* row) {
+      if (w < bb) {
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < RMAXB; ++k)
+          if (k <= c) mma2(acc, kf[k], ldn(row + k * RBLK, L));
+        stn(R1 + (w * ab + c) * RBLK, L, acc);
+      }
+    });
+  }
+  dbg_dump(1);
+
+  // ---- P2: S = K_jj + nv I - L_ji L_ji^T (lower blocks; rows split by column parity over two warps) ----
+  __syncthreads();
+  for (int part = 0; part < 2; ++part) {
+    if (w >= bb) break;
+    const int row = part ? bb - 1 - w : w;
+    double2 nla[RMAXB];
+    if (pair) {
+#pragma unroll
+      for (int k = 0; k < RMAXB; ++k)
+        nla[k] = (k < ab) ? neg2(ldn(R1 + (row * ab + k) * RBLK, L)) : make_double2(0.0, 0.0);
+    }
+    for (int c = part; c <= row; c += 2) {
+      double2 acc = cov_frag(ab + row, ab + c, true);
+      if (pair) {
+#pragma unroll
+        for (int k = 0; k < RMAXB; ++k)
+          if (k < ab) mma2(acc, nla[k], ldn(R1 + (c * ab + k) * RBLK, L));
+      }
+      stn(R2 + (rtri(row) + c) * RBLK, L, acc);
+    }
+  }
+  __syncthreads();
+  dbg_dump(2);
+
+  // ---- P3a: blocked Cholesky of S in place (jitchol's first, jitter-free attempt) ---------------------
+  for (int J = 0; J < bb; ++J) {
+    if (w == 0) {
+      double av[8], wv[8];
+      const int r = L.lane & 7;
+      const double* src = R2 + (rtri(J) + J) * RBLK;
+      if (L.lane < 8) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) av[v] = src[sw_off(r, v)];
+      } else {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) av[v] = (v == r) ? 1.0 : 0.0;
+      }
+      const int f = chol8_inv8(av, wv, L.lane);
+      if (L.lane == 0 && f != 0 && *s_fail == 0) *s_fail = J * 8 + f;
+      if (L.lane < 8) {
+        double* dl = R2 + (rtri(J) + J) * RBLK;
+        double* dw = WD + J * RBLK;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          dl[sw_off(r, v)] = av[v];
+          dw[sw_off(v, r)] = wv[v];            // lane r holds column r of W_JJ = L_JJ^-1
+        }
+      }
+    }
+    __syncthreads();
+    // panel: L_IJ = C_IJ W_JJ^T
+    {
+      const double2 bw = ldn(WD + J * RBLK, L);
+      for (int I = J + 1 + w; I < bb; I += RNW) {
+        double* pc = R2 + (rtri(I) + J) * RBLK;
+        double2 o = make_double2(0.0, 0.0);
+        mma2(o, ldn(pc, L), bw);
+        stn(pc, L, o);
+      }
+    }
+    __syncthreads();
+    // trailing update: C_IK -= L_IJ L_KJ^T, J < K <= I
+    {
+      const int m = bb - J - 1;
+      const int ntask = m * (m + 1) / 2;
+      for (int t = w; t < ntask; t += RNW) {
+        int ii = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
+        while (ii * (ii + 1) / 2 > t) --ii;
+        const int kk = t - ii * (ii + 1) / 2;
+        const int I = J + 1 + ii, K = J + 1 + kk;
+        double* pc = R2 + (rtri(I) + K) * RBLK;
+        double2 c = ldn(pc, L);
+        mma2(c, neg2(ldn(R2 + (rtri(I) + J) * RBLK, L)), ldn(R2 + (rtri(K) + J) * RBLK, L));
+        stn(pc, L, c);
+      }
+    }
+    __syncthreads();
+  }
+  dbg_dump(3);
+  // log-determinant: sum of log L_tt over the unit's j rows, fixed order
+  {
+    double lv = 0.0;
+    if (tid < bb * 8) lv = log(R2[(rtri(tid >> 3) + (tid >> 3)) * RBLK + sw_off(tid & 7, tid & 7)]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
+    if (L.lane == 0) s_ld[w] = lv;
+  }
+  // ---- P3b: W_S = L_S^-1 in place, by descending block columns ----------------------------------------
+  for (int K = bb - 1; K >= 0; --K) {
+    double2 o = make_double2(0.0, 0.0);
+    const int I = K + 1 + w;
+    if (I < bb) {
+      double2 acc = make_double2(0.0, 0.0);
+      for (int J = K + 1; J <= I; ++J)
+        mma2(acc, ldn(R2 + (rtri(I) + J) * RBLK, L), ldt(R2 + (rtri(J) + K) * RBLK, L));
+      mma2(o, acc, ldt(WD + K * RBLK, L));
+    }
+    __syncthreads();
+    if (I < bb) stn(R2 + (rtri(I) + K) * RBLK, L, neg2(o));
+    if (w == 0) stn(R2 + (rtri(K) + K) * RBLK, L, ldn(WD + K * RBLK, L));
+    __syncthreads();
+  }
+  dbg_dump(4);
+  if (is_export) {                                  // W_b for this block's pairs
+    double* dst = oexp + EXP_W;
+    for (int e = tid; e < rtri(bb) * RBLK / 2; e += RNT)
+      reinterpret_cast<double2*>(dst)[e] = reinterpret_cast<const double2*>(R2)[e];
+  }
+
+  // ---- P4: Z_j = W_S (Y_j - L_ji Z_i), alpha_j = W_S^T Z_j, one block of 8 outputs at a time ----------
+  double qsum = 0.0;
+  {
+    double2 nla[RMAXB];
+    if (pair && w < bb) {
+#pragma unroll
+      for (int k = 0; k < RMAXB; ++k)
+        nla[k] = (k < ab) ? neg2(ldn(R1 + (w * ab + k) * RBLK, L)) : make_double2(0.0, 0.0);
+    }
+    auto ybody = [&](int yb, const double* zi) {
+      if (w < bb) {
+        const int idx = IDX[ab * 8 + w * 8 + L.g];
+        const int y0 = yb * 8 + 2 * L.q;
+        double2 acc = make_double2(0.0, 0.0);
+        if (idx >= 0) {
+          if (y0 < P.dy) acc.x = __ldg(P.Y + (long long)idx * P.dy + y0);
+          if (y0 + 1 < P.dy) acc.y = __ldg(P.Y + (long long)idx * P.dy + y0 + 1);
+        }
+        if (pair) {
+#pragma unroll
+          for (int k = 0; k < RMAXB; ++k)
+            if (k < ab) mma2(acc, nla[k], ldt(zi + k * RBLK, L));
+        }
+        stn(RB + w * RBLK, L, acc);
+      }
+      __syncthreads();
+      double2 z = make_double2(0.0, 0.0);
+      if (w < bb) {
+        for (int k = 0; k <= w; ++k) mma2(z, ldn(R2 + (rtri(w) + k) * RBLK, L), ldt(RB + k * RBLK, L));
+        qsum += z.x * z.x + z.y * z.y;
+      }
+      __syncthreads();
+      if (w < bb) {
+        stn(RB + w * RBLK, L, z);
+        stn(Zy + (yb * RMAXB + w) * RBLK, L, z);
+      }
+      __syncthreads();
+      if (P.want_grad && w < bb) {
+        double2 al = make_double2(0.0, 0.0);
+        for (int k = w; k < bb; ++k) mma2(al, ldt(R2 + (rtri(k) + w) * RBLK, L), ldt(RB + k * RBLK, L));
+        stn(Arow + ((long long)(ab + w) * RNYB + yb) * RBLK, L, al);
+      }
+      __syncthreads();
+    };
+    if (pair) {
+      stream_rows<2>(ring, pexp + EXP_ZY, P.nyb, [](int) { return RMAXB; }, ybody);
+    } else {
+      __syncthreads();
+      for (int yb = 0; yb < P.nyb; ++yb) ybody(yb, nullptr);
+    }
+  }
+  // |Z_j|^2 and the log-likelihood (gprf.py:542-544)
+  {
+    double qv = qsum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
+    if (L.lane == 0) s_q[w] = qv;
+    __syncthreads();
+    if (tid == 0) {
+      double qt = 0.0, lt = 0.0;
+      for (int i = 0; i < RNW; ++i) {
+        qt += s_q[i];
+        lt += s_ld[i];
+      }
+      double logdet = 2.0 * lt;
+      if (pair) {
+        qt += pexp[EXP_SCAL + 1];
+        logdet += pexp[EXP_SCAL + 0];
+      }
+      if (is_export) {
+        oexp[EXP_SCAL + 0] = logdet;
+        oexp[EXP_SCAL + 1] = qt;
+      }
+      P.ll_u[u.uid] = -0.5 * qt - 0.5 * P.dy * logdet - 0.5 * P.dy * (double)(a + b) * 1.8378770664093454836;
+      if (*s_fail != 0) {
+        P.info[u.uid] = *s_fail;
+        atomicOr(P.status, ST_NOTPD);
+      }
+    }
+  }
+  if (!P.want_grad) {
+    __syncthreads();
+    return;
+  }
+
+  // ---- P6: T = L_ji W_i (row-local, in place), V = -W_S T (in place) ------------------------------------
+  if (pair) {
+    {
+      double2 acc[RMAXB];
+#pragma unroll
+      for (int c = 0; c < RMAXB; ++c) acc[c] = make_double2(0.0, 0.0);
+      stream_rows<RSTAGES>(ring, pexp + EXP_W, ab, [](int r) { return r + 1; }, [&](int k, const double* row) {
+        if (w < bb) {
+          const double2 av = ldn(R1 + (w * ab + k) * RBLK, L);
+#pragma unroll
+          for (int c = 0; c < RMAXB; ++c)
+            if (c <= k) mma2(acc[c], av, ldt(row + c * RBLK, L));
+        }
+      });
+      if (w < bb) {
+#pragma unroll
+        for (int c = 0; c < RMAXB; ++c)
+          if (c < ab) stn(R1 + (w * ab + c) * RBLK, L, acc[c]);
+      }
+    }
+    __syncthreads();
+    dbg_dump(6);
+    {
+      double2 acc[RMAXB];
+#pragma unroll
+      for (int c = 0; c < RMAXB; ++c) acc[c] = make_double2(0.0, 0.0);
+      if (w < bb) {
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          const int row = part ? bb - 1 - w : w;
+          for (int k = 0; k <= row; ++k) {
+            const double2 av = ldn(R2 + (rtri(row) + k) * RBLK, L);
+#pragma unroll
+            for (int cc = 0; cc < RMAXB / 2; ++cc) {
+              const int c = 2 * cc + part;
+              if (c < ab) mma2(acc[part * (RMAXB / 2) + cc], av, ldt(R1 + (k * ab + c) * RBLK, L));
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (w < bb) {
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          const int row = part ? bb - 1 - w : w;
+#pragma unroll
+          for (int cc = 0; cc < RMAXB / 2; ++cc) {
+            const int c = 2 * cc + part;
+            if (c < ab) stn(R1 + (row * ab + c) * RBLK, L, neg2(acc[part * (RMAXB / 2) + cc]));
+          }
+        }
+      }
+    }
+    __syncthreads();
+    dbg_dump(7);
+
+    // ---- P7: alpha_i = alpha_i(block) + V^T Z_j -------------------------------------------------------
+    {
+      double2 va[RMAXB];
+      if (w < ab) {
+#pragma unroll
+        for (int k = 0; k < RMAXB; ++k)
+          va[k] = (k < bb) ? ldt(R1 + (k * ab + w) * RBLK, L) : make_double2(0.0, 0.0);
+      }
+      asm volatile("fence.proxy.async;\n" ::: "memory");   // Z_j was written with ordinary stores
+      stream_rows<RSTAGES>(ring, Zy, P.nyb, [](int) { return RMAXB; }, [&](int yb, const double* zj) {
+        if (w < ab) {
+          double2 acc = ldn(pexp + EXP_AROW + ((long long)w * RNYB + yb) * RBLK, L);
+#pragma unroll
+          for (int k = 0; k < RMAXB; ++k)
+            if (k < bb) mma2(acc, va[k], ldt(zj + k * RBLK, L));
+          stn(Arow + ((long long)w * RNYB + yb) * RBLK, L, acc);
+        }
+      });
+    }
+  }
+  __syncthreads();
+
+  // ---- P8: G = alpha alpha^T - dy K^-1, contracted with dK in registers (gprf.py:547-584) ------------
+  // warp w owns block row w of the i part and block row w of the j part; alpha rows are streamed.
+  {
+    double2 ai[RNYB], aj[RNYB];
+#pragma unroll
+    for (int y = 0; y < RNYB; ++y) {
+      ai[y] = (w < ab && y < P.nyb) ? ldn(Arow + ((long long)w * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
+      aj[y] = (w < bb && y < P.nyb) ? ldn(Arow + ((long long)(ab + w) * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
+    }
+    double rsi[3] = {0.0, 0.0, 0.0}, rsj[3] = {0.0, 0.0, 0.0};
+    double th[MAX_NCOV];
+#pragma unroll
+    for (int t = 0; t < MAX_NCOV; ++t) th[t] = 0.0;
+    const double ndy = -(double)P.dy;
+
+    // contraction of one G block (block row rb, block column cb, cb <= rb) held as accumulator fragment
+    auto epilogue = [&](int rb, int cb, double2 G, double (&rs)[3]) {
+      const int tr = rb * 8 + L.g;
+      const bool rv = IDX[tr] >= 0;
+      const double* xr = xs_row(XS, tr);
+      double cs[2][3];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int tc = cb * 8 + 2 * L.q + e;
+        const double Gv = e == 0 ? G.x : G.y;
+        const bool cv = rv && IDX[tc] >= 0;
+        if (cv && tc == tr) {
+          th[0] += 0.5 * Gv;
+          th[1] += 0.5 * Gv * cp.s2;
+        }
+        const bool off = cv && tc < tr;
+        double k, gp[MAX_DX], gq[MAX_DX], gl[MAX_NLS];
+        cov_grad<DFN, WFN, false>(xr, xs_row(XS, tc), cp, k, gp, gq, gl);
+        const double Gm = off ? Gv : 0.0;
+        th[1] += off ? Gm * k : 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          rs[d] += off ? Gm * gp[d] : 0.0;
+          cs[e][d] = off ? Gm * gq[d] : 0.0;
+          th[2 + d] += off ? Gm * gl[d] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          double v = cs[e][d];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (L.g == 0) colp[(long long)(rtri(rb) + cb) * COLP + (2 * L.q + e) * 3 + d] = v;
+        }
+    };
+    auto finish = [&](double2 acc, const double2 (&af)[RNYB], const double* arow, int rb, int cb, double (&rs)[3]) {
+      acc.x *= ndy;
+      acc.y *= ndy;
+#pragma unroll
+      for (int y = 0; y < RNYB; ++y)
+        if (y < P.nyb) mma2(acc, af[y], ldn(arow + y * RBLK, L));
+      epilogue(rb, cb, acc, rs);
+    };
+
+    asm volatile("fence.proxy.async;\n" ::: "memory");     // alpha rows were written with ordinary stores
+    stream_rows<RSTAGES>(ring, Arow, nr, [](int) { return RNYB; }, [&](int c, const double* arow) {
+      if (pair && w < ab && c <= w) {               // (i row w, column c): K_ii^-1 + V^T V
+        double2 acc = ldn(pexp + EXP_KINV + (long long)(rtri(w) + c) * RBLK, L);
+        for (int k = 0; k < bb; ++k) mma2(acc, ldt(R1 + (k * ab + w) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
+        finish(acc, ai, arow, w, c, rsi);
+      }
+      if (w < bb && c <= ab + w) {
+        double2 acc = make_double2(0.0, 0.0);
+        if (c < ab) {                               // (j row w, i column c): W_S^T V
+          for (int k = w; k < bb; ++k)
+            mma2(acc, ldt(R2 + (rtri(k) + w) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
+        } else {                                    // (j row w, j column c - ab): W_S^T W_S
+          const int cc = c - ab;
+          for (int k = w; k < bb; ++k)
+            mma2(acc, ldt(R2 + (rtri(k) + w) * RBLK, L), ldt(R2 + (rtri(k) + cc) * RBLK, L));
+          if (is_export) stn(oexp + EXP_KINV + (long long)(rtri(w) + cc) * RBLK, L, acc);
+        }
+        finish(acc, aj, arow, ab + w, c, rsj);
+      }
+    });
+
+    // row sums -> unit gradX rows; theta partials -> shared
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double vi = rsi[d], vj = rsj[d];
+      vi += __shfl_xor_sync(0xffffffffu, vi, 1);
+      vi += __shfl_xor_sync(0xffffffffu, vi, 2);
+      vj += __shfl_xor_sync(0xffffffffu, vj, 1);
+      vj += __shfl_xor_sync(0xffffffffu, vj, 2);
+      if (L.q == 0) {
+        if (w < ab) gx[(w * 8 + L.g) * 3 + d] = vi;
+        if (w < bb) gx[((ab + w) * 8 + L.g) * 3 + d] = vj;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < MAX_NCOV; ++t) {
+      double v = th[t];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (L.lane == 0) s_th[w * MAX_NCOV + t] = v;
+    }
+  }
+  __syncthreads();
+  // column sums, fixed order; theta
+  for (int t = tid; t < nr * 8; t += RNT) {
+    const int cb = t >> 3, g0 = t & 7;
+    double v[3] = {gx[t * 3], gx[t * 3 + 1], gx[t * 3 + 2]};
+    for (int rb = cb; rb < nr; ++rb) {
+      const double* pc = colp + (long long)(rtri(rb) + cb) * COLP + g0 * 3;
+      v[0] += pc[0];
+      v[1] += pc[1];
+      v[2] += pc[2];
+    }
+    gx[t * 3] = v[0];
+    gx[t * 3 + 1] = v[1];
+    gx[t * 3 + 2] = v[2];
+  }
+  if (tid < MAX_NCOV) {
+    double v = 0.0;
+    for (int i = 0; i < RNW; ++i) v += s_th[i * MAX_NCOV + tid];
+    if (tid == 1) v /= cp.s2;
+    P.gth_u[(long long)u.uid * MAX_NCOV + tid] = v;
+  }
+  __syncthreads();
+}
+
+// grid: persistent CTAs (<= one per SM), RNT threads, R_SMEM_BYTES dynamic shared memory.
+template <int DFN, int WFN>
+__global__ void __launch_bounds__(RNT, 1) k_resident(ResParams P) {
+  extern __shared__ __align__(16) double smem[];
+  double* MISC = smem + R_XS_DOUBLES + R_RING_DOUBLES;
+  Ring ring;
+  ring.buf = smem + R_XS_DOUBLES;
+  ring.bar = reinterpret_cast<uint64_t*>(MISC);
+  ring.par = 0;
+  int* s_unit = reinterpret_cast<int*>(MISC + 4);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RSTAGES; ++s) mbar_init(ring.bar + s, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  double* scratch = P.scratch + (long long)blockIdx.x * SCR_STRIDE;
+  const int n_units = *P.n_order;
+  while (true) {
+    if (threadIdx.x == 0) *s_unit = atomicAdd(P.counter, 1);
+    __syncthreads();
+    const int slot = *s_unit;
+    __syncthreads();
+    if (slot >= n_units) break;
+    Unit u;
+    u.uid = P.order[slot];
+    if (u.uid < P.B) {
+      u.bi = -1;
+      u.bj = u.uid;
+    } else {
+      u.bi = P.edges[2 * (u.uid - P.B)];
+      u.bj = P.edges[2 * (u.uid - P.B) + 1];
+    }
+    u.ja = P.block_ptr[u.bj];
+    u.b = (int)(P.block_ptr[u.bj + 1] - u.ja);
+    u.ia = 0;
+    u.a = 0;
+    if (u.bi >= 0) {
+      u.ia = P.block_ptr[u.bi];
+      u.a = (int)(P.block_ptr[u.bi + 1] - u.ia);
+    }
+    if (u.bi >= 0 && u.b == 0) {
+      // pair with an empty second block: the unit IS block i (computed by the block launch)
+      const long long src = u.bi;
+      if (threadIdx.x == 0) P.ll_u[u.uid] = P.ll_u[src];
+      if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)u.uid * MAX_NCOV + threadIdx.x] = P.gth_u[src * MAX_NCOV + threadIdx.x];
+      for (int e = threadIdx.x; e < GX_STRIDE; e += RNT) P.gx_u[(long long)u.uid * GX_STRIDE + e] = P.gx_u[src * GX_STRIDE + e];
+      continue;
+    }
+    u.ab = (u.a + 7) >> 3;
+    u.bb = (u.b + 7) >> 3;
+    if (!res_fits(u.ab, u.bb)) {
+      if (threadIdx.x == 0) atomicOr(P.status, ST_OVERFLOW);
+      continue;
+    }
+    if (u.b == 0) {                // empty block unit
+      if (threadIdx.x == 0) {
+        P.ll_u[u.uid] = 0.0;
+        double* oexp = P.exports + (long long)u.bj * EXP_STRIDE;
+        oexp[EXP_SCAL + 0] = 0.0;
+        oexp[EXP_SCAL + 1] = 0.0;
+      }
+      if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)u.uid * MAX_NCOV + threadIdx.x] = 0.0;
+      continue;
+    }
+    run_unit<DFN, WFN>(P, u, smem, ring, scratch);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Launch plan on the device (one CTA): which blocks have to be factored, the pair units in
+// descending size order (longest first on the dynamic queue), the fit check.  No host round trip:
+// block sizes never leave the GPU.
+struct PlanParams {
+  const long long* block_ptr;
+  const int* edges;
+  const unsigned char* active;     // per unit (B + E), or nullptr = all
+  int B, E;
+  int* order_blocks;               // out
+  int* order_pairs;                // out
+  int* counts;                     // out: [n_blocks, n_pairs, queue counter blocks, queue counter pairs]
+  int* status;                     // out (reset here)
+  int* info;                       // per unit, reset here
+};
+
+#ifndef GPRF_RES_KERNEL_ONLY
+__global__ void k_res_plan(PlanParams Q) {
+  extern __shared__ int sh[];          // need[B] | key[E]
+  int* need = sh;
+  int* key = sh + Q.B;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int s_over, s_nb, s_np;
+  if (tid == 0) {
+    s_over = 0;
+    s_nb = 0;
+    s_np = 0;
+  }
+  for (int bq = tid; bq < Q.B; bq += nt) need[bq] = (!Q.active || Q.active[bq]) ? 1 : 0;
+  for (int u = tid; u < Q.B + Q.E; u += nt) Q.info[u] = 0;
+  __syncthreads();
+  for (int e = tid; e < Q.E; e += nt) {
+    const bool act = !Q.active || Q.active[Q.B + e];
+    const int i = Q.edges[2 * e], j = Q.edges[2 * e + 1];
+    const int a = (int)(Q.block_ptr[i + 1] - Q.block_ptr[i]);
+    const int b = (int)(Q.block_ptr[j + 1] - Q.block_ptr[j]);
+    key[e] = act ? (a + b) : -1;
+    if (act) {
+      need[i] = 1;                      // benign race: everybody writes 1
+      if (b > 0 && !res_fits((a + 7) >> 3, (b + 7) >> 3)) s_over = 1;
+    }
+  }
+  __syncthreads();
+  for (int bq = tid; bq < Q.B; bq += nt) {
+    const int s = (int)(Q.block_ptr[bq + 1] - Q.block_ptr[bq]);
+    if (need[bq] && !res_fits(0, (s + 7) >> 3)) s_over = 1;
+  }
+  __syncthreads();
+  // blocks: ascending id (they are all about the same size); stable compaction by one thread per 32
+  if (tid == 0) {
+    int nb = 0;
+    for (int bq = 0; bq < Q.B; ++bq)
+      if (need[bq]) Q.order_blocks[nb++] = bq;
+    s_nb = nb;
+  }
+  // pairs: rank sort by (size descending, id ascending)
+  for (int e = tid; e < Q.E; e += nt) {
+    const int ke = key[e];
+    if (ke < 0) continue;
+    int rank = 0;
+    for (int f = 0; f < Q.E; ++f) {
+      const int kf = key[f];
+      rank += (kf > ke || (kf == ke && f < e)) ? 1 : 0;
+    }
+    Q.order_pairs[rank] = Q.B + e;
+    atomicAdd(&s_np, 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    Q.counts[0] = s_nb;
+    Q.counts[1] = s_np;
+    Q.counts[2] = 0;
+    Q.counts[3] = 0;
+    *Q.status = s_over ? ST_OVERFLOW : 0;
+  }
+}
+
+#endif  // GPRF_RES_KERNEL_ONLY
+
+// ---------------------------------------------------------------------------------------------------
+// combine (gprf.py:245-291) over the resident path's per-unit results
+struct ResCombine {
+  const long long* perm;
+  const int* pos_block;
+  const long long* block_ptr;
+  const int* adj_ptr;
+  const int* adj_edge;
+  const int* adj_side;
+  const int* edges;
+  const int* deg;                  // per block
+  const unsigned char* active;     // per unit or nullptr
+  const double* ll_u;
+  const double* gth_u;
+  const double* gx_u;
+  const int* status;
+  int B, E, dx;
+  long long plen;
+};
+
+// blocks [1, ...): one thread per perm position; block 0: the scalars (ll, grad theta) and the status
+#ifndef GPRF_RES_KERNEL_ONLY
+__global__ void k_res_combine(ResCombine C, double* out, int want_gx, int want_cov, double* status_out) {
+  if (blockIdx.x == 0) {
+    __shared__ double red[256][1 + MAX_NCOV];
+    const int tid = threadIdx.x;
+    double v[1 + MAX_NCOV];
+#pragma unroll
+    for (int t = 0; t < 1 + MAX_NCOV; ++t) v[t] = 0.0;
+    for (int u = tid; u < C.B + C.E; u += 256) {
+      if (C.active && !C.active[u]) continue;
+      long long s;
+      double wgt;
+      if (u < C.B) {
+        s = C.block_ptr[u + 1] - C.block_ptr[u];
+        wgt = 1.0 - (double)C.deg[u];
+      } else {
+        const int i = C.edges[2 * (u - C.B)], j = C.edges[2 * (u - C.B) + 1];
+        s = (C.block_ptr[i + 1] - C.block_ptr[i]) + (C.block_ptr[j + 1] - C.block_ptr[j]);
+        wgt = 1.0;
+      }
+      if (s == 0) continue;
+      v[0] += wgt * C.ll_u[u];
+      if (want_cov)
+#pragma unroll
+        for (int t = 0; t < MAX_NCOV; ++t) v[1 + t] += wgt * C.gth_u[(long long)u * MAX_NCOV + t];
+    }
+#pragma unroll
+    for (int t = 0; t < 1 + MAX_NCOV; ++t) red[tid][t] = v[t];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (tid < o)
+#pragma unroll
+        for (int t = 0; t < 1 + MAX_NCOV; ++t) red[tid][t] += red[tid + o][t];
+      __syncthreads();
+    }
+    if (tid < 1 + MAX_NCOV) out[tid] = red[0][tid];
+    if (tid == 0 && status_out) *status_out = (double)*C.status;
+    return;
+  }
+  if (!want_gx) return;
+  const long long pos = (long long)(blockIdx.x - 1) * blockDim.x + threadIdx.x;
+  if (pos >= C.plen) return;
+  const int bq = C.pos_block[pos];
+  const int lp = (int)(pos - C.block_ptr[bq]);
+  double g[3] = {0.0, 0.0, 0.0};
+  if (!C.active || C.active[bq]) {
+    const double wgt = 1.0 - (double)C.deg[bq];
+    const double* p = C.gx_u + (long long)bq * GX_STRIDE + (long long)lp * 3;
+    g[0] += wgt * p[0];
+    g[1] += wgt * p[1];
+    g[2] += wgt * p[2];
+  }
+  for (int aidx = C.adj_ptr[bq]; aidx < C.adj_ptr[bq + 1]; ++aidx) {
+    const int e = C.adj_edge[aidx];
+    if (C.active && !C.active[C.B + e]) continue;
+    int off = 0;
+    if (C.adj_side[aidx]) {
+      const int i = C.edges[2 * e];
+      const int a = (int)(C.block_ptr[i + 1] - C.block_ptr[i]);
+      off = ((a + 7) >> 3) * 8;
+    }
+    const double* p = C.gx_u + (long long)(C.B + e) * GX_STRIDE + (long long)(off + lp) * 3;
+    g[0] += p[0];
+    g[1] += p[1];
+    g[2] += p[2];
+  }
+  const long long n = C.perm[pos];
+  for (int d = 0; d < C.dx; ++d) out[1 + MAX_NCOV + n * C.dx + d] = g[d];
+}
+#endif  // GPRF_RES_KERNEL_ONLY
+
+}  // namespace res
+}  // namespace gprf

@@ -377,6 +377,79 @@ class GPRF(object):
         self._check(self._lib.gprf_factor_reuse_stats(self._h, C.byref(nu), C.byref(ntl)))
         return nu.value, ntl.value
 
+    # -- resident (shared-memory) unit path: switches and introspection ----------------------
+    def set_resident(self, on=True):
+        """Small-block structures are evaluated by the resident kernels (one CTA per unit, the pair
+        factorisations reuse block i's factor; include/gprf_b200.h).  ``on=False``: tile pipeline only."""
+        self._check(self._lib.gprf_set_resident(self._h, int(bool(on))))
+
+    def resident_stats(self):
+        """(evaluations tried on the resident path, of which re-run by the tile pipeline, last status)."""
+        ev, fb, st = C.c_longlong(), C.c_longlong(), C.c_int()
+        self._check(self._lib.gprf_resident_stats(self._h, C.byref(ev), C.byref(fb), C.byref(st)))
+        return ev.value, fb.value, st.value
+
+    @staticmethod
+    def _resident_layout():
+        lib = _lib.load()
+        v = np.zeros(16, dtype=np.int64)
+        m = lib.gprf_resident_layout(v.ctypes.data_as(C.POINTER(C.c_longlong)), 16)
+        names = ["MAXB", "NYB", "BLK", "EXP_W", "EXP_KINV", "EXP_ZY", "EXP_AROW", "EXP_SCAL", "EXP_STRIDE",
+                 "GX_STRIDE", "MAT_BLOCKS"]
+        return dict(zip(names, (int(x) for x in v[:m])))
+
+    @staticmethod
+    def _unswizzle(blk):
+        """64 doubles of one packed 8x8 block -> (8, 8) array (resident.cuh: sw_off)."""
+        out = np.empty((8, 8))
+        for r in range(8):
+            for c in range(8):
+                out[r, c] = blk[((r ^ ((r >> 1) & 1)) << 3) + (c ^ (r & 4))]
+        return out
+
+    def resident_debug(self, unit, phase):
+        """Select the (unit, phase) whose shared-memory matrices the next evaluation dumps."""
+        self._check(self._lib.gprf_set_resident_debug(self._h, int(unit), int(phase)))
+
+    def resident_dump(self):
+        """(R1, R2) as dense 128 x 128 arrays, from the last evaluation with resident_debug set."""
+        out = np.zeros((2, 128, 128))
+        self._check(self._lib.gprf_get_resident_debug(self._h, _lib.ptr(out), -1, None, -1, None))
+        return out[0], out[1]
+
+    def resident_export(self, block, nb):
+        """Export record of a block unit with ``nb`` points: dict(W, Kinv, Z, alpha, logdet, q)."""
+        lay = self._resident_layout()
+        raw = np.zeros(lay["EXP_STRIDE"])
+        self._check(self._lib.gprf_get_resident_debug(self._h, None, int(block), _lib.ptr(raw), -1, None))
+        bb = (nb + 7) // 8
+        BL, MAXB, NYB = lay["BLK"], lay["MAXB"], lay["NYB"]
+
+        def tri_mat(off):
+            M = np.zeros((bb * 8, bb * 8))
+            for i in range(bb):
+                for j in range(i + 1):
+                    o = off + (i * (i + 1) // 2 + j) * BL
+                    M[8 * i:8 * i + 8, 8 * j:8 * j + 8] = self._unswizzle(raw[o:o + BL])
+            return M
+        Z = np.zeros((bb * 8, NYB * 8))
+        A = np.zeros((bb * 8, NYB * 8))
+        for k in range(bb):
+            for y in range(NYB):
+                o = lay["EXP_ZY"] + (y * MAXB + k) * BL
+                Z[8 * k:8 * k + 8, 8 * y:8 * y + 8] = self._unswizzle(raw[o:o + BL])
+                o = lay["EXP_AROW"] + (k * NYB + y) * BL
+                A[8 * k:8 * k + 8, 8 * y:8 * y + 8] = self._unswizzle(raw[o:o + BL])
+        return dict(W=tri_mat(lay["EXP_W"]), Kinv=tri_mat(lay["EXP_KINV"]), Z=Z, alpha=A,
+                    logdet=raw[lay["EXP_SCAL"]], q=raw[lay["EXP_SCAL"] + 1])
+
+    def resident_unit(self, unit):
+        """(ll, grad theta (5), gradX rows in the unit's padded local order (GX_STRIDE/3, 3))."""
+        lay = self._resident_layout()
+        raw = np.zeros(1 + _lib.MAX_NCOV + lay["GX_STRIDE"])
+        self._check(self._lib.gprf_get_resident_debug(self._h, None, -1, None, int(unit), _lib.ptr(raw)))
+        return raw[0], raw[1:1 + _lib.MAX_NCOV], raw[1 + _lib.MAX_NCOV:].reshape(-1, 3)
+
     def set_profiling(self, on=True):
         self._lib.gprf_set_profiling(self._h, int(bool(on)))
 

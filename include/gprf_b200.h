@@ -188,10 +188,27 @@ int gprf_factor_reuse_stats(gprf_handle h, int* n_units, long long* n_tiles);
  * events on the launching stream; gprf_family_timing returns, for the last
  * evaluation, the summed device time (ms) and launch count of each family
  * (gprf_family_name(i), i < GPRF_N_FAMILIES). */
-#define GPRF_N_FAMILIES 9
+#define GPRF_N_FAMILIES 13
 int gprf_set_profiling(gprf_handle h, int on);
 int gprf_family_timing(gprf_handle h, float* ms, int* launches);
 const char* gprf_family_name(int fam);
+
+/* ---- resident path (gprf_b200/csrc/resident.cuh) -------------------------------------------------
+ * Units of small blocks (<= 128 points per block, dy <= 64) are evaluated by one CTA each, entirely
+ * out of shared memory: block units export their factor, pair units factor only the Schur complement
+ * of block j on top of block i's exported factor (the reference computes an independent pdinv per
+ * unit, gprf.py:299-330; same values to rounding).  Tried automatically by gprf_llgrad*,
+ * with ONE host synchronisation per evaluation; an evaluation in which a unit does not fit or a
+ * Cholesky pivot fails (the jitter rule, gpy_linalg.py:77-97) is re-run by the tile pipeline.
+ * gprf_set_resident(h, 0) switches it off (env GPRF_RESIDENT=0 likewise). */
+int gprf_set_resident(gprf_handle h, int on);
+int gprf_resident_stats(gprf_handle h, long long* evals, long long* fallbacks, int* last_status);
+/* Layout constants of the resident path's export records (tests): returns their number. */
+int gprf_resident_layout(long long* out, int n);
+/* Debug: dump the shared-memory matrices of `unit` after `phase` during the next evaluations. */
+int gprf_set_resident_debug(gprf_handle h, int unit, int phase);
+int gprf_get_resident_debug(gprf_handle h, double* out_dump, int block, double* out_export, int unit,
+                            double* out_unit);
 
 const char* gprf_strerror(int code);
 const char* gprf_last_error(gprf_handle h);
