@@ -48,6 +48,8 @@ _SIGNATURES = {
     "gprf_block_max_kernel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gprf_kernel_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
                                      C.c_void_p, C.c_int, C.c_void_p]),
+    "gprf_kernel_deriv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p]),
     "gprf_debug_unit": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _ip, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gprf_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), _ip]),
     "gprf_debug_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

@@ -1054,6 +1054,31 @@ __global__ void k_kernel_matrix(const double* X1, long long n1, const double* X2
   }
 }
 
+// GPRF.dKdx / GPRF.dKdi (gprf.py:345-375): derivatives of the covariance matrix of one point set.
+//   mode 0: out[q] = d k(x_p, x_q) / d x_{p, which}, q < n  (treegp kernel_deriv_wrt_xi_row; entry p is 0)
+//   mode 1: out[a n + b] = d k(x_a, x_b) / d l_which          (treegp kernel_deriv_wrt_i)
+template <int DFN, int WFN>
+__global__ void k_kernel_deriv(const double* X, long long n, int dx, CovParams cp, int mode, int p, int which,
+                               double* out) {
+  const long long tot = mode == 0 ? n : n * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long a = mode == 0 ? p : e / n, b = mode == 0 ? e : e % n;
+    double xa[XD] = {0, 0, 0, 0, 0, 0}, xb[XD] = {0, 0, 0, 0, 0, 0};
+    for (int d = 0; d < dx; ++d) {
+      xa[d] = X[a * dx + d];
+      xb[d] = X[b * dx + d];
+    }
+    point_terms(DFN, xa);
+    point_terms(DFN, xb);
+    double k, gp[MAX_DX], gq[MAX_DX], gl[MAX_NLS];
+    cov_grad<DFN, WFN, false>(xa, xb, cp, k, gp, gq, gl);
+    double v = mode == 0 ? gp[which] : gl[which];
+    if (a == b) v = 0.0;
+    out[e] = v;
+  }
+}
+
 // one CTA per ordered block pair index (i*B + j), j < i
 template <int DFN, int WFN>
 __global__ void k_block_maxk(const double* X, int dx, const long long* perm, const long long* block_ptr, int B,

@@ -1151,7 +1151,7 @@ static int res_alloc(gprf_ctx* h, int grid) {
     CUDA_OK(cudaMemset(h->dResGx, 0, cu * res::GX_STRIDE * sizeof(double)));
     h->capResU = cu;
   }
-  if (!h->dResDbg) CUDA_OK(cudaMalloc((void**)&h->dResDbg, 2 * 128 * 128 * sizeof(double)));
+  if (!h->dResDbg) CUDA_OK(cudaMalloc((void**)&h->dResDbg, 2 * 160 * 160 * sizeof(double)));
   return GPRF_OK;
 }
 
@@ -1205,6 +1205,9 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   P.dbg_unit = h->res_dbg_unit;
   P.dbg_phase = h->res_dbg_phase;
   P.dbg_out = h->dResDbg;
+  // debug timeline (gprf_debug_trace with 2 x n_sm CTAs): pairs' launch first, blocks' launch behind it
+  const size_t trace_half = (size_t)h->n_sm * 2 * res::RTRACE_SLOTS;
+  P.trace = (h->dTrace && h->capTrace >= 2 * trace_half) ? h->dTrace + trace_half : nullptr;
   P.order = h->dResOrderB;
   P.n_order = h->dResCounts + 0;
   P.counter = h->dResCounts + 2;
@@ -1214,6 +1217,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
     P.order = h->dResOrderP;
     P.n_order = h->dResCounts + 1;
     P.counter = h->dResCounts + 3;
+    if (P.trace) P.trace = h->dTrace;
 #define CALL_RESP(D, W) res::resident_launch<D, W>(P, grid_p, st)
     LAUNCH(11, DISPATCH_COV(h, CALL_RESP));
   }
@@ -1521,8 +1525,8 @@ extern "C" int gprf_resident_stats(gprf_handle h, long long* evals, long long* f
 }
 
 extern "C" int gprf_resident_layout(long long* out, int n) {
-  const long long v[] = {res::RMAXB, res::RNYB, res::RBLK, res::EXP_W, res::EXP_KINV, res::EXP_ZY, res::EXP_AROW,
-                         res::EXP_SCAL, res::EXP_STRIDE, res::GX_STRIDE, res::R_MAT_BLOCKS};
+  const long long v[] = {res::EMAXB, res::RNYB, res::RBLK, res::EXP_W, res::EXP_KINV, res::EXP_ZY, res::EXP_AROW,
+                         res::EXP_SCAL, res::EXP_STRIDE, res::GX_STRIDE, res::R_CAP_DOUBLES};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   if (!out || n < m) return m;
   for (int i = 0; i < m; ++i) out[i] = v[i];
@@ -1544,7 +1548,7 @@ extern "C" int gprf_get_resident_debug(gprf_handle h, double* out_dump, int bloc
   if (!h || !h->dResLL) return GPRF_ERR_NO_STRUCTURE;
   CUDA_OK(cudaSetDevice(h->device));
   CUDA_OK(cudaDeviceSynchronize());
-  if (out_dump) CUDA_OK(cudaMemcpy(out_dump, h->dResDbg, 2 * 128 * 128 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out_dump) CUDA_OK(cudaMemcpy(out_dump, h->dResDbg, 2 * 160 * 160 * sizeof(double), cudaMemcpyDeviceToHost));
   if (out_export) {
     if (block < 0 || block >= h->B) return GPRF_ERR_ARG;
     CUDA_OK(cudaMemcpy(out_export, h->dResExports + (size_t)block * res::EXP_STRIDE, res::EXP_STRIDE * sizeof(double),
@@ -1629,6 +1633,30 @@ extern "C" int gprf_kernel_matrix(gprf_handle h, const double* X1, long long n1,
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpy(K, dK, (size_t)n1 * n2 * sizeof(double), cudaMemcpyDeviceToHost));
   cudaFree(d1); cudaFree(d2); cudaFree(dK);
+  return GPRF_OK;
+}
+
+extern "C" int gprf_kernel_deriv(gprf_handle h, const double* X, long long n, const double* theta, int ncov,
+                                 int mode, int p, int which, double* out) {
+  if (!h || !X || !theta || !out || n < 0 || mode < 0 || mode > 1 || which < 0) return GPRF_ERR_ARG;
+  if (mode == 0 && (p < 0 || p >= n || which >= h->dx)) return GPRF_ERR_ARG;
+  if (mode == 1 && which >= h->nls) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  CovParams cp;
+  if (make_cov(h, theta, ncov, &cp) != GPRF_OK) return GPRF_ERR_ARG;
+  if (n == 0) return GPRF_OK;
+  const long long tot = mode == 0 ? n : n * n;
+  double *dXq = nullptr, *dO = nullptr;
+  CUDA_OK(cudaMalloc((void**)&dXq, (size_t)n * h->dx * sizeof(double)));
+  CUDA_OK(cudaMalloc((void**)&dO, (size_t)tot * sizeof(double)));
+  CUDA_OK(cudaMemcpy(dXq, X, (size_t)n * h->dx * sizeof(double), cudaMemcpyHostToDevice));
+  const int grid = (int)std::min<long long>((tot + 255) / 256, 148 * 16);
+#define CALL_KD(D, W) k_kernel_deriv<D, W><<<grid, 256>>>(dXq, n, h->dx, cp, mode, p, which, dO)
+  DISPATCH_COV(h, CALL_KD);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpy(out, dO, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dXq);
+  cudaFree(dO);
   return GPRF_OK;
 }
 

@@ -29,8 +29,10 @@
 // Padding rows/columns (sizes are rounded up to 8 separately for block i and block j) form an
 // identity block, as in the tile pipeline.
 //
-// Limits: every block of the unit has at most 8*RMAXB = 128 points, bb*ab + tri(bb) <= R_MAT_BLOCKS
-// and dy <= 64.  Units outside them, and evaluations in which a pivot fails (the jitter rule of
+// Limits: every block has at most 8*BMAXB = 160 points and dy <= 64.  A pair whose R1 does not fit in
+// shared memory next to R2 (res_class 1: roughly two blocks of more than 120 points) keeps R1 in this
+// CTA's L2-resident scratch instead - same code, generic loads; those few units are queued first.
+// Structures outside the limits, and evaluations in which a pivot fails (the jitter rule of
 // gpy_linalg.py:77-97), are reported in the status word and re-run through the tile pipeline.
 #pragma once
 #include "covfn.cuh"
@@ -40,40 +42,48 @@
 namespace gprf {
 namespace res {
 
-constexpr int RMAXB = 16;                 // 8x8 blocks per side of one block of points
+constexpr int RMAXB = 16;                 // 8x8 blocks per side of one block of points, register-array size
+constexpr int BMAXB = 20;                 // ... of the "big unit" instantiation (up to 160 points per block)
+constexpr int EMAXB = BMAXB;              // row length of the exported / scratch layouts
 constexpr int RNYB = 8;                   // y blocks per row in the exported layouts (dy <= 64)
 constexpr int RNW = 16;                   // warps per CTA
 constexpr int RNT = RNW * 32;
 constexpr int RBLK = 64;                  // doubles per 8x8 block
-constexpr int RSTAGE_BLK = 16;            // blocks per ring stage (8 KB)
+constexpr int RSTAGE_BLK = EMAXB;         // blocks per ring stage (10 KB)
 constexpr int RSTAGES = 3;
-constexpr int R_XS_DOUBLES = 2 * RMAXB * 8 * XD;
 constexpr int R_RING_DOUBLES = RSTAGES * RSTAGE_BLK * RBLK;
 constexpr int R_MISC_DOUBLES = 320;
 constexpr int R_SMEM_BYTES = 232448;      // 227 KB, the sm_100 per-CTA maximum
-constexpr int R_MAT_BLOCKS = (R_SMEM_BYTES / 8 - R_XS_DOUBLES - R_RING_DOUBLES - R_MISC_DOUBLES) / RBLK;
+// doubles left for XS (coordinate records), R2 and R1
+constexpr int R_CAP_DOUBLES = R_SMEM_BYTES / 8 - R_RING_DOUBLES - R_MISC_DOUBLES;
 
-constexpr int RTRI = RMAXB * (RMAXB + 1) / 2;          // 136
+constexpr int RTRI = EMAXB * (EMAXB + 1) / 2;
 // per-block export (doubles)
 constexpr long long EXP_W = 0;
 constexpr long long EXP_KINV = (long long)RTRI * RBLK;
-constexpr long long EXP_ZY = 2LL * RTRI * RBLK;                     // (yb * RMAXB + k)
-constexpr long long EXP_AROW = EXP_ZY + (long long)RNYB * RMAXB * RBLK;     // (k * RNYB + yb)
-constexpr long long EXP_SCAL = EXP_AROW + (long long)RMAXB * RNYB * RBLK;   // logdet, |Z|^2
+constexpr long long EXP_ZY = 2LL * RTRI * RBLK;                     // (yb * EMAXB + k)
+constexpr long long EXP_AROW = EXP_ZY + (long long)RNYB * EMAXB * RBLK;     // (k * RNYB + yb)
+constexpr long long EXP_SCAL = EXP_AROW + (long long)EMAXB * RNYB * RBLK;   // logdet, |Z|^2
 constexpr long long EXP_STRIDE = EXP_SCAL + 16;
 // per-CTA scratch (doubles)
 constexpr long long SCR_ZY = 0;
-constexpr long long SCR_AROW = (long long)RNYB * RMAXB * RBLK;              // 2*RMAXB rows
-constexpr long long SCR_COLP = SCR_AROW + 2LL * RMAXB * RNYB * RBLK;
+constexpr long long SCR_AROW = (long long)RNYB * EMAXB * RBLK;              // 2*EMAXB rows
+constexpr long long SCR_COLP = SCR_AROW + 2LL * EMAXB * RNYB * RBLK;
 constexpr int COLP = 24;
-constexpr long long SCR_STRIDE = SCR_COLP + (long long)(2 * RMAXB) * (2 * RMAXB + 1) / 2 * COLP;
-constexpr int GX_STRIDE = 2 * RMAXB * 8 * 3;           // per-unit gradX rows (padded local order)
+constexpr long long SCR_R1 = SCR_COLP + (long long)(2 * EMAXB) * (2 * EMAXB + 1) / 2 * COLP;   // R1 of units too big for smem
+constexpr long long SCR_STRIDE = SCR_R1 + (long long)EMAXB * EMAXB * RBLK;
+constexpr int GX_STRIDE = 2 * EMAXB * 8 * 3;           // per-unit gradX rows (padded local order)
 
 enum { ST_OVERFLOW = 1, ST_NOTPD = 2 };
 
 __host__ __device__ __forceinline__ int rtri(int i) { return i * (i + 1) / 2; }
-__host__ __device__ __forceinline__ bool res_fits(int ab, int bb) {
-  return ab <= RMAXB && bb <= RMAXB && bb * ab + rtri(bb) <= R_MAT_BLOCKS;
+// 0: everything in shared memory; 1: R1 (the bb x ab coupling matrix) in this CTA's L2-resident
+// scratch, the rest in shared memory; 2: does not fit (tile pipeline).
+__host__ __device__ __forceinline__ int res_class(int ab, int bb) {
+  if (ab > BMAXB || bb > BMAXB) return 2;
+  const int xs = (ab + bb) * 8 * XD;
+  if ((bb * ab + rtri(bb)) * RBLK + xs <= R_CAP_DOUBLES) return 0;
+  return 1;
 }
 
 struct ResParams {
@@ -96,7 +106,8 @@ struct ResParams {
   int* info;                    // per unit: 1 + first failing local row
   int* status;
   int dbg_unit, dbg_phase;      // debug dump of R1 / R2 after a phase (-1: off)
-  double* dbg_out;              // 2 x (128 x 128) doubles
+  double* dbg_out;              // 2 x (160 x 160) doubles
+  unsigned long long* trace;    // debug timeline (RTRACE_SLOTS (tag, ns) pairs per CTA) or nullptr
 };
 
 // ---- swizzled 8x8 block ---------------------------------------------------------------------
@@ -210,10 +221,26 @@ struct Unit {
 // coordinates of local row t (i part: [0, 8 ab), j part: [8 ab, 8 ab + 8 bb))
 __device__ __forceinline__ const double* xs_row(const double* XS, int t) { return XS + t * XD; }
 
+constexpr int RTRACE_SLOTS = 512;
+// Debug timeline: thread 0 appends (unit << 16 | tag, %globaltimer) to this CTA's slots.
+__device__ __forceinline__ void rtrace(const ResParams& P, int* cursor, int uid, int tag) {
+  if (P.trace && threadIdx.x == 0 && *cursor < RTRACE_SLOTS) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    unsigned long long* wp = P.trace + ((long long)blockIdx.x * RTRACE_SLOTS + *cursor) * 2;
+    wp[0] = ((unsigned long long)uid << 16) | (unsigned long long)tag;
+    wp[1] = t;
+    ++*cursor;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
-template <int DFN, int WFN>
+// MB: size of the per-warp register arrays = upper bound on ab and bb (RMAXB for ordinary units,
+// BMAXB for the few big ones).  Rows of a phase are dealt to the 16 warps RNW at a time; units
+// with more than 16 block rows take a second pass (and stream their operands twice).
+template <int DFN, int WFN, int MB>
 __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, double* smem, Ring& ring,
-                                         double* scratch) {
+                                         double* scratch, bool r1_global) {
   const Lane L = make_lane();
   const int tid = threadIdx.x;
   const int w = L.w;
@@ -221,16 +248,17 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
   const int nr = ab + bb;                          // block rows of the whole unit
   const bool pair = ab > 0;
   const bool is_export = u.bi < 0;                 // block units export for their pairs
-  double* XS = smem;
-  double* RING = XS + R_XS_DOUBLES;
+  double* RING = smem;
   double* MISC = RING + R_RING_DOUBLES;
-  double* R2 = MISC + R_MISC_DOUBLES;
-  double* R1 = R2 + rtri(bb) * RBLK;
+  double* XS = MISC + R_MISC_DOUBLES;
+  double* R2 = XS + nr * 8 * XD;
+  double* R1 = r1_global ? scratch + SCR_R1 : R2 + rtri(bb) * RBLK;
   int* s_fail = reinterpret_cast<int*>(MISC + 4) + 1;
+  int* s_tcur = reinterpret_cast<int*>(MISC + 5);
   double* s_q = MISC + 8;                          // [RNW]
   double* s_th = MISC + 24;                        // [RNW][MAX_NCOV]
   double* s_ld = MISC + 104;                       // [RNW]
-  int* IDX = reinterpret_cast<int*>(MISC + 120);   // [2 * RMAXB * 8] global point index or -1
+  int* IDX = reinterpret_cast<int*>(MISC + 120);   // [2 * EMAXB * 8] global point index or -1
   double* WD = RING;                               // diagonal-block inverses during the factorisation
   double* RB = RING + 2 * RSTAGE_BLK * RBLK;       // stage 2: work buffer of the Y part
   const double* pexp = pair ? P.exports + (long long)u.bi * EXP_STRIDE : nullptr;
@@ -240,18 +268,19 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
   double* colp = scratch + SCR_COLP;
   double* gx = P.gx_u + (long long)u.uid * GX_STRIDE;
   const CovParams& cp = P.cp;
+  rtrace(P, s_tcur, u.uid, 1);
 
   auto dbg_dump = [&](int phase) {
     if (P.dbg_unit != u.uid || P.dbg_phase != phase) return;
     __syncthreads();
-    for (int e = tid; e < 128 * 128; e += RNT) {
-      const int r = e >> 7, c = e & 127;
+    for (int e = tid; e < 160 * 160; e += RNT) {
+      const int r = e / 160, c = e % 160;
       double v1 = 0.0, v2 = 0.0;
       if (pair && r < bb * 8 && c < ab * 8) v1 = R1[((r >> 3) * ab + (c >> 3)) * RBLK + sw_off(r & 7, c & 7)];
-      if (r < bb * 8 && c <= (r | 7) && c < bb * 8 && (c >> 3) <= (r >> 3))
+      if (r < bb * 8 && c < bb * 8 && (c >> 3) <= (r >> 3))
         v2 = R2[(rtri(r >> 3) + (c >> 3)) * RBLK + sw_off(r & 7, c & 7)];
       P.dbg_out[e] = v1;
-      P.dbg_out[128 * 128 + e] = v2;
+      P.dbg_out[160 * 160 + e] = v2;
     }
     __syncthreads();
   };
@@ -292,48 +321,55 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     return make_double2(v0, v1);
   };
 
-  // ---- P1: L_ji = K_ji W_i^T  (row w of L_ji per warp; W_i streamed row by row) -----------------------
+  // ---- P1: L_ji = K_ji W_i^T  (one row of L_ji per warp; W_i streamed row by row) ---------------------
   if (pair) {
-    double2 kf[RMAXB];
-    if (w < bb) {
+    for (int rbase = 0; rbase < bb; rbase += RNW) {
+      const int row = rbase + w;
+      double2 kf[MB];
+      if (row < bb) {
 #pragma unroll
-      for (int k = 0; k < RMAXB; ++k) kf[k] = (k < ab) ? cov_frag(ab + w, k, false) : make_double2(0.0, 0.0);
-    }
-    stream_rows<RSTAGES>(ring, pexp + EXP_W, ab, [](int r) { return r + 1; }, [&](int c, const double* row) {
-      if (w < bb) {
-        double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int k = 0; k < RMAXB; ++k)
-          if (k <= c) mma2(acc, kf[k], ldn(row + k * RBLK, L));
-        stn(R1 + (w * ab + c) * RBLK, L, acc);
+        for (int k = 0; k < MB; ++k) kf[k] = (k < ab) ? cov_frag(ab + row, k, false) : make_double2(0.0, 0.0);
       }
-    });
+      stream_rows<RSTAGES>(ring, pexp + EXP_W, ab, [](int r) { return r + 1; }, [&](int c, const double* wrow) {
+        if (row < bb) {
+          double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int k = 0; k < MB; ++k)
+            if (k <= c) mma2(acc, kf[k], ldn(wrow + k * RBLK, L));
+          stn(R1 + (row * ab + c) * RBLK, L, acc);
+        }
+      });
+    }
   }
   dbg_dump(1);
+  rtrace(P, s_tcur, u.uid, 2);
 
-  // ---- P2: S = K_jj + nv I - L_ji L_ji^T (lower blocks; rows split by column parity over two warps) ----
+  // ---- P2: S = K_jj + nv I - L_ji L_ji^T (lower blocks; a row's columns split by parity over two tasks) ----
   __syncthreads();
-  for (int part = 0; part < 2; ++part) {
-    if (w >= bb) break;
-    const int row = part ? bb - 1 - w : w;
-    double2 nla[RMAXB];
-    if (pair) {
-#pragma unroll
-      for (int k = 0; k < RMAXB; ++k)
-        nla[k] = (k < ab) ? neg2(ldn(R1 + (row * ab + k) * RBLK, L)) : make_double2(0.0, 0.0);
-    }
-    for (int c = part; c <= row; c += 2) {
-      double2 acc = cov_frag(ab + row, ab + c, true);
+  for (int t = w; t < bb; t += RNW) {
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+      const int row = part ? bb - 1 - t : t;
+      double2 nla[MB];
       if (pair) {
 #pragma unroll
-        for (int k = 0; k < RMAXB; ++k)
-          if (k < ab) mma2(acc, nla[k], ldn(R1 + (c * ab + k) * RBLK, L));
+        for (int k = 0; k < MB; ++k)
+          nla[k] = (k < ab) ? neg2(ldn(R1 + (row * ab + k) * RBLK, L)) : make_double2(0.0, 0.0);
       }
-      stn(R2 + (rtri(row) + c) * RBLK, L, acc);
+      for (int c = part; c <= row; c += 2) {
+        double2 acc = cov_frag(ab + row, ab + c, true);
+        if (pair) {
+#pragma unroll
+          for (int k = 0; k < MB; ++k)
+            if (k < ab) mma2(acc, nla[k], ldn(R1 + (c * ab + k) * RBLK, L));
+        }
+        stn(R2 + (rtri(row) + c) * RBLK, L, acc);
+      }
     }
   }
   __syncthreads();
   dbg_dump(2);
+  rtrace(P, s_tcur, u.uid, 3);
 
   // ---- P3a: blocked Cholesky of S in place (jitchol's first, jitter-free attempt) ---------------------
   for (int J = 0; J < bb; ++J) {
@@ -391,6 +427,7 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     __syncthreads();
   }
   dbg_dump(3);
+  rtrace(P, s_tcur, u.uid, 4);
   // log-determinant: sum of log L_tt over the unit's j rows, fixed order
   {
     double lv = 0.0;
@@ -401,20 +438,29 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
   }
   // ---- P3b: W_S = L_S^-1 in place, by descending block columns ----------------------------------------
   for (int K = bb - 1; K >= 0; --K) {
-    double2 o = make_double2(0.0, 0.0);
-    const int I = K + 1 + w;
-    if (I < bb) {
-      double2 acc = make_double2(0.0, 0.0);
-      for (int J = K + 1; J <= I; ++J)
-        mma2(acc, ldn(R2 + (rtri(I) + J) * RBLK, L), ldt(R2 + (rtri(J) + K) * RBLK, L));
-      mma2(o, acc, ldt(WD + K * RBLK, L));
+    double2 o[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      o[rr] = make_double2(0.0, 0.0);
+      const int I = K + 1 + w + rr * RNW;
+      if (I < bb) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int J = K + 1; J <= I; ++J)
+          mma2(acc, ldn(R2 + (rtri(I) + J) * RBLK, L), ldt(R2 + (rtri(J) + K) * RBLK, L));
+        mma2(o[rr], acc, ldt(WD + K * RBLK, L));
+      }
     }
     __syncthreads();
-    if (I < bb) stn(R2 + (rtri(I) + K) * RBLK, L, neg2(o));
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int I = K + 1 + w + rr * RNW;
+      if (I < bb) stn(R2 + (rtri(I) + K) * RBLK, L, neg2(o[rr]));
+    }
     if (w == 0) stn(R2 + (rtri(K) + K) * RBLK, L, ldn(WD + K * RBLK, L));
     __syncthreads();
   }
   dbg_dump(4);
+  rtrace(P, s_tcur, u.uid, 5);
   if (is_export) {                                  // W_b for this block's pairs
     double* dst = oexp + EXP_W;
     for (int e = tid; e < rtri(bb) * RBLK / 2; e += RNT)
@@ -424,15 +470,9 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
   // ---- P4: Z_j = W_S (Y_j - L_ji Z_i), alpha_j = W_S^T Z_j, one block of 8 outputs at a time ----------
   double qsum = 0.0;
   {
-    double2 nla[RMAXB];
-    if (pair && w < bb) {
-#pragma unroll
-      for (int k = 0; k < RMAXB; ++k)
-        nla[k] = (k < ab) ? neg2(ldn(R1 + (w * ab + k) * RBLK, L)) : make_double2(0.0, 0.0);
-    }
     auto ybody = [&](int yb, const double* zi) {
-      if (w < bb) {
-        const int idx = IDX[ab * 8 + w * 8 + L.g];
+      for (int row = w; row < bb; row += RNW) {
+        const int idx = IDX[ab * 8 + row * 8 + L.g];
         const int y0 = yb * 8 + 2 * L.q;
         double2 acc = make_double2(0.0, 0.0);
         if (idx >= 0) {
@@ -440,38 +480,48 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
           if (y0 + 1 < P.dy) acc.y = __ldg(P.Y + (long long)idx * P.dy + y0 + 1);
         }
         if (pair) {
-#pragma unroll
-          for (int k = 0; k < RMAXB; ++k)
-            if (k < ab) mma2(acc, nla[k], ldt(zi + k * RBLK, L));
+          for (int k = 0; k < ab; ++k) mma2(acc, neg2(ldn(R1 + (row * ab + k) * RBLK, L)), ldt(zi + k * RBLK, L));
         }
-        stn(RB + w * RBLK, L, acc);
+        stn(RB + row * RBLK, L, acc);
       }
       __syncthreads();
-      double2 z = make_double2(0.0, 0.0);
-      if (w < bb) {
-        for (int k = 0; k <= w; ++k) mma2(z, ldn(R2 + (rtri(w) + k) * RBLK, L), ldt(RB + k * RBLK, L));
-        qsum += z.x * z.x + z.y * z.y;
+      double2 z[2];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        z[rr] = make_double2(0.0, 0.0);
+        const int row = w + rr * RNW;
+        if (row < bb) {
+          for (int k = 0; k <= row; ++k) mma2(z[rr], ldn(R2 + (rtri(row) + k) * RBLK, L), ldt(RB + k * RBLK, L));
+          qsum += z[rr].x * z[rr].x + z[rr].y * z[rr].y;
+        }
       }
       __syncthreads();
-      if (w < bb) {
-        stn(RB + w * RBLK, L, z);
-        stn(Zy + (yb * RMAXB + w) * RBLK, L, z);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = w + rr * RNW;
+        if (row < bb) {
+          stn(RB + row * RBLK, L, z[rr]);
+          stn(Zy + (yb * EMAXB + row) * RBLK, L, z[rr]);
+        }
       }
       __syncthreads();
-      if (P.want_grad && w < bb) {
-        double2 al = make_double2(0.0, 0.0);
-        for (int k = w; k < bb; ++k) mma2(al, ldt(R2 + (rtri(k) + w) * RBLK, L), ldt(RB + k * RBLK, L));
-        stn(Arow + ((long long)(ab + w) * RNYB + yb) * RBLK, L, al);
+      if (P.want_grad) {
+        for (int row = w; row < bb; row += RNW) {
+          double2 al = make_double2(0.0, 0.0);
+          for (int k = row; k < bb; ++k) mma2(al, ldt(R2 + (rtri(k) + row) * RBLK, L), ldt(RB + k * RBLK, L));
+          stn(Arow + ((long long)(ab + row) * RNYB + yb) * RBLK, L, al);
+        }
       }
       __syncthreads();
     };
     if (pair) {
-      stream_rows<2>(ring, pexp + EXP_ZY, P.nyb, [](int) { return RMAXB; }, ybody);
+      stream_rows<2>(ring, pexp + EXP_ZY, P.nyb, [](int) { return EMAXB; }, ybody);
     } else {
       __syncthreads();
       for (int yb = 0; yb < P.nyb; ++yb) ybody(yb, nullptr);
     }
   }
+  rtrace(P, s_tcur, u.uid, 6);
   // |Z_j|^2 and the log-likelihood (gprf.py:542-544)
   {
     double qv = qsum;
@@ -508,92 +558,111 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
 
   // ---- P6: T = L_ji W_i (row-local, in place), V = -W_S T (in place) ------------------------------------
   if (pair) {
-    {
-      double2 acc[RMAXB];
+    for (int rbase = 0; rbase < bb; rbase += RNW) {
+      const int row = rbase + w;
+      double2 acc[MB];
 #pragma unroll
-      for (int c = 0; c < RMAXB; ++c) acc[c] = make_double2(0.0, 0.0);
-      stream_rows<RSTAGES>(ring, pexp + EXP_W, ab, [](int r) { return r + 1; }, [&](int k, const double* row) {
-        if (w < bb) {
-          const double2 av = ldn(R1 + (w * ab + k) * RBLK, L);
+      for (int c = 0; c < MB; ++c) acc[c] = make_double2(0.0, 0.0);
+      stream_rows<RSTAGES>(ring, pexp + EXP_W, ab, [](int r) { return r + 1; }, [&](int k, const double* wrow) {
+        if (row < bb) {
+          const double2 av = ldn(R1 + (row * ab + k) * RBLK, L);
 #pragma unroll
-          for (int c = 0; c < RMAXB; ++c)
-            if (c <= k) mma2(acc[c], av, ldt(row + c * RBLK, L));
+          for (int c = 0; c < MB; ++c)
+            if (c <= k) mma2(acc[c], av, ldt(wrow + c * RBLK, L));
         }
       });
-      if (w < bb) {
+      if (row < bb) {
 #pragma unroll
-        for (int c = 0; c < RMAXB; ++c)
-          if (c < ab) stn(R1 + (w * ab + c) * RBLK, L, acc[c]);
+        for (int c = 0; c < MB; ++c)
+          if (c < ab) stn(R1 + (row * ab + c) * RBLK, L, acc[c]);
       }
     }
     __syncthreads();
     dbg_dump(6);
-    {
-      double2 acc[RMAXB];
+    rtrace(P, s_tcur, u.uid, 7);
+    // V(I, .) = -sum_{k <= I} W_S(I, k) T(k, .) overwrites T(I, .), which only rows >= I read: rows
+    // beyond the first 16 go first (one per warp), then rows [0, nb) with their columns split by parity
+    const int nb = min(bb, RNW);
+    for (int pass = (bb > RNW ? 0 : 1); pass < 2; ++pass) {
+      double2 acc[MB];
 #pragma unroll
-      for (int c = 0; c < RMAXB; ++c) acc[c] = make_double2(0.0, 0.0);
-      if (w < bb) {
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          const int row = part ? bb - 1 - w : w;
+      for (int c = 0; c < MB; ++c) acc[c] = make_double2(0.0, 0.0);
+      if (pass == 0) {
+        const int row = RNW + w;
+        if (row < bb) {
           for (int k = 0; k <= row; ++k) {
             const double2 av = ldn(R2 + (rtri(row) + k) * RBLK, L);
 #pragma unroll
-            for (int cc = 0; cc < RMAXB / 2; ++cc) {
+            for (int c = 0; c < MB; ++c)
+              if (c < ab) mma2(acc[c], av, ldt(R1 + (k * ab + c) * RBLK, L));
+          }
+        }
+        __syncthreads();
+        if (row < bb) {
+#pragma unroll
+          for (int c = 0; c < MB; ++c)
+            if (c < ab) stn(R1 + (row * ab + c) * RBLK, L, neg2(acc[c]));
+        }
+      } else {
+        if (w < nb) {
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            const int row = part ? nb - 1 - w : w;
+            for (int k = 0; k <= row; ++k) {
+              const double2 av = ldn(R2 + (rtri(row) + k) * RBLK, L);
+#pragma unroll
+              for (int cc = 0; cc < MB / 2; ++cc) {
+                const int c = 2 * cc + part;
+                if (c < ab) mma2(acc[part * (MB / 2) + cc], av, ldt(R1 + (k * ab + c) * RBLK, L));
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (w < nb) {
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            const int row = part ? nb - 1 - w : w;
+#pragma unroll
+            for (int cc = 0; cc < MB / 2; ++cc) {
               const int c = 2 * cc + part;
-              if (c < ab) mma2(acc[part * (RMAXB / 2) + cc], av, ldt(R1 + (k * ab + c) * RBLK, L));
+              if (c < ab) stn(R1 + (row * ab + c) * RBLK, L, neg2(acc[part * (MB / 2) + cc]));
             }
           }
         }
       }
       __syncthreads();
-      if (w < bb) {
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          const int row = part ? bb - 1 - w : w;
-#pragma unroll
-          for (int cc = 0; cc < RMAXB / 2; ++cc) {
-            const int c = 2 * cc + part;
-            if (c < ab) stn(R1 + (row * ab + c) * RBLK, L, neg2(acc[part * (RMAXB / 2) + cc]));
-          }
-        }
-      }
     }
-    __syncthreads();
     dbg_dump(7);
+    rtrace(P, s_tcur, u.uid, 8);
 
     // ---- P7: alpha_i = alpha_i(block) + V^T Z_j -------------------------------------------------------
-    {
-      double2 va[RMAXB];
-      if (w < ab) {
+    asm volatile("fence.proxy.async;\n" ::: "memory");   // Z_j was written with ordinary stores
+    for (int rbase = 0; rbase < ab; rbase += RNW) {
+      const int row = rbase + w;
+      double2 va[MB];
+      if (row < ab) {
 #pragma unroll
-        for (int k = 0; k < RMAXB; ++k)
-          va[k] = (k < bb) ? ldt(R1 + (k * ab + w) * RBLK, L) : make_double2(0.0, 0.0);
+        for (int k = 0; k < MB; ++k)
+          va[k] = (k < bb) ? ldt(R1 + (k * ab + row) * RBLK, L) : make_double2(0.0, 0.0);
       }
-      asm volatile("fence.proxy.async;\n" ::: "memory");   // Z_j was written with ordinary stores
-      stream_rows<RSTAGES>(ring, Zy, P.nyb, [](int) { return RMAXB; }, [&](int yb, const double* zj) {
-        if (w < ab) {
-          double2 acc = ldn(pexp + EXP_AROW + ((long long)w * RNYB + yb) * RBLK, L);
+      stream_rows<RSTAGES>(ring, Zy, P.nyb, [](int) { return EMAXB; }, [&](int yb, const double* zj) {
+        if (row < ab) {
+          double2 acc = ldn(pexp + EXP_AROW + ((long long)row * RNYB + yb) * RBLK, L);
 #pragma unroll
-          for (int k = 0; k < RMAXB; ++k)
+          for (int k = 0; k < MB; ++k)
             if (k < bb) mma2(acc, va[k], ldt(zj + k * RBLK, L));
-          stn(Arow + ((long long)w * RNYB + yb) * RBLK, L, acc);
+          stn(Arow + ((long long)row * RNYB + yb) * RBLK, L, acc);
         }
       });
     }
   }
   __syncthreads();
+  rtrace(P, s_tcur, u.uid, 9);
 
   // ---- P8: G = alpha alpha^T - dy K^-1, contracted with dK in registers (gprf.py:547-584) ------------
-  // warp w owns block row w of the i part and block row w of the j part; alpha rows are streamed.
+  // warp w owns block row rbase + w of the i part and of the j part; alpha rows are streamed.
   {
-    double2 ai[RNYB], aj[RNYB];
-#pragma unroll
-    for (int y = 0; y < RNYB; ++y) {
-      ai[y] = (w < ab && y < P.nyb) ? ldn(Arow + ((long long)w * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
-      aj[y] = (w < bb && y < P.nyb) ? ldn(Arow + ((long long)(ab + w) * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
-    }
-    double rsi[3] = {0.0, 0.0, 0.0}, rsj[3] = {0.0, 0.0, 0.0};
     double th[MAX_NCOV];
 #pragma unroll
     for (int t = 0; t < MAX_NCOV; ++t) th[t] = 0.0;
@@ -647,38 +716,47 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     };
 
     asm volatile("fence.proxy.async;\n" ::: "memory");     // alpha rows were written with ordinary stores
-    stream_rows<RSTAGES>(ring, Arow, nr, [](int) { return RNYB; }, [&](int c, const double* arow) {
-      if (pair && w < ab && c <= w) {               // (i row w, column c): K_ii^-1 + V^T V
-        double2 acc = ldn(pexp + EXP_KINV + (long long)(rtri(w) + c) * RBLK, L);
-        for (int k = 0; k < bb; ++k) mma2(acc, ldt(R1 + (k * ab + w) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
-        finish(acc, ai, arow, w, c, rsi);
-      }
-      if (w < bb && c <= ab + w) {
-        double2 acc = make_double2(0.0, 0.0);
-        if (c < ab) {                               // (j row w, i column c): W_S^T V
-          for (int k = w; k < bb; ++k)
-            mma2(acc, ldt(R2 + (rtri(k) + w) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
-        } else {                                    // (j row w, j column c - ab): W_S^T W_S
-          const int cc = c - ab;
-          for (int k = w; k < bb; ++k)
-            mma2(acc, ldt(R2 + (rtri(k) + w) * RBLK, L), ldt(R2 + (rtri(k) + cc) * RBLK, L));
-          if (is_export) stn(oexp + EXP_KINV + (long long)(rtri(w) + cc) * RBLK, L, acc);
-        }
-        finish(acc, aj, arow, ab + w, c, rsj);
-      }
-    });
-
-    // row sums -> unit gradX rows; theta partials -> shared
+    for (int rbase = 0; rbase < max(ab, bb); rbase += RNW) {
+      const int wi = rbase + w;                     // this warp's row in the i part and in the j part
+      double2 ai[RNYB], aj[RNYB];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      double vi = rsi[d], vj = rsj[d];
-      vi += __shfl_xor_sync(0xffffffffu, vi, 1);
-      vi += __shfl_xor_sync(0xffffffffu, vi, 2);
-      vj += __shfl_xor_sync(0xffffffffu, vj, 1);
-      vj += __shfl_xor_sync(0xffffffffu, vj, 2);
-      if (L.q == 0) {
-        if (w < ab) gx[(w * 8 + L.g) * 3 + d] = vi;
-        if (w < bb) gx[((ab + w) * 8 + L.g) * 3 + d] = vj;
+      for (int y = 0; y < RNYB; ++y) {
+        ai[y] = (wi < ab && y < P.nyb) ? ldn(Arow + ((long long)wi * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
+        aj[y] = (wi < bb && y < P.nyb) ? ldn(Arow + ((long long)(ab + wi) * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
+      }
+      double rsi[3] = {0.0, 0.0, 0.0}, rsj[3] = {0.0, 0.0, 0.0};
+      stream_rows<RSTAGES>(ring, Arow, nr, [](int) { return RNYB; }, [&](int c, const double* arow) {
+        if (pair && wi < ab && c <= wi) {             // (i row wi, column c): K_ii^-1 + V^T V
+          double2 acc = ldn(pexp + EXP_KINV + (long long)(rtri(wi) + c) * RBLK, L);
+          for (int k = 0; k < bb; ++k) mma2(acc, ldt(R1 + (k * ab + wi) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
+          finish(acc, ai, arow, wi, c, rsi);
+        }
+        if (wi < bb && c <= ab + wi) {
+          double2 acc = make_double2(0.0, 0.0);
+          if (c < ab) {                               // (j row wi, i column c): W_S^T V
+            for (int k = wi; k < bb; ++k)
+              mma2(acc, ldt(R2 + (rtri(k) + wi) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
+          } else {                                    // (j row wi, j column c - ab): W_S^T W_S
+            const int cc = c - ab;
+            for (int k = wi; k < bb; ++k)
+              mma2(acc, ldt(R2 + (rtri(k) + wi) * RBLK, L), ldt(R2 + (rtri(k) + cc) * RBLK, L));
+            if (is_export) stn(oexp + EXP_KINV + (long long)(rtri(wi) + cc) * RBLK, L, acc);
+          }
+          finish(acc, aj, arow, ab + wi, c, rsj);
+        }
+      });
+      // row sums -> unit gradX rows
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double vi = rsi[d], vj = rsj[d];
+        vi += __shfl_xor_sync(0xffffffffu, vi, 1);
+        vi += __shfl_xor_sync(0xffffffffu, vi, 2);
+        vj += __shfl_xor_sync(0xffffffffu, vj, 1);
+        vj += __shfl_xor_sync(0xffffffffu, vj, 2);
+        if (L.q == 0) {
+          if (wi < ab) gx[(wi * 8 + L.g) * 3 + d] = vi;
+          if (wi < bb) gx[((ab + wi) * 8 + L.g) * 3 + d] = vj;
+        }
       }
     }
 #pragma unroll
@@ -690,6 +768,7 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     }
   }
   __syncthreads();
+  rtrace(P, s_tcur, u.uid, 10);
   // column sums, fixed order; theta
   for (int t = tid; t < nr * 8; t += RNT) {
     const int cb = t >> 3, g0 = t & 7;
@@ -711,21 +790,24 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     P.gth_u[(long long)u.uid * MAX_NCOV + tid] = v;
   }
   __syncthreads();
+  rtrace(P, s_tcur, u.uid, 11);
 }
 
 // grid: persistent CTAs (<= one per SM), RNT threads, R_SMEM_BYTES dynamic shared memory.
 template <int DFN, int WFN>
 __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams P) {
-  extern __shared__ __align__(16) double smem[];
-  double* MISC = smem + R_XS_DOUBLES + R_RING_DOUBLES;
+  extern __shared__ __align__(128) double smem[];
+  double* MISC = smem + R_RING_DOUBLES;
   Ring ring;
-  ring.buf = smem + R_XS_DOUBLES;
+  ring.buf = smem;
   ring.bar = reinterpret_cast<uint64_t*>(MISC);
   ring.par = 0;
   int* s_unit = reinterpret_cast<int*>(MISC + 4);
+  int* s_tcur = reinterpret_cast<int*>(MISC + 5);
   if (threadIdx.x == 0) {
     for (int s = 0; s < RSTAGES; ++s) mbar_init(ring.bar + s, 1);
     fence_mbar_init();
+    *s_tcur = 0;
   }
   __syncthreads();
   double* scratch = P.scratch + (long long)blockIdx.x * SCR_STRIDE;
@@ -763,7 +845,8 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams P) {
     }
     u.ab = (u.a + 7) >> 3;
     u.bb = (u.b + 7) >> 3;
-    if (!res_fits(u.ab, u.bb)) {
+    const int cls = res_class(u.ab, u.bb);
+    if (cls == 2) {
       if (threadIdx.x == 0) atomicOr(P.status, ST_OVERFLOW);
       continue;
     }
@@ -777,7 +860,10 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams P) {
       if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)u.uid * MAX_NCOV + threadIdx.x] = 0.0;
       continue;
     }
-    run_unit<DFN, WFN>(P, u, smem, ring, scratch);
+    if (u.ab <= RMAXB && u.bb <= RMAXB)
+      run_unit<DFN, WFN, RMAXB>(P, u, smem, ring, scratch, cls == 1);
+    else
+      run_unit<DFN, WFN, BMAXB>(P, u, smem, ring, scratch, cls == 1);
   }
 }
 
@@ -820,13 +906,13 @@ __global__ void k_res_plan(PlanParams Q) {
     key[e] = act ? (a + b) : -1;
     if (act) {
       need[i] = 1;                      // benign race: everybody writes 1
-      if (b > 0 && !res_fits((a + 7) >> 3, (b + 7) >> 3)) s_over = 1;
+      if (b > 0 && res_class((a + 7) >> 3, (b + 7) >> 3) == 2) s_over = 1;
     }
   }
   __syncthreads();
   for (int bq = tid; bq < Q.B; bq += nt) {
     const int s = (int)(Q.block_ptr[bq + 1] - Q.block_ptr[bq]);
-    if (need[bq] && !res_fits(0, (s + 7) >> 3)) s_over = 1;
+    if (need[bq] && res_class(0, (s + 7) >> 3) == 2) s_over = 1;
   }
   __syncthreads();
   // blocks: ascending id (they are all about the same size); stable compaction by one thread per 32

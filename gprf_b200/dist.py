@@ -21,15 +21,19 @@ from .gprf import GPRF, LinAlgError
 COST_DY = 50.0
 
 
-def unit_costs(block_ptr, edges):
-    """Work model W(s) = s^3 + 4 s^2 dy per unit."""
+def unit_costs(block_ptr, edges, nominal=False):
+    """Work model W(s) = s^3 + 4 s^2 dy per unit.  ``nominal``: every block
+    counts as 100 points - the split the library uses for small-block structures, whose block
+    sizes never reach the host (resident path; ``shard_sizes`` in gprf_lib.cu)."""
     sizes = np.diff(np.asarray(block_ptr, dtype=np.int64)).astype(np.float64)
+    if nominal:
+        sizes = np.full_like(sizes, 100.0)
     e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
     s = np.concatenate([sizes, sizes[e[:, 0]] + sizes[e[:, 1]]]) if len(e) else sizes
     return s ** 3 + 4.0 * COST_DY * s ** 2
 
 
-def shard_owners(block_ptr, edges, world):
+def shard_owners(block_ptr, edges, world, nominal=False):
     """Owner rank of every unit (blocks, then edges).
 
     The unit of assignment is a *group*: block i together with every edge (i, j) whose stacked
@@ -38,7 +42,7 @@ def shard_owners(block_ptr, edges, world):
     longest-processing-time greedy on the work model; deterministic, so every rank derives
     the same global assignment without communication (same rule as ``lpt_mask`` in C++).
     """
-    cost = unit_costs(block_ptr, edges)
+    cost = unit_costs(block_ptr, edges, nominal)
     B = len(block_ptr) - 1
     e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
     group = cost[:B].copy()
@@ -56,9 +60,9 @@ def shard_owners(block_ptr, edges, world):
     return np.concatenate([owner_b, owner_b[e[:, 0]]]) if len(e) else owner_b
 
 
-def shard_units(block_ptr, edges, rank, world):
+def shard_units(block_ptr, edges, rank, world, nominal=False):
     """uint8 mask over units (blocks, then edges): 1 = evaluated on ``rank``."""
-    return np.ascontiguousarray((shard_owners(block_ptr, edges, world) == rank).astype(np.uint8))
+    return np.ascontiguousarray((shard_owners(block_ptr, edges, world, nominal) == rank).astype(np.uint8))
 
 
 def pack(ll, gX, gC, n, dx):
@@ -122,7 +126,7 @@ class ShardedGPRF(GPRF):
                                grad_X=grad_X, grad_cov=grad_cov,
                                reblock=self._blocks_stale and self._device_part is not None)
             self._out[0] = 0.0
-        except LinAlgError as exc:
+        except Exception as exc:          # any failure: flag it, still take part in the collective
             error = exc
             self._out[:used].zero_()
             self._out[0] = 1.0
@@ -132,5 +136,5 @@ class ShardedGPRF(GPRF):
         if error is not None:
             raise error
         if self._outh[0].item() != 0.0:
-            raise LinAlgError("a unit on another rank was not positive definite")
+            raise LinAlgError("the evaluation failed on another rank (e.g. a unit was not positive definite)")
         return unpack(self._outh.numpy()[1:], n, dx, 2 + len(self.cov.dfn_params), grad_X, grad_cov)

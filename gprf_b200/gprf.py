@@ -97,6 +97,7 @@ class GPRF(object):
                                    self._Yc.shape[1], _lib.ptr(self._Yc), dfn_id, wfn_id)
         self._h = h
         self._check(rc)
+        self._shape = (int(X.shape[0]), int(X.shape[1]))
         self._edges_key = None
         self._blocks_key = None
         self._blocks_stale = False
@@ -113,6 +114,21 @@ class GPRF(object):
         if rc == _lib.ERR_ARG:
             raise ValueError(msg)
         raise RuntimeError(msg)
+
+    def _Xc(self, X=None):
+        """C-contiguous float64 view of X, checked against the (n, dx) the native handle was created
+        with (the library copies exactly n*dx doubles in and out)."""
+        Xc = np.ascontiguousarray(self.X if X is None else X, dtype=np.float64)
+        if Xc.ndim != 2 or Xc.shape != self._shape:
+            raise ValueError("X has shape %s, the GPRF was built for %s" % (Xc.shape, self._shape))
+        return Xc
+
+    def _points(self, X):
+        """Free-standing point set for the kernel wrappers: (m, dx) with the handle's dx."""
+        Xc = np.ascontiguousarray(X, dtype=np.float64)
+        if Xc.ndim != 2 or Xc.shape[1] != self._shape[1]:
+            raise ValueError("points have shape %s, expected (m, %d)" % (Xc.shape, self._shape[1]))
+        return Xc
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._lib is not None:
@@ -150,7 +166,7 @@ class GPRF(object):
         the device it is downloaded on first access."""
         if self._block_idxs is None:
             if self._blocks_stale:
-                Xc = np.ascontiguousarray(self.X, dtype=np.float64)
+                Xc = self._Xc()
                 self._check(self._lib.gprf_reblock(self._h, _lib.ptr(Xc)))
                 self._blocks_stale = False
             B = C.c_int()
@@ -187,7 +203,7 @@ class GPRF(object):
         self._check(rc)
         # proof on the actual data: device partition == host partition
         host = self.block_fn(self.X)
-        Xc = np.ascontiguousarray(self.X, dtype=np.float64)
+        Xc = self._Xc()
         self._check(self._lib.gprf_reblock(self._h, _lib.ptr(Xc)))
         saved = self._block_idxs
         self._block_idxs = None
@@ -215,6 +231,8 @@ class GPRF(object):
 
     def update_X(self, new_X, update_blocks=True, recompute_neighbors=False):
         """gprf.py:169-174."""
+        if np.shape(new_X) != self._shape:
+            raise ValueError("new_X has shape %s, the GPRF was built for %s" % (np.shape(new_X), self._shape))
         self.X = new_X
         if self.block_fn is not None:
             if self._device_part is not None:
@@ -248,14 +266,16 @@ class GPRF(object):
         return self._all_pairs
 
     def _sync_edges(self, edges):
-        key = (id(edges), len(edges))
+        # keyed on the CONTENTS (an in-place edit of self.neighbors must reach the device); the
+        # (1 - deg) weights of gprf.py:253-264 are derived from this edge list
+        e = _edge_array(edges)
+        key = e.tobytes()
         if key == self._edges_key:
             return
-        e = _edge_array(edges)
         rank, world = self.unit_shard if self.unit_shard is not None else (0, 1)
         self._check(self._lib.gprf_set_edges(self._h, len(e), _lib.ptr(e), int(rank), int(world)))
         self._edges_key = key
-        self._keep_edges = (edges, e)             # keeps id(edges) unique while cached
+        self._keep_edges = (edges, e)
 
     def _sync_blocks(self):
         """Host-held block lists -> device (no-op when the device already holds them)."""
@@ -279,7 +299,7 @@ class GPRF(object):
         self._sync_blocks()
         B = len(blocks)
         maxk = np.empty((B, B), dtype=np.float64)
-        Xc = np.ascontiguousarray(self.X, dtype=np.float64)
+        Xc = self._Xc()
         th = self._theta()
         self._check(self._lib.gprf_block_max_kernel(self._h, _lib.ptr(Xc), _lib.ptr(th), len(th), _lib.ptr(maxk)))
         self.maxk_cache = maxk
@@ -294,8 +314,10 @@ class GPRF(object):
         grad_cov = bool(kwargs.get("grad_cov", False))
         if kwargs.get("sparse", False):
             raise NotImplementedError("sparse (CHOLMOD) unit likelihoods are outside the hot path")
+        Xc = self._Xc()
+        if not self._blocks_stale:
+            self._sync_blocks()                     # block count first: edges are validated against it
         self._sync_edges(self._edges_for(local))
-        Xc = np.ascontiguousarray(self.X, dtype=np.float64)
         th = self._theta()
         ll = C.c_double()
         failed = C.c_int(-1)
@@ -306,7 +328,6 @@ class GPRF(object):
             self._blocks_stale = False
             self._blocks_key = None
         else:
-            self._sync_blocks()
             fn = self._lib.gprf_llgrad
         rc = fn(self._h, _lib.ptr(Xc), _lib.ptr(th), len(th), int(grad_X), int(grad_cov),
                 C.byref(ll), _lib.ptr(gX), _lib.ptr(gC), C.byref(failed))
@@ -395,7 +416,7 @@ class GPRF(object):
         v = np.zeros(16, dtype=np.int64)
         m = lib.gprf_resident_layout(v.ctypes.data_as(C.POINTER(C.c_longlong)), 16)
         names = ["MAXB", "NYB", "BLK", "EXP_W", "EXP_KINV", "EXP_ZY", "EXP_AROW", "EXP_SCAL", "EXP_STRIDE",
-                 "GX_STRIDE", "MAT_BLOCKS"]
+                 "GX_STRIDE", "CAP_DOUBLES"]
         return dict(zip(names, (int(x) for x in v[:m])))
 
     @staticmethod
@@ -412,8 +433,8 @@ class GPRF(object):
         self._check(self._lib.gprf_set_resident_debug(self._h, int(unit), int(phase)))
 
     def resident_dump(self):
-        """(R1, R2) as dense 128 x 128 arrays, from the last evaluation with resident_debug set."""
-        out = np.zeros((2, 128, 128))
+        """(R1, R2) as dense 160 x 160 arrays, from the last evaluation with resident_debug set."""
+        out = np.zeros((2, 160, 160))
         self._check(self._lib.gprf_get_resident_debug(self._h, _lib.ptr(out), -1, None, -1, None))
         return out[0], out[1]
 
@@ -569,11 +590,69 @@ class GPRF(object):
 
     # -- kernel wrappers (gprf.py:333-375) --------------------------------------
     def kernel(self, X, X2=None):
-        X1 = np.ascontiguousarray(X, dtype=np.float64)
-        Xb = None if X2 is None else np.ascontiguousarray(X2, dtype=np.float64)
+        X1 = self._points(X)
+        Xb = None if X2 is None else self._points(X2)
         n2 = X1.shape[0] if Xb is None else Xb.shape[0]
         K = np.empty((X1.shape[0], n2), dtype=np.float64)
         th = self._theta()
         self._check(self._lib.gprf_kernel_matrix(self._h, _lib.ptr(X1), X1.shape[0], _lib.ptr(Xb), n2,
                                                  _lib.ptr(th), len(th), _lib.ptr(K)))
         return K
+
+    def dKdx(self, X, p, i, return_vec=False, dKv=None):
+        """gprf.py:345-360: derivative of kernel(X, X) wrt coordinate ``i`` of point ``p``.
+        ``return_vec``: row p of d k(x_p, .)/d x_{p,i} (entry p zero), written into ``dKv`` when
+        given; otherwise the symmetric matrix whose row and column p hold that vector."""
+        Xc = self._points(X)
+        n = Xc.shape[0]
+        th = self._theta()
+        row = np.empty(n, dtype=np.float64)
+        self._check(self._lib.gprf_kernel_deriv(self._h, _lib.ptr(Xc), n, _lib.ptr(th), len(th), 0, int(p), int(i),
+                                                _lib.ptr(row)))
+        if return_vec:
+            if dKv is None:
+                return row
+            dKv[:] = row
+            return dKv
+        dK = np.zeros((n, n))
+        dK[p, :] = row
+        return dK + dK.T
+
+    def dKdi(self, X1, i):
+        """gprf.py:362-375: d(kernel(X1) + nv I)/d theta_i for theta = [nv, s2, lengthscales...]."""
+        Xc = self._points(X1)
+        n = Xc.shape[0]
+        if i == 0:
+            return np.eye(n)
+        if i == 1:
+            if len(self.cov.wfn_params) != 1:
+                raise ValueError("gradient computation currently assumes just a single scaling parameter for "
+                                 "weight function, but currently wfn_params=%s" % self.cov.wfn_params)
+            return self.kernel(Xc, Xc) / self.cov.wfn_params[0]
+        th = self._theta()
+        out = np.empty((n, n), dtype=np.float64)
+        self._check(self._lib.gprf_kernel_deriv(self._h, _lib.ptr(Xc), n, _lib.ptr(th), len(th), 1, 0, int(i) - 2,
+                                                _lib.ptr(out)))
+        return out
+
+    def subset_llgrad(self, blocks):
+        """gprf.py:182-204: objective of the sub-field induced by ``blocks`` (unaries of the subset,
+        pairs inside it, neighbour counts restricted to it).  One masked device evaluation."""
+        blocks = [int(b) for b in blocks]
+        bset = set(blocks)
+        inside = [(i, j) for (i, j) in self.neighbors if i in bset and j in bset]
+        cnt = defaultdict(int)
+        for (i, j) in inside:
+            cnt[i] += 1
+            cnt[j] += 1
+        sub = GPRF(self._Xc(), self._Yc, None, self.cov, self.noise_var, block_idxs=self.block_idxs,
+                   neighbors=inside, device=self.device)
+        try:
+            sub.llgrad()
+            lls, _ = sub.unit_results()
+        finally:
+            sub.close()
+        B = self.n_blocks
+        ll = float(np.sum(lls[B:B + len(inside)])) if inside else 0.0
+        ll += float(np.sum([(1 - cnt[b]) * lls[b] for b in blocks]))
+        return ll

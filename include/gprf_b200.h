@@ -141,6 +141,12 @@ int gprf_kernel_matrix(gprf_handle h, const double* X1, long long n1,
 
 /* Debug / test access: copy unit u's working matrix ((sp+yr) x sp, row major)
  * and sizes after the last evaluation.  Any pointer may be NULL. */
+/* GPRF.dKdx (gprf.py:345-355; mode 0: row p of d k(x_p, .)/d x_{p,which}, entry p zeroed, n doubles)
+ * and the lengthscale part of GPRF.dKdi (gprf.py:372-374; mode 1: d K / d l_which, n x n doubles)
+ * for one point set X (n x dx, host). */
+int gprf_kernel_deriv(gprf_handle h, const double* X, long long n, const double* theta, int ncov,
+                      int mode, int p, int which, double* out);
+
 int gprf_debug_unit(gprf_handle h, int unit, int* s, int* sp, int* yr,
                     double* M, double* alpha, double* gx_unit);
 
