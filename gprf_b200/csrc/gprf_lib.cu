@@ -1526,7 +1526,7 @@ extern "C" int gprf_resident_stats(gprf_handle h, long long* evals, long long* f
 
 extern "C" int gprf_resident_layout(long long* out, int n) {
   const long long v[] = {res::EMAXB, res::RNYB, res::RBLK, res::EXP_W, res::EXP_KINV, res::EXP_ZY, res::EXP_AROW,
-                         res::EXP_SCAL, res::EXP_STRIDE, res::GX_STRIDE, res::R_CAP_DOUBLES};
+                         res::EXP_SCAL, res::EXP_STRIDE, res::GX_STRIDE, res::R_CAP_DOUBLES, res::EXP_KSAVE};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   if (!out || n < m) return m;
   for (int i = 0; i < m; ++i) out[i] = v[i];

@@ -44,45 +44,55 @@ namespace res {
 
 constexpr int RMAXB = 16;                 // 8x8 blocks per side of one block of points, register-array size
 constexpr int BMAXB = 20;                 // ... of the "big unit" instantiation (up to 160 points per block)
-constexpr int EMAXB = BMAXB;              // row length of the exported / scratch layouts
-constexpr int RNYB = 8;                   // y blocks per row in the exported layouts (dy <= 64)
+constexpr int EMAXB = BMAXB;              // bound used by the exported / scratch layouts
+constexpr int RNYB = 8;                   // y blocks per alpha row in the exported layouts (dy <= 64)
 constexpr int RNW = 16;                   // warps per CTA
 constexpr int RNT = RNW * 32;
 constexpr int RBLK = 64;                  // doubles per 8x8 block
-constexpr int RSTAGE_BLK = EMAXB;         // blocks per ring stage (10 KB)
-constexpr int RSTAGES = 3;
-constexpr int R_RING_DOUBLES = RSTAGES * RSTAGE_BLK * RBLK;
+constexpr int R_WB_BLOCKS = 60;           // fixed work buffer (30 KB): diagonal inverses, right-hand sides, task table
 constexpr int R_MISC_DOUBLES = 320;
 constexpr int R_SMEM_BYTES = 232448;      // 227 KB, the sm_100 per-CTA maximum
-// doubles left for XS (coordinate records), R2 and R1
-constexpr int R_CAP_DOUBLES = R_SMEM_BYTES / 8 - R_RING_DOUBLES - R_MISC_DOUBLES;
+// doubles left for XS (coordinate records), R1, R2 and the staging area F behind them
+constexpr int R_CAP_DOUBLES = R_SMEM_BYTES / 8 - R_WB_BLOCKS * RBLK - R_MISC_DOUBLES;
+constexpr int R_MIN_STAGE_BLOCKS = 32;    // F must at least hold one exported row (EMAXB blocks) / GCOLS alpha rows
 
 constexpr int RTRI = EMAXB * (EMAXB + 1) / 2;
-// per-block export (doubles)
-constexpr long long EXP_W = 0;
-constexpr long long EXP_KINV = (long long)RTRI * RBLK;
-constexpr long long EXP_ZY = 2LL * RTRI * RBLK;                     // (yb * EMAXB + k)
-constexpr long long EXP_AROW = EXP_ZY + (long long)RNYB * EMAXB * RBLK;     // (k * RNYB + yb)
+// per-block export (doubles); nb = the block's own number of 8-blocks
+constexpr long long EXP_W = 0;                                       // lower packed: rtri(k) + c
+constexpr long long EXP_KINV = (long long)RTRI * RBLK;               // lower packed
+constexpr long long EXP_KSAVE = 2LL * RTRI * RBLK;                   // lower packed: covariance values
+constexpr long long EXP_ZY = 3LL * RTRI * RBLK;                      // yb * nb + k   (compact)
+constexpr long long EXP_AROW = EXP_ZY + (long long)RNYB * EMAXB * RBLK;     // k * RNYB + yb
 constexpr long long EXP_SCAL = EXP_AROW + (long long)EMAXB * RNYB * RBLK;   // logdet, |Z|^2
 constexpr long long EXP_STRIDE = EXP_SCAL + 16;
 // per-CTA scratch (doubles)
-constexpr long long SCR_ZY = 0;
-constexpr long long SCR_AROW = (long long)RNYB * EMAXB * RBLK;              // 2*EMAXB rows
+constexpr long long SCR_ZY = 0;                                              // yb * bb + k
+constexpr long long SCR_AROW = (long long)RNYB * EMAXB * RBLK;              // 2*EMAXB rows x RNYB
 constexpr long long SCR_COLP = SCR_AROW + 2LL * EMAXB * RNYB * RBLK;
-constexpr int COLP = 24;
-constexpr long long SCR_R1 = SCR_COLP + (long long)(2 * EMAXB) * (2 * EMAXB + 1) / 2 * COLP;   // R1 of units too big for smem
+constexpr int COLP = 24;                                                     // per G block: column sums 8 x 3
+constexpr long long SCR_TASKP = SCR_COLP + (long long)(2 * EMAXB) * (2 * EMAXB + 1) / 2 * COLP;
+constexpr int TASKP = 32;                                                    // per task: row sums 8 x 3, theta 5
+constexpr int GCOLS = 4;                                                     // G blocks per task
+constexpr int MAXG = (2 * EMAXB + GCOLS - 1) / GCOLS;                        // column groups per row
+constexpr long long SCR_KJI = SCR_TASKP + (long long)(2 * EMAXB) * MAXG * TASKP;   // saved K_ji: row * ab + c
+constexpr long long SCR_KJJ = SCR_KJI + (long long)EMAXB * EMAXB * RBLK;           // saved K_jj: lower packed
+constexpr long long SCR_R1 = SCR_KJJ + (long long)RTRI * RBLK;                      // R1 of units too big for smem
 constexpr long long SCR_STRIDE = SCR_R1 + (long long)EMAXB * EMAXB * RBLK;
 constexpr int GX_STRIDE = 2 * EMAXB * 8 * 3;           // per-unit gradX rows (padded local order)
 
 enum { ST_OVERFLOW = 1, ST_NOTPD = 2 };
 
 __host__ __device__ __forceinline__ int rtri(int i) { return i * (i + 1) / 2; }
+// free staging blocks behind XS / R1 / R2 (negative: does not fit)
+__host__ __device__ __forceinline__ int res_free_blocks(int ab, int bb, bool r1_global) {
+  const int used = (ab + bb) * 8 * XD + ((r1_global ? 0 : bb * ab) + rtri(bb)) * RBLK;
+  return (R_CAP_DOUBLES - used) / RBLK - (R_CAP_DOUBLES < used ? 1 : 0);
+}
 // 0: everything in shared memory; 1: R1 (the bb x ab coupling matrix) in this CTA's L2-resident
 // scratch, the rest in shared memory; 2: does not fit (tile pipeline).
 __host__ __device__ __forceinline__ int res_class(int ab, int bb) {
   if (ab > BMAXB || bb > BMAXB) return 2;
-  const int xs = (ab + bb) * 8 * XD;
-  if ((bb * ab + rtri(bb)) * RBLK + xs <= R_CAP_DOUBLES) return 0;
+  if (res_free_blocks(ab, bb, false) >= R_MIN_STAGE_BLOCKS) return 0;
   return 1;
 }
 
@@ -127,6 +137,9 @@ __device__ __forceinline__ Lane make_lane() {
   L.on = sw_off(L.g, 2 * L.q);
   L.ot0 = sw_off(2 * L.q, L.g);
   L.ot1 = sw_off(2 * L.q + 1, L.g);
+  // opaque to the optimiser: under register pressure it would otherwise recompute these from
+  // %tid at every use (measured: 13 % of all executed instructions)
+  asm volatile("" : "+r"(L.on), "+r"(L.ot0), "+r"(L.ot1), "+r"(L.g), "+r"(L.q));
   return L;
 }
 // row-major fragment: (M[g][2q], M[g][2q+1])  - A operand of C = A B^T, B operand given as [n][k],
@@ -147,68 +160,79 @@ __device__ __forceinline__ void mma2(double2& c, double2 a, double2 b) {
 }
 __device__ __forceinline__ double2 neg2(double2 v) { return make_double2(-v.x, -v.y); }
 
-// ---- staging ring ------------------------------------------------------------------------------
-struct Ring {
-  double* buf;
-  uint64_t* bar;
-  unsigned par;                 // bit s: parity the next wait on stage s expects
+// f(integral_constant<K>) for K = n-1, n-2, ..., 0: one indexed jump into straight-line code, so that
+// loops whose register arrays need compile-time indices run without a branch per element and the
+// compiler can hoist the fragment loads of a whole pass in front of its DMMAs.
+template <int K>
+struct IC {
+  static constexpr int value = K;
 };
-__device__ __forceinline__ void ring_issue(const Ring& R, int stage, const double* src, int nblk) {
+#define RES_CASE(K) \
+  case K + 1:       \
+    if constexpr (K < MB) f(IC<K>{});
+template <int MB, class F>
+__device__ __forceinline__ void for_desc(int n, F&& f) {
+  switch (n) {
+    RES_CASE(19) RES_CASE(18) RES_CASE(17) RES_CASE(16) RES_CASE(15) RES_CASE(14) RES_CASE(13) RES_CASE(12)
+    RES_CASE(11) RES_CASE(10) RES_CASE(9) RES_CASE(8) RES_CASE(7) RES_CASE(6) RES_CASE(5) RES_CASE(4)
+    RES_CASE(3) RES_CASE(2) RES_CASE(1) RES_CASE(0)
+    default: break;
+  }
+}
+#undef RES_CASE
+
+// ---- TMA staging --------------------------------------------------------------------------------
+// One mbarrier; every thread tracks its phase parity.  tma_issue: ONE thread, after a CTA barrier
+// that retired all earlier accesses to the destination.
+struct Stage {
+  uint64_t* bar;
+  unsigned par;
+};
+__device__ __forceinline__ void tma_issue(const Stage& S, double* dst, const double* src, int nblk) {
   fence_proxy_async();
   const uint32_t bytes = (uint32_t)nblk * RBLK * 8;
-  mbar_expect_tx(R.bar + stage, bytes);
-  bulk_g2s(R.buf + stage * RSTAGE_BLK * RBLK, src, bytes, R.bar + stage);
+  mbar_expect_tx(S.bar, bytes);
+  bulk_g2s(dst, src, bytes, S.bar);
 }
-__device__ __forceinline__ void ring_wait(Ring& R, int stage) {
-  mbar_wait(R.bar + stage, (R.par >> stage) & 1u);
-  R.par ^= 1u << stage;
+__device__ __forceinline__ void tma_wait(Stage& S) {
+  mbar_wait(S.bar, S.par & 1u);
+  S.par ^= 1u;
 }
 
-// Stream `nrows` rows of blocks (row r has rowlen(r) <= RSTAGE_BLK blocks, rows contiguous in
-// `src`) through NS stages of the ring; body(r, rowptr) is executed by every thread for every
-// row, in order.  All threads of the CTA must call it (it synchronises the CTA once per stage).
-template <int NS, class RowLen, class Body>
-__device__ __forceinline__ void stream_rows(Ring& R, const double* src, int nrows, RowLen rowlen, Body body) {
-  auto next = [&](int r0, int& nb) {
-    int r = r0;
-    nb = 0;
-    while (r < nrows && nb + rowlen(r) <= RSTAGE_BLK) {
-      nb += rowlen(r);
-      ++r;
-    }
-    return r;
-  };
-  __syncthreads();              // earlier users of the ring (any proxy) are done
-  int ir = 0, issued = 0;
-  long long ipos = 0;
-  auto issue_one = [&]() {
-    if (ir < nrows) {
-      int nb;
-      const int r1 = next(ir, nb);
-      if (threadIdx.x == 0) ring_issue(R, issued % NS, src + ipos * RBLK, nb);
-      ir = r1;
-      ipos += nb;
-      ++issued;
-    }
-  };
-#pragma unroll
-  for (int s = 0; s < NS - 1; ++s) issue_one();
-  int r = 0, consumed = 0;
+// Bring rows [0, nrows) of a packed operand (row r = rowlen(r) blocks at block offset rowpos(r),
+// rows contiguous) through the staging area `area` (cap blocks) in as few pieces as fit, and run
+// body(r0, r1, base) on each piece (base = address of row r0).  The first piece may have been
+// issued ahead by the caller (`ahead`, with the same area / cap).  CTA-wide: every thread calls it.
+template <class RowLen, class RowPos, class Body>
+__device__ __forceinline__ void staged_rows(Stage& S, double* area, int cap, const double* src, int nrows,
+                                            RowLen rowlen, RowPos rowpos, bool ahead, Body body) {
+  int r = 0;
   while (r < nrows) {
-    int nb;
-    const int r1 = next(r, nb);
-    issue_one();                // into the stage consumed one iteration ago (CTA-synchronised since)
-    const int st = consumed % NS;
-    ring_wait(R, st);
-    const double* p = R.buf + st * RSTAGE_BLK * RBLK;
-    for (int rr = r; rr < r1; ++rr) {
-      body(rr, p);
-      p += rowlen(rr) * RBLK;
+    int r1 = r, nb = 0;
+    while (r1 < nrows && nb + rowlen(r1) <= cap) {
+      nb += rowlen(r1);
+      ++r1;
     }
-    __syncthreads();
+    if (!ahead) {
+      __syncthreads();
+      if (threadIdx.x == 0) tma_issue(S, area, src + (long long)rowpos(r) * RBLK, nb);
+    }
+    ahead = false;
+    tma_wait(S);
+    body(r, r1, area);
     r = r1;
-    ++consumed;
+    if (r < nrows) __syncthreads();
   }
+}
+// the piece staged_rows() will ask for first: number of blocks of rows [0, r1)
+template <class RowLen>
+__device__ __forceinline__ int first_piece(int cap, int nrows, RowLen rowlen) {
+  int r1 = 0, nb = 0;
+  while (r1 < nrows && nb + rowlen(r1) <= cap) {
+    nb += rowlen(r1);
+    ++r1;
+  }
+  return nb;
 }
 
 // ---- per-unit geometry ---------------------------------------------------------------------------
@@ -236,36 +260,42 @@ __device__ __forceinline__ void rtrace(const ResParams& P, int* cursor, int uid,
 
 // ---------------------------------------------------------------------------------------------------
 // MB: size of the per-warp register arrays = upper bound on ab and bb (RMAXB for ordinary units,
-// BMAXB for the few big ones).  Rows of a phase are dealt to the 16 warps RNW at a time; units
-// with more than 16 block rows take a second pass (and stream their operands twice).
+// BMAXB for the few big ones).  Row-owned phases deal rows to the 16 warps RNW at a time; units
+// with more than 16 block rows take a second pass.
 template <int DFN, int WFN, int MB>
-__device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, double* smem, Ring& ring,
+__device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, double* smem, Stage& stage,
                                          double* scratch, bool r1_global) {
   const Lane L = make_lane();
   const int tid = threadIdx.x;
   const int w = L.w;
   const int a = u.a, b = u.b, ab = u.ab, bb = u.bb;
   const int nr = ab + bb;                          // block rows of the whole unit
+  const int nyb = P.nyb;
   const bool pair = ab > 0;
   const bool is_export = u.bi < 0;                 // block units export for their pairs
-  double* RING = smem;
-  double* MISC = RING + R_RING_DOUBLES;
+  double* WB = smem;
+  double* MISC = WB + R_WB_BLOCKS * RBLK;
   double* XS = MISC + R_MISC_DOUBLES;
-  double* R2 = XS + nr * 8 * XD;
-  double* R1 = r1_global ? scratch + SCR_R1 : R2 + rtri(bb) * RBLK;
+  double* R1 = r1_global ? scratch + SCR_R1 : XS + nr * 8 * XD;
+  double* R2 = XS + nr * 8 * XD + (r1_global ? 0 : bb * ab * RBLK);
+  double* F = R2 + rtri(bb) * RBLK;                // staging area behind the matrices
+  const int nF = res_free_blocks(ab, bb, r1_global);
   int* s_fail = reinterpret_cast<int*>(MISC + 4) + 1;
   int* s_tcur = reinterpret_cast<int*>(MISC + 5);
+  int* s_task = reinterpret_cast<int*>(MISC + 5) + 1;
+  int* s_ntask = reinterpret_cast<int*>(MISC + 6);
   double* s_q = MISC + 8;                          // [RNW]
-  double* s_th = MISC + 24;                        // [RNW][MAX_NCOV]
   double* s_ld = MISC + 104;                       // [RNW]
   int* IDX = reinterpret_cast<int*>(MISC + 120);   // [2 * EMAXB * 8] global point index or -1
-  double* WD = RING;                               // diagonal-block inverses during the factorisation
-  double* RB = RING + 2 * RSTAGE_BLK * RBLK;       // stage 2: work buffer of the Y part
+  double* WD = WB;                                 // diagonal-block inverses during the factorisation
   const double* pexp = pair ? P.exports + (long long)u.bi * EXP_STRIDE : nullptr;
   double* oexp = is_export ? P.exports + (long long)u.bj * EXP_STRIDE : nullptr;
   double* Zy = is_export ? oexp + EXP_ZY : scratch + SCR_ZY;
   double* Arow = is_export ? oexp + EXP_AROW : scratch + SCR_AROW;
+  double* Kjj = is_export ? oexp + EXP_KSAVE : scratch + SCR_KJJ;
+  double* Kji = scratch + SCR_KJI;
   double* colp = scratch + SCR_COLP;
+  double* taskp = scratch + SCR_TASKP;
   double* gx = P.gx_u + (long long)u.uid * GX_STRIDE;
   const CovParams& cp = P.cp;
   rtrace(P, s_tcur, u.uid, 1);
@@ -284,8 +314,12 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     }
     __syncthreads();
   };
+  auto tri_len = [](int r) { return r + 1; };
+  auto tri_pos = [](int r) { return rtri(r); };
 
-  // ---- P0: gather coordinates --------------------------------------------------------------------
+  // ---- P0: W_i on its way into [R2 | F] (both still unused), gather coordinates ----------------------
+  const int capW1 = rtri(bb) + nF;                 // staging capacity for W_i before S exists
+  if (pair && tid == 0) tma_issue(stage, R2, pexp + EXP_W, first_piece(capW1, ab, tri_len));
   if (tid == 0) *s_fail = 0;
   for (int t = tid; t < nr * 8; t += RNT) {
     long long idx = -1;
@@ -321,24 +355,33 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     return make_double2(v0, v1);
   };
 
-  // ---- P1: L_ji = K_ji W_i^T  (one row of L_ji per warp; W_i streamed row by row) ---------------------
+  // ---- P1: L_ji = K_ji W_i^T  (one row of L_ji per warp, its K_ji fragments in registers) ----------------
   if (pair) {
+    bool ahead = true;
     for (int rbase = 0; rbase < bb; rbase += RNW) {
       const int row = rbase + w;
       double2 kf[MB];
       if (row < bb) {
 #pragma unroll
-        for (int k = 0; k < MB; ++k) kf[k] = (k < ab) ? cov_frag(ab + row, k, false) : make_double2(0.0, 0.0);
+        for (int k = 0; k < MB; ++k) {
+          kf[k] = (k < ab) ? cov_frag(ab + row, k, false) : make_double2(0.0, 0.0);
+          if (k < ab && P.want_grad) stn(Kji + (row * ab + k) * RBLK, L, kf[k]);   // saved for the gradient
+        }
       }
-      stream_rows<RSTAGES>(ring, pexp + EXP_W, ab, [](int r) { return r + 1; }, [&](int c, const double* wrow) {
+      staged_rows(stage, R2, capW1, pexp + EXP_W, ab, tri_len, tri_pos, ahead, [&](int c0, int c1, const double* base) {
         if (row < bb) {
-          double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-          for (int k = 0; k < MB; ++k)
-            if (k <= c) mma2(acc, kf[k], ldn(wrow + k * RBLK, L));
-          stn(R1 + (row * ab + c) * RBLK, L, acc);
+          for (int c = c0; c < c1; ++c) {
+            const double* wrow = base + (rtri(c) - rtri(c0)) * RBLK;
+            double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+            for_desc<MB>(c + 1, [&](auto kc) {
+              constexpr int k = decltype(kc)::value;
+              mma2((k & 1) ? acc1 : acc0, kf[k], ldn(wrow + k * RBLK, L));
+            });
+            stn(R1 + (row * ab + c) * RBLK, L, make_double2(acc0.x + acc1.x, acc0.y + acc1.y));
+          }
         }
       });
+      ahead = false;
     }
   }
   dbg_dump(1);
@@ -358,10 +401,16 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
       }
       for (int c = part; c <= row; c += 2) {
         double2 acc = cov_frag(ab + row, ab + c, true);
+        if (P.want_grad) stn(Kjj + (rtri(row) + c) * RBLK, L, acc);
         if (pair) {
-#pragma unroll
-          for (int k = 0; k < MB; ++k)
-            if (k < ab) mma2(acc, nla[k], ldn(R1 + (c * ab + k) * RBLK, L));
+          double2 acc1 = make_double2(0.0, 0.0);
+          const double* lc = R1 + c * ab * RBLK;
+          for_desc<MB>(ab, [&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            mma2((k & 1) ? acc1 : acc, nla[k], ldn(lc + k * RBLK, L));
+          });
+          acc.x += acc1.x;
+          acc.y += acc1.y;
         }
         stn(R2 + (rtri(row) + c) * RBLK, L, acc);
       }
@@ -370,6 +419,10 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
   __syncthreads();
   dbg_dump(2);
   rtrace(P, s_tcur, u.uid, 3);
+
+  // Z_i (all of it, or its first piece) travels into F while S is factored
+  const int nyc = pair ? max(1, min(nyb, min(nF / ab, R_WB_BLOCKS / bb))) : max(1, min(nyb, R_WB_BLOCKS / bb));
+  if (pair && tid == 0) tma_issue(stage, F, pexp + EXP_ZY, min(nyc, nyb) * ab);
 
   // ---- P3a: blocked Cholesky of S in place (jitchol's first, jitter-free attempt) ---------------------
   for (int J = 0; J < bb; ++J) {
@@ -467,61 +520,76 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
       reinterpret_cast<double2*>(dst)[e] = reinterpret_cast<const double2*>(R2)[e];
   }
 
-  // ---- P4: Z_j = W_S (Y_j - L_ji Z_i), alpha_j = W_S^T Z_j, one block of 8 outputs at a time ----------
+  // ---- P4: Z_j = W_S (Y_j - L_ji Z_i), alpha_j = W_S^T Z_j, nyc blocks of 8 outputs at a time -------------
+  // tasks (row, y) of a piece are dealt round-robin to the warps; right-hand sides live in WB.
   double qsum = 0.0;
   {
-    auto ybody = [&](int yb, const double* zi) {
-      for (int row = w; row < bb; row += RNW) {
+    double* RB = WB;                                 // (yl * bb + row)
+    bool ahead = pair;
+    for (int y0 = 0; y0 < nyb; y0 += nyc) {
+      const int ny = min(nyc, nyb - y0);
+      const int ntask = ny * bb;
+      if (pair) {
+        if (!ahead) {
+          if (tid == 0) tma_issue(stage, F, pexp + EXP_ZY + (long long)y0 * ab * RBLK, ny * ab);
+        }
+        ahead = false;
+        tma_wait(stage);
+      }
+      for (int t = w; t < ntask; t += RNW) {
+        const int yl = t / bb, row = t - yl * bb;
         const int idx = IDX[ab * 8 + row * 8 + L.g];
-        const int y0 = yb * 8 + 2 * L.q;
+        const int yc = (y0 + yl) * 8 + 2 * L.q;
         double2 acc = make_double2(0.0, 0.0);
         if (idx >= 0) {
-          if (y0 < P.dy) acc.x = __ldg(P.Y + (long long)idx * P.dy + y0);
-          if (y0 + 1 < P.dy) acc.y = __ldg(P.Y + (long long)idx * P.dy + y0 + 1);
+          if (yc < P.dy) acc.x = __ldg(P.Y + (long long)idx * P.dy + yc);
+          if (yc + 1 < P.dy) acc.y = __ldg(P.Y + (long long)idx * P.dy + yc + 1);
         }
         if (pair) {
+          const double* zi = F + yl * ab * RBLK;
           for (int k = 0; k < ab; ++k) mma2(acc, neg2(ldn(R1 + (row * ab + k) * RBLK, L)), ldt(zi + k * RBLK, L));
         }
-        stn(RB + row * RBLK, L, acc);
+        stn(RB + t * RBLK, L, acc);
       }
       __syncthreads();
-      double2 z[2];
+      double2 z[4];
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        z[rr] = make_double2(0.0, 0.0);
-        const int row = w + rr * RNW;
-        if (row < bb) {
-          for (int k = 0; k <= row; ++k) mma2(z[rr], ldn(R2 + (rtri(row) + k) * RBLK, L), ldt(RB + k * RBLK, L));
-          qsum += z[rr].x * z[rr].x + z[rr].y * z[rr].y;
+      for (int i = 0; i < 4; ++i) {
+        z[i] = make_double2(0.0, 0.0);
+        const int t = w + i * RNW;
+        if (t < ntask) {
+          const int yl = t / bb, row = t - yl * bb;
+          for (int k = 0; k <= row; ++k)
+            mma2(z[i], ldn(R2 + (rtri(row) + k) * RBLK, L), ldt(RB + (yl * bb + k) * RBLK, L));
+          qsum += z[i].x * z[i].x + z[i].y * z[i].y;
         }
       }
       __syncthreads();
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int row = w + rr * RNW;
-        if (row < bb) {
-          stn(RB + row * RBLK, L, z[rr]);
-          stn(Zy + (yb * EMAXB + row) * RBLK, L, z[rr]);
+      for (int i = 0; i < 4; ++i) {
+        const int t = w + i * RNW;
+        if (t < ntask) {
+          const int yl = t / bb, row = t - yl * bb;
+          stn(RB + t * RBLK, L, z[i]);
+          stn(Zy + ((y0 + yl) * bb + row) * RBLK, L, z[i]);
         }
       }
       __syncthreads();
       if (P.want_grad) {
-        for (int row = w; row < bb; row += RNW) {
+        for (int t = w; t < ntask; t += RNW) {
+          const int yl = t / bb, row = t - yl * bb;
           double2 al = make_double2(0.0, 0.0);
-          for (int k = row; k < bb; ++k) mma2(al, ldt(R2 + (rtri(k) + row) * RBLK, L), ldt(RB + k * RBLK, L));
-          stn(Arow + ((long long)(ab + row) * RNYB + yb) * RBLK, L, al);
+          for (int k = row; k < bb; ++k)
+            mma2(al, ldt(R2 + (rtri(k) + row) * RBLK, L), ldt(RB + (yl * bb + k) * RBLK, L));
+          stn(Arow + ((long long)(ab + row) * RNYB + y0 + yl) * RBLK, L, al);
         }
       }
       __syncthreads();
-    };
-    if (pair) {
-      stream_rows<2>(ring, pexp + EXP_ZY, P.nyb, [](int) { return EMAXB; }, ybody);
-    } else {
-      __syncthreads();
-      for (int yb = 0; yb < P.nyb; ++yb) ybody(yb, nullptr);
     }
   }
   rtrace(P, s_tcur, u.uid, 6);
+  // W_i (first piece) back into F for T while the scalars are finished
+  if (pair && P.want_grad && tid == 0) tma_issue(stage, F, pexp + EXP_W, first_piece(nF, ab, tri_len));
   // |Z_j|^2 and the log-likelihood (gprf.py:542-544)
   {
     double qv = qsum;
@@ -555,22 +623,29 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     __syncthreads();
     return;
   }
+  asm volatile("fence.proxy.async;\n" ::: "memory");     // Z_j / alpha_j / saved K: written with ordinary stores
 
   // ---- P6: T = L_ji W_i (row-local, in place), V = -W_S T (in place) ------------------------------------
   if (pair) {
+    bool ahead = true;
     for (int rbase = 0; rbase < bb; rbase += RNW) {
       const int row = rbase + w;
       double2 acc[MB];
 #pragma unroll
       for (int c = 0; c < MB; ++c) acc[c] = make_double2(0.0, 0.0);
-      stream_rows<RSTAGES>(ring, pexp + EXP_W, ab, [](int r) { return r + 1; }, [&](int k, const double* wrow) {
+      staged_rows(stage, F, nF, pexp + EXP_W, ab, tri_len, tri_pos, ahead, [&](int k0, int k1, const double* base) {
         if (row < bb) {
-          const double2 av = ldn(R1 + (row * ab + k) * RBLK, L);
-#pragma unroll
-          for (int c = 0; c < MB; ++c)
-            if (c <= k) mma2(acc[c], av, ldt(wrow + c * RBLK, L));
+          for (int k = k0; k < k1; ++k) {
+            const double* wrow = base + (rtri(k) - rtri(k0)) * RBLK;
+            const double2 av = ldn(R1 + (row * ab + k) * RBLK, L);
+            for_desc<MB>(k + 1, [&](auto cc) {
+              constexpr int c = decltype(cc)::value;
+              mma2(acc[c], av, ldt(wrow + c * RBLK, L));
+            });
+          }
         }
       });
+      ahead = false;
       if (row < bb) {
 #pragma unroll
         for (int c = 0; c < MB; ++c)
@@ -578,6 +653,9 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
       }
     }
     __syncthreads();
+    // own Z_j (all of it, or its first piece) into F for alpha_i, behind the V product
+    const int zrows = max(1, min(nyb, nF / bb));
+    if (tid == 0) tma_issue(stage, F, Zy, zrows * bb);
     dbg_dump(6);
     rtrace(P, s_tcur, u.uid, 7);
     // V(I, .) = -sum_{k <= I} W_S(I, k) T(k, .) overwrites T(I, .), which only rows >= I read: rows
@@ -592,9 +670,11 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
         if (row < bb) {
           for (int k = 0; k <= row; ++k) {
             const double2 av = ldn(R2 + (rtri(row) + k) * RBLK, L);
-#pragma unroll
-            for (int c = 0; c < MB; ++c)
-              if (c < ab) mma2(acc[c], av, ldt(R1 + (k * ab + c) * RBLK, L));
+            const double* tk = R1 + k * ab * RBLK;
+            for_desc<MB>(ab, [&](auto cc) {
+              constexpr int c = decltype(cc)::value;
+              mma2(acc[c], av, ldt(tk + c * RBLK, L));
+            });
           }
         }
         __syncthreads();
@@ -610,11 +690,12 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
             const int row = part ? nb - 1 - w : w;
             for (int k = 0; k <= row; ++k) {
               const double2 av = ldn(R2 + (rtri(row) + k) * RBLK, L);
-#pragma unroll
-              for (int cc = 0; cc < MB / 2; ++cc) {
-                const int c = 2 * cc + part;
-                if (c < ab) mma2(acc[part * (MB / 2) + cc], av, ldt(R1 + (k * ab + c) * RBLK, L));
-              }
+              const double* tk = R1 + (k * ab + part) * RBLK;
+              // columns part, part + 2, ... < ab: (ab - part + 1) / 2 of them
+              for_desc<MB / 2>((ab - part + 1) >> 1, [&](auto ci) {
+                constexpr int cc = decltype(ci)::value;
+                mma2(acc[part * (MB / 2) + cc], av, ldt(tk + 2 * cc * RBLK, L));
+              });
             }
           }
         }
@@ -636,8 +717,8 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     dbg_dump(7);
     rtrace(P, s_tcur, u.uid, 8);
 
-    // ---- P7: alpha_i = alpha_i(block) + V^T Z_j -------------------------------------------------------
-    asm volatile("fence.proxy.async;\n" ::: "memory");   // Z_j was written with ordinary stores
+    // ---- P7: alpha_i = alpha_i(block) + V^T Z_j  (one row of the i part per warp, its V fragments in registers)
+    ahead = true;
     for (int rbase = 0; rbase < ab; rbase += RNW) {
       const int row = rbase + w;
       double2 va[MB];
@@ -646,135 +727,184 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
         for (int k = 0; k < MB; ++k)
           va[k] = (k < bb) ? ldt(R1 + (k * ab + row) * RBLK, L) : make_double2(0.0, 0.0);
       }
-      stream_rows<RSTAGES>(ring, Zy, P.nyb, [](int) { return EMAXB; }, [&](int yb, const double* zj) {
+      staged_rows(stage, F, nF, Zy, nyb, [&](int) { return bb; }, [&](int r) { return r * bb; }, ahead,
+                  [&](int y0, int y1, const double* base) {
         if (row < ab) {
-          double2 acc = ldn(pexp + EXP_AROW + ((long long)row * RNYB + yb) * RBLK, L);
-#pragma unroll
-          for (int k = 0; k < MB; ++k)
-            if (k < bb) mma2(acc, va[k], ldt(zj + k * RBLK, L));
-          stn(Arow + ((long long)row * RNYB + yb) * RBLK, L, acc);
+          for (int yb = y0; yb < y1; ++yb) {
+            const double* zj = base + (yb - y0) * bb * RBLK;
+            double2 acc = ldn(pexp + EXP_AROW + ((long long)row * RNYB + yb) * RBLK, L);
+            double2 acc1 = make_double2(0.0, 0.0);
+            for_desc<MB>(bb, [&](auto kc) {
+              constexpr int k = decltype(kc)::value;
+              mma2((k & 1) ? acc1 : acc, va[k], ldt(zj + k * RBLK, L));
+            });
+            stn(Arow + ((long long)row * RNYB + yb) * RBLK, L, make_double2(acc.x + acc1.x, acc.y + acc1.y));
+          }
         }
       });
+      ahead = false;
     }
+    asm volatile("fence.proxy.async;\n" ::: "memory");   // alpha_i rows
   }
   __syncthreads();
   rtrace(P, s_tcur, u.uid, 9);
 
   // ---- P8: G = alpha alpha^T - dy K^-1, contracted with dK in registers (gprf.py:547-584) ------------
-  // warp w owns block row rbase + w of the i part and of the j part; alpha rows are streamed.
+  // Column pieces: alpha rows [c0, c1) staged in F (B operands).  Tasks = (block row r, up to GCOLS
+  // columns of the piece), taken from a shared counter, biggest rows first; alpha(r) comes from L2.
   {
-    double th[MAX_NCOV];
-#pragma unroll
-    for (int t = 0; t < MAX_NCOV; ++t) th[t] = 0.0;
     const double ndy = -(double)P.dy;
-
-    // contraction of one G block (block row rb, block column cb, cb <= rb) held as accumulator fragment
-    auto epilogue = [&](int rb, int cb, double2 G, double (&rs)[3]) {
-      const int tr = rb * 8 + L.g;
-      const bool rv = IDX[tr] >= 0;
-      const double* xr = xs_row(XS, tr);
-      double cs[2][3];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int tc = cb * 8 + 2 * L.q + e;
-        const double Gv = e == 0 ? G.x : G.y;
-        const bool cv = rv && IDX[tc] >= 0;
-        if (cv && tc == tr) {
-          th[0] += 0.5 * Gv;
-          th[1] += 0.5 * Gv * cp.s2;
+    int* TT = reinterpret_cast<int*>(WB);            // task table of the piece: r | c_lo << 8 | c_hi << 16
+    const int crow = max(GCOLS, (nF / RNYB) & ~(GCOLS - 1));   // alpha rows per piece (a multiple of GCOLS)
+    for (int c0 = 0; c0 < nr; c0 += crow) {
+      const int c1 = min(nr, c0 + crow);
+      if (tid == 0) {
+        tma_issue(stage, F, Arow + (long long)c0 * RNYB * RBLK, (c1 - c0) * RNYB);
+        int nt = 0;
+        for (int r = nr - 1; r >= c0; --r) {
+          const int ce = min(c1, r + 1);
+          for (int cl = c0; cl < ce; cl += GCOLS) TT[nt++] = r | (cl << 8) | (min(ce, cl + GCOLS) << 16);
         }
-        const bool off = cv && tc < tr;
-        double k, gp[MAX_DX], gq[MAX_DX], gl[MAX_NLS];
-        cov_grad<DFN, WFN, false>(xr, xs_row(XS, tc), cp, k, gp, gq, gl);
-        const double Gm = off ? Gv : 0.0;
-        th[1] += off ? Gm * k : 0.0;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          rs[d] += off ? Gm * gp[d] : 0.0;
-          cs[e][d] = off ? Gm * gq[d] : 0.0;
-          th[2 + d] += off ? Gm * gl[d] : 0.0;
-        }
+        *s_ntask = nt;
+        *s_task = 0;
       }
+      __syncthreads();
+      tma_wait(stage);
+      const int ntask = *s_ntask;
+      while (true) {
+        int t = 0;
+        if (L.lane == 0) t = atomicAdd(s_task, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ntask) break;
+        const int code = TT[t];
+        const int r = code & 0xff, cl = (code >> 8) & 0xff, ch = (code >> 16) & 0xff;
+        const bool irow = r < ab;
+        const int wi = irow ? r : r - ab;            // row inside its part
+        double2 af[RNYB];
 #pragma unroll
-      for (int e = 0; e < 2; ++e)
+        for (int y = 0; y < RNYB; ++y)
+          af[y] = (y < nyb) ? ldn(Arow + ((long long)r * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
+        const int tr = r * 8 + L.g;
+        const bool rv = IDX[tr] >= 0;
+        const double* xr = xs_row(XS, tr);
+        double rs[3] = {0.0, 0.0, 0.0};
+        double th[MAX_NCOV];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          double v = cs[e][d];
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (L.g == 0) colp[(long long)(rtri(rb) + cb) * COLP + (2 * L.q + e) * 3 + d] = v;
-        }
-    };
-    auto finish = [&](double2 acc, const double2 (&af)[RNYB], const double* arow, int rb, int cb, double (&rs)[3]) {
-      acc.x *= ndy;
-      acc.y *= ndy;
-#pragma unroll
-      for (int y = 0; y < RNYB; ++y)
-        if (y < P.nyb) mma2(acc, af[y], ldn(arow + y * RBLK, L));
-      epilogue(rb, cb, acc, rs);
-    };
-
-    asm volatile("fence.proxy.async;\n" ::: "memory");     // alpha rows were written with ordinary stores
-    for (int rbase = 0; rbase < max(ab, bb); rbase += RNW) {
-      const int wi = rbase + w;                     // this warp's row in the i part and in the j part
-      double2 ai[RNYB], aj[RNYB];
-#pragma unroll
-      for (int y = 0; y < RNYB; ++y) {
-        ai[y] = (wi < ab && y < P.nyb) ? ldn(Arow + ((long long)wi * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
-        aj[y] = (wi < bb && y < P.nyb) ? ldn(Arow + ((long long)(ab + wi) * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
-      }
-      double rsi[3] = {0.0, 0.0, 0.0}, rsj[3] = {0.0, 0.0, 0.0};
-      stream_rows<RSTAGES>(ring, Arow, nr, [](int) { return RNYB; }, [&](int c, const double* arow) {
-        if (pair && wi < ab && c <= wi) {             // (i row wi, column c): K_ii^-1 + V^T V
-          double2 acc = ldn(pexp + EXP_KINV + (long long)(rtri(wi) + c) * RBLK, L);
-          for (int k = 0; k < bb; ++k) mma2(acc, ldt(R1 + (k * ab + wi) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
-          finish(acc, ai, arow, wi, c, rsi);
-        }
-        if (wi < bb && c <= ab + wi) {
-          double2 acc = make_double2(0.0, 0.0);
-          if (c < ab) {                               // (j row wi, i column c): W_S^T V
-            for (int k = wi; k < bb; ++k)
+        for (int tt = 0; tt < MAX_NCOV; ++tt) th[tt] = 0.0;
+        for (int c = cl; c < ch; ++c) {
+          double2 acc, kv, acc2 = make_double2(0.0, 0.0);
+          if (irow) {                                 // (i row, i column): K_ii^-1 + V^T V
+            acc = ldn(pexp + EXP_KINV + (long long)(rtri(wi) + c) * RBLK, L);
+            kv = ldn(pexp + EXP_KSAVE + (long long)(rtri(wi) + c) * RBLK, L);
+            const double* pa = R1 + wi * RBLK;
+            const double* pb = R1 + c * RBLK;
+            int k = 0;
+            for (; k + 1 < bb; k += 2) {
+              mma2(acc, ldt(pa + k * ab * RBLK, L), ldt(pb + k * ab * RBLK, L));
+              mma2(acc2, ldt(pa + (k + 1) * ab * RBLK, L), ldt(pb + (k + 1) * ab * RBLK, L));
+            }
+            if (k < bb) mma2(acc, ldt(pa + k * ab * RBLK, L), ldt(pb + k * ab * RBLK, L));
+          } else if (c < ab) {                        // (j row, i column): W_S^T V
+            acc = make_double2(0.0, 0.0);
+            kv = ldn(Kji + (wi * ab + c) * RBLK, L);
+            int k = wi;
+            for (; k + 1 < bb; k += 2) {
               mma2(acc, ldt(R2 + (rtri(k) + wi) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
-          } else {                                    // (j row wi, j column c - ab): W_S^T W_S
+              mma2(acc2, ldt(R2 + (rtri(k + 1) + wi) * RBLK, L), ldt(R1 + ((k + 1) * ab + c) * RBLK, L));
+            }
+            if (k < bb) mma2(acc, ldt(R2 + (rtri(k) + wi) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
+          } else {                                    // (j row, j column): W_S^T W_S
             const int cc = c - ab;
-            for (int k = wi; k < bb; ++k)
+            acc = make_double2(0.0, 0.0);
+            kv = ldn(Kjj + (rtri(wi) + cc) * RBLK, L);
+            int k = wi;
+            for (; k + 1 < bb; k += 2) {
               mma2(acc, ldt(R2 + (rtri(k) + wi) * RBLK, L), ldt(R2 + (rtri(k) + cc) * RBLK, L));
-            if (is_export) stn(oexp + EXP_KINV + (long long)(rtri(wi) + cc) * RBLK, L, acc);
+              mma2(acc2, ldt(R2 + (rtri(k + 1) + wi) * RBLK, L), ldt(R2 + (rtri(k + 1) + cc) * RBLK, L));
+            }
+            if (k < bb) mma2(acc, ldt(R2 + (rtri(k) + wi) * RBLK, L), ldt(R2 + (rtri(k) + cc) * RBLK, L));
           }
-          finish(acc, aj, arow, ab + wi, c, rsj);
-        }
-      });
-      // row sums -> unit gradX rows
+          acc.x += acc2.x;
+          acc.y += acc2.y;
+          if (!irow && c >= ab && is_export) stn(oexp + EXP_KINV + (long long)(rtri(wi) + c - ab) * RBLK, L, acc);
+          acc.x *= ndy;
+          acc.y *= ndy;
+          acc2 = make_double2(0.0, 0.0);
+          const double* arow = F + (c - c0) * RNYB * RBLK;
+          for_desc<RNYB>(nyb, [&](auto yc) {
+            constexpr int y = decltype(yc)::value;
+            mma2((y & 1) ? acc2 : acc, af[y], ldn(arow + y * RBLK, L));
+          });
+          acc.x += acc2.x;
+          acc.y += acc2.y;
+          // contraction of the G block with dk/dx, dk/dtheta (covariance values saved by P1 / P2 / the parent)
+          double cs[2][3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        double vi = rsi[d], vj = rsj[d];
-        vi += __shfl_xor_sync(0xffffffffu, vi, 1);
-        vi += __shfl_xor_sync(0xffffffffu, vi, 2);
-        vj += __shfl_xor_sync(0xffffffffu, vj, 1);
-        vj += __shfl_xor_sync(0xffffffffu, vj, 2);
-        if (L.q == 0) {
-          if (wi < ab) gx[(wi * 8 + L.g) * 3 + d] = vi;
-          if (wi < bb) gx[((ab + wi) * 8 + L.g) * 3 + d] = vj;
+          for (int e = 0; e < 2; ++e) {
+            const int tc = c * 8 + 2 * L.q + e;
+            const double Gv = e == 0 ? acc.x : acc.y;
+            const bool cv = rv && IDX[tc] >= 0;
+            if (cv && tc == tr) {
+              th[0] += 0.5 * Gv;
+              th[1] += 0.5 * Gv * cp.s2;
+            }
+            const bool off = cv && tc < tr;
+            double k = e == 0 ? kv.x : kv.y;
+            double gp[MAX_DX], gq[MAX_DX], gl[MAX_NLS];
+            cov_grad<DFN, WFN, true>(xr, xs_row(XS, tc), cp, k, gp, gq, gl);
+            const double Gm = off ? Gv : 0.0;
+            th[1] += off ? Gm * k : 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              rs[d] += off ? Gm * gp[d] : 0.0;
+              cs[e][d] = off ? Gm * gq[d] : 0.0;
+              th[2 + d] += off ? Gm * gl[d] : 0.0;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              double v = cs[e][d];
+              v += __shfl_xor_sync(0xffffffffu, v, 4);
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              if (L.g == 0) colp[(long long)(rtri(r) + c) * COLP + (2 * L.q + e) * 3 + d] = v;
+            }
+        }
+        // the task's row sums and theta partials
+        double* tp = taskp + ((long long)r * MAXG + (cl / GCOLS)) * TASKP;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          double v = rs[d];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          if (L.q == 0) tp[L.g * 3 + d] = v;
+        }
+#pragma unroll
+        for (int tt = 0; tt < MAX_NCOV; ++tt) {
+          double v = th[tt];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (L.lane == 0) tp[24 + tt] = v;
         }
       }
-    }
-#pragma unroll
-    for (int t = 0; t < MAX_NCOV; ++t) {
-      double v = th[t];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (L.lane == 0) s_th[w * MAX_NCOV + t] = v;
+      __syncthreads();
     }
   }
-  __syncthreads();
   rtrace(P, s_tcur, u.uid, 10);
-  // column sums, fixed order; theta
+  // row sums + column sums, fixed order; theta
   for (int t = tid; t < nr * 8; t += RNT) {
-    const int cb = t >> 3, g0 = t & 7;
-    double v[3] = {gx[t * 3], gx[t * 3 + 1], gx[t * 3 + 2]};
-    for (int rb = cb; rb < nr; ++rb) {
-      const double* pc = colp + (long long)(rtri(rb) + cb) * COLP + g0 * 3;
+    const int rb = t >> 3, g0 = t & 7;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int gi = 0; gi * GCOLS <= rb; ++gi) {
+      const double* tp = taskp + ((long long)rb * MAXG + gi) * TASKP + g0 * 3;
+      v[0] += tp[0];
+      v[1] += tp[1];
+      v[2] += tp[2];
+    }
+    for (int r2 = rb; r2 < nr; ++r2) {
+      const double* pc = colp + (long long)(rtri(r2) + rb) * COLP + g0 * 3;
       v[0] += pc[0];
       v[1] += pc[1];
       v[2] += pc[2];
@@ -783,11 +913,18 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     gx[t * 3 + 1] = v[1];
     gx[t * 3 + 2] = v[2];
   }
-  if (tid < MAX_NCOV) {
+  // theta: one warp per parameter; lanes stride over the task records in a fixed order, then a
+  // fixed shuffle tree - the summation order does not depend on which warp ran which task
+  if (w < MAX_NCOV) {
     double v = 0.0;
-    for (int i = 0; i < RNW; ++i) v += s_th[i * MAX_NCOV + tid];
-    if (tid == 1) v /= cp.s2;
-    P.gth_u[(long long)u.uid * MAX_NCOV + tid] = v;
+    for (int e = L.lane; e < nr * MAXG; e += 32) {
+      const int rb = e / MAXG, gi = e - rb * MAXG;
+      if (gi * GCOLS <= rb) v += taskp[(long long)e * TASKP + 24 + w];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (w == 1) v /= cp.s2;
+    if (L.lane == 0) P.gth_u[(long long)u.uid * MAX_NCOV + w] = v;
   }
   __syncthreads();
   rtrace(P, s_tcur, u.uid, 11);
@@ -797,15 +934,14 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
 template <int DFN, int WFN>
 __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams P) {
   extern __shared__ __align__(128) double smem[];
-  double* MISC = smem + R_RING_DOUBLES;
-  Ring ring;
-  ring.buf = smem;
-  ring.bar = reinterpret_cast<uint64_t*>(MISC);
-  ring.par = 0;
+  double* MISC = smem + R_WB_BLOCKS * RBLK;
+  Stage stage;
+  stage.bar = reinterpret_cast<uint64_t*>(MISC);
+  stage.par = 0;
   int* s_unit = reinterpret_cast<int*>(MISC + 4);
   int* s_tcur = reinterpret_cast<int*>(MISC + 5);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RSTAGES; ++s) mbar_init(ring.bar + s, 1);
+    mbar_init(stage.bar, 1);
     fence_mbar_init();
     *s_tcur = 0;
   }
@@ -861,9 +997,9 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams P) {
       continue;
     }
     if (u.ab <= RMAXB && u.bb <= RMAXB)
-      run_unit<DFN, WFN, RMAXB>(P, u, smem, ring, scratch, cls == 1);
+      run_unit<DFN, WFN, RMAXB>(P, u, smem, stage, scratch, cls == 1);
     else
-      run_unit<DFN, WFN, BMAXB>(P, u, smem, ring, scratch, cls == 1);
+      run_unit<DFN, WFN, BMAXB>(P, u, smem, stage, scratch, cls == 1);
   }
 }
 

@@ -416,7 +416,7 @@ class GPRF(object):
         v = np.zeros(16, dtype=np.int64)
         m = lib.gprf_resident_layout(v.ctypes.data_as(C.POINTER(C.c_longlong)), 16)
         names = ["MAXB", "NYB", "BLK", "EXP_W", "EXP_KINV", "EXP_ZY", "EXP_AROW", "EXP_SCAL", "EXP_STRIDE",
-                 "GX_STRIDE", "CAP_DOUBLES"]
+                 "GX_STRIDE", "CAP_DOUBLES", "EXP_KSAVE"]
         return dict(zip(names, (int(x) for x in v[:m])))
 
     @staticmethod
@@ -457,7 +457,7 @@ class GPRF(object):
         A = np.zeros((bb * 8, NYB * 8))
         for k in range(bb):
             for y in range(NYB):
-                o = lay["EXP_ZY"] + (y * MAXB + k) * BL
+                o = lay["EXP_ZY"] + (y * bb + k) * BL
                 Z[8 * k:8 * k + 8, 8 * y:8 * y + 8] = self._unswizzle(raw[o:o + BL])
                 o = lay["EXP_AROW"] + (k * NYB + y) * BL
                 A[8 * k:8 * k + 8, 8 * y:8 * y + 8] = self._unswizzle(raw[o:o + BL])

@@ -18,8 +18,10 @@ def line_table(obj, kern):
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, stdout=subprocess.DEVNULL)
     cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
-    table, cur, inside = {}, None, False
+    txt = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    # an instruction is preceded by its inline chain, innermost first; attribute it to the first
+    # frame that is not one of the small helpers (fragment loads, mma2, staging loops)
+    table, chain, inside = {}, [], False
     for ln in txt.splitlines():
         if ln.startswith("\t.section\t.text."):
             inside = kern in ln
@@ -28,12 +30,26 @@ def line_table(obj, kern):
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
-            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            chain.append((os.path.basename(m.group(1)), int(m.group(2))))
             continue
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(\S.*);", ln)
-        if m and cur:
-            table[int(m.group(1), 16)] = cur
+        if m:
+            if chain:
+                pick = chain[0]
+                for f, l in chain:
+                    if f == MAIN and l >= MAIN_FROM:
+                        pick = (f, l)
+                        break
+                table[int(m.group(1), 16)] = pick
+                last = pick
+                chain = []
+            elif table:
+                table[int(m.group(1), 16)] = last
     return table
+
+
+MAIN = "resident.cuh"
+MAIN_FROM = 241          # first line of run_unit: frames above it are helpers
 
 
 def main():
