@@ -50,7 +50,7 @@ constexpr int RNW = 16;                   // warps per CTA
 constexpr int RNT = RNW * 32;
 constexpr int RBLK = 64;                  // doubles per 8x8 block
 constexpr int R_WB_BLOCKS = 60;           // fixed work buffer (30 KB): diagonal inverses, right-hand sides, task table
-constexpr int R_MISC_DOUBLES = 320;
+constexpr int R_MISC_DOUBLES = 400;
 constexpr int R_SMEM_BYTES = 232448;      // 227 KB, the sm_100 per-CTA maximum
 // doubles left for XS (coordinate records), R1, R2 and the staging area F behind them
 constexpr int R_CAP_DOUBLES = R_SMEM_BYTES / 8 - R_WB_BLOCKS * RBLK - R_MISC_DOUBLES;
@@ -92,7 +92,8 @@ __host__ __device__ __forceinline__ int res_free_blocks(int ab, int bb, bool r1_
 // scratch, the rest in shared memory; 2: does not fit (tile pipeline).
 __host__ __device__ __forceinline__ int res_class(int ab, int bb) {
   if (ab > BMAXB || bb > BMAXB) return 2;
-  if (res_free_blocks(ab, bb, false) >= R_MIN_STAGE_BLOCKS) return 0;
+  const int nf = res_free_blocks(ab, bb, false);
+  if (nf >= R_MIN_STAGE_BLOCKS && rtri(ab) <= nf + rtri(bb)) return 0;
   return 1;
 }
 
@@ -235,196 +236,223 @@ __device__ __forceinline__ int first_piece(int cap, int nrows, RowLen rowlen) {
   return nb;
 }
 
-// ---- per-unit geometry ---------------------------------------------------------------------------
-struct Unit {
-  int uid, bi, bj;              // bi < 0: block unit
-  int a, b, ab, bb;             // points / 8-blocks of the i part (0 for block units) and the j part
-  long long ia, ja;             // offsets of the two blocks in perm
+// ---- per-unit context (shared memory) -----------------------------------------------------------------
+// Every phase is a separate __noinline__ function that reads what it needs from this record: the
+// phases then do not compete for registers (as ONE inlined function the per-warp fragment arrays
+// were demoted to local memory and the lane offsets recomputed at every use).
+struct Ctx {
+  int uid, bi, bj, a, b, ab, bb, nr, nyb, pair, is_export, nF, want_grad, dx, dy, capW1;
+  long long ia, ja;
+  double *WB, *XS, *R1, *R2, *F;
+  int *IDX, *s_fail, *s_task, *s_ntask, *s_tcur;
+  double *s_q, *s_ld;
+  const double* pexp;
+  double *oexp, *Zy, *Arow, *Kjj, *Kji, *colp, *taskp, *gx;
 };
-
-// coordinates of local row t (i part: [0, 8 ab), j part: [8 ab, 8 ab + 8 bb))
-__device__ __forceinline__ const double* xs_row(const double* XS, int t) { return XS + t * XD; }
+constexpr int MISC_CTX = 40;          // doubles
+constexpr int MISC_IDX = 120;
+constexpr int MISC_PARAMS = 288;
+static_assert(sizeof(Ctx) <= (MISC_IDX - MISC_CTX) * 8, "Ctx does not fit");
+static_assert(sizeof(ResParams) <= (R_MISC_DOUBLES - MISC_PARAMS) * 8, "ResParams copy does not fit");
 
 constexpr int RTRACE_SLOTS = 512;
 // Debug timeline: thread 0 appends (unit << 16 | tag, %globaltimer) to this CTA's slots.
-__device__ __forceinline__ void rtrace(const ResParams& P, int* cursor, int uid, int tag) {
-  if (P.trace && threadIdx.x == 0 && *cursor < RTRACE_SLOTS) {
+__device__ __forceinline__ void rtrace(const ResParams& P, const Ctx& c, int tag) {
+  if (P.trace && threadIdx.x == 0 && *c.s_tcur < RTRACE_SLOTS) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    unsigned long long* wp = P.trace + ((long long)blockIdx.x * RTRACE_SLOTS + *cursor) * 2;
-    wp[0] = ((unsigned long long)uid << 16) | (unsigned long long)tag;
+    unsigned long long* wp = P.trace + ((long long)blockIdx.x * RTRACE_SLOTS + *c.s_tcur) * 2;
+    wp[0] = ((unsigned long long)c.uid << 16) | (unsigned long long)tag;
     wp[1] = t;
-    ++*cursor;
+    ++*c.s_tcur;
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// MB: size of the per-warp register arrays = upper bound on ab and bb (RMAXB for ordinary units,
-// BMAXB for the few big ones).  Row-owned phases deal rows to the 16 warps RNW at a time; units
-// with more than 16 block rows take a second pass.
-template <int DFN, int WFN, int MB>
-__device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, double* smem, Stage& stage,
-                                         double* scratch, bool r1_global) {
-  const Lane L = make_lane();
-  const int tid = threadIdx.x;
-  const int w = L.w;
-  const int a = u.a, b = u.b, ab = u.ab, bb = u.bb;
-  const int nr = ab + bb;                          // block rows of the whole unit
-  const int nyb = P.nyb;
-  const bool pair = ab > 0;
-  const bool is_export = u.bi < 0;                 // block units export for their pairs
-  double* WB = smem;
-  double* MISC = WB + R_WB_BLOCKS * RBLK;
-  double* XS = MISC + R_MISC_DOUBLES;
-  double* R1 = r1_global ? scratch + SCR_R1 : XS + nr * 8 * XD;
-  double* R2 = XS + nr * 8 * XD + (r1_global ? 0 : bb * ab * RBLK);
-  double* F = R2 + rtri(bb) * RBLK;                // staging area behind the matrices
-  const int nF = res_free_blocks(ab, bb, r1_global);
-  int* s_fail = reinterpret_cast<int*>(MISC + 4) + 1;
-  int* s_tcur = reinterpret_cast<int*>(MISC + 5);
-  int* s_task = reinterpret_cast<int*>(MISC + 5) + 1;
-  int* s_ntask = reinterpret_cast<int*>(MISC + 6);
-  double* s_q = MISC + 8;                          // [RNW]
-  double* s_ld = MISC + 104;                       // [RNW]
-  int* IDX = reinterpret_cast<int*>(MISC + 120);   // [2 * EMAXB * 8] global point index or -1
-  double* WD = WB;                                 // diagonal-block inverses during the factorisation
-  const double* pexp = pair ? P.exports + (long long)u.bi * EXP_STRIDE : nullptr;
-  double* oexp = is_export ? P.exports + (long long)u.bj * EXP_STRIDE : nullptr;
-  double* Zy = is_export ? oexp + EXP_ZY : scratch + SCR_ZY;
-  double* Arow = is_export ? oexp + EXP_AROW : scratch + SCR_AROW;
-  double* Kjj = is_export ? oexp + EXP_KSAVE : scratch + SCR_KJJ;
-  double* Kji = scratch + SCR_KJI;
-  double* colp = scratch + SCR_COLP;
-  double* taskp = scratch + SCR_TASKP;
-  double* gx = P.gx_u + (long long)u.uid * GX_STRIDE;
-  const CovParams& cp = P.cp;
-  rtrace(P, s_tcur, u.uid, 1);
+static __device__ __noinline__ void dbg_dump(const ResParams& P, const Ctx& c, int phase) {
+  if (P.dbg_unit != c.uid || P.dbg_phase != phase) return;
+  __syncthreads();
+  for (int e = threadIdx.x; e < 160 * 160; e += RNT) {
+    const int r = e / 160, cc = e % 160;
+    double v1 = 0.0, v2 = 0.0;
+    if (c.pair && r < c.bb * 8 && cc < c.ab * 8) v1 = c.R1[((r >> 3) * c.ab + (cc >> 3)) * RBLK + sw_off(r & 7, cc & 7)];
+    if (r < c.bb * 8 && cc < c.bb * 8 && (cc >> 3) <= (r >> 3))
+      v2 = c.R2[(rtri(r >> 3) + (cc >> 3)) * RBLK + sw_off(r & 7, cc & 7)];
+    P.dbg_out[e] = v1;
+    P.dbg_out[160 * 160 + e] = v2;
+  }
+  __syncthreads();
+}
 
-  auto dbg_dump = [&](int phase) {
-    if (P.dbg_unit != u.uid || P.dbg_phase != phase) return;
-    __syncthreads();
-    for (int e = tid; e < 160 * 160; e += RNT) {
-      const int r = e / 160, c = e % 160;
-      double v1 = 0.0, v2 = 0.0;
-      if (pair && r < bb * 8 && c < ab * 8) v1 = R1[((r >> 3) * ab + (c >> 3)) * RBLK + sw_off(r & 7, c & 7)];
-      if (r < bb * 8 && c < bb * 8 && (c >> 3) <= (r >> 3))
-        v2 = R2[(rtri(r >> 3) + (c >> 3)) * RBLK + sw_off(r & 7, c & 7)];
-      P.dbg_out[e] = v1;
-      P.dbg_out[160 * 160 + e] = v2;
+// ---- 1 x 4 register tile ---------------------------------------------------------------------------------
+// acc[j] += sum_{k0 <= k < k1} A(k) B_j(k)^T-or-plain for j < NJ: one A fragment per k feeds up to four
+// independent accumulator chains (the DMMA latency is ~37 cycles, four chains hide it).
+//   A(k)   = block at pa + k * sa          (AT: stored [k][m], read transposed)
+//   B_j(k) = block at pb[j] + k * sbk      (BT: stored [k][n], read transposed)
+template <bool AT, bool BT, int NJ>
+__device__ __forceinline__ void mk_loop(double2 (&acc)[4], const double* pa, int sa, const double* const (&pb)[4],
+                                        int sbk, int k0, int k1, const Lane& L) {
+#pragma unroll 2
+  for (int k = k0; k < k1; ++k) {
+    const double2 av = AT ? ldt(pa + k * sa, L) : ldn(pa + k * sa, L);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const double2 bv = BT ? ldt(pb[j] + k * sbk, L) : ldn(pb[j] + k * sbk, L);
+      mma2(acc[j], av, bv);
     }
-    __syncthreads();
-  };
-  auto tri_len = [](int r) { return r + 1; };
-  auto tri_pos = [](int r) { return rtri(r); };
+  }
+}
+template <bool AT, bool BT>
+__device__ __forceinline__ void mk(double2 (&acc)[4], const double* pa, int sa, const double* const (&pb)[4], int sbk,
+                                   int k0, int k1, int nj, const Lane& L) {
+  switch (nj) {
+    case 4: mk_loop<AT, BT, 4>(acc, pa, sa, pb, sbk, k0, k1, L); break;
+    case 3: mk_loop<AT, BT, 3>(acc, pa, sa, pb, sbk, k0, k1, L); break;
+    case 2: mk_loop<AT, BT, 2>(acc, pa, sa, pb, sbk, k0, k1, L); break;
+    case 1: mk_loop<AT, BT, 1>(acc, pa, sa, pb, sbk, k0, k1, L); break;
+    default: break;
+  }
+}
+__device__ __forceinline__ void zero4(double2 (&acc)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = make_double2(0.0, 0.0);
+}
 
-  // ---- P0: W_i on its way into [R2 | F] (both still unused), gather coordinates ----------------------
-  const int capW1 = rtri(bb) + nF;                 // staging capacity for W_i before S exists
-  if (pair && tid == 0) tma_issue(stage, R2, pexp + EXP_W, first_piece(capW1, ab, tri_len));
-  if (tid == 0) *s_fail = 0;
-  for (int t = tid; t < nr * 8; t += RNT) {
+// covariance fragment of block (rb, cb) in local block coordinates: rows 8 rb + g, cols 8 cb + 2q, +1
+template <int DFN, int WFN>
+__device__ __forceinline__ double2 cov_frag(const ResParams& P, const Ctx& c, const Lane& L, int rb, int cb,
+                                            bool with_diag) {
+  const int tr = rb * 8 + L.g;
+  const int tc = cb * 8 + 2 * L.q;
+  const bool rv = c.IDX[tr] >= 0;
+  const double* xr = c.XS + tr * XD;
+  double v0 = cov_value<DFN, WFN>(xr, c.XS + tc * XD, P.cp);
+  double v1 = cov_value<DFN, WFN>(xr, c.XS + (tc + 1) * XD, P.cp);
+  v0 = (rv && c.IDX[tc] >= 0) ? v0 : 0.0;
+  v1 = (rv && c.IDX[tc + 1] >= 0) ? v1 : 0.0;
+  if (with_diag) {
+    if (tr == tc) v0 = rv ? P.cp.s2 + P.cp.nv : 1.0;
+    if (tr == tc + 1) v1 = rv ? P.cp.s2 + P.cp.nv : 1.0;
+  }
+  return make_double2(v0, v1);
+}
+
+__device__ __forceinline__ int tri_len(int r) { return r + 1; }
+
+// ---- P0 / P1: gather, K_ji, L_ji = K_ji W_i^T ------------------------------------------------------------
+template <int DFN, int WFN>
+static __device__ __noinline__ void ph_gather_lji(const ResParams& P, const Ctx& c, Stage& stage) {
+  const Lane L = make_lane();
+  const int tid = threadIdx.x, w = L.w;
+  const int ab = c.ab, bb = c.bb;
+  // W_i on its way into [R2 | F] (both still unused; res_class guarantees that all of it fits)
+  if (c.pair && tid == 0) tma_issue(stage, c.R2, c.pexp + EXP_W, rtri(ab));
+  if (tid == 0) *c.s_fail = 0;
+  for (int t = tid; t < c.nr * 8; t += RNT) {
     long long idx = -1;
     if (t < ab * 8) {
-      if (t < a) idx = P.perm[u.ia + t];
-    } else if (t - ab * 8 < b) {
-      idx = P.perm[u.ja + (t - ab * 8)];
+      if (t < c.a) idx = P.perm[c.ia + t];
+    } else if (t - ab * 8 < c.b) {
+      idx = P.perm[c.ja + (t - ab * 8)];
     }
-    IDX[t] = (int)idx;
+    c.IDX[t] = (int)idx;
     double rec[XD];
 #pragma unroll
-    for (int d = 0; d < MAX_DX + 1; ++d) rec[d] = (idx >= 0 && d < P.dx) ? P.X[idx * P.dx + d] : 0.0;
+    for (int d = 0; d < MAX_DX + 1; ++d) rec[d] = (idx >= 0 && d < c.dx) ? P.X[idx * c.dx + d] : 0.0;
     point_terms(DFN, rec);
 #pragma unroll
-    for (int d = 0; d < XD; ++d) XS[t * XD + d] = rec[d];
+    for (int d = 0; d < XD; ++d) c.XS[t * XD + d] = rec[d];
   }
   __syncthreads();
-
-  // covariance fragment of block (rb, cb) in local block coordinates: rows 8 rb + g, cols 8 cb + 2q, +1
-  auto cov_frag = [&](int rb, int cb, bool with_diag) {
-    const int tr = rb * 8 + L.g;
-    const int tc = cb * 8 + 2 * L.q;
-    const bool rv = IDX[tr] >= 0;
-    const double* xr = xs_row(XS, tr);
-    double v0 = cov_value<DFN, WFN>(xr, xs_row(XS, tc), cp);
-    double v1 = cov_value<DFN, WFN>(xr, xs_row(XS, tc + 1), cp);
-    v0 = (rv && IDX[tc] >= 0) ? v0 : 0.0;
-    v1 = (rv && IDX[tc + 1] >= 0) ? v1 : 0.0;
-    if (with_diag) {
-      if (tr == tc) v0 = rv ? cp.s2 + cp.nv : 1.0;
-      if (tr == tc + 1) v1 = rv ? cp.s2 + cp.nv : 1.0;
-    }
-    return make_double2(v0, v1);
-  };
-
-  // ---- P1: L_ji = K_ji W_i^T  (one row of L_ji per warp, its K_ji fragments in registers) ----------------
-  if (pair) {
-    bool ahead = true;
-    for (int rbase = 0; rbase < bb; rbase += RNW) {
-      const int row = rbase + w;
-      double2 kf[MB];
-      if (row < bb) {
+  if (!c.pair) return;
+  // K_ji -> R1 (and to scratch for the gradient contraction), one block per task
+  for (int t = w; t < bb * ab; t += RNW) {
+    const int row = t / ab, k = t - row * ab;
+    const double2 kv = cov_frag<DFN, WFN>(P, c, L, ab + row, k, false);
+    stn(c.R1 + t * RBLK, L, kv);
+    if (c.want_grad) stn(c.Kji + t * RBLK, L, kv);
+  }
+  __syncthreads();
+  tma_wait(stage);
+  // L_ji(row, c0 .. c0+3) = sum_{k <= c} K_ji(row, k) W_i(c, k)^T, in place: rounds of whole rows; every
+  // task of a round holds its blocks until all of the round's reads are done
+  const double* Wst = c.R2;
+  const int ng = (ab + 3) >> 2;
+  const int rows_round = max(1, (4 * RNW) / ng);
+  for (int r0 = 0; r0 < bb; r0 += rows_round) {
+    const int ntask = min(rows_round, bb - r0) * ng;
+    double2 acc[4][4];
 #pragma unroll
-        for (int k = 0; k < MB; ++k) {
-          kf[k] = (k < ab) ? cov_frag(ab + row, k, false) : make_double2(0.0, 0.0);
-          if (k < ab && P.want_grad) stn(Kji + (row * ab + k) * RBLK, L, kf[k]);   // saved for the gradient
-        }
-      }
-      staged_rows(stage, R2, capW1, pexp + EXP_W, ab, tri_len, tri_pos, ahead, [&](int c0, int c1, const double* base) {
-        if (row < bb) {
-          for (int c = c0; c < c1; ++c) {
-            const double* wrow = base + (rtri(c) - rtri(c0)) * RBLK;
-            double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
-            for_desc<MB>(c + 1, [&](auto kc) {
-              constexpr int k = decltype(kc)::value;
-              mma2((k & 1) ? acc1 : acc0, kf[k], ldn(wrow + k * RBLK, L));
-            });
-            stn(R1 + (row * ab + c) * RBLK, L, make_double2(acc0.x + acc1.x, acc0.y + acc1.y));
-          }
-        }
-      });
-      ahead = false;
-    }
-  }
-  dbg_dump(1);
-  rtrace(P, s_tcur, u.uid, 2);
-
-  // ---- P2: S = K_jj + nv I - L_ji L_ji^T (lower blocks; a row's columns split by parity over two tasks) ----
-  __syncthreads();
-  for (int t = w; t < bb; t += RNW) {
-#pragma unroll 1
-    for (int part = 0; part < 2; ++part) {
-      const int row = part ? bb - 1 - t : t;
-      double2 nla[MB];
-      if (pair) {
+    for (int i = 0; i < 4; ++i) {
+      zero4(acc[i]);
+      const int t = w + i * RNW;
+      if (t < ntask) {
+        const int row = r0 + t / ng, c0 = (t % ng) * 4;
+        const int nj = min(4, ab - c0);
+        const double* pa = c.R1 + row * ab * RBLK;
+        const double* pb[4];
 #pragma unroll
-        for (int k = 0; k < MB; ++k)
-          nla[k] = (k < ab) ? neg2(ldn(R1 + (row * ab + k) * RBLK, L)) : make_double2(0.0, 0.0);
+        for (int j = 0; j < 4; ++j) pb[j] = Wst + rtri(c0 + min(j, nj - 1)) * RBLK;
+        mk<false, false>(acc[i], pa, RBLK, pb, RBLK, 0, c0 + 1, nj, L);
+#pragma unroll
+        for (int j = 1; j < 4; ++j)                    // column c0 + j also takes k = c0 + 1 .. c0 + j
+          if (j < nj)
+            for (int k = c0 + 1; k <= c0 + j; ++k) mma2(acc[i][j], ldn(pa + k * RBLK, L), ldn(pb[j] + k * RBLK, L));
       }
-      for (int c = part; c <= row; c += 2) {
-        double2 acc = cov_frag(ab + row, ab + c, true);
-        if (P.want_grad) stn(Kjj + (rtri(row) + c) * RBLK, L, acc);
-        if (pair) {
-          double2 acc1 = make_double2(0.0, 0.0);
-          const double* lc = R1 + c * ab * RBLK;
-          for_desc<MB>(ab, [&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            mma2((k & 1) ? acc1 : acc, nla[k], ldn(lc + k * RBLK, L));
-          });
-          acc.x += acc1.x;
-          acc.y += acc1.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = w + i * RNW;
+      if (t < ntask) {
+        const int row = r0 + t / ng, c0 = (t % ng) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + j < ab) stn(c.R1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- P2: S = K_jj + nv I - L_ji L_ji^T (lower blocks, tasks of up to 4 columns) --------------------------
+template <int DFN, int WFN>
+static __device__ __noinline__ void ph_schur(const ResParams& P, const Ctx& c) {
+  const Lane L = make_lane();
+  const int ab = c.ab, bb = c.bb;
+  // task list: rows descending (longest first), column groups of 4
+  int t = 0;
+  for (int row = bb - 1; row >= 0; --row) {
+    for (int c0 = 0; c0 <= row; c0 += 4, ++t) {
+      if ((t & (RNW - 1)) != L.w) continue;
+      const int nj = min(4, row + 1 - c0);
+      double2 acc[4];
+      zero4(acc);
+      if (c.pair) {
+        const double* pb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb[j] = c.R1 + (c0 + min(j, nj - 1)) * ab * RBLK;
+        mk<false, false>(acc, c.R1 + row * ab * RBLK, RBLK, pb, RBLK, 0, ab, nj, L);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nj) {
+          const double2 kv = cov_frag<DFN, WFN>(P, c, L, ab + row, ab + c0 + j, true);
+          if (c.want_grad) stn(c.Kjj + (rtri(row) + c0 + j) * RBLK, L, kv);
+          stn(c.R2 + (rtri(row) + c0 + j) * RBLK, L, make_double2(kv.x - acc[j].x, kv.y - acc[j].y));
         }
-        stn(R2 + (rtri(row) + c) * RBLK, L, acc);
       }
     }
   }
   __syncthreads();
-  dbg_dump(2);
-  rtrace(P, s_tcur, u.uid, 3);
+}
 
-  // Z_i (all of it, or its first piece) travels into F while S is factored
-  const int nyc = pair ? max(1, min(nyb, min(nF / ab, R_WB_BLOCKS / bb))) : max(1, min(nyb, R_WB_BLOCKS / bb));
-  if (pair && tid == 0) tma_issue(stage, F, pexp + EXP_ZY, min(nyc, nyb) * ab);
-
-  // ---- P3a: blocked Cholesky of S in place (jitchol's first, jitter-free attempt) ---------------------
+// ---- P3: Cholesky of S and W_S = L_S^-1, both in place -----------------------------------------------------
+static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c) {
+  const Lane L = make_lane();
+  const int tid = threadIdx.x, w = L.w;
+  const int bb = c.bb;
+  double* R2 = c.R2;
+  double* WD = c.WB;                               // diagonal-block inverses
   for (int J = 0; J < bb; ++J) {
     if (w == 0) {
       double av[8], wv[8];
@@ -438,7 +466,7 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
         for (int v = 0; v < 8; ++v) av[v] = (v == r) ? 1.0 : 0.0;
       }
       const int f = chol8_inv8(av, wv, L.lane);
-      if (L.lane == 0 && f != 0 && *s_fail == 0) *s_fail = J * 8 + f;
+      if (L.lane == 0 && f != 0 && *c.s_fail == 0) *c.s_fail = J * 8 + f;
       if (L.lane < 8) {
         double* dl = R2 + (rtri(J) + J) * RBLK;
         double* dw = WD + J * RBLK;
@@ -472,24 +500,24 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
         const int kk = t - ii * (ii + 1) / 2;
         const int I = J + 1 + ii, K = J + 1 + kk;
         double* pc = R2 + (rtri(I) + K) * RBLK;
-        double2 c = ldn(pc, L);
-        mma2(c, neg2(ldn(R2 + (rtri(I) + J) * RBLK, L)), ldn(R2 + (rtri(K) + J) * RBLK, L));
-        stn(pc, L, c);
+        double2 cv = ldn(pc, L);
+        mma2(cv, neg2(ldn(R2 + (rtri(I) + J) * RBLK, L)), ldn(R2 + (rtri(K) + J) * RBLK, L));
+        stn(pc, L, cv);
       }
     }
     __syncthreads();
   }
-  dbg_dump(3);
-  rtrace(P, s_tcur, u.uid, 4);
+  dbg_dump(P, c, 3);
+  rtrace(P, c, 4);
   // log-determinant: sum of log L_tt over the unit's j rows, fixed order
   {
     double lv = 0.0;
     if (tid < bb * 8) lv = log(R2[(rtri(tid >> 3) + (tid >> 3)) * RBLK + sw_off(tid & 7, tid & 7)]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
-    if (L.lane == 0) s_ld[w] = lv;
+    if (L.lane == 0) c.s_ld[w] = lv;
   }
-  // ---- P3b: W_S = L_S^-1 in place, by descending block columns ----------------------------------------
+  // W_S = L_S^-1 in place, by descending block columns
   for (int K = bb - 1; K >= 0; --K) {
     double2 o[2];
 #pragma unroll
@@ -497,10 +525,16 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
       o[rr] = make_double2(0.0, 0.0);
       const int I = K + 1 + w + rr * RNW;
       if (I < bb) {
-        double2 acc = make_double2(0.0, 0.0);
-        for (int J = K + 1; J <= I; ++J)
-          mma2(acc, ldn(R2 + (rtri(I) + J) * RBLK, L), ldt(R2 + (rtri(J) + K) * RBLK, L));
-        mma2(o[rr], acc, ldt(WD + K * RBLK, L));
+        double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+        int J = K + 1;
+        for (; J + 1 <= I; J += 2) {
+          mma2(a0, ldn(R2 + (rtri(I) + J) * RBLK, L), ldt(R2 + (rtri(J) + K) * RBLK, L));
+          mma2(a1, ldn(R2 + (rtri(I) + J + 1) * RBLK, L), ldt(R2 + (rtri(J + 1) + K) * RBLK, L));
+        }
+        if (J <= I) mma2(a0, ldn(R2 + (rtri(I) + J) * RBLK, L), ldt(R2 + (rtri(J) + K) * RBLK, L));
+        a0.x += a1.x;
+        a0.y += a1.y;
+        mma2(o[rr], a0, ldt(WD + K * RBLK, L));
       }
     }
     __syncthreads();
@@ -512,406 +546,463 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     if (w == 0) stn(R2 + (rtri(K) + K) * RBLK, L, ldn(WD + K * RBLK, L));
     __syncthreads();
   }
-  dbg_dump(4);
-  rtrace(P, s_tcur, u.uid, 5);
-  if (is_export) {                                  // W_b for this block's pairs
-    double* dst = oexp + EXP_W;
+  if (c.is_export) {                                // W_b for this block's pairs
+    double* dst = c.oexp + EXP_W;
     for (int e = tid; e < rtri(bb) * RBLK / 2; e += RNT)
       reinterpret_cast<double2*>(dst)[e] = reinterpret_cast<const double2*>(R2)[e];
   }
+}
 
-  // ---- P4: Z_j = W_S (Y_j - L_ji Z_i), alpha_j = W_S^T Z_j, nyc blocks of 8 outputs at a time -------------
-  // tasks (row, y) of a piece are dealt round-robin to the warps; right-hand sides live in WB.
+// ---- P4: Z_j = W_S (Y_j - L_ji Z_i), alpha_j = W_S^T Z_j, the log-likelihood ---------------------------------
+// Pieces of up to nyc blocks of 8 outputs; tasks (row, 4 output blocks) dealt round-robin; the
+// right-hand sides live in WB as (yl * bb + row).
+static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, Stage& stage, int nyc) {
+  const Lane L = make_lane();
+  const int tid = threadIdx.x, w = L.w;
+  const int ab = c.ab, bb = c.bb, nyb = c.nyb;
+  double* RB = c.WB;
   double qsum = 0.0;
-  {
-    double* RB = WB;                                 // (yl * bb + row)
-    bool ahead = pair;
-    for (int y0 = 0; y0 < nyb; y0 += nyc) {
-      const int ny = min(nyc, nyb - y0);
-      const int ntask = ny * bb;
-      if (pair) {
-        if (!ahead) {
-          if (tid == 0) tma_issue(stage, F, pexp + EXP_ZY + (long long)y0 * ab * RBLK, ny * ab);
-        }
-        ahead = false;
-        tma_wait(stage);
-      }
-      for (int t = w; t < ntask; t += RNW) {
-        const int yl = t / bb, row = t - yl * bb;
-        const int idx = IDX[ab * 8 + row * 8 + L.g];
-        const int yc = (y0 + yl) * 8 + 2 * L.q;
-        double2 acc = make_double2(0.0, 0.0);
-        if (idx >= 0) {
-          if (yc < P.dy) acc.x = __ldg(P.Y + (long long)idx * P.dy + yc);
-          if (yc + 1 < P.dy) acc.y = __ldg(P.Y + (long long)idx * P.dy + yc + 1);
-        }
-        if (pair) {
-          const double* zi = F + yl * ab * RBLK;
-          for (int k = 0; k < ab; ++k) mma2(acc, neg2(ldn(R1 + (row * ab + k) * RBLK, L)), ldt(zi + k * RBLK, L));
-        }
-        stn(RB + t * RBLK, L, acc);
-      }
-      __syncthreads();
-      double2 z[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        z[i] = make_double2(0.0, 0.0);
-        const int t = w + i * RNW;
-        if (t < ntask) {
-          const int yl = t / bb, row = t - yl * bb;
-          for (int k = 0; k <= row; ++k)
-            mma2(z[i], ldn(R2 + (rtri(row) + k) * RBLK, L), ldt(RB + (yl * bb + k) * RBLK, L));
-          qsum += z[i].x * z[i].x + z[i].y * z[i].y;
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int t = w + i * RNW;
-        if (t < ntask) {
-          const int yl = t / bb, row = t - yl * bb;
-          stn(RB + t * RBLK, L, z[i]);
-          stn(Zy + ((y0 + yl) * bb + row) * RBLK, L, z[i]);
-        }
-      }
-      __syncthreads();
-      if (P.want_grad) {
-        for (int t = w; t < ntask; t += RNW) {
-          const int yl = t / bb, row = t - yl * bb;
-          double2 al = make_double2(0.0, 0.0);
-          for (int k = row; k < bb; ++k)
-            mma2(al, ldt(R2 + (rtri(k) + row) * RBLK, L), ldt(RB + (yl * bb + k) * RBLK, L));
-          stn(Arow + ((long long)(ab + row) * RNYB + y0 + yl) * RBLK, L, al);
-        }
-      }
-      __syncthreads();
-    }
-  }
-  rtrace(P, s_tcur, u.uid, 6);
-  // W_i (first piece) back into F for T while the scalars are finished
-  if (pair && P.want_grad && tid == 0) tma_issue(stage, F, pexp + EXP_W, first_piece(nF, ab, tri_len));
-  // |Z_j|^2 and the log-likelihood (gprf.py:542-544)
-  {
-    double qv = qsum;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
-    if (L.lane == 0) s_q[w] = qv;
-    __syncthreads();
-    if (tid == 0) {
-      double qt = 0.0, lt = 0.0;
-      for (int i = 0; i < RNW; ++i) {
-        qt += s_q[i];
-        lt += s_ld[i];
-      }
-      double logdet = 2.0 * lt;
-      if (pair) {
-        qt += pexp[EXP_SCAL + 1];
-        logdet += pexp[EXP_SCAL + 0];
-      }
-      if (is_export) {
-        oexp[EXP_SCAL + 0] = logdet;
-        oexp[EXP_SCAL + 1] = qt;
-      }
-      P.ll_u[u.uid] = -0.5 * qt - 0.5 * P.dy * logdet - 0.5 * P.dy * (double)(a + b) * 1.8378770664093454836;
-      if (*s_fail != 0) {
-        P.info[u.uid] = *s_fail;
-        atomicOr(P.status, ST_NOTPD);
-      }
-    }
-  }
-  if (!P.want_grad) {
-    __syncthreads();
-    return;
-  }
-  asm volatile("fence.proxy.async;\n" ::: "memory");     // Z_j / alpha_j / saved K: written with ordinary stores
-
-  // ---- P6: T = L_ji W_i (row-local, in place), V = -W_S T (in place) ------------------------------------
-  if (pair) {
-    bool ahead = true;
-    for (int rbase = 0; rbase < bb; rbase += RNW) {
-      const int row = rbase + w;
-      double2 acc[MB];
-#pragma unroll
-      for (int c = 0; c < MB; ++c) acc[c] = make_double2(0.0, 0.0);
-      staged_rows(stage, F, nF, pexp + EXP_W, ab, tri_len, tri_pos, ahead, [&](int k0, int k1, const double* base) {
-        if (row < bb) {
-          for (int k = k0; k < k1; ++k) {
-            const double* wrow = base + (rtri(k) - rtri(k0)) * RBLK;
-            const double2 av = ldn(R1 + (row * ab + k) * RBLK, L);
-            for_desc<MB>(k + 1, [&](auto cc) {
-              constexpr int c = decltype(cc)::value;
-              mma2(acc[c], av, ldt(wrow + c * RBLK, L));
-            });
-          }
-        }
-      });
+  bool ahead = c.pair != 0;
+  for (int y0 = 0; y0 < nyb; y0 += nyc) {
+    const int ny = min(nyc, nyb - y0);
+    const int ngy = (ny + 3) >> 2;
+    const int ntask = bb * ngy;
+    if (c.pair) {
+      if (!ahead && tid == 0) tma_issue(stage, c.F, c.pexp + EXP_ZY + (long long)y0 * ab * RBLK, ny * ab);
       ahead = false;
-      if (row < bb) {
-#pragma unroll
-        for (int c = 0; c < MB; ++c)
-          if (c < ab) stn(R1 + (row * ab + c) * RBLK, L, acc[c]);
-      }
-    }
-    __syncthreads();
-    // own Z_j (all of it, or its first piece) into F for alpha_i, behind the V product
-    const int zrows = max(1, min(nyb, nF / bb));
-    if (tid == 0) tma_issue(stage, F, Zy, zrows * bb);
-    dbg_dump(6);
-    rtrace(P, s_tcur, u.uid, 7);
-    // V(I, .) = -sum_{k <= I} W_S(I, k) T(k, .) overwrites T(I, .), which only rows >= I read: rows
-    // beyond the first 16 go first (one per warp), then rows [0, nb) with their columns split by parity
-    const int nb = min(bb, RNW);
-    for (int pass = (bb > RNW ? 0 : 1); pass < 2; ++pass) {
-      double2 acc[MB];
-#pragma unroll
-      for (int c = 0; c < MB; ++c) acc[c] = make_double2(0.0, 0.0);
-      if (pass == 0) {
-        const int row = RNW + w;
-        if (row < bb) {
-          for (int k = 0; k <= row; ++k) {
-            const double2 av = ldn(R2 + (rtri(row) + k) * RBLK, L);
-            const double* tk = R1 + k * ab * RBLK;
-            for_desc<MB>(ab, [&](auto cc) {
-              constexpr int c = decltype(cc)::value;
-              mma2(acc[c], av, ldt(tk + c * RBLK, L));
-            });
-          }
-        }
-        __syncthreads();
-        if (row < bb) {
-#pragma unroll
-          for (int c = 0; c < MB; ++c)
-            if (c < ab) stn(R1 + (row * ab + c) * RBLK, L, neg2(acc[c]));
-        }
-      } else {
-        if (w < nb) {
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            const int row = part ? nb - 1 - w : w;
-            for (int k = 0; k <= row; ++k) {
-              const double2 av = ldn(R2 + (rtri(row) + k) * RBLK, L);
-              const double* tk = R1 + (k * ab + part) * RBLK;
-              // columns part, part + 2, ... < ab: (ab - part + 1) / 2 of them
-              for_desc<MB / 2>((ab - part + 1) >> 1, [&](auto ci) {
-                constexpr int cc = decltype(ci)::value;
-                mma2(acc[part * (MB / 2) + cc], av, ldt(tk + 2 * cc * RBLK, L));
-              });
-            }
-          }
-        }
-        __syncthreads();
-        if (w < nb) {
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            const int row = part ? nb - 1 - w : w;
-#pragma unroll
-            for (int cc = 0; cc < MB / 2; ++cc) {
-              const int c = 2 * cc + part;
-              if (c < ab) stn(R1 + (row * ab + c) * RBLK, L, neg2(acc[part * (MB / 2) + cc]));
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    dbg_dump(7);
-    rtrace(P, s_tcur, u.uid, 8);
-
-    // ---- P7: alpha_i = alpha_i(block) + V^T Z_j  (one row of the i part per warp, its V fragments in registers)
-    ahead = true;
-    for (int rbase = 0; rbase < ab; rbase += RNW) {
-      const int row = rbase + w;
-      double2 va[MB];
-      if (row < ab) {
-#pragma unroll
-        for (int k = 0; k < MB; ++k)
-          va[k] = (k < bb) ? ldt(R1 + (k * ab + row) * RBLK, L) : make_double2(0.0, 0.0);
-      }
-      staged_rows(stage, F, nF, Zy, nyb, [&](int) { return bb; }, [&](int r) { return r * bb; }, ahead,
-                  [&](int y0, int y1, const double* base) {
-        if (row < ab) {
-          for (int yb = y0; yb < y1; ++yb) {
-            const double* zj = base + (yb - y0) * bb * RBLK;
-            double2 acc = ldn(pexp + EXP_AROW + ((long long)row * RNYB + yb) * RBLK, L);
-            double2 acc1 = make_double2(0.0, 0.0);
-            for_desc<MB>(bb, [&](auto kc) {
-              constexpr int k = decltype(kc)::value;
-              mma2((k & 1) ? acc1 : acc, va[k], ldt(zj + k * RBLK, L));
-            });
-            stn(Arow + ((long long)row * RNYB + yb) * RBLK, L, make_double2(acc.x + acc1.x, acc.y + acc1.y));
-          }
-        }
-      });
-      ahead = false;
-    }
-    asm volatile("fence.proxy.async;\n" ::: "memory");   // alpha_i rows
-  }
-  __syncthreads();
-  rtrace(P, s_tcur, u.uid, 9);
-
-  // ---- P8: G = alpha alpha^T - dy K^-1, contracted with dK in registers (gprf.py:547-584) ------------
-  // Column pieces: alpha rows [c0, c1) staged in F (B operands).  Tasks = (block row r, up to GCOLS
-  // columns of the piece), taken from a shared counter, biggest rows first; alpha(r) comes from L2.
-  {
-    const double ndy = -(double)P.dy;
-    int* TT = reinterpret_cast<int*>(WB);            // task table of the piece: r | c_lo << 8 | c_hi << 16
-    const int crow = max(GCOLS, (nF / RNYB) & ~(GCOLS - 1));   // alpha rows per piece (a multiple of GCOLS)
-    for (int c0 = 0; c0 < nr; c0 += crow) {
-      const int c1 = min(nr, c0 + crow);
-      if (tid == 0) {
-        tma_issue(stage, F, Arow + (long long)c0 * RNYB * RBLK, (c1 - c0) * RNYB);
-        int nt = 0;
-        for (int r = nr - 1; r >= c0; --r) {
-          const int ce = min(c1, r + 1);
-          for (int cl = c0; cl < ce; cl += GCOLS) TT[nt++] = r | (cl << 8) | (min(ce, cl + GCOLS) << 16);
-        }
-        *s_ntask = nt;
-        *s_task = 0;
-      }
-      __syncthreads();
       tma_wait(stage);
-      const int ntask = *s_ntask;
-      while (true) {
-        int t = 0;
-        if (L.lane == 0) t = atomicAdd(s_task, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= ntask) break;
-        const int code = TT[t];
-        const int r = code & 0xff, cl = (code >> 8) & 0xff, ch = (code >> 16) & 0xff;
-        const bool irow = r < ab;
-        const int wi = irow ? r : r - ab;            // row inside its part
-        double2 af[RNYB];
+    }
+    // R = Y_j - L_ji Z_i
+    for (int t = w; t < ntask; t += RNW) {
+      const int row = t / ngy, yl0 = (t - row * ngy) * 4;
+      const int nj = min(4, ny - yl0);
+      double2 acc[4];
+      zero4(acc);
+      if (c.pair) {
+        const double* pb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb[j] = c.F + (yl0 + min(j, nj - 1)) * ab * RBLK;
+        mk<false, true>(acc, c.R1 + row * ab * RBLK, RBLK, pb, RBLK, 0, ab, nj, L);
+      }
+      const int idx = c.IDX[ab * 8 + row * 8 + L.g];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nj) {
+          const int yc = (y0 + yl0 + j) * 8 + 2 * L.q;
+          double2 yv = make_double2(0.0, 0.0);
+          if (idx >= 0) {
+            if (yc < c.dy) yv.x = __ldg(P.Y + (long long)idx * c.dy + yc);
+            if (yc + 1 < c.dy) yv.y = __ldg(P.Y + (long long)idx * c.dy + yc + 1);
+          }
+          stn(RB + ((yl0 + j) * bb + row) * RBLK, L, make_double2(yv.x - acc[j].x, yv.y - acc[j].y));
+        }
+      }
+    }
+    __syncthreads();
+    // Z = W_S R  (held in registers until every read of R is done)
+    const int nslot = (ntask + RNW - 1) / RNW;     // <= 4: ntask <= bb * 2 <= 40 ... (ny <= 8)
+    double2 z[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      zero4(z[i]);
+      const int t = w + i * RNW;
+      if (i < nslot && t < ntask) {
+        const int row = t / ngy, yl0 = (t - row * ngy) * 4;
+        const int nj = min(4, ny - yl0);
+        const double* pb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb[j] = RB + (yl0 + min(j, nj - 1)) * bb * RBLK;
+        mk<false, true>(z[i], c.R2 + rtri(row) * RBLK, RBLK, pb, RBLK, 0, row + 1, nj, L);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nj) qsum += z[i][j].x * z[i][j].x + z[i][j].y * z[i][j].y;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int t = w + i * RNW;
+      if (i < nslot && t < ntask) {
+        const int row = t / ngy, yl0 = (t - row * ngy) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (yl0 + j < ny) {
+            stn(RB + ((yl0 + j) * bb + row) * RBLK, L, z[i][j]);
+            stn(c.Zy + ((y0 + yl0 + j) * bb + row) * RBLK, L, z[i][j]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // alpha_j = W_S^T Z
+    if (c.want_grad) {
+      for (int t = w; t < ntask; t += RNW) {
+        const int row = t / ngy, yl0 = (t - row * ngy) * 4;
+        const int nj = min(4, ny - yl0);
+        double2 acc[4];
+        zero4(acc);
+        const double* pb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb[j] = RB + (yl0 + min(j, nj - 1)) * bb * RBLK;
+        // A(k) = W_S(k, row) read transposed: block (k, row) of the packed lower triangle
+        for (int k = row; k < bb; ++k) {
+          const double2 av = ldt(c.R2 + (rtri(k) + row) * RBLK, L);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nj) mma2(acc[j], av, ldt(pb[j] + k * RBLK, L));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nj) stn(c.Arow + ((long long)(ab + row) * RNYB + y0 + yl0 + j) * RBLK, L, acc[j]);
+      }
+    }
+    __syncthreads();
+  }
+  // |Z_j|^2 and the log-likelihood (gprf.py:542-544)
+  double qv = qsum;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
+  if (L.lane == 0) c.s_q[w] = qv;
+  __syncthreads();
+  if (tid == 0) {
+    double qt = 0.0, lt = 0.0;
+    for (int i = 0; i < RNW; ++i) {
+      qt += c.s_q[i];
+      lt += c.s_ld[i];
+    }
+    double logdet = 2.0 * lt;
+    if (c.pair) {
+      qt += c.pexp[EXP_SCAL + 1];
+      logdet += c.pexp[EXP_SCAL + 0];
+    }
+    if (c.is_export) {
+      c.oexp[EXP_SCAL + 0] = logdet;
+      c.oexp[EXP_SCAL + 1] = qt;
+    }
+    P.ll_u[c.uid] = -0.5 * qt - 0.5 * c.dy * logdet - 0.5 * c.dy * (double)(c.a + c.b) * 1.8378770664093454836;
+    if (*c.s_fail != 0) {
+      P.info[c.uid] = *c.s_fail;
+      atomicOr(P.status, ST_NOTPD);
+    }
+  }
+}
+
+// ---- P6a: T = L_ji W_i, in place (tasks of 4 columns, rounds of whole rows, W_i rows staged in F) -----------
+static __device__ __noinline__ void ph_t(const ResParams& P, const Ctx& c, Stage& stage) {
+  const Lane L = make_lane();
+  const int w = L.w;
+  const int ab = c.ab, bb = c.bb, nF = c.nF;
+  const int ng = (ab + 3) >> 2;
+  const int rows_round = max(1, (4 * RNW) / ng);
+  bool ahead = true;
+  for (int r0 = 0; r0 < bb; r0 += rows_round) {
+    const int ntask = min(rows_round, bb - r0) * ng;
+    double2 acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) zero4(acc[i]);
+    staged_rows(stage, c.F, nF, c.pexp + EXP_W, ab, tri_len, rtri, ahead, [&](int k0, int k1, const double* base) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = w + i * RNW;
+        if (t < ntask) {
+          const int row = r0 + t / ng, c0 = (t % ng) * 4;
+          const int nj = min(4, ab - c0);
+          const double* pa = c.R1 + row * ab * RBLK;
+          // T(row, c0 + j) += sum_{k >= c0 + j} L_ji(row, k) W_i(k, c0 + j)
+          for (int k = max(k0, c0); k < k1; ++k) {
+            const double2 av = ldn(pa + k * RBLK, L);
+            const double* pk = base + (rtri(k) - rtri(k0) + c0) * RBLK;
+            const int nk = min(nj, k - c0 + 1);      // columns c0 .. c0 + nk - 1 exist in row k of W_i
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < nk) mma2(acc[i][j], av, ldt(pk + j * RBLK, L));
+          }
+        }
+      }
+    });
+    ahead = false;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = w + i * RNW;
+      if (t < ntask) {
+        const int row = r0 + t / ng, c0 = (t % ng) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + j < ab) stn(c.R1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- P6b: V = -W_S T, in place: rounds of whole rows, highest rows first (row I is read by rows >= I only) ---
+static __device__ __noinline__ void ph_v(const ResParams& P, const Ctx& c) {
+  const Lane L = make_lane();
+  const int w = L.w;
+  const int ab = c.ab, bb = c.bb;
+  const int ng = (ab + 3) >> 2;
+  const int rows_round = max(1, (4 * RNW) / ng);
+  for (int rhi = bb; rhi > 0; rhi -= rows_round) {
+    const int rlo = max(0, rhi - rows_round);
+    const int ntask = (rhi - rlo) * ng;
+    double2 acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      zero4(acc[i]);
+      const int t = w + i * RNW;
+      if (t < ntask) {
+        const int row = rhi - 1 - t / ng, c0 = (t % ng) * 4;     // longest rows first
+        const int nj = min(4, ab - c0);
+        const double* pb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb[j] = c.R1 + (c0 + min(j, nj - 1)) * RBLK;
+        mk<false, true>(acc[i], c.R2 + rtri(row) * RBLK, RBLK, pb, ab * RBLK, 0, row + 1, nj, L);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = w + i * RNW;
+      if (t < ntask) {
+        const int row = rhi - 1 - t / ng, c0 = (t % ng) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + j < ab) stn(c.R1 + (row * ab + c0 + j) * RBLK, L, neg2(acc[i][j]));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- P7: alpha_i = alpha_i(block) + V^T Z_j  (tasks (row of i, 4 output blocks); Z_j rows staged in F) --------
+static __device__ __noinline__ void ph_alpha_i(const ResParams& P, const Ctx& c, Stage& stage) {
+  const Lane L = make_lane();
+  const int w = L.w;
+  const int ab = c.ab, bb = c.bb, nyb = c.nyb;
+  auto rl = [&](int) { return bb; };
+  auto rp = [&](int r) { return r * bb; };
+  staged_rows(stage, c.F, c.nF, c.Zy, nyb, rl, rp, true, [&](int y0, int y1, const double* base) {
+    const int ngy = (y1 - y0 + 3) >> 2;
+    const int ntask = ab * ngy;
+    for (int t = w; t < ntask; t += RNW) {
+      const int row = t / ngy, yl0 = (t - row * ngy) * 4;
+      const int nj = min(4, y1 - y0 - yl0);
+      double2 acc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        acc[j] = (j < nj) ? ldn(c.pexp + EXP_AROW + ((long long)row * RNYB + y0 + yl0 + j) * RBLK, L)
+                          : make_double2(0.0, 0.0);
+      const double* pb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pb[j] = base + (yl0 + min(j, nj - 1)) * bb * RBLK;
+      mk<true, true>(acc, c.R1 + row * RBLK, ab * RBLK, pb, RBLK, 0, bb, nj, L);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nj) stn(c.Arow + ((long long)row * RNYB + y0 + yl0 + j) * RBLK, L, acc[j]);
+    }
+  });
+}
+
+// ---- P8: G = alpha alpha^T - dy K^-1, contracted with dK in registers (gprf.py:547-584) ------------------
+// Column pieces: alpha rows [c0, c1) staged in F (B operands).  Tasks = (block row r, up to GCOLS
+// columns of the piece) taken from a shared counter, biggest rows first; alpha(r) comes from L2.
+template <int DFN, int WFN>
+static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, Stage& stage) {
+  const Lane L = make_lane();
+  const int tid = threadIdx.x;
+  const int ab = c.ab, bb = c.bb, nr = c.nr, nyb = c.nyb;
+  const double ndy = -(double)c.dy;
+  const CovParams& cp = P.cp;
+  int* TT = reinterpret_cast<int*>(c.WB);          // task table of the piece: r | c_lo << 8 | c_hi << 16
+  const int crow = max(GCOLS, (c.nF / RNYB) & ~(GCOLS - 1));   // alpha rows per piece (a multiple of GCOLS)
+  for (int c0 = 0; c0 < nr; c0 += crow) {
+    const int c1 = min(nr, c0 + crow);
+    if (tid == 0) {
+      tma_issue(stage, c.F, c.Arow + (long long)c0 * RNYB * RBLK, (c1 - c0) * RNYB);
+      int nt = 0;
+      for (int r = nr - 1; r >= c0; --r) {
+        const int ce = min(c1, r + 1);
+        for (int cl = c0; cl < ce; cl += GCOLS) TT[nt++] = r | (cl << 8) | (min(ce, cl + GCOLS) << 16);
+      }
+      *c.s_ntask = nt;
+      *c.s_task = 0;
+    }
+    __syncthreads();
+    tma_wait(stage);
+    const int ntask = *c.s_ntask;
+    while (true) {
+      int t = 0;
+      if (L.lane == 0) t = atomicAdd(c.s_task, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= ntask) break;
+      const int code = TT[t];
+      const int r = code & 0xff, cl = (code >> 8) & 0xff, ch = (code >> 16) & 0xff;
+      const int nj = ch - cl;
+      const bool irow = r < ab;
+      const int wi = irow ? r : r - ab;            // row inside its part
+      // ---- K^-1 blocks (r, cl .. ch-1)
+      double2 acc[4];
+      zero4(acc);
+      {
+        // a task's columns lie in one part unless it straddles ab: split there
+        int j0 = 0;
+        while (j0 < nj) {
+          const int cc0 = cl + j0;
+          const bool icol = cc0 < ab;
+          const int jn = icol ? min(nj, ab - cl) : nj;         // end (exclusive) of this part's columns
+          const int m = jn - j0;
+          double2 part[4];
+          zero4(part);
+          const double* pb[4];
+          if (irow) {                                // (i row, i columns): V^T V   (+ K_ii^-1 below)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pb[j] = c.R1 + (cc0 + min(j, m - 1)) * RBLK;
+            mk<true, true>(part, c.R1 + wi * RBLK, ab * RBLK, pb, ab * RBLK, 0, bb, m, L);
+          } else if (icol) {                         // (j row, i columns): W_S^T V
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pb[j] = c.R1 + (cc0 + min(j, m - 1)) * RBLK;
+            for (int k = wi; k < bb; ++k) {
+              const double2 av = ldt(c.R2 + (rtri(k) + wi) * RBLK, L);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < m) mma2(part[j], av, ldt(pb[j] + k * ab * RBLK, L));
+            }
+          } else {                                   // (j row, j columns): W_S^T W_S
+            for (int k = wi; k < bb; ++k) {
+              const double* rowk = c.R2 + rtri(k) * RBLK;
+              const double2 av = ldt(rowk + wi * RBLK, L);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < m) mma2(part[j], av, ldt(rowk + (cc0 - ab + j) * RBLK, L));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < m) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (jj == j0 + j) acc[jj] = part[j];
+            }
+          j0 = jn;
+        }
+      }
+      // alpha(r) fragments from L2, alpha(c) from the staged piece
+      double2 af[RNYB];
+#pragma unroll
+      for (int y = 0; y < RNYB; ++y)
+        af[y] = (y < nyb) ? ldn(c.Arow + ((long long)r * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
+      const int tr = r * 8 + L.g;
+      const bool rv = c.IDX[tr] >= 0;
+      const double* xr = c.XS + tr * XD;
+      double rs[3] = {0.0, 0.0, 0.0};
+      double th[MAX_NCOV];
+#pragma unroll
+      for (int tt = 0; tt < MAX_NCOV; ++tt) th[tt] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= nj) break;
+        const int cc = cl + j;
+        double2 g = acc[j], kv;
+        if (irow) {
+          const double2 ki = ldn(c.pexp + EXP_KINV + (long long)(rtri(wi) + cc) * RBLK, L);
+          g.x += ki.x;
+          g.y += ki.y;
+          kv = ldn(c.pexp + EXP_KSAVE + (long long)(rtri(wi) + cc) * RBLK, L);
+        } else if (cc < ab) {
+          kv = ldn(c.Kji + (wi * ab + cc) * RBLK, L);
+        } else {
+          kv = ldn(c.Kjj + (rtri(wi) + cc - ab) * RBLK, L);
+          if (c.is_export) stn(c.oexp + EXP_KINV + (long long)(rtri(wi) + cc - ab) * RBLK, L, g);
+        }
+        g.x *= ndy;
+        g.y *= ndy;
+        double2 g2 = make_double2(0.0, 0.0);
+        const double* arow = c.F + (cc - c0) * RNYB * RBLK;
 #pragma unroll
         for (int y = 0; y < RNYB; ++y)
-          af[y] = (y < nyb) ? ldn(Arow + ((long long)r * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
-        const int tr = r * 8 + L.g;
-        const bool rv = IDX[tr] >= 0;
-        const double* xr = xs_row(XS, tr);
-        double rs[3] = {0.0, 0.0, 0.0};
-        double th[MAX_NCOV];
+          if (y < nyb) mma2((y & 1) ? g2 : g, af[y], ldn(arow + y * RBLK, L));
+        g.x += g2.x;
+        g.y += g2.y;
+        // contraction of the G block with dk/dx, dk/dtheta (covariance values saved by P1 / P2 / the parent)
+        double cs[2][3];
 #pragma unroll
-        for (int tt = 0; tt < MAX_NCOV; ++tt) th[tt] = 0.0;
-        for (int c = cl; c < ch; ++c) {
-          double2 acc, kv, acc2 = make_double2(0.0, 0.0);
-          if (irow) {                                 // (i row, i column): K_ii^-1 + V^T V
-            acc = ldn(pexp + EXP_KINV + (long long)(rtri(wi) + c) * RBLK, L);
-            kv = ldn(pexp + EXP_KSAVE + (long long)(rtri(wi) + c) * RBLK, L);
-            const double* pa = R1 + wi * RBLK;
-            const double* pb = R1 + c * RBLK;
-            int k = 0;
-            for (; k + 1 < bb; k += 2) {
-              mma2(acc, ldt(pa + k * ab * RBLK, L), ldt(pb + k * ab * RBLK, L));
-              mma2(acc2, ldt(pa + (k + 1) * ab * RBLK, L), ldt(pb + (k + 1) * ab * RBLK, L));
-            }
-            if (k < bb) mma2(acc, ldt(pa + k * ab * RBLK, L), ldt(pb + k * ab * RBLK, L));
-          } else if (c < ab) {                        // (j row, i column): W_S^T V
-            acc = make_double2(0.0, 0.0);
-            kv = ldn(Kji + (wi * ab + c) * RBLK, L);
-            int k = wi;
-            for (; k + 1 < bb; k += 2) {
-              mma2(acc, ldt(R2 + (rtri(k) + wi) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
-              mma2(acc2, ldt(R2 + (rtri(k + 1) + wi) * RBLK, L), ldt(R1 + ((k + 1) * ab + c) * RBLK, L));
-            }
-            if (k < bb) mma2(acc, ldt(R2 + (rtri(k) + wi) * RBLK, L), ldt(R1 + (k * ab + c) * RBLK, L));
-          } else {                                    // (j row, j column): W_S^T W_S
-            const int cc = c - ab;
-            acc = make_double2(0.0, 0.0);
-            kv = ldn(Kjj + (rtri(wi) + cc) * RBLK, L);
-            int k = wi;
-            for (; k + 1 < bb; k += 2) {
-              mma2(acc, ldt(R2 + (rtri(k) + wi) * RBLK, L), ldt(R2 + (rtri(k) + cc) * RBLK, L));
-              mma2(acc2, ldt(R2 + (rtri(k + 1) + wi) * RBLK, L), ldt(R2 + (rtri(k + 1) + cc) * RBLK, L));
-            }
-            if (k < bb) mma2(acc, ldt(R2 + (rtri(k) + wi) * RBLK, L), ldt(R2 + (rtri(k) + cc) * RBLK, L));
+        for (int e = 0; e < 2; ++e) {
+          const int tc = cc * 8 + 2 * L.q + e;
+          const double Gv = e == 0 ? g.x : g.y;
+          const bool cv = rv && c.IDX[tc] >= 0;
+          if (cv && tc == tr) {
+            th[0] += 0.5 * Gv;
+            th[1] += 0.5 * Gv * cp.s2;
           }
-          acc.x += acc2.x;
-          acc.y += acc2.y;
-          if (!irow && c >= ab && is_export) stn(oexp + EXP_KINV + (long long)(rtri(wi) + c - ab) * RBLK, L, acc);
-          acc.x *= ndy;
-          acc.y *= ndy;
-          acc2 = make_double2(0.0, 0.0);
-          const double* arow = F + (c - c0) * RNYB * RBLK;
-          for_desc<RNYB>(nyb, [&](auto yc) {
-            constexpr int y = decltype(yc)::value;
-            mma2((y & 1) ? acc2 : acc, af[y], ldn(arow + y * RBLK, L));
-          });
-          acc.x += acc2.x;
-          acc.y += acc2.y;
-          // contraction of the G block with dk/dx, dk/dtheta (covariance values saved by P1 / P2 / the parent)
-          double cs[2][3];
+          const bool off = cv && tc < tr;
+          double k = e == 0 ? kv.x : kv.y;
+          double gp[MAX_DX], gq[MAX_DX], gl[MAX_NLS];
+          cov_grad<DFN, WFN, true>(xr, c.XS + tc * XD, cp, k, gp, gq, gl);
+          const double Gm = off ? Gv : 0.0;
+          th[1] += off ? Gm * k : 0.0;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int tc = c * 8 + 2 * L.q + e;
-            const double Gv = e == 0 ? acc.x : acc.y;
-            const bool cv = rv && IDX[tc] >= 0;
-            if (cv && tc == tr) {
-              th[0] += 0.5 * Gv;
-              th[1] += 0.5 * Gv * cp.s2;
-            }
-            const bool off = cv && tc < tr;
-            double k = e == 0 ? kv.x : kv.y;
-            double gp[MAX_DX], gq[MAX_DX], gl[MAX_NLS];
-            cov_grad<DFN, WFN, true>(xr, xs_row(XS, tc), cp, k, gp, gq, gl);
-            const double Gm = off ? Gv : 0.0;
-            th[1] += off ? Gm * k : 0.0;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              rs[d] += off ? Gm * gp[d] : 0.0;
-              cs[e][d] = off ? Gm * gq[d] : 0.0;
-              th[2 + d] += off ? Gm * gl[d] : 0.0;
-            }
+          for (int d = 0; d < 3; ++d) {
+            rs[d] += off ? Gm * gp[d] : 0.0;
+            cs[e][d] = off ? Gm * gq[d] : 0.0;
+            th[2 + d] += off ? Gm * gl[d] : 0.0;
           }
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              double v = cs[e][d];
-              v += __shfl_xor_sync(0xffffffffu, v, 4);
-              v += __shfl_xor_sync(0xffffffffu, v, 8);
-              v += __shfl_xor_sync(0xffffffffu, v, 16);
-              if (L.g == 0) colp[(long long)(rtri(r) + c) * COLP + (2 * L.q + e) * 3 + d] = v;
-            }
-        }
-        // the task's row sums and theta partials
-        double* tp = taskp + ((long long)r * MAXG + (cl / GCOLS)) * TASKP;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          double v = rs[d];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          if (L.q == 0) tp[L.g * 3 + d] = v;
         }
 #pragma unroll
-        for (int tt = 0; tt < MAX_NCOV; ++tt) {
-          double v = th[tt];
+        for (int e = 0; e < 2; ++e)
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (L.lane == 0) tp[24 + tt] = v;
-        }
+          for (int d = 0; d < 3; ++d) {
+            double v = cs[e][d];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (L.g == 0) c.colp[(long long)(rtri(r) + cc) * COLP + (2 * L.q + e) * 3 + d] = v;
+          }
       }
-      __syncthreads();
+      // the task's row sums and theta partials
+      double* tp = c.taskp + ((long long)r * MAXG + (cl / GCOLS)) * TASKP;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double v = rs[d];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (L.q == 0) tp[L.g * 3 + d] = v;
+      }
+#pragma unroll
+      for (int tt = 0; tt < MAX_NCOV; ++tt) {
+        double v = th[tt];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (L.lane == 0) tp[24 + tt] = v;
+      }
     }
+    __syncthreads();
   }
-  rtrace(P, s_tcur, u.uid, 10);
-  // row sums + column sums, fixed order; theta
+}
+
+// ---- finalize: row sums + column sums in a fixed order; theta ------------------------------------------------
+static __device__ __noinline__ void ph_finalize(const ResParams& P, const Ctx& c) {
+  const Lane L = make_lane();
+  const int tid = threadIdx.x, w = L.w;
+  const int nr = c.nr;
   for (int t = tid; t < nr * 8; t += RNT) {
     const int rb = t >> 3, g0 = t & 7;
     double v[3] = {0.0, 0.0, 0.0};
     for (int gi = 0; gi * GCOLS <= rb; ++gi) {
-      const double* tp = taskp + ((long long)rb * MAXG + gi) * TASKP + g0 * 3;
+      const double* tp = c.taskp + ((long long)rb * MAXG + gi) * TASKP + g0 * 3;
       v[0] += tp[0];
       v[1] += tp[1];
       v[2] += tp[2];
     }
     for (int r2 = rb; r2 < nr; ++r2) {
-      const double* pc = colp + (long long)(rtri(r2) + rb) * COLP + g0 * 3;
+      const double* pc = c.colp + (long long)(rtri(r2) + rb) * COLP + g0 * 3;
       v[0] += pc[0];
       v[1] += pc[1];
       v[2] += pc[2];
     }
-    gx[t * 3] = v[0];
-    gx[t * 3 + 1] = v[1];
-    gx[t * 3 + 2] = v[2];
+    c.gx[t * 3] = v[0];
+    c.gx[t * 3 + 1] = v[1];
+    c.gx[t * 3 + 2] = v[2];
   }
   // theta: one warp per parameter; lanes stride over the task records in a fixed order, then a
   // fixed shuffle tree - the summation order does not depend on which warp ran which task
@@ -919,33 +1010,89 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Unit& u, doub
     double v = 0.0;
     for (int e = L.lane; e < nr * MAXG; e += 32) {
       const int rb = e / MAXG, gi = e - rb * MAXG;
-      if (gi * GCOLS <= rb) v += taskp[(long long)e * TASKP + 24 + w];
+      if (gi * GCOLS <= rb) v += c.taskp[(long long)e * TASKP + 24 + w];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (w == 1) v /= cp.s2;
-    if (L.lane == 0) P.gth_u[(long long)u.uid * MAX_NCOV + w] = v;
+    if (w == 1) v /= P.cp.s2;
+    if (L.lane == 0) P.gth_u[(long long)c.uid * MAX_NCOV + w] = v;
   }
   __syncthreads();
-  rtrace(P, s_tcur, u.uid, 11);
+}
+
+// ---- one unit ---------------------------------------------------------------------------------------------------
+template <int DFN, int WFN>
+__device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage& stage) {
+  const int tid = threadIdx.x;
+  rtrace(P, c, 1);
+  ph_gather_lji<DFN, WFN>(P, c, stage);
+  dbg_dump(P, c, 1);
+  rtrace(P, c, 2);
+  ph_schur<DFN, WFN>(P, c);
+  dbg_dump(P, c, 2);
+  rtrace(P, c, 3);
+  // Z_i (all of it, or its first piece) travels into F while S is factored
+  const int nyc = c.pair ? max(1, min(c.nyb, min(c.nF / c.ab, R_WB_BLOCKS / c.bb))) : max(1, min(c.nyb, R_WB_BLOCKS / c.bb));
+  if (c.pair && tid == 0) tma_issue(stage, c.F, c.pexp + EXP_ZY, min(nyc, c.nyb) * c.ab);
+  ph_chol_inv(P, c);
+  dbg_dump(P, c, 4);
+  rtrace(P, c, 5);
+  ph_ypart(P, c, stage, nyc);
+  rtrace(P, c, 6);
+  if (!c.want_grad) {
+    __syncthreads();
+    return;
+  }
+  asm volatile("fence.proxy.async;\n" ::: "memory");     // Z_j / alpha_j / saved K: written with ordinary stores
+  if (c.pair) {
+    __syncthreads();
+    // W_i (first piece) back into F for T
+    if (tid == 0) {
+      int r1 = 0, nb = 0;
+      while (r1 < c.ab && nb + r1 + 1 <= c.nF) {
+        nb += r1 + 1;
+        ++r1;
+      }
+      tma_issue(stage, c.F, c.pexp + EXP_W, nb);
+    }
+    ph_t(P, c, stage);
+    // own Z_j (all of it, or its first piece) into F for alpha_i, behind the V product
+    if (tid == 0) tma_issue(stage, c.F, c.Zy, max(1, min(c.nyb, c.nF / c.bb)) * c.bb);
+    dbg_dump(P, c, 6);
+    rtrace(P, c, 7);
+    ph_v(P, c);
+    dbg_dump(P, c, 7);
+    rtrace(P, c, 8);
+    ph_alpha_i(P, c, stage);
+    asm volatile("fence.proxy.async;\n" ::: "memory");   // alpha_i rows
+  }
+  __syncthreads();
+  rtrace(P, c, 9);
+  ph_grad<DFN, WFN>(P, c, stage);
+  rtrace(P, c, 10);
+  ph_finalize(P, c);
+  rtrace(P, c, 11);
 }
 
 // grid: persistent CTAs (<= one per SM), RNT threads, R_SMEM_BYTES dynamic shared memory.
 template <int DFN, int WFN>
-__global__ void __launch_bounds__(RNT, 1) k_resident(ResParams P) {
+__global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
   extern __shared__ __align__(128) double smem[];
   double* MISC = smem + R_WB_BLOCKS * RBLK;
   Stage stage;
   stage.bar = reinterpret_cast<uint64_t*>(MISC);
   stage.par = 0;
   int* s_unit = reinterpret_cast<int*>(MISC + 4);
-  int* s_tcur = reinterpret_cast<int*>(MISC + 5);
+  Ctx* ctx = reinterpret_cast<Ctx*>(MISC + MISC_CTX);
+  ResParams* Ps = reinterpret_cast<ResParams*>(MISC + MISC_PARAMS);
   if (threadIdx.x == 0) {
     mbar_init(stage.bar, 1);
     fence_mbar_init();
-    *s_tcur = 0;
+    *Ps = Pk;
+    *(reinterpret_cast<int*>(MISC + 5)) = 0;       // trace cursor
   }
   __syncthreads();
+  const ResParams& P = *Ps;
   double* scratch = P.scratch + (long long)blockIdx.x * SCR_STRIDE;
   const int n_units = *P.n_order;
   while (true) {
@@ -954,52 +1101,76 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams P) {
     const int slot = *s_unit;
     __syncthreads();
     if (slot >= n_units) break;
-    Unit u;
-    u.uid = P.order[slot];
-    if (u.uid < P.B) {
-      u.bi = -1;
-      u.bj = u.uid;
-    } else {
-      u.bi = P.edges[2 * (u.uid - P.B)];
-      u.bj = P.edges[2 * (u.uid - P.B) + 1];
+    const int uid = P.order[slot];
+    int bi = -1, bj = uid;
+    if (uid >= P.B) {
+      bi = P.edges[2 * (uid - P.B)];
+      bj = P.edges[2 * (uid - P.B) + 1];
     }
-    u.ja = P.block_ptr[u.bj];
-    u.b = (int)(P.block_ptr[u.bj + 1] - u.ja);
-    u.ia = 0;
-    u.a = 0;
-    if (u.bi >= 0) {
-      u.ia = P.block_ptr[u.bi];
-      u.a = (int)(P.block_ptr[u.bi + 1] - u.ia);
+    const long long ja = P.block_ptr[bj];
+    const int b = (int)(P.block_ptr[bj + 1] - ja);
+    long long ia = 0;
+    int a = 0;
+    if (bi >= 0) {
+      ia = P.block_ptr[bi];
+      a = (int)(P.block_ptr[bi + 1] - ia);
     }
-    if (u.bi >= 0 && u.b == 0) {
+    if (bi >= 0 && b == 0) {
       // pair with an empty second block: the unit IS block i (computed by the block launch)
-      const long long src = u.bi;
-      if (threadIdx.x == 0) P.ll_u[u.uid] = P.ll_u[src];
-      if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)u.uid * MAX_NCOV + threadIdx.x] = P.gth_u[src * MAX_NCOV + threadIdx.x];
-      for (int e = threadIdx.x; e < GX_STRIDE; e += RNT) P.gx_u[(long long)u.uid * GX_STRIDE + e] = P.gx_u[src * GX_STRIDE + e];
+      const long long src = bi;
+      if (threadIdx.x == 0) P.ll_u[uid] = P.ll_u[src];
+      if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)uid * MAX_NCOV + threadIdx.x] = P.gth_u[src * MAX_NCOV + threadIdx.x];
+      for (int e = threadIdx.x; e < GX_STRIDE; e += RNT) P.gx_u[(long long)uid * GX_STRIDE + e] = P.gx_u[src * GX_STRIDE + e];
       continue;
     }
-    u.ab = (u.a + 7) >> 3;
-    u.bb = (u.b + 7) >> 3;
-    const int cls = res_class(u.ab, u.bb);
+    const int ab = (a + 7) >> 3, bb = (b + 7) >> 3;
+    const int cls = res_class(ab, bb);
     if (cls == 2) {
       if (threadIdx.x == 0) atomicOr(P.status, ST_OVERFLOW);
       continue;
     }
-    if (u.b == 0) {                // empty block unit
+    if (b == 0) {                  // empty block unit
       if (threadIdx.x == 0) {
-        P.ll_u[u.uid] = 0.0;
-        double* oexp = P.exports + (long long)u.bj * EXP_STRIDE;
+        P.ll_u[uid] = 0.0;
+        double* oexp = P.exports + (long long)bj * EXP_STRIDE;
         oexp[EXP_SCAL + 0] = 0.0;
         oexp[EXP_SCAL + 1] = 0.0;
       }
-      if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)u.uid * MAX_NCOV + threadIdx.x] = 0.0;
+      if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)uid * MAX_NCOV + threadIdx.x] = 0.0;
       continue;
     }
-    if (u.ab <= RMAXB && u.bb <= RMAXB)
-      run_unit<DFN, WFN, RMAXB>(P, u, smem, stage, scratch, cls == 1);
-    else
-      run_unit<DFN, WFN, BMAXB>(P, u, smem, stage, scratch, cls == 1);
+    if (threadIdx.x == 0) {
+      Ctx& c = *ctx;
+      const bool r1g = cls == 1;
+      c.uid = uid; c.bi = bi; c.bj = bj; c.a = a; c.b = b; c.ab = ab; c.bb = bb; c.nr = ab + bb;
+      c.nyb = P.nyb; c.pair = ab > 0; c.is_export = bi < 0; c.want_grad = P.want_grad; c.dx = P.dx; c.dy = P.dy;
+      c.ia = ia; c.ja = ja;
+      c.WB = smem;
+      c.XS = MISC + R_MISC_DOUBLES;
+      c.R1 = r1g ? scratch + SCR_R1 : c.XS + c.nr * 8 * XD;
+      c.R2 = c.XS + c.nr * 8 * XD + (r1g ? 0 : bb * ab * RBLK);
+      c.F = c.R2 + rtri(bb) * RBLK;
+      c.nF = res_free_blocks(ab, bb, r1g);
+      c.capW1 = rtri(bb) + c.nF;
+      c.IDX = reinterpret_cast<int*>(MISC + MISC_IDX);
+      c.s_fail = reinterpret_cast<int*>(MISC + 4) + 1;
+      c.s_tcur = reinterpret_cast<int*>(MISC + 5);
+      c.s_task = reinterpret_cast<int*>(MISC + 5) + 1;
+      c.s_ntask = reinterpret_cast<int*>(MISC + 6);
+      c.s_q = MISC + 8;
+      c.s_ld = MISC + 24;
+      c.pexp = c.pair ? P.exports + (long long)bi * EXP_STRIDE : nullptr;
+      c.oexp = c.is_export ? P.exports + (long long)bj * EXP_STRIDE : nullptr;
+      c.Zy = c.is_export ? c.oexp + EXP_ZY : scratch + SCR_ZY;
+      c.Arow = c.is_export ? c.oexp + EXP_AROW : scratch + SCR_AROW;
+      c.Kjj = c.is_export ? c.oexp + EXP_KSAVE : scratch + SCR_KJJ;
+      c.Kji = scratch + SCR_KJI;
+      c.colp = scratch + SCR_COLP;
+      c.taskp = scratch + SCR_TASKP;
+      c.gx = P.gx_u + (long long)uid * GX_STRIDE;
+    }
+    __syncthreads();
+    run_unit<DFN, WFN>(P, *ctx, stage);
   }
 }
 
