@@ -73,7 +73,7 @@ constexpr int COLP = 24;                                                     // 
 constexpr long long SCR_TASKP = SCR_COLP + (long long)(2 * EMAXB) * (2 * EMAXB + 1) / 2 * COLP;
 constexpr int TASKP = 32;                                                    // per task: row sums 8 x 3, theta 5
 constexpr int GCOLS = 4;                                                     // G blocks per task
-constexpr int MAXG = (2 * EMAXB + GCOLS - 1) / GCOLS;                        // column groups per row
+constexpr int MAXG = 24;                                                     // tasks per block row, at most
 constexpr long long SCR_KJI = SCR_TASKP + (long long)(2 * EMAXB) * MAXG * TASKP;   // saved K_ji: row * ab + c
 constexpr long long SCR_KJJ = SCR_KJI + (long long)EMAXB * EMAXB * RBLK;           // saved K_jj: lower packed
 constexpr long long SCR_R1 = SCR_KJJ + (long long)RTRI * RBLK;                      // R1 of units too big for smem
@@ -142,6 +142,20 @@ __device__ __forceinline__ Lane make_lane() {
   // %tid at every use (measured: 13 % of all executed instructions)
   asm volatile("" : "+r"(L.on), "+r"(L.ot0), "+r"(L.ot1), "+r"(L.g), "+r"(L.q));
   return L;
+}
+// Shared-memory operands are addressed by their offset (in doubles) into the CTA's dynamic shared
+// memory: the compiler then emits LDS / STS with 32-bit address arithmetic.  (Generic pointers, as
+// handed around in a struct, cost a 64-bit add chain per fragment load and the slower generic LD.)
+// Operands in HBM / L2 use the pointer overloads.
+extern __shared__ __align__(128) double g_smem[];
+__device__ __forceinline__ double2 ldn(int off, const Lane& L) {
+  return *reinterpret_cast<const double2*>(g_smem + off + L.on);
+}
+__device__ __forceinline__ double2 ldt(int off, const Lane& L) {
+  return make_double2(g_smem[off + L.ot0], g_smem[off + L.ot1]);
+}
+__device__ __forceinline__ void stn(int off, const Lane& L, double2 v) {
+  *reinterpret_cast<double2*>(g_smem + off + L.on) = v;
 }
 // row-major fragment: (M[g][2q], M[g][2q+1])  - A operand of C = A B^T, B operand given as [n][k],
 // and the accumulator layout
@@ -241,32 +255,57 @@ __device__ __forceinline__ int first_piece(int cap, int nrows, RowLen rowlen) {
 // phases then do not compete for registers (as ONE inlined function the per-warp fragment arrays
 // were demoted to local memory and the lane offsets recomputed at every use).
 struct Ctx {
-  int uid, bi, bj, a, b, ab, bb, nr, nyb, pair, is_export, nF, want_grad, dx, dy, capW1;
+  int uid, bi, bj, a, b, ab, bb, nr, nyb, pair, is_export, nF, want_grad, dx, dy, r1g;
+  int oXS, oR1, oR2, oF;            // offsets (doubles) into the dynamic shared memory
   long long ia, ja;
-  double *WB, *XS, *R1, *R2, *F;
-  int *IDX, *s_fail, *s_task, *s_ntask, *s_tcur;
-  double *s_q, *s_ld;
+  double* R1g;                      // R1 in this CTA's scratch (units of res_class 1)
   const double* pexp;
   double *oexp, *Zy, *Arow, *Kjj, *Kji, *colp, *taskp, *gx;
 };
+constexpr int OFF_MISC = R_WB_BLOCKS * RBLK;
+constexpr int OFF_XS = OFF_MISC + R_MISC_DOUBLES;
+constexpr int MISC_Q = 8;             // [RNW] partial |Z|^2
+constexpr int MISC_LD = 24;           // [RNW] partial log det
 constexpr int MISC_CTX = 40;          // doubles
-constexpr int MISC_IDX = 120;
+constexpr int MISC_IDX = 120;         // [2 * EMAXB * 8] ints: global point index or -1
 constexpr int MISC_PARAMS = 288;
+constexpr int MISC_ROWCNT = 360;      // [2 * EMAXB] ints: gradient tasks per block row
 static_assert(sizeof(Ctx) <= (MISC_IDX - MISC_CTX) * 8, "Ctx does not fit");
-static_assert(sizeof(ResParams) <= (R_MISC_DOUBLES - MISC_PARAMS) * 8, "ResParams copy does not fit");
+static_assert(sizeof(ResParams) <= (MISC_ROWCNT - MISC_PARAMS) * 8, "ResParams copy does not fit");
+static_assert(MISC_ROWCNT + EMAXB <= R_MISC_DOUBLES, "MISC too small");
+
+__device__ __forceinline__ int* misc_int(int dbl_off, int idx) {
+  return reinterpret_cast<int*>(g_smem + OFF_MISC + dbl_off) + idx;
+}
+#define S_FAIL misc_int(4, 1)
+#define S_TCUR misc_int(5, 0)
+#define S_TASK misc_int(5, 1)
+#define S_NTASK misc_int(6, 0)
+#define S_IDX misc_int(MISC_IDX, 0)
+#define S_ROWCNT misc_int(MISC_ROWCNT, 0)
 
 constexpr int RTRACE_SLOTS = 512;
 // Debug timeline: thread 0 appends (unit << 16 | tag, %globaltimer) to this CTA's slots.
 __device__ __forceinline__ void rtrace(const ResParams& P, const Ctx& c, int tag) {
-  if (P.trace && threadIdx.x == 0 && *c.s_tcur < RTRACE_SLOTS) {
+  if (P.trace && threadIdx.x == 0 && *S_TCUR < RTRACE_SLOTS) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    unsigned long long* wp = P.trace + ((long long)blockIdx.x * RTRACE_SLOTS + *c.s_tcur) * 2;
+    unsigned long long* wp = P.trace + ((long long)blockIdx.x * RTRACE_SLOTS + *S_TCUR) * 2;
     wp[0] = ((unsigned long long)c.uid << 16) | (unsigned long long)tag;
     wp[1] = t;
-    ++*c.s_tcur;
+    ++*S_TCUR;
   }
 }
+
+// R1 is addressed either as a shared-memory offset (int) or as a pointer into the scratch (class 1)
+struct R1Smem {
+  typedef int T;
+  static __device__ __forceinline__ int get(const Ctx& c) { return c.oR1; }
+};
+struct R1Glob {
+  typedef double* T;
+  static __device__ __forceinline__ double* get(const Ctx& c) { return c.R1g; }
+};
 
 static __device__ __noinline__ void dbg_dump(const ResParams& P, const Ctx& c, int phase) {
   if (P.dbg_unit != c.uid || P.dbg_phase != phase) return;
@@ -274,23 +313,27 @@ static __device__ __noinline__ void dbg_dump(const ResParams& P, const Ctx& c, i
   for (int e = threadIdx.x; e < 160 * 160; e += RNT) {
     const int r = e / 160, cc = e % 160;
     double v1 = 0.0, v2 = 0.0;
-    if (c.pair && r < c.bb * 8 && cc < c.ab * 8) v1 = c.R1[((r >> 3) * c.ab + (cc >> 3)) * RBLK + sw_off(r & 7, cc & 7)];
+    if (c.pair && r < c.bb * 8 && cc < c.ab * 8) {
+      const int o = ((r >> 3) * c.ab + (cc >> 3)) * RBLK + sw_off(r & 7, cc & 7);
+      v1 = c.r1g ? c.R1g[o] : g_smem[c.oR1 + o];
+    }
     if (r < c.bb * 8 && cc < c.bb * 8 && (cc >> 3) <= (r >> 3))
-      v2 = c.R2[(rtri(r >> 3) + (cc >> 3)) * RBLK + sw_off(r & 7, cc & 7)];
+      v2 = g_smem[c.oR2 + (rtri(r >> 3) + (cc >> 3)) * RBLK + sw_off(r & 7, cc & 7)];
     P.dbg_out[e] = v1;
     P.dbg_out[160 * 160 + e] = v2;
   }
   __syncthreads();
 }
 
-// ---- 1 x 4 register tile ---------------------------------------------------------------------------------
-// acc[j] += sum_{k0 <= k < k1} A(k) B_j(k)^T-or-plain for j < NJ: one A fragment per k feeds up to four
-// independent accumulator chains (the DMMA latency is ~37 cycles, four chains hide it).
+// ---- 1 x NJ register tile --------------------------------------------------------------------------------
+// acc[j] += sum_{k0 <= k < k1} A(k) B_j(k) for j < NJ: one A fragment per k feeds up to four
+// independent accumulator chains (the DMMA latency is ~37 cycles, the chains hide it).
 //   A(k)   = block at pa + k * sa          (AT: stored [k][m], read transposed)
 //   B_j(k) = block at pb[j] + k * sbk      (BT: stored [k][n], read transposed)
-template <bool AT, bool BT, int NJ>
-__device__ __forceinline__ void mk_loop(double2 (&acc)[4], const double* pa, int sa, const double* const (&pb)[4],
-                                        int sbk, int k0, int k1, const Lane& L) {
+// PA / PB: int (shared-memory offset) or pointer (HBM / L2).
+template <bool AT, bool BT, int NJ, class PA, class PB>
+__device__ __forceinline__ void mk_loop(double2 (&acc)[4], PA pa, int sa, const PB (&pb)[4], int sbk, int k0, int k1,
+                                        const Lane& L) {
 #pragma unroll 2
   for (int k = k0; k < k1; ++k) {
     const double2 av = AT ? ldt(pa + k * sa, L) : ldn(pa + k * sa, L);
@@ -301,9 +344,9 @@ __device__ __forceinline__ void mk_loop(double2 (&acc)[4], const double* pa, int
     }
   }
 }
-template <bool AT, bool BT>
-__device__ __forceinline__ void mk(double2 (&acc)[4], const double* pa, int sa, const double* const (&pb)[4], int sbk,
-                                   int k0, int k1, int nj, const Lane& L) {
+template <bool AT, bool BT, class PA, class PB>
+__device__ __forceinline__ void mk(double2 (&acc)[4], PA pa, int sa, const PB (&pb)[4], int sbk, int k0, int k1, int nj,
+                                   const Lane& L) {
   switch (nj) {
     case 4: mk_loop<AT, BT, 4>(acc, pa, sa, pb, sbk, k0, k1, L); break;
     case 3: mk_loop<AT, BT, 3>(acc, pa, sa, pb, sbk, k0, k1, L); break;
@@ -323,12 +366,14 @@ __device__ __forceinline__ double2 cov_frag(const ResParams& P, const Ctx& c, co
                                             bool with_diag) {
   const int tr = rb * 8 + L.g;
   const int tc = cb * 8 + 2 * L.q;
-  const bool rv = c.IDX[tr] >= 0;
-  const double* xr = c.XS + tr * XD;
-  double v0 = cov_value<DFN, WFN>(xr, c.XS + tc * XD, P.cp);
-  double v1 = cov_value<DFN, WFN>(xr, c.XS + (tc + 1) * XD, P.cp);
-  v0 = (rv && c.IDX[tc] >= 0) ? v0 : 0.0;
-  v1 = (rv && c.IDX[tc + 1] >= 0) ? v1 : 0.0;
+  const int* IDX = S_IDX;
+  const double* XS = g_smem + c.oXS;
+  const bool rv = IDX[tr] >= 0;
+  const double* xr = XS + tr * XD;
+  double v0 = cov_value<DFN, WFN>(xr, XS + tc * XD, P.cp);
+  double v1 = cov_value<DFN, WFN>(xr, XS + (tc + 1) * XD, P.cp);
+  v0 = (rv && IDX[tc] >= 0) ? v0 : 0.0;
+  v1 = (rv && IDX[tc + 1] >= 0) ? v1 : 0.0;
   if (with_diag) {
     if (tr == tc) v0 = rv ? P.cp.s2 + P.cp.nv : 1.0;
     if (tr == tc + 1) v1 = rv ? P.cp.s2 + P.cp.nv : 1.0;
@@ -338,44 +383,50 @@ __device__ __forceinline__ double2 cov_frag(const ResParams& P, const Ctx& c, co
 
 __device__ __forceinline__ int tri_len(int r) { return r + 1; }
 
-// ---- P0 / P1: gather, K_ji, L_ji = K_ji W_i^T ------------------------------------------------------------
-template <int DFN, int WFN>
-static __device__ __noinline__ void ph_gather_lji(const ResParams& P, const Ctx& c, Stage& stage) {
-  const Lane L = make_lane();
-  const int tid = threadIdx.x, w = L.w;
-  const int ab = c.ab, bb = c.bb;
-  // W_i on its way into [R2 | F] (both still unused; res_class guarantees that all of it fits)
-  if (c.pair && tid == 0) tma_issue(stage, c.R2, c.pexp + EXP_W, rtri(ab));
-  if (tid == 0) *c.s_fail = 0;
+// ---- P0: gather the unit's coordinate records --------------------------------------------------------------
+template <int DFN>
+static __device__ __noinline__ void ph_gather(const ResParams& P, const Ctx& c) {
+  const int tid = threadIdx.x;
+  int* IDX = S_IDX;
+  double* XS = g_smem + c.oXS;
+  if (tid == 0) *S_FAIL = 0;
   for (int t = tid; t < c.nr * 8; t += RNT) {
     long long idx = -1;
-    if (t < ab * 8) {
+    if (t < c.ab * 8) {
       if (t < c.a) idx = P.perm[c.ia + t];
-    } else if (t - ab * 8 < c.b) {
-      idx = P.perm[c.ja + (t - ab * 8)];
+    } else if (t - c.ab * 8 < c.b) {
+      idx = P.perm[c.ja + (t - c.ab * 8)];
     }
-    c.IDX[t] = (int)idx;
+    IDX[t] = (int)idx;
     double rec[XD];
 #pragma unroll
     for (int d = 0; d < MAX_DX + 1; ++d) rec[d] = (idx >= 0 && d < c.dx) ? P.X[idx * c.dx + d] : 0.0;
     point_terms(DFN, rec);
 #pragma unroll
-    for (int d = 0; d < XD; ++d) c.XS[t * XD + d] = rec[d];
+    for (int d = 0; d < XD; ++d) XS[t * XD + d] = rec[d];
   }
   __syncthreads();
-  if (!c.pair) return;
+}
+
+// ---- P1: K_ji, L_ji = K_ji W_i^T -------------------------------------------------------------------------------
+template <int DFN, int WFN, class R1>
+static __device__ __noinline__ void ph_lji(const ResParams& P, const Ctx& c, Stage& stage) {
+  const Lane L = make_lane();
+  const int w = L.w;
+  const int ab = c.ab, bb = c.bb;
+  const typename R1::T r1 = R1::get(c);
   // K_ji -> R1 (and to scratch for the gradient contraction), one block per task
   for (int t = w; t < bb * ab; t += RNW) {
     const int row = t / ab, k = t - row * ab;
     const double2 kv = cov_frag<DFN, WFN>(P, c, L, ab + row, k, false);
-    stn(c.R1 + t * RBLK, L, kv);
+    stn(r1 + t * RBLK, L, kv);
     if (c.want_grad) stn(c.Kji + t * RBLK, L, kv);
   }
   __syncthreads();
-  tma_wait(stage);
+  tma_wait(stage);                    // W_i, issued by run_unit into [R2 | F]
   // L_ji(row, c0 .. c0+3) = sum_{k <= c} K_ji(row, k) W_i(c, k)^T, in place: rounds of whole rows; every
   // task of a round holds its blocks until all of the round's reads are done
-  const double* Wst = c.R2;
+  const int Wst = c.oR2;
   const int ng = (ab + 3) >> 2;
   const int rows_round = max(1, (4 * RNW) / ng);
   for (int r0 = 0; r0 < bb; r0 += rows_round) {
@@ -388,8 +439,8 @@ static __device__ __noinline__ void ph_gather_lji(const ResParams& P, const Ctx&
       if (t < ntask) {
         const int row = r0 + t / ng, c0 = (t % ng) * 4;
         const int nj = min(4, ab - c0);
-        const double* pa = c.R1 + row * ab * RBLK;
-        const double* pb[4];
+        const typename R1::T pa = r1 + row * ab * RBLK;
+        int pb[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) pb[j] = Wst + rtri(c0 + min(j, nj - 1)) * RBLK;
         mk<false, false>(acc[i], pa, RBLK, pb, RBLK, 0, c0 + 1, nj, L);
@@ -407,7 +458,7 @@ static __device__ __noinline__ void ph_gather_lji(const ResParams& P, const Ctx&
         const int row = r0 + t / ng, c0 = (t % ng) * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (c0 + j < ab) stn(c.R1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
+          if (c0 + j < ab) stn(r1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
       }
     }
     __syncthreads();
@@ -415,10 +466,11 @@ static __device__ __noinline__ void ph_gather_lji(const ResParams& P, const Ctx&
 }
 
 // ---- P2: S = K_jj + nv I - L_ji L_ji^T (lower blocks, tasks of up to 4 columns) --------------------------
-template <int DFN, int WFN>
+template <int DFN, int WFN, class R1>
 static __device__ __noinline__ void ph_schur(const ResParams& P, const Ctx& c) {
   const Lane L = make_lane();
   const int ab = c.ab, bb = c.bb;
+  const typename R1::T r1 = R1::get(c);
   // task list: rows descending (longest first), column groups of 4
   int t = 0;
   for (int row = bb - 1; row >= 0; --row) {
@@ -428,17 +480,17 @@ static __device__ __noinline__ void ph_schur(const ResParams& P, const Ctx& c) {
       double2 acc[4];
       zero4(acc);
       if (c.pair) {
-        const double* pb[4];
+        typename R1::T pb[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pb[j] = c.R1 + (c0 + min(j, nj - 1)) * ab * RBLK;
-        mk<false, false>(acc, c.R1 + row * ab * RBLK, RBLK, pb, RBLK, 0, ab, nj, L);
+        for (int j = 0; j < 4; ++j) pb[j] = r1 + (c0 + min(j, nj - 1)) * ab * RBLK;
+        mk<false, false>(acc, r1 + row * ab * RBLK, RBLK, pb, RBLK, 0, ab, nj, L);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (j < nj) {
           const double2 kv = cov_frag<DFN, WFN>(P, c, L, ab + row, ab + c0 + j, true);
           if (c.want_grad) stn(c.Kjj + (rtri(row) + c0 + j) * RBLK, L, kv);
-          stn(c.R2 + (rtri(row) + c0 + j) * RBLK, L, make_double2(kv.x - acc[j].x, kv.y - acc[j].y));
+          stn(c.oR2 + (rtri(row) + c0 + j) * RBLK, L, make_double2(kv.x - acc[j].x, kv.y - acc[j].y));
         }
       }
     }
@@ -451,13 +503,13 @@ static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c
   const Lane L = make_lane();
   const int tid = threadIdx.x, w = L.w;
   const int bb = c.bb;
-  double* R2 = c.R2;
-  double* WD = c.WB;                               // diagonal-block inverses
+  const int R2 = c.oR2;
+  const int WD = 0;                                // diagonal-block inverses, in WB
   for (int J = 0; J < bb; ++J) {
     if (w == 0) {
       double av[8], wv[8];
       const int r = L.lane & 7;
-      const double* src = R2 + (rtri(J) + J) * RBLK;
+      const double* src = g_smem + R2 + (rtri(J) + J) * RBLK;
       if (L.lane < 8) {
 #pragma unroll
         for (int v = 0; v < 8; ++v) av[v] = src[sw_off(r, v)];
@@ -466,10 +518,10 @@ static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c
         for (int v = 0; v < 8; ++v) av[v] = (v == r) ? 1.0 : 0.0;
       }
       const int f = chol8_inv8(av, wv, L.lane);
-      if (L.lane == 0 && f != 0 && *c.s_fail == 0) *c.s_fail = J * 8 + f;
+      if (L.lane == 0 && f != 0 && *S_FAIL == 0) *S_FAIL = J * 8 + f;
       if (L.lane < 8) {
-        double* dl = R2 + (rtri(J) + J) * RBLK;
-        double* dw = WD + J * RBLK;
+        double* dl = g_smem + R2 + (rtri(J) + J) * RBLK;
+        double* dw = g_smem + WD + J * RBLK;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
           dl[sw_off(r, v)] = av[v];
@@ -482,7 +534,7 @@ static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c
     {
       const double2 bw = ldn(WD + J * RBLK, L);
       for (int I = J + 1 + w; I < bb; I += RNW) {
-        double* pc = R2 + (rtri(I) + J) * RBLK;
+        const int pc = R2 + (rtri(I) + J) * RBLK;
         double2 o = make_double2(0.0, 0.0);
         mma2(o, ldn(pc, L), bw);
         stn(pc, L, o);
@@ -499,7 +551,7 @@ static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c
         while (ii * (ii + 1) / 2 > t) --ii;
         const int kk = t - ii * (ii + 1) / 2;
         const int I = J + 1 + ii, K = J + 1 + kk;
-        double* pc = R2 + (rtri(I) + K) * RBLK;
+        const int pc = R2 + (rtri(I) + K) * RBLK;
         double2 cv = ldn(pc, L);
         mma2(cv, neg2(ldn(R2 + (rtri(I) + J) * RBLK, L)), ldn(R2 + (rtri(K) + J) * RBLK, L));
         stn(pc, L, cv);
@@ -512,10 +564,10 @@ static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c
   // log-determinant: sum of log L_tt over the unit's j rows, fixed order
   {
     double lv = 0.0;
-    if (tid < bb * 8) lv = log(R2[(rtri(tid >> 3) + (tid >> 3)) * RBLK + sw_off(tid & 7, tid & 7)]);
+    if (tid < bb * 8) lv = log(g_smem[R2 + (rtri(tid >> 3) + (tid >> 3)) * RBLK + sw_off(tid & 7, tid & 7)]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
-    if (L.lane == 0) c.s_ld[w] = lv;
+    if (L.lane == 0) g_smem[OFF_MISC + MISC_LD + w] = lv;
   }
   // W_S = L_S^-1 in place, by descending block columns
   for (int K = bb - 1; K >= 0; --K) {
@@ -548,84 +600,111 @@ static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c
   }
   if (c.is_export) {                                // W_b for this block's pairs
     double* dst = c.oexp + EXP_W;
+    const double* src = g_smem + R2;
     for (int e = tid; e < rtri(bb) * RBLK / 2; e += RNT)
-      reinterpret_cast<double2*>(dst)[e] = reinterpret_cast<const double2*>(R2)[e];
+      reinterpret_cast<double2*>(dst)[e] = reinterpret_cast<const double2*>(src)[e];
   }
 }
 
 // ---- P4: Z_j = W_S (Y_j - L_ji Z_i), alpha_j = W_S^T Z_j, the log-likelihood ---------------------------------
-// Pieces of up to nyc blocks of 8 outputs; tasks (row, 4 output blocks) dealt round-robin; the
-// right-hand sides live in WB as (yl * bb + row).
+// Pieces of up to nyc blocks of 8 outputs (normally all of them at once).  Z_i of the piece is staged in F;
+// the right-hand sides then take its place, as (yl * bb + row).  Tasks = (row, 2 output blocks), dealt
+// round-robin; the in-place steps hold their results in registers until every read is done.
+constexpr int YSLOTS = 5;             // tasks per warp and piece: bb * ceil(ny / 2) <= 20 * 4 = 80 <= 16 * 5
+template <class R1>
 static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, Stage& stage, int nyc) {
   const Lane L = make_lane();
   const int tid = threadIdx.x, w = L.w;
   const int ab = c.ab, bb = c.bb, nyb = c.nyb;
-  double* RB = c.WB;
+  const typename R1::T r1 = R1::get(c);
+  const int RB = c.oF, R2 = c.oR2;
+  const int* IDX = S_IDX;
   double qsum = 0.0;
   bool ahead = c.pair != 0;
   for (int y0 = 0; y0 < nyb; y0 += nyc) {
     const int ny = min(nyc, nyb - y0);
-    const int ngy = (ny + 3) >> 2;
+    const int ngy = (ny + 1) >> 1;
     const int ntask = bb * ngy;
     if (c.pair) {
-      if (!ahead && tid == 0) tma_issue(stage, c.F, c.pexp + EXP_ZY + (long long)y0 * ab * RBLK, ny * ab);
+      if (!ahead && tid == 0) tma_issue(stage, g_smem + c.oF, c.pexp + EXP_ZY + (long long)y0 * ab * RBLK, ny * ab);
       ahead = false;
       tma_wait(stage);
     }
     // R = Y_j - L_ji Z_i
-    for (int t = w; t < ntask; t += RNW) {
-      const int row = t / ngy, yl0 = (t - row * ngy) * 4;
-      const int nj = min(4, ny - yl0);
-      double2 acc[4];
-      zero4(acc);
-      if (c.pair) {
-        const double* pb[4];
+    double2 z[YSLOTS][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pb[j] = c.F + (yl0 + min(j, nj - 1)) * ab * RBLK;
-        mk<false, true>(acc, c.R1 + row * ab * RBLK, RBLK, pb, RBLK, 0, ab, nj, L);
-      }
-      const int idx = c.IDX[ab * 8 + row * 8 + L.g];
+    for (int i = 0; i < YSLOTS; ++i) {
+      const int t = w + i * RNW;
+      z[i][0] = z[i][1] = make_double2(0.0, 0.0);
+      if (t < ntask) {
+        const int row = t / ngy, yl0 = (t - row * ngy) * 2;
+        const int nj = min(2, ny - yl0);
+        const int idx = IDX[ab * 8 + row * 8 + L.g];
+        double2 yv[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < nj) {
+        for (int j = 0; j < 2; ++j) {
           const int yc = (y0 + yl0 + j) * 8 + 2 * L.q;
-          double2 yv = make_double2(0.0, 0.0);
-          if (idx >= 0) {
-            if (yc < c.dy) yv.x = __ldg(P.Y + (long long)idx * c.dy + yc);
-            if (yc + 1 < c.dy) yv.y = __ldg(P.Y + (long long)idx * c.dy + yc + 1);
+          yv[j] = make_double2(0.0, 0.0);
+          if (idx >= 0 && j < nj) {
+            if (yc < c.dy) yv[j].x = __ldg(P.Y + (long long)idx * c.dy + yc);
+            if (yc + 1 < c.dy) yv[j].y = __ldg(P.Y + (long long)idx * c.dy + yc + 1);
           }
-          stn(RB + ((yl0 + j) * bb + row) * RBLK, L, make_double2(yv.x - acc[j].x, yv.y - acc[j].y));
         }
+        if (c.pair) {
+          double2 acc[4];
+          zero4(acc);
+          int pb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pb[j] = c.oF + (yl0 + min(j, nj - 1)) * ab * RBLK;
+          mk<false, true>(acc, r1 + row * ab * RBLK, RBLK, pb, RBLK, 0, ab, nj, L);
+          yv[0].x -= acc[0].x;
+          yv[0].y -= acc[0].y;
+          yv[1].x -= acc[1].x;
+          yv[1].y -= acc[1].y;
+        }
+        z[i][0] = yv[0];
+        z[i][1] = yv[1];
+      }
+    }
+    __syncthreads();                                 // Z_i is no longer needed: the right-hand sides replace it
+#pragma unroll
+    for (int i = 0; i < YSLOTS; ++i) {
+      const int t = w + i * RNW;
+      if (t < ntask) {
+        const int row = t / ngy, yl0 = (t - row * ngy) * 2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (yl0 + j < ny) stn(RB + ((yl0 + j) * bb + row) * RBLK, L, z[i][j]);
       }
     }
     __syncthreads();
     // Z = W_S R  (held in registers until every read of R is done)
-    const int nslot = (ntask + RNW - 1) / RNW;     // <= 4: ntask <= bb * 2 <= 40 ... (ny <= 8)
-    double2 z[3][4];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      zero4(z[i]);
+    for (int i = 0; i < YSLOTS; ++i) {
       const int t = w + i * RNW;
-      if (i < nslot && t < ntask) {
-        const int row = t / ngy, yl0 = (t - row * ngy) * 4;
-        const int nj = min(4, ny - yl0);
-        const double* pb[4];
+      if (t < ntask) {
+        const int row = t / ngy, yl0 = (t - row * ngy) * 2;
+        const int nj = min(2, ny - yl0);
+        double2 acc[4];
+        zero4(acc);
+        int pb[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) pb[j] = RB + (yl0 + min(j, nj - 1)) * bb * RBLK;
-        mk<false, true>(z[i], c.R2 + rtri(row) * RBLK, RBLK, pb, RBLK, 0, row + 1, nj, L);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < nj) qsum += z[i][j].x * z[i][j].x + z[i][j].y * z[i][j].y;
+        mk<false, true>(acc, R2 + rtri(row) * RBLK, RBLK, pb, RBLK, 0, row + 1, nj, L);
+        z[i][0] = acc[0];
+        z[i][1] = acc[1];
+        qsum += acc[0].x * acc[0].x + acc[0].y * acc[0].y;
+        if (nj > 1) qsum += acc[1].x * acc[1].x + acc[1].y * acc[1].y;
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < YSLOTS; ++i) {
       const int t = w + i * RNW;
-      if (i < nslot && t < ntask) {
-        const int row = t / ngy, yl0 = (t - row * ngy) * 4;
+      if (t < ntask) {
+        const int row = t / ngy, yl0 = (t - row * ngy) * 2;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           if (yl0 + j < ny) {
             stn(RB + ((yl0 + j) * bb + row) * RBLK, L, z[i][j]);
             stn(c.Zy + ((y0 + yl0 + j) * bb + row) * RBLK, L, z[i][j]);
@@ -637,23 +716,19 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
     // alpha_j = W_S^T Z
     if (c.want_grad) {
       for (int t = w; t < ntask; t += RNW) {
-        const int row = t / ngy, yl0 = (t - row * ngy) * 4;
-        const int nj = min(4, ny - yl0);
-        double2 acc[4];
-        zero4(acc);
-        const double* pb[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pb[j] = RB + (yl0 + min(j, nj - 1)) * bb * RBLK;
+        const int row = t / ngy, yl0 = (t - row * ngy) * 2;
+        const int nj = min(2, ny - yl0);
+        double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+        const int p0 = RB + yl0 * bb * RBLK, p1 = RB + (yl0 + nj - 1) * bb * RBLK;
         // A(k) = W_S(k, row) read transposed: block (k, row) of the packed lower triangle
+#pragma unroll 2
         for (int k = row; k < bb; ++k) {
-          const double2 av = ldt(c.R2 + (rtri(k) + row) * RBLK, L);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < nj) mma2(acc[j], av, ldt(pb[j] + k * RBLK, L));
+          const double2 av = ldt(R2 + (rtri(k) + row) * RBLK, L);
+          mma2(a0, av, ldt(p0 + k * RBLK, L));
+          mma2(a1, av, ldt(p1 + k * RBLK, L));
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < nj) stn(c.Arow + ((long long)(ab + row) * RNYB + y0 + yl0 + j) * RBLK, L, acc[j]);
+        stn(c.Arow + ((long long)(ab + row) * RNYB + y0 + yl0) * RBLK, L, a0);
+        if (nj > 1) stn(c.Arow + ((long long)(ab + row) * RNYB + y0 + yl0 + 1) * RBLK, L, a1);
       }
     }
     __syncthreads();
@@ -662,13 +737,13 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
   double qv = qsum;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) qv += __shfl_xor_sync(0xffffffffu, qv, o);
-  if (L.lane == 0) c.s_q[w] = qv;
+  if (L.lane == 0) g_smem[OFF_MISC + MISC_Q + w] = qv;
   __syncthreads();
   if (tid == 0) {
     double qt = 0.0, lt = 0.0;
     for (int i = 0; i < RNW; ++i) {
-      qt += c.s_q[i];
-      lt += c.s_ld[i];
+      qt += g_smem[OFF_MISC + MISC_Q + i];
+      lt += g_smem[OFF_MISC + MISC_LD + i];
     }
     double logdet = 2.0 * lt;
     if (c.pair) {
@@ -680,42 +755,63 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
       c.oexp[EXP_SCAL + 1] = qt;
     }
     P.ll_u[c.uid] = -0.5 * qt - 0.5 * c.dy * logdet - 0.5 * c.dy * (double)(c.a + c.b) * 1.8378770664093454836;
-    if (*c.s_fail != 0) {
-      P.info[c.uid] = *c.s_fail;
+    if (*S_FAIL != 0) {
+      P.info[c.uid] = *S_FAIL;
       atomicOr(P.status, ST_NOTPD);
     }
   }
 }
 
 // ---- P6a: T = L_ji W_i, in place (tasks of 4 columns, rounds of whole rows, W_i rows staged in F) -----------
+template <class R1>
 static __device__ __noinline__ void ph_t(const ResParams& P, const Ctx& c, Stage& stage) {
   const Lane L = make_lane();
   const int w = L.w;
   const int ab = c.ab, bb = c.bb, nF = c.nF;
+  const typename R1::T r1 = R1::get(c);
   const int ng = (ab + 3) >> 2;
   const int rows_round = max(1, (4 * RNW) / ng);
+  const int oF = c.oF;
   bool ahead = true;
   for (int r0 = 0; r0 < bb; r0 += rows_round) {
     const int ntask = min(rows_round, bb - r0) * ng;
     double2 acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) zero4(acc[i]);
-    staged_rows(stage, c.F, nF, c.pexp + EXP_W, ab, tri_len, rtri, ahead, [&](int k0, int k1, const double* base) {
+    staged_rows(stage, g_smem + oF, nF, c.pexp + EXP_W, ab, tri_len, rtri, ahead, [&](int k0, int k1, const double*) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int t = w + i * RNW;
         if (t < ntask) {
           const int row = r0 + t / ng, c0 = (t % ng) * 4;
           const int nj = min(4, ab - c0);
-          const double* pa = c.R1 + row * ab * RBLK;
+          const typename R1::T pa = r1 + row * ab * RBLK;
           // T(row, c0 + j) += sum_{k >= c0 + j} L_ji(row, k) W_i(k, c0 + j)
-          for (int k = max(k0, c0); k < k1; ++k) {
+          int k = max(k0, c0);
+          for (; k < min(k1, c0 + 3); ++k) {        // rows of W_i that do not reach all four columns yet
             const double2 av = ldn(pa + k * RBLK, L);
-            const double* pk = base + (rtri(k) - rtri(k0) + c0) * RBLK;
-            const int nk = min(nj, k - c0 + 1);      // columns c0 .. c0 + nk - 1 exist in row k of W_i
+            const int pk = oF + (rtri(k) - rtri(k0) + c0) * RBLK;
+            const int nk = min(nj, k - c0 + 1);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               if (j < nk) mma2(acc[i][j], av, ldt(pk + j * RBLK, L));
+          }
+          if (nj == 4) {
+#pragma unroll 2
+            for (; k < k1; ++k) {
+              const double2 av = ldn(pa + k * RBLK, L);
+              const int pk = oF + (rtri(k) - rtri(k0) + c0) * RBLK;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) mma2(acc[i][j], av, ldt(pk + j * RBLK, L));
+            }
+          } else {
+            for (; k < k1; ++k) {
+              const double2 av = ldn(pa + k * RBLK, L);
+              const int pk = oF + (rtri(k) - rtri(k0) + c0) * RBLK;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < nj) mma2(acc[i][j], av, ldt(pk + j * RBLK, L));
+            }
           }
         }
       }
@@ -729,7 +825,7 @@ static __device__ __noinline__ void ph_t(const ResParams& P, const Ctx& c, Stage
         const int row = r0 + t / ng, c0 = (t % ng) * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (c0 + j < ab) stn(c.R1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
+          if (c0 + j < ab) stn(r1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
       }
     }
     __syncthreads();
@@ -737,10 +833,12 @@ static __device__ __noinline__ void ph_t(const ResParams& P, const Ctx& c, Stage
 }
 
 // ---- P6b: V = -W_S T, in place: rounds of whole rows, highest rows first (row I is read by rows >= I only) ---
+template <class R1>
 static __device__ __noinline__ void ph_v(const ResParams& P, const Ctx& c) {
   const Lane L = make_lane();
   const int w = L.w;
   const int ab = c.ab, bb = c.bb;
+  const typename R1::T r1 = R1::get(c);
   const int ng = (ab + 3) >> 2;
   const int rows_round = max(1, (4 * RNW) / ng);
   for (int rhi = bb; rhi > 0; rhi -= rows_round) {
@@ -754,10 +852,10 @@ static __device__ __noinline__ void ph_v(const ResParams& P, const Ctx& c) {
       if (t < ntask) {
         const int row = rhi - 1 - t / ng, c0 = (t % ng) * 4;     // longest rows first
         const int nj = min(4, ab - c0);
-        const double* pb[4];
+        typename R1::T pb[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pb[j] = c.R1 + (c0 + min(j, nj - 1)) * RBLK;
-        mk<false, true>(acc[i], c.R2 + rtri(row) * RBLK, RBLK, pb, ab * RBLK, 0, row + 1, nj, L);
+        for (int j = 0; j < 4; ++j) pb[j] = r1 + (c0 + min(j, nj - 1)) * RBLK;
+        mk<false, true>(acc[i], c.oR2 + rtri(row) * RBLK, RBLK, pb, ab * RBLK, 0, row + 1, nj, L);
       }
     }
     __syncthreads();
@@ -768,7 +866,7 @@ static __device__ __noinline__ void ph_v(const ResParams& P, const Ctx& c) {
         const int row = rhi - 1 - t / ng, c0 = (t % ng) * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (c0 + j < ab) stn(c.R1 + (row * ab + c0 + j) * RBLK, L, neg2(acc[i][j]));
+          if (c0 + j < ab) stn(r1 + (row * ab + c0 + j) * RBLK, L, neg2(acc[i][j]));
       }
     }
     __syncthreads();
@@ -776,29 +874,32 @@ static __device__ __noinline__ void ph_v(const ResParams& P, const Ctx& c) {
 }
 
 // ---- P7: alpha_i = alpha_i(block) + V^T Z_j  (tasks (row of i, 4 output blocks); Z_j rows staged in F) --------
+template <class R1>
 static __device__ __noinline__ void ph_alpha_i(const ResParams& P, const Ctx& c, Stage& stage) {
   const Lane L = make_lane();
   const int w = L.w;
   const int ab = c.ab, bb = c.bb, nyb = c.nyb;
+  const typename R1::T r1 = R1::get(c);
+  const int oF = c.oF;
   auto rl = [&](int) { return bb; };
   auto rp = [&](int r) { return r * bb; };
-  staged_rows(stage, c.F, c.nF, c.Zy, nyb, rl, rp, true, [&](int y0, int y1, const double* base) {
-    const int ngy = (y1 - y0 + 3) >> 2;
+  staged_rows(stage, g_smem + oF, c.nF, c.Zy, nyb, rl, rp, true, [&](int y0, int y1, const double*) {
+    const int ngy = (y1 - y0 + 1) >> 1;
     const int ntask = ab * ngy;
     for (int t = w; t < ntask; t += RNW) {
-      const int row = t / ngy, yl0 = (t - row * ngy) * 4;
-      const int nj = min(4, y1 - y0 - yl0);
+      const int row = t / ngy, yl0 = (t - row * ngy) * 2;
+      const int nj = min(2, y1 - y0 - yl0);
       double2 acc[4];
+      zero4(acc);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        acc[j] = (j < nj) ? ldn(c.pexp + EXP_AROW + ((long long)row * RNYB + y0 + yl0 + j) * RBLK, L)
-                          : make_double2(0.0, 0.0);
-      const double* pb[4];
+      for (int j = 0; j < 2; ++j)
+        if (j < nj) acc[j] = ldn(c.pexp + EXP_AROW + ((long long)row * RNYB + y0 + yl0 + j) * RBLK, L);
+      int pb[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pb[j] = base + (yl0 + min(j, nj - 1)) * bb * RBLK;
-      mk<true, true>(acc, c.R1 + row * RBLK, ab * RBLK, pb, RBLK, 0, bb, nj, L);
+      for (int j = 0; j < 4; ++j) pb[j] = oF + (yl0 + min(j, nj - 1)) * bb * RBLK;
+      mk<true, true>(acc, r1 + row * RBLK, ab * RBLK, pb, RBLK, 0, bb, nj, L);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 2; ++j)
         if (j < nj) stn(c.Arow + ((long long)row * RNYB + y0 + yl0 + j) * RBLK, L, acc[j]);
     }
   });
@@ -806,95 +907,108 @@ static __device__ __noinline__ void ph_alpha_i(const ResParams& P, const Ctx& c,
 
 // ---- P8: G = alpha alpha^T - dy K^-1, contracted with dK in registers (gprf.py:547-584) ------------------
 // Column pieces: alpha rows [c0, c1) staged in F (B operands).  Tasks = (block row r, up to GCOLS
-// columns of the piece) taken from a shared counter, biggest rows first; alpha(r) comes from L2.
-template <int DFN, int WFN>
+// columns of the piece, never straddling the i / j boundary) taken from a shared counter, biggest rows
+// first; alpha(r), the saved covariance values and K_ii^-1 come from L2 and are requested before the
+// K^-1 products so that their latency hides behind them.
+template <int DFN, int WFN, class R1>
 static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, Stage& stage) {
   const Lane L = make_lane();
   const int tid = threadIdx.x;
   const int ab = c.ab, bb = c.bb, nr = c.nr, nyb = c.nyb;
+  const typename R1::T r1 = R1::get(c);
+  const int R2 = c.oR2, oF = c.oF;
   const double ndy = -(double)c.dy;
   const CovParams& cp = P.cp;
-  int* TT = reinterpret_cast<int*>(c.WB);          // task table of the piece: r | c_lo << 8 | c_hi << 16
+  const int* IDX = S_IDX;
+  const double* XS = g_smem + c.oXS;
+  int* TT = reinterpret_cast<int*>(g_smem);        // task table of the piece (in WB)
+  int* rowcnt = S_ROWCNT;
+  if (tid < nr) rowcnt[tid] = 0;
   const int crow = max(GCOLS, (c.nF / RNYB) & ~(GCOLS - 1));   // alpha rows per piece (a multiple of GCOLS)
   for (int c0 = 0; c0 < nr; c0 += crow) {
     const int c1 = min(nr, c0 + crow);
+    __syncthreads();
+    rtrace(P, c, 19);
     if (tid == 0) {
-      tma_issue(stage, c.F, c.Arow + (long long)c0 * RNYB * RBLK, (c1 - c0) * RNYB);
+      tma_issue(stage, g_smem + oF, c.Arow + (long long)c0 * RNYB * RBLK, (c1 - c0) * RNYB);
       int nt = 0;
       for (int r = nr - 1; r >= c0; --r) {
         const int ce = min(c1, r + 1);
-        for (int cl = c0; cl < ce; cl += GCOLS) TT[nt++] = r | (cl << 8) | (min(ce, cl + GCOLS) << 16);
+        int gi = rowcnt[r];
+        for (int part = 0; part < 2; ++part) {       // columns of the i part, then of the j part
+          const int lo = part ? max(c0, ab) : c0, hi = part ? ce : min(ce, ab);
+          for (int cl = lo; cl < hi; cl += GCOLS, ++gi)
+            TT[nt++] = r | (cl << 6) | (min(hi, cl + GCOLS) << 12) | (gi << 18);
+        }
+        rowcnt[r] = gi;
       }
-      *c.s_ntask = nt;
-      *c.s_task = 0;
+      *S_NTASK = nt;
+      *S_TASK = 0;
     }
     __syncthreads();
+    rtrace(P, c, 20);
     tma_wait(stage);
-    const int ntask = *c.s_ntask;
+    rtrace(P, c, 21);
+    const int ntask = *S_NTASK;
     while (true) {
       int t = 0;
-      if (L.lane == 0) t = atomicAdd(c.s_task, 1);
+      if (L.lane == 0) t = atomicAdd(S_TASK, 1);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= ntask) break;
       const int code = TT[t];
-      const int r = code & 0xff, cl = (code >> 8) & 0xff, ch = (code >> 16) & 0xff;
+      const int r = code & 63, cl = (code >> 6) & 63, ch = (code >> 12) & 63, gi = code >> 18;
       const int nj = ch - cl;
       const bool irow = r < ab;
+      const bool icol = cl < ab;
       const int wi = irow ? r : r - ab;            // row inside its part
-      // ---- K^-1 blocks (r, cl .. ch-1)
-      double2 acc[4];
-      zero4(acc);
-      {
-        // a task's columns lie in one part unless it straddles ab: split there
-        int j0 = 0;
-        while (j0 < nj) {
-          const int cc0 = cl + j0;
-          const bool icol = cc0 < ab;
-          const int jn = icol ? min(nj, ab - cl) : nj;         // end (exclusive) of this part's columns
-          const int m = jn - j0;
-          double2 part[4];
-          zero4(part);
-          const double* pb[4];
-          if (irow) {                                // (i row, i columns): V^T V   (+ K_ii^-1 below)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pb[j] = c.R1 + (cc0 + min(j, m - 1)) * RBLK;
-            mk<true, true>(part, c.R1 + wi * RBLK, ab * RBLK, pb, ab * RBLK, 0, bb, m, L);
-          } else if (icol) {                         // (j row, i columns): W_S^T V
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pb[j] = c.R1 + (cc0 + min(j, m - 1)) * RBLK;
-            for (int k = wi; k < bb; ++k) {
-              const double2 av = ldt(c.R2 + (rtri(k) + wi) * RBLK, L);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j < m) mma2(part[j], av, ldt(pb[j] + k * ab * RBLK, L));
-            }
-          } else {                                   // (j row, j columns): W_S^T W_S
-            for (int k = wi; k < bb; ++k) {
-              const double* rowk = c.R2 + rtri(k) * RBLK;
-              const double2 av = ldt(rowk + wi * RBLK, L);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j < m) mma2(part[j], av, ldt(rowk + (cc0 - ab + j) * RBLK, L));
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < m) {
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                if (jj == j0 + j) acc[jj] = part[j];
-            }
-          j0 = jn;
-        }
-      }
-      // alpha(r) fragments from L2, alpha(c) from the staged piece
-      double2 af[RNYB];
+      // requests to L2 first
+      double2 af[RNYB], kv[4], ki[4];
 #pragma unroll
       for (int y = 0; y < RNYB; ++y)
         af[y] = (y < nyb) ? ldn(c.Arow + ((long long)r * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cc = cl + min(j, nj - 1);
+        ki[j] = make_double2(0.0, 0.0);
+        if (irow) {
+          ki[j] = ldn(c.pexp + EXP_KINV + (long long)(rtri(wi) + cc) * RBLK, L);
+          kv[j] = ldn(c.pexp + EXP_KSAVE + (long long)(rtri(wi) + cc) * RBLK, L);
+        } else if (icol) {
+          kv[j] = ldn(c.Kji + (wi * ab + cc) * RBLK, L);
+        } else {
+          kv[j] = ldn(c.Kjj + (rtri(wi) + cc - ab) * RBLK, L);
+        }
+      }
+      // ---- K^-1 blocks (r, cl .. ch-1)
+      double2 acc[4];
+      zero4(acc);
+      if (irow) {                                  // (i row, i columns): V^T V   (+ K_ii^-1)
+        typename R1::T pb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb[j] = r1 + (cl + min(j, nj - 1)) * RBLK;
+        mk<true, true>(acc, r1 + wi * RBLK, ab * RBLK, pb, ab * RBLK, 0, bb, nj, L);
+      } else if (icol) {                           // (j row, i columns): W_S^T V
+        typename R1::T pb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb[j] = r1 + (cl + min(j, nj - 1)) * RBLK;
+        for (int k = wi; k < bb; ++k) {
+          const double2 av = ldt(R2 + (rtri(k) + wi) * RBLK, L);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nj) mma2(acc[j], av, ldt(pb[j] + k * ab * RBLK, L));
+        }
+      } else {                                     // (j row, j columns): W_S^T W_S
+        for (int k = wi; k < bb; ++k) {
+          const int rowk = R2 + rtri(k) * RBLK;
+          const double2 av = ldt(rowk + wi * RBLK, L);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nj) mma2(acc[j], av, ldt(rowk + (cl - ab + j) * RBLK, L));
+        }
+      }
       const int tr = r * 8 + L.g;
-      const bool rv = c.IDX[tr] >= 0;
-      const double* xr = c.XS + tr * XD;
+      const bool rv = IDX[tr] >= 0;
+      const double* xr = XS + tr * XD;
       double rs[3] = {0.0, 0.0, 0.0};
       double th[MAX_NCOV];
 #pragma unroll
@@ -903,22 +1017,12 @@ static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, St
       for (int j = 0; j < 4; ++j) {
         if (j >= nj) break;
         const int cc = cl + j;
-        double2 g = acc[j], kv;
-        if (irow) {
-          const double2 ki = ldn(c.pexp + EXP_KINV + (long long)(rtri(wi) + cc) * RBLK, L);
-          g.x += ki.x;
-          g.y += ki.y;
-          kv = ldn(c.pexp + EXP_KSAVE + (long long)(rtri(wi) + cc) * RBLK, L);
-        } else if (cc < ab) {
-          kv = ldn(c.Kji + (wi * ab + cc) * RBLK, L);
-        } else {
-          kv = ldn(c.Kjj + (rtri(wi) + cc - ab) * RBLK, L);
-          if (c.is_export) stn(c.oexp + EXP_KINV + (long long)(rtri(wi) + cc - ab) * RBLK, L, g);
-        }
+        double2 g = make_double2(acc[j].x + ki[j].x, acc[j].y + ki[j].y);
+        if (!irow && !icol && c.is_export) stn(c.oexp + EXP_KINV + (long long)(rtri(wi) + cc - ab) * RBLK, L, g);
         g.x *= ndy;
         g.y *= ndy;
         double2 g2 = make_double2(0.0, 0.0);
-        const double* arow = c.F + (cc - c0) * RNYB * RBLK;
+        const int arow = oF + (cc - c0) * RNYB * RBLK;
 #pragma unroll
         for (int y = 0; y < RNYB; ++y)
           if (y < nyb) mma2((y & 1) ? g2 : g, af[y], ldn(arow + y * RBLK, L));
@@ -930,15 +1034,15 @@ static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, St
         for (int e = 0; e < 2; ++e) {
           const int tc = cc * 8 + 2 * L.q + e;
           const double Gv = e == 0 ? g.x : g.y;
-          const bool cv = rv && c.IDX[tc] >= 0;
+          const bool cv = rv && IDX[tc] >= 0;
           if (cv && tc == tr) {
             th[0] += 0.5 * Gv;
             th[1] += 0.5 * Gv * cp.s2;
           }
           const bool off = cv && tc < tr;
-          double k = e == 0 ? kv.x : kv.y;
+          double k = e == 0 ? kv[j].x : kv[j].y;
           double gp[MAX_DX], gq[MAX_DX], gl[MAX_NLS];
-          cov_grad<DFN, WFN, true>(xr, c.XS + tc * XD, cp, k, gp, gq, gl);
+          cov_grad<DFN, WFN, true>(xr, XS + tc * XD, cp, k, gp, gq, gl);
           const double Gm = off ? Gv : 0.0;
           th[1] += off ? Gm * k : 0.0;
 #pragma unroll
@@ -960,7 +1064,7 @@ static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, St
           }
       }
       // the task's row sums and theta partials
-      double* tp = c.taskp + ((long long)r * MAXG + (cl / GCOLS)) * TASKP;
+      double* tp = c.taskp + ((long long)r * MAXG + gi) * TASKP;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         double v = rs[d];
@@ -976,8 +1080,9 @@ static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, St
         if (L.lane == 0) tp[24 + tt] = v;
       }
     }
-    __syncthreads();
+    rtrace(P, c, 22);
   }
+  __syncthreads();
 }
 
 // ---- finalize: row sums + column sums in a fixed order; theta ------------------------------------------------
@@ -985,10 +1090,11 @@ static __device__ __noinline__ void ph_finalize(const ResParams& P, const Ctx& c
   const Lane L = make_lane();
   const int tid = threadIdx.x, w = L.w;
   const int nr = c.nr;
+  const int* rowcnt = S_ROWCNT;
   for (int t = tid; t < nr * 8; t += RNT) {
     const int rb = t >> 3, g0 = t & 7;
     double v[3] = {0.0, 0.0, 0.0};
-    for (int gi = 0; gi * GCOLS <= rb; ++gi) {
+    for (int gi = 0; gi < rowcnt[rb]; ++gi) {
       const double* tp = c.taskp + ((long long)rb * MAXG + gi) * TASKP + g0 * 3;
       v[0] += tp[0];
       v[1] += tp[1];
@@ -1010,7 +1116,7 @@ static __device__ __noinline__ void ph_finalize(const ResParams& P, const Ctx& c
     double v = 0.0;
     for (int e = L.lane; e < nr * MAXG; e += 32) {
       const int rb = e / MAXG, gi = e - rb * MAXG;
-      if (gi * GCOLS <= rb) v += c.taskp[(long long)e * TASKP + 24 + w];
+      if (gi < rowcnt[rb]) v += c.taskp[(long long)e * TASKP + 24 + w];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1021,23 +1127,26 @@ static __device__ __noinline__ void ph_finalize(const ResParams& P, const Ctx& c
 }
 
 // ---- one unit ---------------------------------------------------------------------------------------------------
-template <int DFN, int WFN>
+template <int DFN, int WFN, class R1>
 __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage& stage) {
   const int tid = threadIdx.x;
   rtrace(P, c, 1);
-  ph_gather_lji<DFN, WFN>(P, c, stage);
+  // W_i on its way into [R2 | F] (both still unused; res_class guarantees that all of it fits)
+  if (c.pair && tid == 0) tma_issue(stage, g_smem + c.oR2, c.pexp + EXP_W, rtri(c.ab));
+  ph_gather<DFN>(P, c);
+  if (c.pair) ph_lji<DFN, WFN, R1>(P, c, stage);
   dbg_dump(P, c, 1);
   rtrace(P, c, 2);
-  ph_schur<DFN, WFN>(P, c);
+  ph_schur<DFN, WFN, R1>(P, c);
   dbg_dump(P, c, 2);
   rtrace(P, c, 3);
   // Z_i (all of it, or its first piece) travels into F while S is factored
-  const int nyc = c.pair ? max(1, min(c.nyb, min(c.nF / c.ab, R_WB_BLOCKS / c.bb))) : max(1, min(c.nyb, R_WB_BLOCKS / c.bb));
-  if (c.pair && tid == 0) tma_issue(stage, c.F, c.pexp + EXP_ZY, min(nyc, c.nyb) * c.ab);
+  const int nyc = max(1, min(c.nyb, c.nF / max(c.ab, c.bb)));
+  if (c.pair && tid == 0) tma_issue(stage, g_smem + c.oF, c.pexp + EXP_ZY, min(nyc, c.nyb) * c.ab);
   ph_chol_inv(P, c);
   dbg_dump(P, c, 4);
   rtrace(P, c, 5);
-  ph_ypart(P, c, stage, nyc);
+  ph_ypart<R1>(P, c, stage, nyc);
   rtrace(P, c, 6);
   if (!c.want_grad) {
     __syncthreads();
@@ -1053,22 +1162,22 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
         nb += r1 + 1;
         ++r1;
       }
-      tma_issue(stage, c.F, c.pexp + EXP_W, nb);
+      tma_issue(stage, g_smem + c.oF, c.pexp + EXP_W, nb);
     }
-    ph_t(P, c, stage);
+    ph_t<R1>(P, c, stage);
     // own Z_j (all of it, or its first piece) into F for alpha_i, behind the V product
-    if (tid == 0) tma_issue(stage, c.F, c.Zy, max(1, min(c.nyb, c.nF / c.bb)) * c.bb);
+    if (tid == 0) tma_issue(stage, g_smem + c.oF, c.Zy, max(1, min(c.nyb, c.nF / c.bb)) * c.bb);
     dbg_dump(P, c, 6);
     rtrace(P, c, 7);
-    ph_v(P, c);
+    ph_v<R1>(P, c);
     dbg_dump(P, c, 7);
     rtrace(P, c, 8);
-    ph_alpha_i(P, c, stage);
+    ph_alpha_i<R1>(P, c, stage);
     asm volatile("fence.proxy.async;\n" ::: "memory");   // alpha_i rows
   }
   __syncthreads();
   rtrace(P, c, 9);
-  ph_grad<DFN, WFN>(P, c, stage);
+  ph_grad<DFN, WFN, R1>(P, c, stage);
   rtrace(P, c, 10);
   ph_finalize(P, c);
   rtrace(P, c, 11);
@@ -1077,8 +1186,7 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
 // grid: persistent CTAs (<= one per SM), RNT threads, R_SMEM_BYTES dynamic shared memory.
 template <int DFN, int WFN>
 __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
-  extern __shared__ __align__(128) double smem[];
-  double* MISC = smem + R_WB_BLOCKS * RBLK;
+  double* MISC = g_smem + OFF_MISC;
   Stage stage;
   stage.bar = reinterpret_cast<uint64_t*>(MISC);
   stage.par = 0;
@@ -1089,7 +1197,7 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
     mbar_init(stage.bar, 1);
     fence_mbar_init();
     *Ps = Pk;
-    *(reinterpret_cast<int*>(MISC + 5)) = 0;       // trace cursor
+    *S_TCUR = 0;
   }
   __syncthreads();
   const ResParams& P = *Ps;
@@ -1139,26 +1247,19 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
       if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)uid * MAX_NCOV + threadIdx.x] = 0.0;
       continue;
     }
+    const bool r1g = cls == 1;
     if (threadIdx.x == 0) {
       Ctx& c = *ctx;
-      const bool r1g = cls == 1;
       c.uid = uid; c.bi = bi; c.bj = bj; c.a = a; c.b = b; c.ab = ab; c.bb = bb; c.nr = ab + bb;
       c.nyb = P.nyb; c.pair = ab > 0; c.is_export = bi < 0; c.want_grad = P.want_grad; c.dx = P.dx; c.dy = P.dy;
+      c.r1g = r1g;
       c.ia = ia; c.ja = ja;
-      c.WB = smem;
-      c.XS = MISC + R_MISC_DOUBLES;
-      c.R1 = r1g ? scratch + SCR_R1 : c.XS + c.nr * 8 * XD;
-      c.R2 = c.XS + c.nr * 8 * XD + (r1g ? 0 : bb * ab * RBLK);
-      c.F = c.R2 + rtri(bb) * RBLK;
+      c.oXS = OFF_XS;
+      c.oR1 = OFF_XS + c.nr * 8 * XD;
+      c.oR2 = c.oR1 + (r1g ? 0 : bb * ab * RBLK);
+      c.oF = c.oR2 + rtri(bb) * RBLK;
       c.nF = res_free_blocks(ab, bb, r1g);
-      c.capW1 = rtri(bb) + c.nF;
-      c.IDX = reinterpret_cast<int*>(MISC + MISC_IDX);
-      c.s_fail = reinterpret_cast<int*>(MISC + 4) + 1;
-      c.s_tcur = reinterpret_cast<int*>(MISC + 5);
-      c.s_task = reinterpret_cast<int*>(MISC + 5) + 1;
-      c.s_ntask = reinterpret_cast<int*>(MISC + 6);
-      c.s_q = MISC + 8;
-      c.s_ld = MISC + 24;
+      c.R1g = scratch + SCR_R1;
       c.pexp = c.pair ? P.exports + (long long)bi * EXP_STRIDE : nullptr;
       c.oexp = c.is_export ? P.exports + (long long)bj * EXP_STRIDE : nullptr;
       c.Zy = c.is_export ? c.oexp + EXP_ZY : scratch + SCR_ZY;
@@ -1170,7 +1271,8 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
       c.gx = P.gx_u + (long long)uid * GX_STRIDE;
     }
     __syncthreads();
-    run_unit<DFN, WFN>(P, *ctx, stage);
+    if (r1g) run_unit<DFN, WFN, R1Glob>(P, *ctx, stage);
+    else run_unit<DFN, WFN, R1Smem>(P, *ctx, stage);
   }
 }
 

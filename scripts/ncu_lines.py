@@ -49,7 +49,7 @@ def line_table(obj, kern):
 
 
 MAIN = "resident.cuh"
-MAIN_FROM = 241          # first line of run_unit: frames above it are helpers
+MAIN_FROM = 330          # first line of run_unit: frames above it are helpers
 
 
 def main():
