@@ -50,7 +50,7 @@ constexpr int RNW = 16;                   // warps per CTA
 constexpr int RNT = RNW * 32;
 constexpr int RBLK = 64;                  // doubles per 8x8 block
 constexpr int R_WB_BLOCKS = 60;           // fixed work buffer (30 KB): diagonal inverses, right-hand sides, task table
-constexpr int R_MISC_DOUBLES = 400;
+constexpr int R_MISC_DOUBLES = 448;      // 7 blocks
 constexpr int R_SMEM_BYTES = 232448;      // 227 KB, the sm_100 per-CTA maximum
 // doubles left for XS (coordinate records), R1, R2 and the staging area F behind them
 constexpr int R_CAP_DOUBLES = R_SMEM_BYTES / 8 - R_WB_BLOCKS * RBLK - R_MISC_DOUBLES;
@@ -62,16 +62,16 @@ constexpr long long EXP_W = 0;                                       // lower pa
 constexpr long long EXP_KINV = (long long)RTRI * RBLK;               // lower packed
 constexpr long long EXP_KSAVE = 2LL * RTRI * RBLK;                   // lower packed: covariance values
 constexpr long long EXP_ZY = 3LL * RTRI * RBLK;                      // yb * nb + k   (compact)
-constexpr long long EXP_AROW = EXP_ZY + (long long)RNYB * EMAXB * RBLK;     // k * RNYB + yb
+constexpr long long EXP_AROW = EXP_ZY + (long long)RNYB * EMAXB * RBLK;     // k * nyb + yb  (compact)
 constexpr long long EXP_SCAL = EXP_AROW + (long long)EMAXB * RNYB * RBLK;   // logdet, |Z|^2
 constexpr long long EXP_STRIDE = EXP_SCAL + 16;
 // per-CTA scratch (doubles)
 constexpr long long SCR_ZY = 0;                                              // yb * bb + k
 constexpr long long SCR_AROW = (long long)RNYB * EMAXB * RBLK;              // 2*EMAXB rows x RNYB
 constexpr long long SCR_COLP = SCR_AROW + 2LL * EMAXB * RNYB * RBLK;
-constexpr int COLP = 24;                                                     // per G block: column sums 8 x 3
+constexpr int COLP = 32;                                                     // per G block: 8 columns x 4 raw sums
 constexpr long long SCR_TASKP = SCR_COLP + (long long)(2 * EMAXB) * (2 * EMAXB + 1) / 2 * COLP;
-constexpr int TASKP = 32;                                                    // per task: row sums 8 x 3, theta 5
+constexpr int TASKP = 72;                                                    // per task: 8 rows x 8 raw sums, 2 scalars
 constexpr int GCOLS = 4;                                                     // G blocks per task
 constexpr int MAXG = 24;                                                     // tasks per block row, at most
 constexpr long long SCR_KJI = SCR_TASKP + (long long)(2 * EMAXB) * MAXG * TASKP;   // saved K_ji: row * ab + c
@@ -83,10 +83,12 @@ constexpr int GX_STRIDE = 2 * EMAXB * 8 * 3;           // per-unit gradX rows (p
 enum { ST_OVERFLOW = 1, ST_NOTPD = 2 };
 
 __host__ __device__ __forceinline__ int rtri(int i) { return i * (i + 1) / 2; }
-// free staging blocks behind XS / R1 / R2 (negative: does not fit)
+// shared memory, in whole 8x8 blocks:  MISC | XS | R1 | R2 | F | WB
+// XS: one block per 8 points (48 doubles of coordinate records; the gradient phase rebuilds it as 8 x 8 feature blocks)
+__host__ __device__ __forceinline__ int res_xs_blocks(int ab, int bb) { return ab + bb; }
+// free staging blocks F between R2 and WB (negative: does not fit)
 __host__ __device__ __forceinline__ int res_free_blocks(int ab, int bb, bool r1_global) {
-  const int used = (ab + bb) * 8 * XD + ((r1_global ? 0 : bb * ab) + rtri(bb)) * RBLK;
-  return (R_CAP_DOUBLES - used) / RBLK - (R_CAP_DOUBLES < used ? 1 : 0);
+  return R_CAP_DOUBLES / RBLK - res_xs_blocks(ab, bb) - (r1_global ? 0 : bb * ab) - rtri(bb);
 }
 // 0: everything in shared memory; 1: R1 (the bb x ab coupling matrix) in this CTA's L2-resident
 // scratch, the rest in shared memory; 2: does not fit (tile pipeline).
@@ -262,14 +264,19 @@ struct Ctx {
   const double* pexp;
   double *oexp, *Zy, *Arow, *Kjj, *Kji, *colp, *taskp, *gx;
 };
-constexpr int OFF_MISC = R_WB_BLOCKS * RBLK;
+constexpr int OFF_MISC = 0;
 constexpr int OFF_XS = OFF_MISC + R_MISC_DOUBLES;
+constexpr int OFF_WB = R_SMEM_BYTES / 8 - R_WB_BLOCKS * RBLK;     // work buffer at the end: F | WB is contiguous
+constexpr int WB_TAIL_BLOCKS = 20;                                 // of WB, kept by the gradient phase:
+constexpr int OFF_TT = OFF_WB + (R_WB_BLOCKS - WB_TAIL_BLOCKS) * RBLK;   //   task table (4 blocks = 512 ints)
+constexpr int OFF_TS = OFF_TT + 4 * RBLK;                                //   one transpose block per warp
+static_assert(R_CAP_DOUBLES % RBLK == 0, "region sizes are whole blocks");
 constexpr int MISC_Q = 8;             // [RNW] partial |Z|^2
 constexpr int MISC_LD = 24;           // [RNW] partial log det
 constexpr int MISC_CTX = 40;          // doubles
 constexpr int MISC_IDX = 120;         // [2 * EMAXB * 8] ints: global point index or -1
 constexpr int MISC_PARAMS = 288;
-constexpr int MISC_ROWCNT = 360;      // [2 * EMAXB] ints: gradient tasks per block row
+constexpr int MISC_ROWCNT = 400;      // [2 * EMAXB] ints: gradient tasks per block row
 static_assert(sizeof(Ctx) <= (MISC_IDX - MISC_CTX) * 8, "Ctx does not fit");
 static_assert(sizeof(ResParams) <= (MISC_ROWCNT - MISC_PARAMS) * 8, "ResParams copy does not fit");
 static_assert(MISC_ROWCNT + EMAXB <= R_MISC_DOUBLES, "MISC too small");
@@ -390,6 +397,13 @@ static __device__ __noinline__ void ph_gather(const ResParams& P, const Ctx& c) 
   int* IDX = S_IDX;
   double* XS = g_smem + c.oXS;
   if (tid == 0) *S_FAIL = 0;
+  // euclidean distances depend on differences only: coordinates are taken relative to the unit's first
+  // point, which keeps the products x_p x_q the gradient phase expands (x_p - x_q) into small
+  double ref[MAX_DX] = {0.0, 0.0, 0.0};
+  if (DFN == DFN_EUCLIDEAN) {
+    const long long i0 = P.perm[c.a > 0 ? c.ia : c.ja];
+    for (int d = 0; d < c.dx; ++d) ref[d] = P.X[i0 * c.dx + d];
+  }
   for (int t = tid; t < c.nr * 8; t += RNT) {
     long long idx = -1;
     if (t < c.ab * 8) {
@@ -400,7 +414,7 @@ static __device__ __noinline__ void ph_gather(const ResParams& P, const Ctx& c) 
     IDX[t] = (int)idx;
     double rec[XD];
 #pragma unroll
-    for (int d = 0; d < MAX_DX + 1; ++d) rec[d] = (idx >= 0 && d < c.dx) ? P.X[idx * c.dx + d] : 0.0;
+    for (int d = 0; d < MAX_DX + 1; ++d) rec[d] = (idx >= 0 && d < c.dx) ? P.X[idx * c.dx + d] - (d < MAX_DX ? ref[d] : 0.0) : 0.0;
     point_terms(DFN, rec);
 #pragma unroll
     for (int d = 0; d < XD; ++d) XS[t * XD + d] = rec[d];
@@ -504,7 +518,7 @@ static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c
   const int tid = threadIdx.x, w = L.w;
   const int bb = c.bb;
   const int R2 = c.oR2;
-  const int WD = 0;                                // diagonal-block inverses, in WB
+  const int WD = OFF_WB;                           // diagonal-block inverses, in WB
   for (int J = 0; J < bb; ++J) {
     if (w == 0) {
       double av[8], wv[8];
@@ -727,8 +741,8 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
           mma2(a0, av, ldt(p0 + k * RBLK, L));
           mma2(a1, av, ldt(p1 + k * RBLK, L));
         }
-        stn(c.Arow + ((long long)(ab + row) * RNYB + y0 + yl0) * RBLK, L, a0);
-        if (nj > 1) stn(c.Arow + ((long long)(ab + row) * RNYB + y0 + yl0 + 1) * RBLK, L, a1);
+        stn(c.Arow + ((long long)(ab + row) * nyb + y0 + yl0) * RBLK, L, a0);
+        if (nj > 1) stn(c.Arow + ((long long)(ab + row) * nyb + y0 + yl0 + 1) * RBLK, L, a1);
       }
     }
     __syncthreads();
@@ -893,23 +907,34 @@ static __device__ __noinline__ void ph_alpha_i(const ResParams& P, const Ctx& c,
       zero4(acc);
 #pragma unroll
       for (int j = 0; j < 2; ++j)
-        if (j < nj) acc[j] = ldn(c.pexp + EXP_AROW + ((long long)row * RNYB + y0 + yl0 + j) * RBLK, L);
+        if (j < nj) acc[j] = ldn(c.pexp + EXP_AROW + ((long long)row * nyb + y0 + yl0 + j) * RBLK, L);
       int pb[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) pb[j] = oF + (yl0 + min(j, nj - 1)) * bb * RBLK;
       mk<true, true>(acc, r1 + row * RBLK, ab * RBLK, pb, RBLK, 0, bb, nj, L);
 #pragma unroll
       for (int j = 0; j < 2; ++j)
-        if (j < nj) stn(c.Arow + ((long long)row * RNYB + y0 + yl0 + j) * RBLK, L, acc[j]);
+        if (j < nj) stn(c.Arow + ((long long)row * nyb + y0 + yl0 + j) * RBLK, L, acc[j]);
     }
   });
 }
 
 // ---- P8: G = alpha alpha^T - dy K^-1, contracted with dK in registers (gprf.py:547-584) ------------------
-// Column pieces: alpha rows [c0, c1) staged in F (B operands).  Tasks = (block row r, up to GCOLS
+// Column pieces: alpha rows [c0, c1) staged in F | WB (B operands).  Tasks = (block row r, up to GCOLS
 // columns of the piece, never straddling the i / j boundary) taken from a shared counter, biggest rows
 // first; alpha(r), the saved covariance values and K_ii^-1 come from L2 and are requested before the
 // K^-1 products so that their latency hides behind them.
+//
+// Contraction with dK.  Euclidean distances: with M = G o w (w = k for SE, k / (1 + sqrt3 r) for
+// Matern-3/2; strictly lower entries only) every sum over a block is linear in M,
+//     sum_q M_pq (x_p - x_q)_d   = x_pd (M 1)_p - (M X)_pd
+//     sum_q M_pq (x_p - x_q)_d^2 = x_pd^2 (M 1)_p - 2 x_pd (M X)_pd + (M X^2)_pd
+// so one DMMA pair per block, M (already in the A-fragment layout) times the feature block
+// FE = [x0 x1 x2 1 x0^2 x1^2 x2^2 0] of the column points, accumulates everything the ROW points need over
+// the task's columns, and a second pair, M^T (through a per-warp transpose block) times FE of the row
+// points, gives what the COLUMN points need - no shuffles, no per-entry derivative arithmetic.  The
+// lengthscale factors are applied by ph_finalize.  (Coordinates are centred, ph_gather.)
+// Great-circle distances (lld) keep the per-entry derivative evaluation.
 template <int DFN, int WFN, class R1>
 static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, Stage& stage) {
   const Lane L = make_lane();
@@ -921,29 +946,81 @@ static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, St
   const CovParams& cp = P.cp;
   const int* IDX = S_IDX;
   const double* XS = g_smem + c.oXS;
-  int* TT = reinterpret_cast<int*>(g_smem);        // task table of the piece (in WB)
+  const int FE = c.oXS;                            // euclidean: feature blocks take the place of XS
+  int* TT = reinterpret_cast<int*>(g_smem + OFF_TT);
+  const int TS = OFF_TS + L.w * RBLK;
   int* rowcnt = S_ROWCNT;
   if (tid < nr) rowcnt[tid] = 0;
-  const int crow = max(GCOLS, (c.nF / RNYB) & ~(GCOLS - 1));   // alpha rows per piece (a multiple of GCOLS)
+  if (DFN == DFN_EUCLIDEAN) {
+    // FE block of 8 points: element (point, feature), stored like every other block
+    double f[8];
+    const bool mine = tid < nr * 8;
+    if (mine) {
+      const double* x = XS + tid * XD;
+      f[0] = x[0]; f[1] = x[1]; f[2] = x[2]; f[3] = 1.0;
+      f[4] = x[0] * x[0]; f[5] = x[1] * x[1]; f[6] = x[2] * x[2]; f[7] = 0.0;
+    }
+    __syncthreads();
+    if (mine) {
+      double* blk = g_smem + FE + (tid >> 3) * RBLK;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) blk[sw_off(tid & 7, n)] = f[n];
+    }
+  }
+  const int cap = c.nF + R_WB_BLOCKS - WB_TAIL_BLOCKS;
+  const int crow = max(GCOLS, (cap / nyb) & ~(GCOLS - 1));     // alpha rows per piece (a multiple of GCOLS)
   for (int c0 = 0; c0 < nr; c0 += crow) {
     const int c1 = min(nr, c0 + crow);
     __syncthreads();
     rtrace(P, c, 19);
-    if (tid == 0) {
-      tma_issue(stage, g_smem + oF, c.Arow + (long long)c0 * RNYB * RBLK, (c1 - c0) * RNYB);
-      int nt = 0;
-      for (int r = nr - 1; r >= c0; --r) {
-        const int ce = min(c1, r + 1);
-        int gi = rowcnt[r];
-        for (int part = 0; part < 2; ++part) {       // columns of the i part, then of the j part
-          const int lo = part ? max(c0, ab) : c0, hi = part ? ce : min(ce, ab);
-          for (int cl = lo; cl < hi; cl += GCOLS, ++gi)
-            TT[nt++] = r | (cl << 6) | (min(hi, cl + GCOLS) << 12) | (gi << 18);
+    if (tid == 0) tma_issue(stage, g_smem + oF, c.Arow + (long long)c0 * nyb * RBLK, (c1 - c0) * nyb);
+    if (L.w == 0) {
+      // task table, rows descending: lanes count their rows' groups, prefix sum, then fill
+      int cnt[2], r_[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = nr - 1 - (L.lane + 32 * h);
+        r_[h] = r;
+        cnt[h] = 0;
+        if (r >= c0) {
+          const int ce = min(c1, r + 1);
+          const int ni = max(0, min(ce, ab) - c0), nj2 = max(0, ce - max(c0, ab));
+          cnt[h] = (ni + GCOLS - 1) / GCOLS + (nj2 + GCOLS - 1) / GCOLS;
         }
-        rowcnt[r] = gi;
       }
-      *S_NTASK = nt;
-      *S_TASK = 0;
+      int pre = cnt[0];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (L.lane >= o) pre += v;
+      }
+      const int tot0 = __shfl_sync(0xffffffffu, pre, 31);
+      int pre1 = cnt[1];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre1, o);
+        if (L.lane >= o) pre1 += v;
+      }
+      const int tot1 = __shfl_sync(0xffffffffu, pre1, 31);
+      int at[2] = {pre - cnt[0], tot0 + pre1 - cnt[1]};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = r_[h];
+        if (r >= c0 && cnt[h] > 0) {
+          const int ce = min(c1, r + 1);
+          int gi = rowcnt[r], nt = at[h];
+          for (int part = 0; part < 2; ++part) {     // columns of the i part, then of the j part
+            const int lo = part ? max(c0, ab) : c0, hi = part ? ce : min(ce, ab);
+            for (int cl = lo; cl < hi; cl += GCOLS, ++gi)
+              TT[nt++] = r | (cl << 6) | (min(hi, cl + GCOLS) << 12) | (gi << 18);
+          }
+          rowcnt[r] = gi;
+        }
+      }
+      if (L.lane == 0) {
+        *S_NTASK = tot0 + tot1;
+        *S_TASK = 0;
+      }
     }
     __syncthreads();
     rtrace(P, c, 20);
@@ -965,7 +1042,7 @@ static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, St
       double2 af[RNYB], kv[4], ki[4];
 #pragma unroll
       for (int y = 0; y < RNYB; ++y)
-        af[y] = (y < nyb) ? ldn(c.Arow + ((long long)r * RNYB + y) * RBLK, L) : make_double2(0.0, 0.0);
+        af[y] = (y < nyb) ? ldn(c.Arow + ((long long)r * nyb + y) * RBLK, L) : make_double2(0.0, 0.0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int cc = cl + min(j, nj - 1);
@@ -1008,76 +1085,130 @@ static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, St
       }
       const int tr = r * 8 + L.g;
       const bool rv = IDX[tr] >= 0;
-      const double* xr = XS + tr * XD;
-      double rs[3] = {0.0, 0.0, 0.0};
-      double th[MAX_NCOV];
+      double* tp = c.taskp + ((long long)r * MAXG + gi) * TASKP;
+      double s1 = 0.0, d0 = 0.0;                   // sum G k (strictly lower), sum G_pp / 2
+      if (DFN == DFN_EUCLIDEAN) {
+        double2 orow = make_double2(0.0, 0.0);
+        const double2 fr = ldt(FE + r * RBLK, L);  // features of the row points, as a [k][n] operand
+        double xr[3];
+        if (WFN != WFN_SE) {
 #pragma unroll
-      for (int tt = 0; tt < MAX_NCOV; ++tt) th[tt] = 0.0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j >= nj) break;
-        const int cc = cl + j;
-        double2 g = make_double2(acc[j].x + ki[j].x, acc[j].y + ki[j].y);
-        if (!irow && !icol && c.is_export) stn(c.oexp + EXP_KINV + (long long)(rtri(wi) + cc - ab) * RBLK, L, g);
-        g.x *= ndy;
-        g.y *= ndy;
-        double2 g2 = make_double2(0.0, 0.0);
-        const int arow = oF + (cc - c0) * RNYB * RBLK;
-#pragma unroll
-        for (int y = 0; y < RNYB; ++y)
-          if (y < nyb) mma2((y & 1) ? g2 : g, af[y], ldn(arow + y * RBLK, L));
-        g.x += g2.x;
-        g.y += g2.y;
-        // contraction of the G block with dk/dx, dk/dtheta (covariance values saved by P1 / P2 / the parent)
-        double cs[2][3];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int tc = cc * 8 + 2 * L.q + e;
-          const double Gv = e == 0 ? g.x : g.y;
-          const bool cv = rv && IDX[tc] >= 0;
-          if (cv && tc == tr) {
-            th[0] += 0.5 * Gv;
-            th[1] += 0.5 * Gv * cp.s2;
-          }
-          const bool off = cv && tc < tr;
-          double k = e == 0 ? kv[j].x : kv[j].y;
-          double gp[MAX_DX], gq[MAX_DX], gl[MAX_NLS];
-          cov_grad<DFN, WFN, true>(xr, XS + tc * XD, cp, k, gp, gq, gl);
-          const double Gm = off ? Gv : 0.0;
-          th[1] += off ? Gm * k : 0.0;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            rs[d] += off ? Gm * gp[d] : 0.0;
-            cs[e][d] = off ? Gm * gq[d] : 0.0;
-            th[2 + d] += off ? Gm * gl[d] : 0.0;
-          }
+          for (int d = 0; d < 3; ++d) xr[d] = g_smem[FE + r * RBLK + sw_off(L.g, d)];
         }
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
+        for (int j = 0; j < 4; ++j) {
+          if (j >= nj) break;
+          const int cc = cl + j;
+          double2 g = make_double2(acc[j].x + ki[j].x, acc[j].y + ki[j].y);
+          if (!irow && !icol && c.is_export) stn(c.oexp + EXP_KINV + (long long)(rtri(wi) + cc - ab) * RBLK, L, g);
+          g.x *= ndy;
+          g.y *= ndy;
+          double2 g2 = make_double2(0.0, 0.0);
+          const int arow = oF + (cc - c0) * nyb * RBLK;
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            double v = cs[e][d];
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (L.g == 0) c.colp[(long long)(rtri(r) + cc) * COLP + (2 * L.q + e) * 3 + d] = v;
+          for (int y = 0; y < RNYB; ++y)
+            if (y < nyb) mma2((y & 1) ? g2 : g, af[y], ldn(arow + y * RBLK, L));
+          g.x += g2.x;
+          g.y += g2.y;
+          const int tc = cc * 8 + 2 * L.q;
+          const bool o0 = rv && IDX[tc] >= 0 && tc < tr, o1 = rv && IDX[tc + 1] >= 0 && tc + 1 < tr;
+          if (rv && tc == tr) d0 += 0.5 * g.x;
+          if (rv && tc + 1 == tr) d0 += 0.5 * g.y;
+          double2 m = make_double2(o0 ? g.x * kv[j].x : 0.0, o1 ? g.y * kv[j].y : 0.0);
+          s1 += m.x + m.y;
+          if (WFN != WFN_SE) {                     // Matern-3/2: w'(r)/r = -3 k / (1 + sqrt3 r)
+            double r2a = 0.0, r2b = 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const double da = xr[d] - g_smem[FE + cc * RBLK + sw_off(2 * L.q, d)];
+              const double db = xr[d] - g_smem[FE + cc * RBLK + sw_off(2 * L.q + 1, d)];
+              r2a += da * da * cp.il2[d];
+              r2b += db * db * cp.il2[d];
+            }
+            m.x /= 1.0 + GPRF_SQRT3 * sqrt(r2a);
+            m.y /= 1.0 + GPRF_SQRT3 * sqrt(r2b);
           }
+          mma2(orow, m, ldt(FE + cc * RBLK, L));   // what the row points need, summed over the columns
+          __syncwarp();
+          stn(TS, L, m);
+          __syncwarp();
+          double2 ocol = make_double2(0.0, 0.0);
+          mma2(ocol, ldt(TS, L), fr);              // what the column points need: (column, feature 2q / 2q+1)
+          if (L.q < 2) *reinterpret_cast<double2*>(c.colp + (long long)(rtri(r) + cc) * COLP + L.g * 4 + 2 * L.q) = ocol;
+        }
+        *reinterpret_cast<double2*>(tp + L.g * 8 + 2 * L.q) = orow;
+      } else {
+        const double* xr = XS + tr * XD;
+        double rs[3] = {0.0, 0.0, 0.0}, thl[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j >= nj) break;
+          const int cc = cl + j;
+          double2 g = make_double2(acc[j].x + ki[j].x, acc[j].y + ki[j].y);
+          if (!irow && !icol && c.is_export) stn(c.oexp + EXP_KINV + (long long)(rtri(wi) + cc - ab) * RBLK, L, g);
+          g.x *= ndy;
+          g.y *= ndy;
+          double2 g2 = make_double2(0.0, 0.0);
+          const int arow = oF + (cc - c0) * nyb * RBLK;
+#pragma unroll
+          for (int y = 0; y < RNYB; ++y)
+            if (y < nyb) mma2((y & 1) ? g2 : g, af[y], ldn(arow + y * RBLK, L));
+          g.x += g2.x;
+          g.y += g2.y;
+          double cs[2][3];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int tc = cc * 8 + 2 * L.q + e;
+            const double Gv = e == 0 ? g.x : g.y;
+            const bool cv = rv && IDX[tc] >= 0;
+            if (cv && tc == tr) d0 += 0.5 * Gv;
+            const bool off = cv && tc < tr;
+            double k = e == 0 ? kv[j].x : kv[j].y;
+            double gp[MAX_DX], gq[MAX_DX], gl[MAX_NLS];
+            cov_grad<DFN, WFN, true>(xr, XS + tc * XD, cp, k, gp, gq, gl);
+            const double Gm = off ? Gv : 0.0;
+            s1 += off ? Gm * k : 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              rs[d] += off ? Gm * gp[d] : 0.0;
+              cs[e][d] = off ? Gm * gq[d] : 0.0;
+              thl[d] += off ? Gm * gl[d] : 0.0;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              double v = cs[e][d];
+              v += __shfl_xor_sync(0xffffffffu, v, 4);
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              if (L.g == 0) c.colp[(long long)(rtri(r) + cc) * COLP + (2 * L.q + e) * 4 + d] = v;
+            }
+        }
+        // row sums (8 x 3, at [g][d]) and the lengthscale partials (at [g][4 + d], summed over the quad)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          double v = rs[d], u = thl[d];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          u += __shfl_xor_sync(0xffffffffu, u, 1);
+          u += __shfl_xor_sync(0xffffffffu, u, 2);
+          if (L.q == 0) {
+            tp[L.g * 8 + d] = v;
+            tp[L.g * 8 + 4 + d] = u;
+          }
+        }
       }
-      // the task's row sums and theta partials
-      double* tp = c.taskp + ((long long)r * MAXG + gi) * TASKP;
+      // scalars of the task: fixed shuffle tree
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        double v = rs[d];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        if (L.q == 0) tp[L.g * 3 + d] = v;
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
       }
-#pragma unroll
-      for (int tt = 0; tt < MAX_NCOV; ++tt) {
-        double v = th[tt];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (L.lane == 0) tp[24 + tt] = v;
+      if (L.lane == 0) {
+        tp[64] = s1;
+        tp[65] = d0;
       }
     }
     rtrace(P, c, 22);
@@ -1085,43 +1216,78 @@ static __device__ __noinline__ void ph_grad(const ResParams& P, const Ctx& c, St
   __syncthreads();
 }
 
-// ---- finalize: row sums + column sums in a fixed order; theta ------------------------------------------------
+// ---- finalize: per-point sums over the task / block records in a fixed order; theta -------------------------
+template <int DFN, int WFN>
 static __device__ __noinline__ void ph_finalize(const ResParams& P, const Ctx& c) {
   const Lane L = make_lane();
   const int tid = threadIdx.x, w = L.w;
   const int nr = c.nr;
+  const CovParams& cp = P.cp;
   const int* rowcnt = S_ROWCNT;
+  const int FE = c.oXS;
+  double th[MAX_NCOV];
+#pragma unroll
+  for (int t = 0; t < MAX_NCOV; ++t) th[t] = 0.0;
+  const double coef = (WFN == WFN_SE) ? -2.0 : -3.0;         // w'(r)/r = coef * (k or k / (1 + sqrt3 r))
   for (int t = tid; t < nr * 8; t += RNT) {
     const int rb = t >> 3, g0 = t & 7;
-    double v[3] = {0.0, 0.0, 0.0};
+    double o[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
     for (int gi = 0; gi < rowcnt[rb]; ++gi) {
-      const double* tp = c.taskp + ((long long)rb * MAXG + gi) * TASKP + g0 * 3;
-      v[0] += tp[0];
-      v[1] += tp[1];
-      v[2] += tp[2];
+      const double* tp = c.taskp + ((long long)rb * MAXG + gi) * TASKP + g0 * 8;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) o[n] += tp[n];
     }
     for (int r2 = rb; r2 < nr; ++r2) {
-      const double* pc = c.colp + (long long)(rtri(r2) + rb) * COLP + g0 * 3;
-      v[0] += pc[0];
-      v[1] += pc[1];
-      v[2] += pc[2];
+      const double* pc = c.colp + (long long)(rtri(r2) + rb) * COLP + g0 * 4;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) cc[n] += pc[n];
     }
-    c.gx[t * 3] = v[0];
-    c.gx[t * 3 + 1] = v[1];
-    c.gx[t * 3 + 2] = v[2];
+    double gxv[3];
+    if (DFN == DFN_EUCLIDEAN) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double x = g_smem[FE + rb * RBLK + sw_off(g0, d)];
+        gxv[d] = coef * cp.il2[d] * ((x * o[3] - o[d]) + (x * cc[3] - cc[d]));
+        th[2 + d] += -coef * cp.il3[d] * (x * x * o[3] - 2.0 * x * o[d] + o[4 + d]);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        gxv[d] = o[d] + cc[d];
+        th[2 + d] += o[4 + d];
+      }
+    }
+    c.gx[t * 3] = gxv[0];
+    c.gx[t * 3 + 1] = gxv[1];
+    c.gx[t * 3 + 2] = gxv[2];
   }
-  // theta: one warp per parameter; lanes stride over the task records in a fixed order, then a
-  // fixed shuffle tree - the summation order does not depend on which warp ran which task
-  if (w < MAX_NCOV) {
-    double v = 0.0;
-    for (int e = L.lane; e < nr * MAXG; e += 32) {
-      const int rb = e / MAXG, gi = e - rb * MAXG;
-      if (gi < rowcnt[rb]) v += c.taskp[(long long)e * TASKP + 24 + w];
+  // scalars of the tasks: lanes stride over the records in a fixed order
+  for (int e = tid; e < nr * MAXG; e += RNT) {
+    const int rb = e / MAXG, gi = e - rb * MAXG;
+    if (gi < rowcnt[rb]) {
+      th[1] += c.taskp[(long long)e * TASKP + 64];
+      th[0] += c.taskp[(long long)e * TASKP + 65];
     }
+  }
+  // block reduction in a fixed order: shuffle tree, then the warps' partials in warp order
+  double* red = g_smem + OFF_TS;                   // RNW x MAX_NCOV
+#pragma unroll
+  for (int t = 0; t < MAX_NCOV; ++t) {
+    double v = th[t];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (w == 1) v /= P.cp.s2;
-    if (L.lane == 0) P.gth_u[(long long)c.uid * MAX_NCOV + w] = v;
+    if (L.lane == 0) red[w * MAX_NCOV + t] = v;
+  }
+  __syncthreads();
+  if (tid < MAX_NCOV) {
+    // theta = [nv, s2, l...]:  d/dnv = sum_p G_pp / 2;  d/ds2 = sum_p G_pp / 2 + sum_{q<p} G_pq k_pq / s2
+    double v = 0.0, dg = 0.0;
+    for (int i = 0; i < RNW; ++i) {
+      v += red[i * MAX_NCOV + tid];
+      dg += red[i * MAX_NCOV + 0];
+    }
+    if (tid == 1) v = v / cp.s2 + dg;
+    P.gth_u[(long long)c.uid * MAX_NCOV + tid] = v;
   }
   __syncthreads();
 }
@@ -1179,7 +1345,7 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
   rtrace(P, c, 9);
   ph_grad<DFN, WFN, R1>(P, c, stage);
   rtrace(P, c, 10);
-  ph_finalize(P, c);
+  ph_finalize<DFN, WFN>(P, c);
   rtrace(P, c, 11);
 }
 
@@ -1255,7 +1421,7 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
       c.r1g = r1g;
       c.ia = ia; c.ja = ja;
       c.oXS = OFF_XS;
-      c.oR1 = OFF_XS + c.nr * 8 * XD;
+      c.oR1 = OFF_XS + res_xs_blocks(ab, bb) * RBLK;
       c.oR2 = c.oR1 + (r1g ? 0 : bb * ab * RBLK);
       c.oF = c.oR2 + rtri(bb) * RBLK;
       c.nF = res_free_blocks(ab, bb, r1g);

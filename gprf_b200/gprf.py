@@ -445,6 +445,7 @@ class GPRF(object):
         self._check(self._lib.gprf_get_resident_debug(self._h, None, int(block), _lib.ptr(raw), -1, None))
         bb = (nb + 7) // 8
         BL, MAXB, NYB = lay["BLK"], lay["MAXB"], lay["NYB"]
+        nyb = (self._Yc.shape[1] + 7) // 8
 
         def tri_mat(off):
             M = np.zeros((bb * 8, bb * 8))
@@ -456,10 +457,10 @@ class GPRF(object):
         Z = np.zeros((bb * 8, NYB * 8))
         A = np.zeros((bb * 8, NYB * 8))
         for k in range(bb):
-            for y in range(NYB):
+            for y in range(nyb):
                 o = lay["EXP_ZY"] + (y * bb + k) * BL
                 Z[8 * k:8 * k + 8, 8 * y:8 * y + 8] = self._unswizzle(raw[o:o + BL])
-                o = lay["EXP_AROW"] + (k * NYB + y) * BL
+                o = lay["EXP_AROW"] + (k * nyb + y) * BL
                 A[8 * k:8 * k + 8, 8 * y:8 * y + 8] = self._unswizzle(raw[o:o + BL])
         return dict(W=tri_mat(lay["EXP_W"]), Kinv=tri_mat(lay["EXP_KINV"]), Z=Z, alpha=A,
                     logdet=raw[lay["EXP_SCAL"]], q=raw[lay["EXP_SCAL"] + 1])
