@@ -125,7 +125,8 @@ struct gprf_ctx {
   double* dResExports = nullptr;
   double* dResScratch = nullptr;
   double *dResLL = nullptr, *dResGth = nullptr, *dResGx = nullptr;
-  int *dResInfo = nullptr, *dResOrderB = nullptr, *dResOrderP = nullptr, *dResCounts = nullptr;
+  int *dResInfo = nullptr, *dResOrderB = nullptr, *dResOrderP = nullptr, *dResCounts = nullptr, *dResReady = nullptr;
+  int res_epoch = 0;
   int *dResEdges = nullptr, *dResDeg = nullptr;
   unsigned char* dResActive = nullptr;
   bool res_have_mask = false;
@@ -391,7 +392,7 @@ extern "C" int gprf_destroy(gprf_handle h) {
   cudaFree(h->dPartA); cudaFree(h->dPartB); cudaFree(h->dPartC); cudaFree(h->dPartChild);
   cudaFree(h->dOwner); cudaFree(h->dIota); cudaFree(h->dIdxSorted); cudaFree(h->dCub);
   cudaFree(h->dResExports); cudaFree(h->dResScratch); cudaFree(h->dResLL); cudaFree(h->dResGth); cudaFree(h->dResGx);
-  cudaFree(h->dResInfo); cudaFree(h->dResOrderB); cudaFree(h->dResOrderP); cudaFree(h->dResCounts);
+  cudaFree(h->dResInfo); cudaFree(h->dResOrderB); cudaFree(h->dResOrderP); cudaFree(h->dResCounts); cudaFree(h->dResReady);
   cudaFree(h->dResEdges); cudaFree(h->dResDeg); cudaFree(h->dResActive); cudaFree(h->dResDbg);
   if (h->hResStatus) cudaFreeHost(h->hResStatus);
   if (h->hUnits) cudaFreeHost(h->hUnits);
@@ -1135,9 +1136,9 @@ static int res_alloc(gprf_ctx* h, int grid) {
   CUDA_OK(ensure(&h->dResScratch, &h->capResScr, (size_t)grid * (size_t)res::SCR_STRIDE));
   if (U > h->capResU || !h->dResLL) {
     cudaFree(h->dResLL); cudaFree(h->dResGth); cudaFree(h->dResGx); cudaFree(h->dResInfo);
-    cudaFree(h->dResOrderB); cudaFree(h->dResOrderP); cudaFree(h->dResCounts);
+    cudaFree(h->dResOrderB); cudaFree(h->dResOrderP); cudaFree(h->dResCounts); cudaFree(h->dResReady);
     h->dResLL = h->dResGth = h->dResGx = nullptr;
-    h->dResInfo = h->dResOrderB = h->dResOrderP = h->dResCounts = nullptr;
+    h->dResInfo = h->dResOrderB = h->dResOrderP = h->dResCounts = h->dResReady = nullptr;
     const size_t cu = U + U / 4 + 16;
     CUDA_OK(cudaMalloc((void**)&h->dResLL, cu * sizeof(double)));
     CUDA_OK(cudaMalloc((void**)&h->dResGth, cu * MAX_NCOV * sizeof(double)));
@@ -1146,6 +1147,9 @@ static int res_alloc(gprf_ctx* h, int grid) {
     CUDA_OK(cudaMalloc((void**)&h->dResOrderB, cu * sizeof(int)));
     CUDA_OK(cudaMalloc((void**)&h->dResOrderP, cu * sizeof(int)));
     CUDA_OK(cudaMalloc((void**)&h->dResCounts, 8 * sizeof(int)));
+    CUDA_OK(cudaMalloc((void**)&h->dResReady, cu * sizeof(int)));
+    CUDA_OK(cudaMemset(h->dResReady, 0, cu * sizeof(int)));
+    h->res_epoch = 0;
     CUDA_OK(cudaMemset(h->dResLL, 0, cu * sizeof(double)));
     CUDA_OK(cudaMemset(h->dResGth, 0, cu * MAX_NCOV * sizeof(double)));
     CUDA_OK(cudaMemset(h->dResGx, 0, cu * res::GX_STRIDE * sizeof(double)));
@@ -1161,9 +1165,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   int rc = res_sync_static(h);
   if (rc != GPRF_OK) return rc;
   const int B = h->B, E = h->E;
-  const int grid_b = std::max(1, std::min(B, h->n_sm));
-  const int grid_p = std::max(1, std::min(E, h->n_sm));
-  rc = res_alloc(h, std::max(grid_b, grid_p));
+  rc = res_alloc(h, std::max(1, std::min(B + E, h->n_sm)));
   if (rc != GPRF_OK) return rc;
   int launches = 0;
   const size_t outlen = 1 + MAX_NCOV + (grad_X ? (size_t)h->n * h->dx : 0);
@@ -1174,8 +1176,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   Q.active = h->res_have_mask ? h->dResActive : nullptr;
   Q.B = B;
   Q.E = E;
-  Q.order_blocks = h->dResOrderB;
-  Q.order_pairs = h->dResOrderP;
+  Q.order = h->dResOrderB;         // sized for all units
   Q.counts = h->dResCounts;
   Q.status = h->dResCounts + 4;
   Q.info = h->dResInfo;
@@ -1205,22 +1206,18 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   P.dbg_unit = h->res_dbg_unit;
   P.dbg_phase = h->res_dbg_phase;
   P.dbg_out = h->dResDbg;
-  // debug timeline (gprf_debug_trace with 2 x n_sm CTAs): pairs' launch first, blocks' launch behind it
-  const size_t trace_half = (size_t)h->n_sm * 2 * res::RTRACE_SLOTS;
-  P.trace = (h->dTrace && h->capTrace >= 2 * trace_half) ? h->dTrace + trace_half : nullptr;
+  // debug timeline (gprf_debug_trace with >= n_sm CTAs)
+  P.trace = (h->dTrace && h->capTrace >= (size_t)h->n_sm * 2 * res::RTRACE_SLOTS) ? h->dTrace : nullptr;
+  P.ready = h->dResReady;
+  P.epoch = ++h->res_epoch;
   P.order = h->dResOrderB;
   P.n_order = h->dResCounts + 0;
   P.counter = h->dResCounts + 2;
-#define CALL_RESB(D, W) res::resident_launch<D, W>(P, grid_b, st)
-  LAUNCH(10, DISPATCH_COV(h, CALL_RESB));
-  if (E > 0) {
-    P.order = h->dResOrderP;
-    P.n_order = h->dResCounts + 1;
-    P.counter = h->dResCounts + 3;
-    if (P.trace) P.trace = h->dTrace;
-#define CALL_RESP(D, W) res::resident_launch<D, W>(P, grid_p, st)
-    LAUNCH(11, DISPATCH_COV(h, CALL_RESP));
-  }
+  // ONE launch: block units first, the pair units behind them wait for their parent's exports
+  const int grid_u = std::max(1, std::min(B + E, h->n_sm));
+  if (P.trace) P.trace = h->dTrace;
+#define CALL_RESU(D, W) res::resident_launch<D, W>(P, grid_u, st)
+  LAUNCH(11, DISPATCH_COV(h, CALL_RESU));
   res::ResCombine C;
   C.perm = h->dPerm;
   C.pos_block = h->dPosBlock;

@@ -118,6 +118,8 @@ struct ResParams {
   double* gx_u;                 // per unit x GX_STRIDE
   int* info;                    // per unit: 1 + first failing local row
   int* status;
+  int* ready;                   // per block: == epoch once the block unit's exports are complete
+  int epoch;
   int dbg_unit, dbg_phase;      // debug dump of R1 / R2 after a phase (-1: off)
   double* dbg_out;              // 2 x (160 x 160) doubles
   unsigned long long* trace;    // debug timeline (RTRACE_SLOTS (tag, ns) pairs per CTA) or nullptr
@@ -206,7 +208,7 @@ struct Stage {
   unsigned par;
 };
 __device__ __forceinline__ void tma_issue(const Stage& S, double* dst, const double* src, int nblk) {
-  fence_proxy_async();
+  asm volatile("fence.proxy.async;\n" ::: "memory");      // generic-proxy writes (this CTA's, or acquired) before the copy
   const uint32_t bytes = (uint32_t)nblk * RBLK * 8;
   mbar_expect_tx(S.bar, bytes);
   bulk_g2s(dst, src, bytes, S.bar);
@@ -451,7 +453,7 @@ static __device__ __noinline__ void ph_lji(const ResParams& P, const Ctx& c, Sta
       zero4(acc[i]);
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = r0 + t / ng, c0 = (t % ng) * 4;
+        const int row = r0 + t / ng, c0 = ((t % ng + t / ng) % ng) * 4;   // rotated: every warp gets short and long column groups
         const int nj = min(4, ab - c0);
         const typename R1::T pa = r1 + row * ab * RBLK;
         int pb[4];
@@ -469,7 +471,7 @@ static __device__ __noinline__ void ph_lji(const ResParams& P, const Ctx& c, Sta
     for (int i = 0; i < 4; ++i) {
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = r0 + t / ng, c0 = (t % ng) * 4;
+        const int row = r0 + t / ng, c0 = ((t % ng + t / ng) % ng) * 4;   // rotated: every warp gets short and long column groups
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (c0 + j < ab) stn(r1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
@@ -797,7 +799,7 @@ static __device__ __noinline__ void ph_t(const ResParams& P, const Ctx& c, Stage
       for (int i = 0; i < 4; ++i) {
         const int t = w + i * RNW;
         if (t < ntask) {
-          const int row = r0 + t / ng, c0 = (t % ng) * 4;
+          const int row = r0 + t / ng, c0 = ((t % ng + t / ng) % ng) * 4;   // rotated: every warp gets short and long column groups
           const int nj = min(4, ab - c0);
           const typename R1::T pa = r1 + row * ab * RBLK;
           // T(row, c0 + j) += sum_{k >= c0 + j} L_ji(row, k) W_i(k, c0 + j)
@@ -836,7 +838,7 @@ static __device__ __noinline__ void ph_t(const ResParams& P, const Ctx& c, Stage
     for (int i = 0; i < 4; ++i) {
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = r0 + t / ng, c0 = (t % ng) * 4;
+        const int row = r0 + t / ng, c0 = ((t % ng + t / ng) % ng) * 4;   // rotated: every warp gets short and long column groups
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (c0 + j < ab) stn(r1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
@@ -1389,8 +1391,16 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
       ia = P.block_ptr[bi];
       a = (int)(P.block_ptr[bi + 1] - ia);
     }
+    if (bi >= 0) {
+      // the parent block's unit (earlier in the queue, possibly still running on another SM)
+      if (threadIdx.x == 0) {
+        while (atomicAdd(P.ready + bi, 0) != P.epoch) __nanosleep(100);
+        __threadfence();
+      }
+      __syncthreads();
+    }
     if (bi >= 0 && b == 0) {
-      // pair with an empty second block: the unit IS block i (computed by the block launch)
+      // pair with an empty second block: the unit IS block i
       const long long src = bi;
       if (threadIdx.x == 0) P.ll_u[uid] = P.ll_u[src];
       if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)uid * MAX_NCOV + threadIdx.x] = P.gth_u[src * MAX_NCOV + threadIdx.x];
@@ -1400,7 +1410,10 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
     const int ab = (a + 7) >> 3, bb = (b + 7) >> 3;
     const int cls = res_class(ab, bb);
     if (cls == 2) {
-      if (threadIdx.x == 0) atomicOr(P.status, ST_OVERFLOW);
+      if (threadIdx.x == 0) {
+        atomicOr(P.status, ST_OVERFLOW);
+        if (bi < 0) atomicExch(P.ready + bj, P.epoch);     // nobody may wait forever; the tile pipeline redoes it
+      }
       continue;
     }
     if (b == 0) {                  // empty block unit
@@ -1411,6 +1424,9 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
         oexp[EXP_SCAL + 1] = 0.0;
       }
       if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)uid * MAX_NCOV + threadIdx.x] = 0.0;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicExch(P.ready + bj, P.epoch);
       continue;
     }
     const bool r1g = cls == 1;
@@ -1439,6 +1455,11 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
     __syncthreads();
     if (r1g) run_unit<DFN, WFN, R1Glob>(P, *ctx, stage);
     else run_unit<DFN, WFN, R1Smem>(P, *ctx, stage);
+    if (bi < 0) {                  // exports complete: release the block's pairs
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicExch(P.ready + bj, P.epoch);
+    }
   }
 }
 
@@ -1451,9 +1472,8 @@ struct PlanParams {
   const int* edges;
   const unsigned char* active;     // per unit (B + E), or nullptr = all
   int B, E;
-  int* order_blocks;               // out
-  int* order_pairs;                // out
-  int* counts;                     // out: [n_blocks, n_pairs, queue counter blocks, queue counter pairs]
+  int* order;                      // out: block units (ascending id), then pair units (largest first)
+  int* counts;                     // out: [n units, n block units, queue counter, -]
   int* status;                     // out (reset here)
   int* info;                       // per unit, reset here
 };
@@ -1494,9 +1514,10 @@ __global__ void k_res_plan(PlanParams Q) {
   if (tid == 0) {
     int nb = 0;
     for (int bq = 0; bq < Q.B; ++bq)
-      if (need[bq]) Q.order_blocks[nb++] = bq;
+      if (need[bq]) Q.order[nb++] = bq;
     s_nb = nb;
   }
+  __syncthreads();
   // pairs: rank sort by (size descending, id ascending)
   for (int e = tid; e < Q.E; e += nt) {
     const int ke = key[e];
@@ -1506,13 +1527,13 @@ __global__ void k_res_plan(PlanParams Q) {
       const int kf = key[f];
       rank += (kf > ke || (kf == ke && f < e)) ? 1 : 0;
     }
-    Q.order_pairs[rank] = Q.B + e;
+    Q.order[s_nb + rank] = Q.B + e;
     atomicAdd(&s_np, 1);
   }
   __syncthreads();
   if (tid == 0) {
-    Q.counts[0] = s_nb;
-    Q.counts[1] = s_np;
+    Q.counts[0] = s_nb + s_np;
+    Q.counts[1] = s_nb;
     Q.counts[2] = 0;
     Q.counts[3] = 0;
     *Q.status = s_over ? ST_OVERFLOW : 0;

@@ -23,7 +23,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 wl = bench.make_workload(name)
 R = bench.Runner(torch, None, wl, 0, 1, 0)
 g = R.g
-nct = 296          # CTAs [0, 148): the pairs' launch, [148, 296): the blocks' launch
+nct = 148
 for _ in range(3):
     R.device_step(reblock=R.reblock)
 torch.cuda.synchronize()
