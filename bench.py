@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 DY = 50
+POOL = 8                         # perturbed copies of X cycled through by the timed steps
 FAMILY_FLOPS = {                 # algorithmic flops per unit of s points (sum = s^3 + 4 s^2 dy)
     "potrf": lambda s, dy: s ** 3 / 3.0 + s ** 2 * dy,      # dpotrf + forward half of dpotrs
     "trtri": lambda s, dy: s ** 3 / 3.0,                    # dpotri, triangular inverse
@@ -40,21 +41,26 @@ FAMILY_FLOPS = {                 # algorithmic flops per unit of s points (sum =
 
 
 # --------------------------------------------------------------------------- workloads
+_README_SD = []
+
+
 def make_workload(name):
     """Returns dict(X, Y, block_fn, block_idxs, neighbors, cov, noise_var, grad_cov, desc)."""
     from gprf_b200 import GPCov, Blocker, grid_centers
     from gprf_b200.synthetic import readme_dataset, SampledData
     if name in ("cfg2", "cfg3"):
-        sd = readme_dataset(ntrain=10000, nblocks=100, ntest=500, yd=DY, seed=0)
+        if not _README_SD:
+            _README_SD.append(readme_dataset(ntrain=10000, nblocks=100, ntest=500, yd=DY, seed=0))
+        sd = _README_SD[0]
         return dict(X=sd.X_obs, Y=sd.SY, block_fn=sd.reblock, block_idxs=sd.block_idxs, neighbors=sd.neighbors,
-                    cov=sd.cov, noise_var=sd.noise_var, grad_cov=(name == "cfg3"),
+                    cov=sd.cov, noise_var=sd.noise_var, grad_cov=(name == "cfg3"), jiggle=0.003, clip01=False,
                     desc="gprfopt README config: n=10000 yd=50 nblocks=100 (342 edges) lscale=0.06 obs_std=0.02 "
                          "seed=0, X=X_obs, task=%s" % ("xcov" if name == "cfg3" else "x"))
     if name == "cfg1":
         sd = SampledData(noise_var=0.01, n=2500, ntrain=2000, lscale=0.06, obs_std=0.006, yd=DY, seed=0)
         sd.set_centers(grid_centers(20))
         return dict(X=sd.X_obs, Y=sd.SY, block_fn=sd.reblock, block_idxs=sd.block_idxs, neighbors=sd.neighbors,
-                    cov=sd.cov, noise_var=0.01, grad_cov=False,
+                    cov=sd.cov, noise_var=0.01, grad_cov=False, jiggle=0.003,
                     desc="gprfopt synthetic n=2000 yd=50 lscale=0.06 nblocks=20 (25 blocks, 72 edges) task=x")
     if name == "cfg5":
         n = 200000
@@ -64,7 +70,7 @@ def make_workload(name):
         bl = Blocker(grid_centers(400))
         lscale = 6.0 / np.sqrt(n)
         return dict(X=X, Y=Y, block_fn=bl.block_clusters, block_idxs=bl.block_clusters(X), neighbors=bl.neighbors(),
-                    cov=GPCov([1.0], [lscale, lscale], "euclidean", "se"), noise_var=0.01, grad_cov=False,
+                    cov=GPCov([1.0], [lscale, lscale], "euclidean", "se"), noise_var=0.01, grad_cov=False, jiggle=0.0005,
                     desc="synthetic n=200000 yd=50 400 blocks (~500 pts, 1482 edges) lscale=6/sqrt(n) Y=randn task=x")
     if name == "cfg4":
         # BASELINE configs[3]: sorted_isc.npy is absent from the reference mount, so a synthetic
@@ -84,7 +90,7 @@ def make_workload(name):
         Y = rng.randn(n, DY)
         idxs, reblock = pdtree_cluster(X, blocksize=210)
         return dict(X=X, Y=Y, block_fn=reblock, block_idxs=idxs, neighbors=None, threshold=0.6,
-                    cov=GPCov([1.0], [40.0, 40.0], "lld", "matern32"), noise_var=0.1, grad_cov=True,
+                    cov=GPCov([1.0], [40.0, 40.0], "lld", "matern32"), noise_var=0.1, grad_cov=True, jiggle=0.01,
                     desc="seismic-style synthetic catalogue n=100000 (60 faults) lld+matern32 l=40km nv=0.1 yd=50 "
                          "pdtree blocksize=210 threshold=0.6 Y=randn task=xcov")
     raise SystemExit("unknown workload %r" % name)
@@ -189,7 +195,39 @@ def cpu_baseline(wl, budget_s=20.0):
         if limiter is not None:
             limiter.restore_original_limits()
     sec = float(np.median(ts))
-    return {"value": 1.0 / sec, "unit": "evals/s", "cores": cores, "kind": "port",
+    modes = {}
+    try:        # (i) one process, BLAS free to use every core (vectorised oracle)
+        o.llgrad(**kw)
+        t0 = time.perf_counter()
+        o.llgrad(**kw)
+        modes["one_process_all_blas_threads"] = {"sec_per_eval": time.perf_counter() - t0, "blas_threads": blas_threads(),
+                                                 "sample": "1 full eval after 1 warm-up"}
+    except Exception as exc:        # noqa: BLE001
+        modes["one_process_all_blas_threads"] = {"error": str(exc)}
+    try:        # (ii) the reference's loop structure (one kernel_deriv row call per point and dimension,
+        #      gprf.py:553-561): a bounded sample of units, scaled to the whole evaluation by flops
+        of = oracle_gprf(wl, mode="faithful")
+        sizes = unit_sizes(wl["block_idxs"], wl["neighbors"])
+        w = sizes ** 3 + 4 * sizes ** 2 * DY
+        nb = of.n_blocks
+        pick_b = list(range(0, nb, max(1, nb // 6)))[:6]
+        pick_e = list(range(0, len(of.neighbors), max(1, len(of.neighbors) // 6)))[:6]
+        t0 = time.perf_counter()
+        for b_ in pick_b:
+            of.llgrad_unary(b_, **kw)
+        for e_ in pick_e:
+            of.llgrad_joint(*of.neighbors[e_], **kw)
+        dt = time.perf_counter() - t0
+        wsum = w[pick_b].sum() + w[[nb + e_ for e_ in pick_e]].sum()
+        modes["faithful_row_loops_serial"] = {"sec_per_eval": dt * w.sum() / wsum,
+                                              "sample": "%d blocks + %d pairs, serial, scaled by flops (%.1f%% of the eval)"
+                                                        % (len(pick_b), len(pick_e), 100 * wsum / w.sum())}
+    except Exception as exc:        # noqa: BLE001
+        modes["faithful_row_loops_serial"] = {"error": str(exc)}
+    return {"value": 1.0 / sec, "unit": "evals/s", "cores": cores, "kind": "port", "modes": modes,
+            "reference_logged": {"sec_per_eval": 7.31, "hardware": "unstated CPU, serial (--parallel off)",
+                                 "source": "gprf_results.tgz: 10000_10500_100_0.060000_0.020000_0.1000_50_l-bfgs-b_x_-1_"
+                                           "0.0100_s0_gprf0/results.txt (README configuration)"},
             "sample": "%d full evals after 1 warm-up (median), all %d units, grad_X" % (len(ts), o.n_blocks + len(o.neighbors)),
             "sec_per_eval": sec,
             "note": "oracle port, Pool(%d) x 1 BLAS thread (the reference's --parallel mode)" % cores}
@@ -280,7 +318,21 @@ class Runner(object):
             wl["neighbors"] = list(self.g.neighbors)
             wl["desc"] += " (%d blocks, %d edges)" % (self.g.n_blocks, len(wl["neighbors"]))
         self.outlen = 1 + _lib.MAX_NCOV + self.n * self.dx
-        self.Xd = torch.tensor(wl["X"], dtype=torch.float64, device=self.dev)
+        # Every step evaluates a DIFFERENT X (as consecutive L-BFGS iterates do): a pool of perturbed
+        # copies, so that points change block, block sizes change and nothing structural can be
+        # carried over from the previous step.
+        rng = np.random.RandomState(1234)
+        scale = wl.get("jiggle", 0.0)
+        self.pool_h = [np.ascontiguousarray(wl["X"], dtype=np.float64)]
+        for _ in range(POOL - 1 if scale > 0 else 0):
+            Xp = np.array(wl["X"], dtype=np.float64)
+            Xp[:, :2] += scale * rng.randn(self.n, 2)
+            if wl.get("clip01"):
+                Xp = np.clip(Xp, 0.0, 1.0)
+            self.pool_h.append(np.ascontiguousarray(Xp))
+        self.pool_d = [torch.tensor(x, dtype=torch.float64, device=self.dev) for x in self.pool_h]
+        self.step_no = 0
+        self.Xd = self.pool_d[0]
         self.out = torch.zeros(self.outlen, dtype=torch.float64, device=self.dev)
         self.Xh = torch.empty((self.n, self.dx), dtype=torch.float64).pin_memory()
         self.outh = torch.empty(self.outlen, dtype=torch.float64).pin_memory()
@@ -293,6 +345,8 @@ class Runner(object):
 
     def device_step(self, reblock=False):
         st = self.torch.cuda.current_stream(self.dev)
+        self.step_no += 1
+        self.Xd = self.pool_d[self.step_no % len(self.pool_d)] if reblock else self.pool_d[0]
         self.g.llgrad_device(self.Xd.data_ptr(), self.out.data_ptr(), st.cuda_stream,
                              grad_X=True, grad_cov=self.grad_cov, reblock=reblock)
         if self.world > 1:
@@ -313,9 +367,12 @@ class Runner(object):
             launches += self.g.last_timing()[1] + (1 if self.world > 1 else 0)
         return total, launches
 
-    def e2e_step(self, X_host):
-        """update_X (host block assignment) + llgrad through host buffers."""
+    def e2e_step(self, X_host=None):
+        """update_X + llgrad through host buffers (the call a user makes), a different X every step."""
         torch = self.torch
+        if X_host is None:
+            self.step_no += 1
+            X_host = self.pool_h[self.step_no % len(self.pool_h)] if self.g.block_fn is not None else self.pool_h[0]
         if self.world == 1:
             self.g.update_X(X_host)
             return self.g.llgrad(grad_X=True, grad_cov=self.grad_cov)
@@ -335,7 +392,10 @@ class Runner(object):
         nb, ne = len(self.wl["block_idxs"]), len(self.wl["neighbors"])
         h2d = self.n * self.dx * 8
         d2h = (1 + 5 + self.n * self.dx) * 8 + 4
-        if self.g._device_part is not None:
+        ev, fb, _ = self.g.resident_stats()
+        if ev > 0 and fb == 0:
+            pass                                      # resident path: X down, [ll, grad] + status word up, nothing else
+        elif self.g._device_part is not None:
             d2h += (nb + 1) * 8
         else:
             h2d += self.n * 8 + self.n * 4 + (nb + 1) * 16 + (nb + ne) * (176 + 4)
@@ -412,10 +472,14 @@ def roofline_from_profile(fam, sizes_local, dy, peak_tflops, peak_note):
     big = sizes_local[~fused]
     merged = {"potrf": [fam["potrf_diag"][0] + fam["potrf_panel"][0], fam["potrf_diag"][1] + fam["potrf_panel"][1]],
               "trtri": fam["trtri"], "alpha": fam["alpha"], "kinv_grad": fam["kinv_grad"],
-              "unit_fused": fam["unit_fused"]}
+              "unit_fused": fam["unit_fused"],
+              # resident path: ONE kernel (k_resident) evaluates every unit out of shared memory
+              "resident": [fam["res_blocks"][0] + fam["res_pairs"][0], fam["res_blocks"][1] + fam["res_pairs"][1]]}
     name = max(merged, key=lambda k: merged[k][0])
     ms, nl = merged[name]
-    if name == "unit_fused":
+    if name == "resident":
+        flops = float(np.sum(sizes_local ** 3 + 4 * sizes_local ** 2 * dy))
+    elif name == "unit_fused":
         sf = sizes_local[fused]
         flops = float(np.sum(sf ** 3 + 4 * sf ** 2 * dy))
     else:
@@ -471,13 +535,12 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
     clocks = sampler.stop()
 
     # end to end through the public host API
-    Xh = np.array(wl["X"])
     for _ in range(2):
-        R.e2e_step(Xh)
+        R.e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        R.e2e_step(Xh)
+        R.e2e_step()
     barrier()
     te = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=R.dev)
     if world > 1:
@@ -493,7 +556,8 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
         from gprf_b200.dist import shard_units
         from gprf_b200.gprf import _blocks_to_csr
         ptr, _ = _blocks_to_csr(wl["block_idxs"])
-        mask = shard_units(ptr, np.asarray(wl["neighbors"]), rank, world).astype(bool)
+        nominal = R.g.resident_stats()[0] > 0          # small-block structures are split on nominal sizes
+        mask = shard_units(ptr, np.asarray(wl["neighbors"]), rank, world, nominal=nominal).astype(bool)
         sizes_local = sizes[mask]
     else:
         sizes_local = sizes
@@ -525,6 +589,8 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
     if ar_ms is not None:
         roof["allreduce_ms"] = ar_ms
         roof["allreduce_bytes"] = int(R.out.numel() * 8)
+    ev, fb, _ = R.g.resident_stats()
+    roof["resident_path"] = {"evaluations": ev, "handed_to_tile_pipeline": fb}
     res = {"wl": wl, "reblock": R.reblock, "ms_per_step": ms_per_step, "value": 1e3 / ms_per_step, "launches": launches // steps,
            "clocks": clocks, "e2e": {"value": 1.0 / e2e_sec, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                                      "d2h_bytes_per_step": d2h, "ms_per_step": e2e_sec * 1e3},
@@ -550,6 +616,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--no-n200k", action="store_true", help="skip the extra n=200k measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg1 / cfg3 / cfg4 sub-lines")
     ap.add_argument("--no-lbfgs", action="store_true", help="skip the full L-BFGS run of the README configuration")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -602,6 +669,22 @@ def main():
             line["lbfgs_full_run"] = lbfgs_full_run()
         except Exception as exc:        # noqa: BLE001
             line["lbfgs_full_run"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    if world == 1 and args.workload == "cfg2" and not args.no_extra:
+        # the other BASELINE.json configurations, one short measurement each (parity-tested in tests/)
+        line["configs"] = {}
+        for name in ("cfg1", "cfg3", "cfg4"):
+            try:
+                kx = max(3, min(args.steps, 10))
+                rx = measure(torch, dist, args, name, rank, world, local_rank, kx, 3, with_cpu=False)
+                line["configs"][name] = {"workload": rx["wl"]["desc"], "value": rx["value"], "unit": "evals/s",
+                                         "ms_per_step": rx["ms_per_step"], "steps": kx, "e2e": rx["e2e"],
+                                         "roofline": rx["roofline"], "clocks": rx["clocks"],
+                                         "gpu_launches_per_step": rx["launches"]}
+                if name == "cfg4":
+                    line["configs"][name]["parity"] = ("lld + Matern-3/2: CUDA == oracle is tested, the oracle itself is "
+                                                       "parity UNPINNED (treegp source and sorted_isc.npy absent)")
+            except Exception as exc:        # noqa: BLE001
+                line["configs"][name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if not args.no_n200k and args.workload != "cfg5":
         try:
             k5 = max(2, min(args.steps, 5))

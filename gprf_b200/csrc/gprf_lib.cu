@@ -883,7 +883,7 @@ static int reblock_launch(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
 #define CALL_ASSIGN(MODE)                                                                                         \
   do {                                                                                                            \
     if (sm > 48 * 1024) cudaFuncSetAttribute(k_assign_grid<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-    k_assign_grid<MODE><<<gb, tb, sm, st>>>(X_dev, n, h->dx, h->dPartA, h->dPartB, B, h->dOwner);              \
+    k_assign_grid<MODE><<<(unsigned)((n * GT + 127) / 128), 128, sm, st>>>(X_dev, n, h->dx, h->dPartA, h->dPartB, B, h->dOwner); \
   } while (0)
     if (h->part_mode == 0) CALL_ASSIGN(0);
     else if (h->part_mode == 1) CALL_ASSIGN(1);

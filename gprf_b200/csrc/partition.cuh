@@ -39,7 +39,12 @@ __device__ __forceinline__ double dot_rounded(const double* x, const double* c, 
   }
 }
 
-// centers: B x dx, csq: B (numpy's sum(c**2)), owner out: int32 per point
+// centers: B x dx, csq: B (numpy's sum(c**2)), owner out: int32 per point.
+// GT threads share a point: thread s scans centres s, s + GT, ... (each distance correctly rounded,
+// independent of the others), then the partial minima are merged with numpy's sequential argmin
+// rule - the smallest distance, the lowest index among equals, and the first NaN beats everything -
+// which is associative, so the result is the one the sequential scan gives.
+constexpr int GT = 8;
 template <int MODE>
 __global__ void k_assign_grid(const double* X, long long n, int dx, const double* centers, const double* csq,
                               int B, int* owner) {
@@ -47,39 +52,42 @@ __global__ void k_assign_grid(const double* X, long long n, int dx, const double
   for (int e = threadIdx.x; e < B * dx; e += blockDim.x) sc[e] = centers[e];
   for (int e = threadIdx.x; e < B; e += blockDim.x) sc[B * dx + e] = csq[e];
   __syncthreads();
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / GT;
+  const int sub = threadIdx.x % GT;
+  const bool live = p < n;
   double x[3] = {0.0, 0.0, 0.0};
-  for (int i = 0; i < dx; ++i) x[i] = X[p * dx + i];
+  if (live)
+    for (int i = 0; i < dx; ++i) x[i] = X[p * dx + i];
   double a = __dmul_rn(x[0], x[0]);
   for (int i = 1; i < dx; ++i) a = __dadd_rn(a, __dmul_rn(x[i], x[i]));
-  int best = 0;
+  // key = (class, distance, index): class 0 = NaN (wins, lowest index first), class 1 = number
+  int best = 0x7fffffff, bcls = 2;
   double bestd = 0.0;
-  bool done = false;
-  // four independent (correctly rounded) distances at a time, then numpy's sequential argmin rule
-  for (int b0 = 0; b0 < B && !done; b0 += 4) {
-    double dist[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int b = min(b0 + u, B - 1);
-      const double dot = dot_rounded<MODE>(x, sc + b * dx, dx);
-      const double t = __dadd_rn(__dsub_rn(a, 2.0 * dot), sc[B * dx + b]);
-      dist[u] = __dsqrt_rn(t);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int b = b0 + u;
-      if (b >= B || done) continue;
-      if (dist[u] != dist[u]) {      // np.argmin: the first NaN is the minimum
-        best = b;
-        done = true;
-      } else if (b == 0 || dist[u] < bestd) {
-        best = b;
-        bestd = dist[u];
-      }
+  for (int b = sub; b < B; b += GT) {
+    const double dot = dot_rounded<MODE>(x, sc + b * dx, dx);
+    const double t = __dadd_rn(__dsub_rn(a, 2.0 * dot), sc[B * dx + b]);
+    const double d = __dsqrt_rn(t);
+    const int cls = (d != d) ? 0 : 1;
+    const bool better = cls < bcls || (cls == bcls && cls == 1 && d < bestd);   // ascending b: ties keep the earlier
+    if (better) {
+      bcls = cls;
+      bestd = d;
+      best = b;
     }
   }
-  owner[p] = best;
+#pragma unroll
+  for (int o = 1; o < GT; o <<= 1) {
+    const int oc = __shfl_xor_sync(0xffffffffu, bcls, o);
+    const double od = __shfl_xor_sync(0xffffffffu, bestd, o);
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const bool better = oc < bcls || (oc == bcls && (oc == 1 ? (od < bestd || (od == bestd && ob < best)) : ob < best));
+    if (better) {
+      bcls = oc;
+      bestd = od;
+      best = ob;
+    }
+  }
+  if (live && sub == 0) owner[p] = best;
 }
 
 struct TreeParams {
