@@ -131,8 +131,10 @@ __host__ __device__ __forceinline__ int sw_off(int r, int c) { return ((r ^ ((r 
 
 struct Lane {
   int w, lane, g, q;
-  int on, ot0, ot1;             // offsets of the row-major / transposed fragment elements
+  int on, ot0, ot1;             // offsets (doubles) of the row-major / transposed fragment elements
+  unsigned bn, bt0, bt1;        // the same as byte addresses in the shared window (base of g_smem included)
 };
+extern __shared__ __align__(128) double g_smem[];
 __device__ __forceinline__ Lane make_lane() {
   Lane L;
   L.w = threadIdx.x >> 5;
@@ -142,25 +144,40 @@ __device__ __forceinline__ Lane make_lane() {
   L.on = sw_off(L.g, 2 * L.q);
   L.ot0 = sw_off(2 * L.q, L.g);
   L.ot1 = sw_off(2 * L.q + 1, L.g);
+  const unsigned base = smem_u32(g_smem);
+  L.bn = base + 8u * L.on;
+  L.bt0 = base + 8u * L.ot0;
+  L.bt1 = base + 8u * L.ot1;
   // opaque to the optimiser: under register pressure it would otherwise recompute these from
   // %tid at every use (measured: 13 % of all executed instructions)
   asm volatile("" : "+r"(L.on), "+r"(L.ot0), "+r"(L.ot1), "+r"(L.g), "+r"(L.q));
+  asm volatile("" : "+r"(L.bn), "+r"(L.bt0), "+r"(L.bt1));
   return L;
 }
 // Shared-memory operands are addressed by their offset (in doubles) into the CTA's dynamic shared
-// memory: the compiler then emits LDS / STS with 32-bit address arithmetic.  (Generic pointers, as
-// handed around in a struct, cost a 64-bit add chain per fragment load and the slower generic LD.)
-// Operands in HBM / L2 use the pointer overloads.
-extern __shared__ __align__(128) double g_smem[];
-__device__ __forceinline__ double2 ldn(int off, const Lane& L) {
-  return *reinterpret_cast<const double2*>(g_smem + off + L.on);
+// memory.  The fragment loads are explicit ld.shared on 32-bit window addresses, lane base + 8 * offset:
+// ONE integer instruction per load.  (Indexing g_smem cost an add and a multiply-add per load - the
+// window base is a run-time value on sm_100 - and the product loops ran at 11 instructions per DMMA,
+// issue-bound; generic pointers, as handed around in a struct, cost a 64-bit add chain and the slower
+// generic LD.)  Operands in HBM / L2 use the pointer overloads.
+__device__ __forceinline__ double2 lds128(unsigned a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+  return v;
 }
+__device__ __forceinline__ double lds64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, double2 v) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ double2 ldn(int off, const Lane& L) { return lds128(L.bn + 8u * (unsigned)off); }
 __device__ __forceinline__ double2 ldt(int off, const Lane& L) {
-  return make_double2(g_smem[off + L.ot0], g_smem[off + L.ot1]);
+  return make_double2(lds64(L.bt0 + 8u * (unsigned)off), lds64(L.bt1 + 8u * (unsigned)off));
 }
-__device__ __forceinline__ void stn(int off, const Lane& L, double2 v) {
-  *reinterpret_cast<double2*>(g_smem + off + L.on) = v;
-}
+__device__ __forceinline__ void stn(int off, const Lane& L, double2 v) { sts128(L.bn + 8u * (unsigned)off, v); }
 // row-major fragment: (M[g][2q], M[g][2q+1])  - A operand of C = A B^T, B operand given as [n][k],
 // and the accumulator layout
 __device__ __forceinline__ double2 ldn(const double* blk, const Lane& L) {
@@ -353,6 +370,44 @@ __device__ __forceinline__ void mk_loop(double2 (&acc)[4], PA pa, int sa, const 
     }
   }
 }
+// both operands in shared memory: running window addresses, one add per load
+template <bool AT, bool BT, int NJ>
+__device__ __forceinline__ void mk_loop(double2 (&acc)[4], int pa, int sa, const int (&pb)[4], int sbk, int k0, int k1,
+                                        const Lane& L) {
+  const unsigned oa = 8u * (unsigned)(pa + k0 * sa);
+  unsigned a0 = (AT ? L.bt0 : L.bn) + oa, a1 = L.bt1 + oa;
+  unsigned b0[NJ], b1[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const unsigned ob = 8u * (unsigned)(pb[j] + k0 * sbk);
+    b0[j] = (BT ? L.bt0 : L.bn) + ob;
+    b1[j] = L.bt1 + ob;
+  }
+  const unsigned sab = 8u * (unsigned)sa, sbb = 8u * (unsigned)sbk;
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k) {
+    double2 av;
+    if (AT) {
+      av = make_double2(lds64(a0), lds64(a1));
+      a1 += sab;
+    } else {
+      av = lds128(a0);
+    }
+    a0 += sab;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      double2 bv;
+      if (BT) {
+        bv = make_double2(lds64(b0[j]), lds64(b1[j]));
+        b1[j] += sbb;
+      } else {
+        bv = lds128(b0[j]);
+      }
+      b0[j] += sbb;
+      mma2(acc[j], av, bv);
+    }
+  }
+}
 template <bool AT, bool BT, class PA, class PB>
 __device__ __forceinline__ void mk(double2 (&acc)[4], PA pa, int sa, const PB (&pb)[4], int sbk, int k0, int k1, int nj,
                                    const Lane& L) {
@@ -391,6 +446,8 @@ __device__ __forceinline__ double2 cov_frag(const ResParams& P, const Ctx& c, co
 }
 
 __device__ __forceinline__ int tri_len(int r) { return r + 1; }
+// n columns in ng = ceil(n / 4) groups of nearly equal width (<= 4): first column of group g
+__device__ __forceinline__ int grp_lo(int g, int n, int ng) { return (g * n) / ng; }
 
 // ---- P0: gather the unit's coordinate records --------------------------------------------------------------
 template <int DFN>
@@ -431,15 +488,27 @@ static __device__ __noinline__ void ph_lji(const ResParams& P, const Ctx& c, Sta
   const int w = L.w;
   const int ab = c.ab, bb = c.bb;
   const typename R1::T r1 = R1::get(c);
-  // K_ji -> R1 (and to scratch for the gradient contraction), one block per task
-  for (int t = w; t < bb * ab; t += RNW) {
+  // K_ji -> R1 (and to scratch for the gradient contraction): two blocks per step, so that four
+  // exponentials are in flight per thread; the stores come after the evaluations (a shared-memory
+  // store in between would order the next block's coordinate loads behind it)
+  for (int t = w; t < bb * ab; t += 2 * RNW) {
+    const int t2 = t + RNW;
     const int row = t / ab, k = t - row * ab;
+    const int row2 = t2 / ab, k2 = t2 - row2 * ab;
+    const bool has2 = t2 < bb * ab;
     const double2 kv = cov_frag<DFN, WFN>(P, c, L, ab + row, k, false);
+    const double2 kv2 = cov_frag<DFN, WFN>(P, c, L, ab + (has2 ? row2 : row), has2 ? k2 : k, false);
     stn(r1 + t * RBLK, L, kv);
     if (c.want_grad) stn(c.Kji + t * RBLK, L, kv);
+    if (has2) {
+      stn(r1 + t2 * RBLK, L, kv2);
+      if (c.want_grad) stn(c.Kji + t2 * RBLK, L, kv2);
+    }
   }
   __syncthreads();
+  rtrace(P, c, 34);
   tma_wait(stage);                    // W_i, issued by run_unit into [R2 | F]
+  rtrace(P, c, 35);
   // L_ji(row, c0 .. c0+3) = sum_{k <= c} K_ji(row, k) W_i(c, k)^T, in place: rounds of whole rows; every
   // task of a round holds its blocks until all of the round's reads are done
   const int Wst = c.oR2;
@@ -453,8 +522,8 @@ static __device__ __noinline__ void ph_lji(const ResParams& P, const Ctx& c, Sta
       zero4(acc[i]);
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = r0 + t / ng, c0 = ((t % ng + t / ng) % ng) * 4;   // rotated: every warp gets short and long column groups
-        const int nj = min(4, ab - c0);
+        const int row = r0 + t / ng, gq = (t % ng + t / ng + (t / ng) / ng) % ng;   // rotated: every warp gets every column group
+        const int c0 = grp_lo(gq, ab, ng), nj = grp_lo(gq + 1, ab, ng) - c0;
         const typename R1::T pa = r1 + row * ab * RBLK;
         int pb[4];
 #pragma unroll
@@ -471,10 +540,11 @@ static __device__ __noinline__ void ph_lji(const ResParams& P, const Ctx& c, Sta
     for (int i = 0; i < 4; ++i) {
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = r0 + t / ng, c0 = ((t % ng + t / ng) % ng) * 4;   // rotated: every warp gets short and long column groups
+        const int row = r0 + t / ng, gq = (t % ng + t / ng + (t / ng) / ng) % ng;
+        const int c0 = grp_lo(gq, ab, ng), nj = grp_lo(gq + 1, ab, ng) - c0;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (c0 + j < ab) stn(r1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
+          if (j < nj) stn(r1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
       }
     }
     __syncthreads();
@@ -487,12 +557,17 @@ static __device__ __noinline__ void ph_schur(const ResParams& P, const Ctx& c) {
   const Lane L = make_lane();
   const int ab = c.ab, bb = c.bb;
   const typename R1::T r1 = R1::get(c);
-  // task list: rows descending (longest first), column groups of 4
+  // task list: rows descending (longest first), column groups of nearly equal width (<= 4)
   int t = 0;
   for (int row = bb - 1; row >= 0; --row) {
-    for (int c0 = 0; c0 <= row; c0 += 4, ++t) {
+    const int ng = (row + 4) >> 2;
+    for (int gq = 0; gq < ng; ++gq, ++t) {
       if ((t & (RNW - 1)) != L.w) continue;
-      const int nj = min(4, row + 1 - c0);
+      const int c0 = grp_lo(gq, row + 1, ng), nj = grp_lo(gq + 1, row + 1, ng) - c0;
+      // the covariance values first (independent chains, nothing stored in between), then the product
+      double2 kv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kv[j] = cov_frag<DFN, WFN>(P, c, L, ab + row, ab + c0 + min(j, nj - 1), true);
       double2 acc[4];
       zero4(acc);
       if (c.pair) {
@@ -504,9 +579,8 @@ static __device__ __noinline__ void ph_schur(const ResParams& P, const Ctx& c) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (j < nj) {
-          const double2 kv = cov_frag<DFN, WFN>(P, c, L, ab + row, ab + c0 + j, true);
-          if (c.want_grad) stn(c.Kjj + (rtri(row) + c0 + j) * RBLK, L, kv);
-          stn(c.oR2 + (rtri(row) + c0 + j) * RBLK, L, make_double2(kv.x - acc[j].x, kv.y - acc[j].y));
+          if (c.want_grad) stn(c.Kjj + (rtri(row) + c0 + j) * RBLK, L, kv[j]);
+          stn(c.oR2 + (rtri(row) + c0 + j) * RBLK, L, make_double2(kv[j].x - acc[j].x, kv[j].y - acc[j].y));
         }
       }
     }
@@ -515,66 +589,113 @@ static __device__ __noinline__ void ph_schur(const ResParams& P, const Ctx& c) {
 }
 
 // ---- P3: Cholesky of S and W_S = L_S^-1, both in place -----------------------------------------------------
+// Named barrier 1: warp 0 arrives, warps 1.. wait (producer / consumer; barrier 0 is __syncthreads).
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Diagonal block J by ONE warp: L_JJ in place, W_JJ = L_JJ^-1 to WD.  Every lane holds the whole block.
+__device__ __forceinline__ void chol_diag_block(int blk, int wd, int row0, bool store_all) {
+  const int lane = threadIdx.x & 31;
+  double A[8][8], wv[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int cp = 0; cp < 4; ++cp) {
+      if (2 * cp > r) continue;
+      const double2 t = *reinterpret_cast<const double2*>(g_smem + blk + sw_off(r, 2 * cp));
+      A[r][2 * cp] = t.x;
+      A[r][2 * cp + 1] = t.y;
+    }
+  const int f = chol8_full(A, wv, lane);
+  if (lane == 0 && f != 0 && *S_FAIL == 0) *S_FAIL = row0 + f;
+  if (lane < 8) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) g_smem[wd + sw_off(v, lane)] = wv[v];   // lane c holds column c of W_JJ
+  }
+  // Of L_JJ only the diagonal is used afterwards (log-determinant); the whole block is written for
+  // the debug dump.  Every lane holds the same L: same-value stores, upper part zeroed.
+  if (!store_all) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) g_smem[blk + sw_off(r, r)] = A[r][r];      // (a lane == r test compiles to a jump table)
+    return;
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int cp = 0; cp < 4; ++cp) {
+      const double v0 = (2 * cp <= r) ? A[r][2 * cp] : 0.0;
+      const double v1 = (2 * cp + 1 <= r) ? A[r][2 * cp + 1] : 0.0;
+      *reinterpret_cast<double2*>(g_smem + blk + sw_off(r, 2 * cp)) = make_double2(v0, v1);
+    }
+}
+
+// Right-looking factorisation with the diagonal blocks looked ahead: in step J warp 0 alone carries
+// the chain  L_{J+1,J} -> C_{J+1,J+1} -> chol / inverse of diagonal block J+1  while the other warps
+// do the rest of panel J and of the trailing update (they form L_{J+1,J} in registers themselves), so
+// that a step costs one diagonal block (~1 us) and ONE CTA barrier.
 static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c) {
   const Lane L = make_lane();
   const int tid = threadIdx.x, w = L.w;
   const int bb = c.bb;
   const int R2 = c.oR2;
   const int WD = OFF_WB;                           // diagonal-block inverses, in WB
-  for (int J = 0; J < bb; ++J) {
-    if (w == 0) {
-      double av[8], wv[8];
-      const int r = L.lane & 7;
-      const double* src = g_smem + R2 + (rtri(J) + J) * RBLK;
-      if (L.lane < 8) {
-#pragma unroll
-        for (int v = 0; v < 8; ++v) av[v] = src[sw_off(r, v)];
-      } else {
-#pragma unroll
-        for (int v = 0; v < 8; ++v) av[v] = (v == r) ? 1.0 : 0.0;
-      }
-      const int f = chol8_inv8(av, wv, L.lane);
-      if (L.lane == 0 && f != 0 && *S_FAIL == 0) *S_FAIL = J * 8 + f;
-      if (L.lane < 8) {
-        double* dl = g_smem + R2 + (rtri(J) + J) * RBLK;
-        double* dw = g_smem + WD + J * RBLK;
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          dl[sw_off(r, v)] = av[v];
-          dw[sw_off(v, r)] = wv[v];            // lane r holds column r of W_JJ = L_JJ^-1
-        }
-      }
+  const bool store_all = P.dbg_unit == c.uid;
+  // Warp 0's scalar FP64 chain shares its sub-partition's FP64 pipe with the DMMAs of warps 4, 8, 12
+  // (measured: the diagonal block takes 2180 cycles next to them, 1250 alone): those three sit out.
+  const int wk = (w & 3) ? w - 1 - (w >> 2) : -1;       // worker index 0 .. NWK-1 of warps 1,2,3,5,6,7,...
+  constexpr int NWK = RNW - RNW / 4;
+  if (w == 0) chol_diag_block(R2, WD, 0, store_all);
+  for (int J = 0; J + 1 < bb; ++J) {
+    __syncthreads();                               // L_JJ, W_JJ and the trailing update of step J - 1
+    rtrace(P, c, 30);
+    if (wk < 0 && w != 0) {
+      nbar_arrive(1, RNT);
+      continue;
     }
-    __syncthreads();
-    // panel: L_IJ = C_IJ W_JJ^T
-    {
-      const double2 bw = ldn(WD + J * RBLK, L);
-      for (int I = J + 1 + w; I < bb; I += RNW) {
+    const int p10 = R2 + (rtri(J + 1) + J) * RBLK;
+    const double2 bw = ldn(WD + J * RBLK, L);
+    const double2 c10 = ldn(p10, L);
+    double2 cv = make_double2(0.0, 0.0);
+    if (w == 0) cv = ldn(p10 + RBLK, L);           // C_{J+1,J+1}: complete since the barrier
+    double2 lp = make_double2(0.0, 0.0);
+    mma2(lp, c10, bw);                             // L_{J+1,J}: every warp forms it in registers
+    if (w == 0) {
+      nbar_arrive(1, RNT);                         // C_{J+1,J} has been read by this warp
+      const int p11 = p10 + RBLK;
+      mma2(cv, neg2(lp), lp);
+      stn(p11, L, cv);
+      __syncwarp();
+      rtrace(P, c, 31);
+      chol_diag_block(p11, WD + (J + 1) * RBLK, (J + 1) * 8, store_all);
+      rtrace(P, c, 32);
+    } else {
+      // panel: L_IJ = C_IJ W_JJ^T, rows I >= J + 2
+      for (int I = J + 2 + wk; I < bb; I += NWK) {
         const int pc = R2 + (rtri(I) + J) * RBLK;
         double2 o = make_double2(0.0, 0.0);
         mma2(o, ldn(pc, L), bw);
         stn(pc, L, o);
       }
-    }
-    __syncthreads();
-    // trailing update: C_IK -= L_IJ L_KJ^T, J < K <= I
-    {
-      const int m = bb - J - 1;
-      const int ntask = m * (m + 1) / 2;
-      for (int t = w; t < ntask; t += RNW) {
-        int ii = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
-        while (ii * (ii + 1) / 2 > t) --ii;
-        const int kk = t - ii * (ii + 1) / 2;
-        const int I = J + 1 + ii, K = J + 1 + kk;
+      nbar_sync(1, RNT);                           // panel J complete; every warp holds L_{J+1,J}
+      if (wk == 0) stn(p10, L, lp);
+      // trailing update: C_IK -= L_IJ L_KJ^T for rows I >= J + 2, columns J + 1 <= K <= I
+      const int m = bb - J - 2;
+      const int ntask = m * (m + 3) / 2;
+      for (int t = wk; t < ntask; t += NWK) {
+        int ii = (int)((sqrtf(8.0f * (float)t + 9.0f) - 3.0f) * 0.5f);
+        while ((ii + 1) * (ii + 4) / 2 <= t) ++ii;
+        while (ii * (ii + 3) / 2 > t) --ii;
+        const int kk = t - ii * (ii + 3) / 2;
+        const int I = J + 2 + ii, K = J + 1 + kk;
         const int pc = R2 + (rtri(I) + K) * RBLK;
-        double2 cv = ldn(pc, L);
-        mma2(cv, neg2(ldn(R2 + (rtri(I) + J) * RBLK, L)), ldn(R2 + (rtri(K) + J) * RBLK, L));
-        stn(pc, L, cv);
+        double2 cu = ldn(pc, L);
+        const double2 bv = (kk == 0) ? lp : ldn(R2 + (rtri(K) + J) * RBLK, L);
+        mma2(cu, neg2(ldn(R2 + (rtri(I) + J) * RBLK, L)), bv);
+        stn(pc, L, cu);
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
   dbg_dump(P, c, 3);
   rtrace(P, c, 4);
   // log-determinant: sum of log L_tt over the unit's j rows, fixed order
@@ -585,35 +706,40 @@ static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c
     for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
     if (L.lane == 0) g_smem[OFF_MISC + MISC_LD + w] = lv;
   }
-  // W_S = L_S^-1 in place, by descending block columns
+  // W_S = L_S^-1 in place, by descending block columns.  Row I belongs to warp I mod RNW for the whole
+  // phase: the W blocks a task reads are its own earlier results, the L blocks it reads (column K) are
+  // overwritten only after the step's barrier - one barrier per step.
   for (int K = bb - 1; K >= 0; --K) {
     double2 o[2];
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       o[rr] = make_double2(0.0, 0.0);
-      const int I = K + 1 + w + rr * RNW;
-      if (I < bb) {
-        double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+      const int I = w + rr * RNW;
+      if (I > K && I < bb) {
+        double2 a[4];
+        zero4(a);
         int J = K + 1;
-        for (; J + 1 <= I; J += 2) {
-          mma2(a0, ldn(R2 + (rtri(I) + J) * RBLK, L), ldt(R2 + (rtri(J) + K) * RBLK, L));
-          mma2(a1, ldn(R2 + (rtri(I) + J + 1) * RBLK, L), ldt(R2 + (rtri(J + 1) + K) * RBLK, L));
+        for (; J + 3 <= I; J += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mma2(a[u], ldn(R2 + (rtri(I) + J + u) * RBLK, L), ldt(R2 + (rtri(J + u) + K) * RBLK, L));
         }
-        if (J <= I) mma2(a0, ldn(R2 + (rtri(I) + J) * RBLK, L), ldt(R2 + (rtri(J) + K) * RBLK, L));
-        a0.x += a1.x;
-        a0.y += a1.y;
-        mma2(o[rr], a0, ldt(WD + K * RBLK, L));
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (J + u <= I) mma2(a[u], ldn(R2 + (rtri(I) + J + u) * RBLK, L), ldt(R2 + (rtri(J + u) + K) * RBLK, L));
+        a[0].x = (a[0].x + a[1].x) + (a[2].x + a[3].x);
+        a[0].y = (a[0].y + a[1].y) + (a[2].y + a[3].y);
+        mma2(o[rr], a[0], ldt(WD + K * RBLK, L));
       }
     }
     __syncthreads();
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const int I = K + 1 + w + rr * RNW;
-      if (I < bb) stn(R2 + (rtri(I) + K) * RBLK, L, neg2(o[rr]));
+      const int I = w + rr * RNW;
+      if (I > K && I < bb) stn(R2 + (rtri(I) + K) * RBLK, L, neg2(o[rr]));
     }
-    if (w == 0) stn(R2 + (rtri(K) + K) * RBLK, L, ldn(WD + K * RBLK, L));
-    __syncthreads();
+    if ((K & (RNW - 1)) == w) stn(R2 + (rtri(K) + K) * RBLK, L, ldn(WD + K * RBLK, L));
   }
+  __syncthreads();
   if (c.is_export) {                                // W_b for this block's pairs
     double* dst = c.oexp + EXP_W;
     const double* src = g_smem + R2;
@@ -641,53 +767,57 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
     const int ny = min(nyc, nyb - y0);
     const int ngy = (ny + 1) >> 1;
     const int ntask = bb * ngy;
-    if (c.pair) {
-      if (!ahead && tid == 0) tma_issue(stage, g_smem + c.oF, c.pexp + EXP_ZY + (long long)y0 * ab * RBLK, ny * ab);
-      ahead = false;
-      tma_wait(stage);
-    }
-    // R = Y_j - L_ji Z_i
+    // R = Y_j - L_ji Z_i.  The Y values of all the warp's tasks are requested first: they come from
+    // HBM / L2 and would otherwise be waited for task by task.
     double2 z[YSLOTS][2];
 #pragma unroll
     for (int i = 0; i < YSLOTS; ++i) {
       const int t = w + i * RNW;
       z[i][0] = z[i][1] = make_double2(0.0, 0.0);
       if (t < ntask) {
-        const int row = t / ngy, yl0 = (t - row * ngy) * 2;
+        const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
         const int nj = min(2, ny - yl0);
         const int idx = IDX[ab * 8 + row * 8 + L.g];
-        double2 yv[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int yc = (y0 + yl0 + j) * 8 + 2 * L.q;
-          yv[j] = make_double2(0.0, 0.0);
           if (idx >= 0 && j < nj) {
-            if (yc < c.dy) yv[j].x = __ldg(P.Y + (long long)idx * c.dy + yc);
-            if (yc + 1 < c.dy) yv[j].y = __ldg(P.Y + (long long)idx * c.dy + yc + 1);
+            if (yc < c.dy) z[i][j].x = __ldg(P.Y + (long long)idx * c.dy + yc);
+            if (yc + 1 < c.dy) z[i][j].y = __ldg(P.Y + (long long)idx * c.dy + yc + 1);
           }
         }
-        if (c.pair) {
+      }
+    }
+    if (c.pair) {
+      if (!ahead && tid == 0) tma_issue(stage, g_smem + c.oF, c.pexp + EXP_ZY + (long long)y0 * ab * RBLK, ny * ab);
+      ahead = false;
+      tma_wait(stage);
+#pragma unroll
+      for (int i = 0; i < YSLOTS; ++i) {
+        const int t = w + i * RNW;
+        if (t < ntask) {
+          const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
+          const int nj = min(2, ny - yl0);
           double2 acc[4];
           zero4(acc);
           int pb[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) pb[j] = c.oF + (yl0 + min(j, nj - 1)) * ab * RBLK;
           mk<false, true>(acc, r1 + row * ab * RBLK, RBLK, pb, RBLK, 0, ab, nj, L);
-          yv[0].x -= acc[0].x;
-          yv[0].y -= acc[0].y;
-          yv[1].x -= acc[1].x;
-          yv[1].y -= acc[1].y;
+          z[i][0].x -= acc[0].x;
+          z[i][0].y -= acc[0].y;
+          z[i][1].x -= acc[1].x;
+          z[i][1].y -= acc[1].y;
         }
-        z[i][0] = yv[0];
-        z[i][1] = yv[1];
       }
     }
     __syncthreads();                                 // Z_i is no longer needed: the right-hand sides replace it
+    rtrace(P, c, 36);
 #pragma unroll
     for (int i = 0; i < YSLOTS; ++i) {
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = t / ngy, yl0 = (t - row * ngy) * 2;
+        const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
 #pragma unroll
         for (int j = 0; j < 2; ++j)
           if (yl0 + j < ny) stn(RB + ((yl0 + j) * bb + row) * RBLK, L, z[i][j]);
@@ -699,7 +829,7 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
     for (int i = 0; i < YSLOTS; ++i) {
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = t / ngy, yl0 = (t - row * ngy) * 2;
+        const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
         const int nj = min(2, ny - yl0);
         double2 acc[4];
         zero4(acc);
@@ -718,7 +848,7 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
     for (int i = 0; i < YSLOTS; ++i) {
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = t / ngy, yl0 = (t - row * ngy) * 2;
+        const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           if (yl0 + j < ny) {
@@ -729,10 +859,11 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
       }
     }
     __syncthreads();
+    rtrace(P, c, 37);
     // alpha_j = W_S^T Z
     if (c.want_grad) {
       for (int t = w; t < ntask; t += RNW) {
-        const int row = t / ngy, yl0 = (t - row * ngy) * 2;
+        const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
         const int nj = min(2, ny - yl0);
         double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
         const int p0 = RB + yl0 * bb * RBLK, p1 = RB + (yl0 + nj - 1) * bb * RBLK;
@@ -799,8 +930,8 @@ static __device__ __noinline__ void ph_t(const ResParams& P, const Ctx& c, Stage
       for (int i = 0; i < 4; ++i) {
         const int t = w + i * RNW;
         if (t < ntask) {
-          const int row = r0 + t / ng, c0 = ((t % ng + t / ng) % ng) * 4;   // rotated: every warp gets short and long column groups
-          const int nj = min(4, ab - c0);
+          const int row = r0 + t / ng, gq = (t % ng + t / ng + (t / ng) / ng) % ng;   // rotated: every warp gets every column group
+          const int c0 = grp_lo(gq, ab, ng), nj = grp_lo(gq + 1, ab, ng) - c0;
           const typename R1::T pa = r1 + row * ab * RBLK;
           // T(row, c0 + j) += sum_{k >= c0 + j} L_ji(row, k) W_i(k, c0 + j)
           int k = max(k0, c0);
@@ -838,10 +969,11 @@ static __device__ __noinline__ void ph_t(const ResParams& P, const Ctx& c, Stage
     for (int i = 0; i < 4; ++i) {
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = r0 + t / ng, c0 = ((t % ng + t / ng) % ng) * 4;   // rotated: every warp gets short and long column groups
+        const int row = r0 + t / ng, gq = (t % ng + t / ng + (t / ng) / ng) % ng;
+        const int c0 = grp_lo(gq, ab, ng), nj = grp_lo(gq + 1, ab, ng) - c0;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (c0 + j < ab) stn(r1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
+          if (j < nj) stn(r1 + (row * ab + c0 + j) * RBLK, L, acc[i][j]);
       }
     }
     __syncthreads();
@@ -866,8 +998,8 @@ static __device__ __noinline__ void ph_v(const ResParams& P, const Ctx& c) {
       zero4(acc[i]);
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = rhi - 1 - t / ng, c0 = (t % ng) * 4;     // longest rows first
-        const int nj = min(4, ab - c0);
+        const int row = rhi - 1 - t / ng, gq = (t % ng + t / ng + (t / ng) / ng) % ng;     // longest rows first, groups rotated
+        const int c0 = grp_lo(gq, ab, ng), nj = grp_lo(gq + 1, ab, ng) - c0;
         typename R1::T pb[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) pb[j] = r1 + (c0 + min(j, nj - 1)) * RBLK;
@@ -879,10 +1011,11 @@ static __device__ __noinline__ void ph_v(const ResParams& P, const Ctx& c) {
     for (int i = 0; i < 4; ++i) {
       const int t = w + i * RNW;
       if (t < ntask) {
-        const int row = rhi - 1 - t / ng, c0 = (t % ng) * 4;
+        const int row = rhi - 1 - t / ng, gq = (t % ng + t / ng + (t / ng) / ng) % ng;
+        const int c0 = grp_lo(gq, ab, ng), nj = grp_lo(gq + 1, ab, ng) - c0;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (c0 + j < ab) stn(r1 + (row * ab + c0 + j) * RBLK, L, neg2(acc[i][j]));
+          if (j < nj) stn(r1 + (row * ab + c0 + j) * RBLK, L, neg2(acc[i][j]));
       }
     }
     __syncthreads();
@@ -1302,6 +1435,7 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
   // W_i on its way into [R2 | F] (both still unused; res_class guarantees that all of it fits)
   if (c.pair && tid == 0) tma_issue(stage, g_smem + c.oR2, c.pexp + EXP_W, rtri(c.ab));
   ph_gather<DFN>(P, c);
+  rtrace(P, c, 33);
   if (c.pair) ph_lji<DFN, WFN, R1>(P, c, stage);
   dbg_dump(P, c, 1);
   rtrace(P, c, 2);

@@ -52,6 +52,37 @@ __device__ __forceinline__ int chol8_inv8(double a[8], double w[8], int lane) {
   return fail;
 }
 
+// Every lane holds the whole lower triangle (A[r][c], c <= r) of an 8x8 SPD block: the factorisation
+// then needs no shuffles, its critical path per pivot is rsqrt -> mul -> fma, and everything else
+// (the other columns' updates, the inverse) fills the latency gaps.  Same operations in the same
+// order as chol8_inv8 => the same bits.  On return A holds L (every lane), lane c < 8 holds column c
+// of W = L^-1 in w[] (w[v] = W[v][c]).  Returns 1 + index of the first non-positive pivot, or 0.
+__device__ __forceinline__ int chol8_full(double (&A)[8][8], double (&w)[8], int lane) {
+  int fail = 0;
+  double dinv[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const double piv = A[c][c];
+    if (!(piv > 0.0) && fail == 0) fail = c + 1;
+    dinv[c] = rsqrt(piv);
+    A[c][c] = piv * dinv[c];
+#pragma unroll
+    for (int r = c + 1; r < 8; ++r) A[r][c] *= dinv[c];
+#pragma unroll
+    for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+      for (int r = c2; r < 8; ++r) A[r][c2] -= A[r][c] * A[c2][c];
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    double s = (lane == r) ? 1.0 : 0.0;
+#pragma unroll
+    for (int m = 0; m < r; ++m) s -= A[r][m] * w[m];
+    w[r] = s * dinv[r];
+  }
+  return fail;
+}
+
 // Whole-CTA routine (all threads must call).  nwarps = blockDim.x / 32.
 // fail_out (shared int, pre-zeroed): 1 + global row of the first bad pivot.
 __device__ __forceinline__ void smem_potrf_trtri(double* S, double* S2, double* Wsm, int ld, int nb,
