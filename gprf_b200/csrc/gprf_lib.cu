@@ -120,6 +120,8 @@ struct gprf_ctx {
   cudaStream_t blocks_stream = nullptr;   // stream the device-held blocks were last written on
   bool res_static_dirty = true;    // edges / degrees / unit mask have to be uploaded again
   bool last_resident = false;      // the last evaluation ran on the resident path
+  bool plan_fused = false;         // the launch plan of the next resident evaluation is already on the device
+  bool bucket_small = true;        // single-CTA bucketing for small problems (GPRF_BUCKET_SMALL=0: cub radix sort)
   long long res_evals = 0, res_fallbacks = 0;
   int res_last_status = 0;
   double* dResExports = nullptr;
@@ -310,6 +312,7 @@ extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, in
   }
   if (const char* e = getenv("GPRF_PANEL_ORDER")) h->panel_order = atoi(e);
   if (const char* e = getenv("GPRF_RESIDENT")) h->res_enable = atoi(e) != 0;
+  if (const char* e = getenv("GPRF_BUCKET_SMALL")) h->bucket_small = atoi(e) != 0;
   CUDA_OK(cudaMallocHost((void**)&h->hResStatus, 4 * sizeof(int)));
   if (const char* e = getenv("GPRF_FUSED_SHARE_MIN")) h->fused_share_min = atoi(e);
   cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
@@ -845,6 +848,10 @@ extern "C" int gprf_set_tree_partitioner(gprf_handle h, int n_nodes, const doubl
   return GPRF_OK;
 }
 
+static int res_sync_static(gprf_ctx* h);
+static int res_alloc(gprf_ctx* h, int grid);
+static void res_plan_params(gprf_ctx* h, res::PlanParams* Q);
+
 // Block membership of X_dev on the device: assignment kernel, stable radix sort, bounds.
 // Leaves perm / pos_block / block_ptr on the device.  Nothing is read back: the resident path never
 // needs the block sizes on the host; reblock_finish() fetches them for the tile pipeline.
@@ -901,13 +908,36 @@ static int reblock_launch(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
     else if (h->part_mode == 1) k_assign_tree<1><<<gb, tb, 0, st>>>(X_dev, n, h->dx, Tp, h->dOwner);
     else k_assign_tree<2><<<gb, tb, 0, st>>>(X_dev, n, h->dx, Tp, h->dOwner);
   }
-  size_t tmp = h->capCub;
-  cub::DeviceRadixSort::SortPairs(h->dCub, tmp, h->dOwner, h->dPosBlock, h->dIota, h->dIdxSorted, (int)n, 0, bits, st);
-  const long long nthr = std::max<long long>(n, B + 1);
-  k_block_bounds<<<(unsigned)((nthr + tb - 1) / tb), tb, 0, st>>>(h->dPosBlock, h->dIdxSorted, n, B, h->dBlockPtr,
-                                                                    h->dPerm);
-  CUDA_OK(cudaGetLastError());
-  h->part_launches = 5;
+  h->plan_fused = false;
+  if (n <= BK_MAXN && B <= BK_MAXB && h->bucket_small) {
+    // one CTA: stable bucketing + bounds, and the resident path's launch plan when that path follows
+    BucketPlan bp;
+    memset(&bp, 0, sizeof(bp));
+    size_t smb = ((size_t)BK_WARPS * B + B + 1) * sizeof(int);
+    if (B == h->B && res_eligible(h) && res_sync_static(h) == GPRF_OK &&
+        res_alloc(h, std::max(1, std::min(h->B + h->E, h->n_sm))) == GPRF_OK) {
+      bp.enabled = 1;
+      res_plan_params(h, &bp.Q);
+      smb = std::max(smb, (size_t)(h->B + h->E) * sizeof(int));
+      h->plan_fused = true;
+    }
+    if (smb > 200 * 1024) {
+      h->err = "bucket kernel: structure too large for one CTA";
+      return GPRF_ERR_ARG;
+    }
+    if (smb > 48 * 1024) cudaFuncSetAttribute(k_bucket_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+    k_bucket_small<<<1, BK_WARPS * 32, smb, st>>>(h->dOwner, n, B, h->dBlockPtr, h->dPerm, h->dPosBlock, bp);
+    CUDA_OK(cudaGetLastError());
+    h->part_launches = 2;
+  } else {
+    size_t tmp = h->capCub;
+    cub::DeviceRadixSort::SortPairs(h->dCub, tmp, h->dOwner, h->dPosBlock, h->dIota, h->dIdxSorted, (int)n, 0, bits, st);
+    const long long nthr = std::max<long long>(n, B + 1);
+    k_block_bounds<<<(unsigned)((nthr + tb - 1) / tb), tb, 0, st>>>(h->dPosBlock, h->dIdxSorted, n, B, h->dBlockPtr,
+                                                                      h->dPerm);
+    CUDA_OK(cudaGetLastError());
+    h->part_launches = 5;
+  }
   if (B != h->B) {
     h->adj_dirty = true;
     h->units_built = false;
@@ -1105,6 +1135,7 @@ static int res_sync_static(gprf_ctx* h) {
     if (rc != GPRF_OK) return rc;
   }
   if (!h->res_static_dirty) return GPRF_OK;
+  h->plan_fused = false;
   const int B = h->B, E = h->E, U = B + E;
   CUDA_OK(ensure(&h->dResEdges, &h->capResE, (size_t)2 * E + 2));
   CUDA_OK(ensure(&h->dResDeg, &h->capResB, (size_t)B + 1));
@@ -1128,6 +1159,18 @@ static int res_sync_static(gprf_ctx* h) {
   }
   h->res_static_dirty = false;
   return GPRF_OK;
+}
+
+static void res_plan_params(gprf_ctx* h, res::PlanParams* Q) {
+  Q->block_ptr = h->dBlockPtr;
+  Q->edges = h->dResEdges;
+  Q->active = h->res_have_mask ? h->dResActive : nullptr;
+  Q->B = h->B;
+  Q->E = h->E;
+  Q->order = h->dResOrderB;        // sized for all units
+  Q->counts = h->dResCounts;
+  Q->status = h->dResCounts + 4;
+  Q->info = h->dResInfo;
 }
 
 static int res_alloc(gprf_ctx* h, int grid) {
@@ -1169,21 +1212,18 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   if (rc != GPRF_OK) return rc;
   int launches = 0;
   const size_t outlen = 1 + MAX_NCOV + (grad_X ? (size_t)h->n * h->dx : 0);
-  CUDA_OK(cudaMemsetAsync(out_dev, 0, outlen * sizeof(double), st));
-  res::PlanParams Q;
-  Q.block_ptr = h->dBlockPtr;
-  Q.edges = h->dResEdges;
-  Q.active = h->res_have_mask ? h->dResActive : nullptr;
-  Q.B = B;
-  Q.E = E;
-  Q.order = h->dResOrderB;         // sized for all units
-  Q.counts = h->dResCounts;
-  Q.status = h->dResCounts + 4;
-  Q.info = h->dResInfo;
-  const size_t plan_sm = (size_t)(B + E) * sizeof(int);
-  if (plan_sm > 48 * 1024)
-    cudaFuncSetAttribute(res::k_res_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_sm);
-  LAUNCH(9, (res::k_res_plan<<<1, 512, plan_sm, st>>>(Q)));
+  // k_res_combine writes every entry of out when the blocks cover all points (always after re-blocking)
+  if (h->plen != (long long)h->n) CUDA_OK(cudaMemsetAsync(out_dev, 0, outlen * sizeof(double), st));
+  if (h->plan_fused) {
+    h->plan_fused = false;           // the bucketing kernel of this evaluation's re-blocking built the plan
+  } else {
+    res::PlanParams Q;
+    res_plan_params(h, &Q);
+    const size_t plan_sm = (size_t)(B + E) * sizeof(int);
+    if (plan_sm > 48 * 1024)
+      cudaFuncSetAttribute(res::k_res_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_sm);
+    LAUNCH(9, (res::k_res_plan<<<1, 512, plan_sm, st>>>(Q)));
+  }
   res::ResParams P;
   P.X = X_dev;
   P.Y = h->dY;

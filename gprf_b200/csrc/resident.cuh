@@ -1613,8 +1613,9 @@ struct PlanParams {
 };
 
 #ifndef GPRF_RES_KERNEL_ONLY
-__global__ void k_res_plan(PlanParams Q) {
-  extern __shared__ int sh[];          // need[B] | key[E]
+// One CTA (any size); sh: (B + E) ints of shared memory.  Also called at the end of the single-CTA
+// bucketing kernel of partition.cuh (k_bucket_small), which saves a launch per evaluation.
+__device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
   int* need = sh;
   int* key = sh + Q.B;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -1644,25 +1645,40 @@ __global__ void k_res_plan(PlanParams Q) {
     if (need[bq] && res_class(0, (s + 7) >> 3) == 2) s_over = 1;
   }
   __syncthreads();
-  // blocks: ascending id (they are all about the same size); stable compaction by one thread per 32
-  if (tid == 0) {
+  // blocks: ascending id (they are all about the same size); stable compaction by ballots of warp 0
+  if (tid < 32) {
     int nb = 0;
-    for (int bq = 0; bq < Q.B; ++bq)
-      if (need[bq]) Q.order[nb++] = bq;
-    s_nb = nb;
+    for (int b0 = 0; b0 < Q.B; b0 += 32) {
+      const int bq = b0 + tid;
+      const bool f = bq < Q.B && need[bq];
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      if (f) Q.order[nb + __popc(m & ((1u << tid) - 1u))] = bq;
+      nb += __popc(m);
+    }
+    if (tid == 0) s_nb = nb;
   }
   __syncthreads();
-  // pairs: rank sort by (size descending, id ascending)
-  for (int e = tid; e < Q.E; e += nt) {
-    const int ke = key[e];
-    if (ke < 0) continue;
-    int rank = 0;
-    for (int f = 0; f < Q.E; ++f) {
-      const int kf = key[f];
-      rank += (kf > ke || (kf == ke && f < e)) ? 1 : 0;
+  // pairs: rank sort by (size descending, id ascending); S lanes share an edge's comparisons
+  {
+    int S = 1;
+    while (S < 32 && 2 * S * Q.E <= nt) S *= 2;
+    const int sub = tid & (S - 1);
+    for (int e0 = 0; e0 < Q.E; e0 += nt / S) {
+      const int e = e0 + tid / S;
+      const int ke = e < Q.E ? key[e] : -1;
+      int rank = 0;
+      if (ke >= 0) {
+        for (int f = sub; f < Q.E; f += S) {
+          const int kf = key[f];
+          rank += (kf > ke || (kf == ke && f < e)) ? 1 : 0;
+        }
+      }
+      for (int o = 1; o < S; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+      if (ke >= 0 && sub == 0) {
+        Q.order[s_nb + rank] = Q.B + e;
+        atomicAdd(&s_np, 1);
+      }
     }
-    Q.order[s_nb + rank] = Q.B + e;
-    atomicAdd(&s_np, 1);
   }
   __syncthreads();
   if (tid == 0) {
@@ -1672,6 +1688,11 @@ __global__ void k_res_plan(PlanParams Q) {
     Q.counts[3] = 0;
     *Q.status = s_over ? ST_OVERFLOW : 0;
   }
+}
+
+__global__ void k_res_plan(PlanParams Q) {
+  extern __shared__ int sh[];          // need[B] | key[E]
+  res_plan_body(Q, sh);
 }
 
 #endif  // GPRF_RES_KERNEL_ONLY

@@ -233,3 +233,44 @@ def test_resident_sharded_partial_sums():
         assert np.abs(acc[1] - full[1]).max() <= 1e-11 * np.abs(full[1]).max()
         assert np.abs(acc[2] - full[2]).max() <= 1e-11 * np.abs(full[2]).max()
     assert_parity(o.llgrad(**kw), full, "full")
+
+
+def test_single_cta_bucketing_equals_radix_sort_path(monkeypatch):
+    """Re-blocking of small problems runs in ONE CTA (stable counting sort + bounds + the resident
+    path's launch plan, partition.cuh: k_bucket_small); GPRF_BUCKET_SMALL=0 keeps the cub radix sort +
+    k_block_bounds + k_res_plan launches.  Same block lists (bit-exact against numpy, empty blocks
+    included), same results to the last bit, three launches fewer."""
+    from gprf_b200 import GPRF, GPCov, Blocker, grid_centers
+    from oracle.blocking import Blocker as OB, grid_centers as ogc
+    rng = np.random.RandomState(8)
+    n, dy = 2500, 50
+    Y = rng.randn(n, dy)
+    bl = Blocker(grid_centers(36))
+    bo = OB(np.asarray(ogc(36)))
+    th = dict(wfn_params=[1.0], dfn_params=[0.1, 0.1], dfn_str="euclidean", wfn_str="se")
+    res = {}
+    Xs = []
+    for step in range(3):
+        X = rng.rand(n, 2)
+        if step == 1:
+            X[:, 0] *= 0.6                     # leaves the right-hand blocks empty
+        Xs.append(X)
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GPRF_BUCKET_SMALL", mode)
+        g = GPRF(Xs[0], Y, bl.block_clusters, GPCov(**th), 0.01, neighbors=bl.neighbors())
+        assert g._device_part == "grid"
+        out = []
+        for X in Xs:
+            g.update_X(X)
+            r = g.llgrad(grad_X=True, grad_cov=True)
+            assert g.resident_stats()[1] == 0
+            launches = g.last_timing()[1]
+            dev = g.block_idxs
+            host = bo.block_clusters(X)
+            assert len(dev) == len(host) and all(np.array_equal(a, b) for a, b in zip(dev, host))
+            out.append((r, launches))
+        res[mode] = out
+        g.close()
+    for (a, la), (b, lb) in zip(res["1"], res["0"]):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert la == lb - 4, (la, lb)          # 3 cub launches + bounds + plan -> 1
