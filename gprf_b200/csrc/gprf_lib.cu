@@ -135,6 +135,7 @@ struct gprf_ctx {
   size_t capResExp = 0, capResScr = 0, capResU = 0, capResB = 0, capResE = 0, capResAct = 0;
   int* hResStatus = nullptr;       // pinned: [status]
   double* dResDbg = nullptr;
+  int* dResListPtr = nullptr;      // n_sm + 1 bounds of the CTAs' unit lists
   int res_dbg_unit = -1, res_dbg_phase = -1;
   std::vector<unsigned char> res_mask;
 
@@ -396,7 +397,7 @@ extern "C" int gprf_destroy(gprf_handle h) {
   cudaFree(h->dOwner); cudaFree(h->dIota); cudaFree(h->dIdxSorted); cudaFree(h->dCub);
   cudaFree(h->dResExports); cudaFree(h->dResScratch); cudaFree(h->dResLL); cudaFree(h->dResGth); cudaFree(h->dResGx);
   cudaFree(h->dResInfo); cudaFree(h->dResOrderB); cudaFree(h->dResOrderP); cudaFree(h->dResCounts); cudaFree(h->dResReady);
-  cudaFree(h->dResEdges); cudaFree(h->dResDeg); cudaFree(h->dResActive); cudaFree(h->dResDbg);
+  cudaFree(h->dResEdges); cudaFree(h->dResDeg); cudaFree(h->dResActive); cudaFree(h->dResDbg); cudaFree(h->dResListPtr);
   if (h->hResStatus) cudaFreeHost(h->hResStatus);
   if (h->hUnits) cudaFreeHost(h->hUnits);
   if (h->hList) cudaFreeHost(h->hList);
@@ -1167,6 +1168,8 @@ static void res_plan_params(gprf_ctx* h, res::PlanParams* Q) {
   Q->active = h->res_have_mask ? h->dResActive : nullptr;
   Q->B = h->B;
   Q->E = h->E;
+  Q->G = std::max(1, std::min(h->B + h->E, h->n_sm));
+  Q->list_ptr = h->dResListPtr;
   Q->order = h->dResOrderB;        // sized for all units
   Q->counts = h->dResCounts;
   Q->status = h->dResCounts + 4;
@@ -1199,6 +1202,7 @@ static int res_alloc(gprf_ctx* h, int grid) {
     h->capResU = cu;
   }
   if (!h->dResDbg) CUDA_OK(cudaMalloc((void**)&h->dResDbg, 2 * 160 * 160 * sizeof(double)));
+  if (!h->dResListPtr) CUDA_OK(cudaMalloc((void**)&h->dResListPtr, ((size_t)h->n_sm + 2) * sizeof(int)));
   return GPRF_OK;
 }
 
@@ -1252,7 +1256,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   P.epoch = ++h->res_epoch;
   P.order = h->dResOrderB;
   P.n_order = h->dResCounts + 0;
-  P.counter = h->dResCounts + 2;
+  P.list_ptr = h->dResListPtr;
   // ONE launch: block units first, the pair units behind them wait for their parent's exports
   const int grid_u = std::max(1, std::min(B + E, h->n_sm));
   if (P.trace) P.trace = h->dTrace;

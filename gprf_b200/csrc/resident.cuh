@@ -107,7 +107,7 @@ struct ResParams {
   const int* edges;             // 2 E
   const int* order;             // units of this launch (block id, or B + edge id)
   const int* n_order;           // their number (device: written by k_res_plan)
-  int* counter;                 // dynamic queue head
+  const int* list_ptr;          // gridDim.x + 1: CTA w evaluates order[list_ptr[w] .. list_ptr[w + 1])
   int B, dx, dy, nyb;
   int want_grad;
   CovParams cp;
@@ -1485,7 +1485,8 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
   rtrace(P, c, 11);
 }
 
-// grid: persistent CTAs (<= one per SM), RNT threads, R_SMEM_BYTES dynamic shared memory.
+// grid: persistent CTAs (<= one per SM, all co-resident: pairs spin on their parent's flag), RNT threads,
+// R_SMEM_BYTES dynamic shared memory.
 template <int DFN, int WFN>
 __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
   double* MISC = g_smem + OFF_MISC;
@@ -1504,13 +1505,9 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
   __syncthreads();
   const ResParams& P = *Ps;
   double* scratch = P.scratch + (long long)blockIdx.x * SCR_STRIDE;
-  const int n_units = *P.n_order;
-  while (true) {
-    if (threadIdx.x == 0) *s_unit = atomicAdd(P.counter, 1);
-    __syncthreads();
-    const int slot = *s_unit;
-    __syncthreads();
-    if (slot >= n_units) break;
+  // Static unit lists (k_res_plan): block units first in every list, so a pair's parent never waits.
+  const int slot_end = P.list_ptr[blockIdx.x + 1];
+  for (int slot = P.list_ptr[blockIdx.x]; slot < slot_end; ++slot) {
     const int uid = P.order[slot];
     int bi = -1, bj = uid;
     if (uid >= P.B) {
@@ -1606,8 +1603,10 @@ struct PlanParams {
   const int* edges;
   const unsigned char* active;     // per unit (B + E), or nullptr = all
   int B, E;
-  int* order;                      // out: block units (ascending id), then pair units (largest first)
-  int* counts;                     // out: [n units, n block units, queue counter, -]
+  int G;                           // CTAs of the resident launch
+  int* order;                      // out: the CTAs' unit lists, back to back
+  int* list_ptr;                   // out: G + 1 list bounds
+  int* counts;                     // out: [n units, n block units, -, -]
   int* status;                     // out (reset here)
   int* info;                       // per unit, reset here
 };
@@ -1633,7 +1632,8 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
     const int i = Q.edges[2 * e], j = Q.edges[2 * e + 1];
     const int a = (int)(Q.block_ptr[i + 1] - Q.block_ptr[i]);
     const int b = (int)(Q.block_ptr[j + 1] - Q.block_ptr[j]);
-    key[e] = act ? (a + b) : -1;
+    // cost key: measured pair times fit 11.5 ab + 19.0 bb - 228 us (8-blocks of block i / block j)
+    key[e] = act ? (b > 0 ? 3 * ((a + 7) >> 3) + 5 * ((b + 7) >> 3) : 0) : -1;
     if (act) {
       need[i] = 1;                      // benign race: everybody writes 1
       if (b > 0 && res_class((a + 7) >> 3, (b + 7) >> 3) == 2) s_over = 1;
@@ -1645,19 +1645,39 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
     if (need[bq] && res_class(0, (s + 7) >> 3) == 2) s_over = 1;
   }
   __syncthreads();
-  // blocks: ascending id (they are all about the same size); stable compaction by ballots of warp 0
+  // Static unit lists, one per CTA of the resident launch.  Measured on the README configuration the
+  // dynamic largest-first queue left 46 CTAs with three ~165 us pair units and 102 with two (the
+  // blocks take ~75 us on 100 CTAs while the other 48 wait for them, so every CTA is "busy" until
+  // then): 545 us against a mean load of 430.  Here the CTAs that must take one pair more get the
+  // SMALLEST pairs, and inside each class the pairs are dealt in snake order (large with small).
+  //   blocks: the k-th needed block -> CTA k % G, slot k / G (ascending id, all about the same size)
+  //   pairs by rank r (size descending): q = np / G, rem = np % G; the first (G - rem) q ranks go to
+  //   CTAs 0 .. G-rem-1 (q each), the rest to CTAs G-rem .. G-1 (q + 1 each)
   if (tid < 32) {
     int nb = 0;
     for (int b0 = 0; b0 < Q.B; b0 += 32) {
       const int bq = b0 + tid;
       const bool f = bq < Q.B && need[bq];
       const unsigned m = __ballot_sync(0xffffffffu, f);
-      if (f) Q.order[nb + __popc(m & ((1u << tid) - 1u))] = bq;
+      if (f) need[bq] = 1 + nb + __popc(m & ((1u << tid) - 1u));      // 1 + its index among the needed blocks
       nb += __popc(m);
     }
     if (tid == 0) s_nb = nb;
   }
+  for (int e = tid; e < Q.E; e += nt)
+    if (key[e] >= 0) atomicAdd(&s_np, 1);
   __syncthreads();
+  const int G = Q.G, nb = s_nb, np_ = s_np;
+  const int kb = nb / G, rb = nb % G, q = np_ / G, rem = np_ % G, mB = G - rem;
+  auto nblk = [&](int w) { return kb + (w < rb ? 1 : 0); };
+  auto lptr = [&](int w) { return w * kb + min(w, rb) + w * q + max(0, w - mB); };
+  for (int w = tid; w <= G; w += nt) Q.list_ptr[w] = lptr(w);
+  for (int bq = tid; bq < Q.B; bq += nt) {
+    if (need[bq]) {
+      const int k = need[bq] - 1, w = k % G;
+      Q.order[lptr(w) + k / G] = bq;
+    }
+  }
   // pairs: rank sort by (size descending, id ascending); S lanes share an edge's comparisons
   {
     int S = 1;
@@ -1675,8 +1695,18 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
       }
       for (int o = 1; o < S; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
       if (ke >= 0 && sub == 0) {
-        Q.order[s_nb + rank] = Q.B + e;
-        atomicAdd(&s_np, 1);
+        int w, round;
+        if (rank < mB * q) {
+          round = rank / mB;
+          const int pos = rank - round * mB;
+          w = (round & 1) ? mB - 1 - pos : pos;
+        } else {
+          const int r2 = rank - mB * q;
+          round = r2 / rem;
+          const int pos = r2 - round * rem;
+          w = mB + ((round & 1) ? rem - 1 - pos : pos);
+        }
+        Q.order[lptr(w) + nblk(w) + round] = Q.B + e;
       }
     }
   }

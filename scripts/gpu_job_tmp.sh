@@ -1,1 +1,1 @@
-python scripts/trace_resident.py cfg2 > gpurun_out/r02q_trace_cfg2.txt 2>&1; grep -E "^## |^#   |CTA end" gpurun_out/r02q_trace_cfg2.txt
+python scripts/trace_resident.py cfg2 gpurun_out/r02x_unit_times.txt > gpurun_out/r02x_trace_cfg2.txt 2>&1; tail -3 gpurun_out/r02x_trace_cfg2.txt

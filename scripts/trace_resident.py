@@ -75,3 +75,23 @@ for c in range(nct):
 ends = np.array(ends)
 print("# CTA end times pct 0/50/90/100: %.1f %.1f %.1f %.1f us" % (ends.min(), np.percentile(ends, 50),
                                                                    np.percentile(ends, 90), ends.max()))
+# per-unit totals with the unit's sizes (a = parent block, b = own block), for the plan's cost model
+if len(sys.argv) > 2:
+    blocks = g.block_idxs
+    sizes = [len(b) for b in blocks]
+    edges = wl["neighbors"]
+    rows = []
+    for c in range(nct):
+        k = int((t[c] > 0).sum())
+        start = {}
+        for i in range(k):
+            u = int(uid[c, i])
+            if tag[c, i] == 1:
+                start[u] = t[c, i]
+            elif tag[c, i] == 11 and u in start:
+                if u < B:
+                    rows.append((u, 0, sizes[u], (t[c, i] - start[u]) / 1e3, c, (start[u] - t0) / 1e3))
+                else:
+                    i_, j_ = edges[u - B]
+                    rows.append((u, sizes[i_], sizes[j_], (t[c, i] - start[u]) / 1e3, c, (start[u] - t0) / 1e3))
+    np.savetxt(sys.argv[2], np.array(rows), fmt="%.3f", header="uid a b us cta start_us")
