@@ -70,6 +70,7 @@ struct gprf_ctx {
   std::vector<long long> block_ptr_h;
   std::vector<unsigned char> explicit_mask, lpt, seen;
   bool use_explicit_mask = false, adj_dirty = true, blocks_from_device = false;
+  bool raw_weights = false;        // masked evaluations: every active unit counts with weight 1
   int shard_rank = 0, shard_world = 1;
   bool keep_kinv = false;          // store K^-1 tiles (gprf_set_keep_kinv)
   bool share_on = true;            // edges reuse block i's factor tiles (gprf_set_factor_reuse)
@@ -545,7 +546,7 @@ static int rebuild_units(gprf_ctx* h, cudaStream_t st) {
     int bi, bj = -1;
     if (uix < B) {
       bi = uix;
-      u.weight = 1.0 - (double)h->deg[bi];
+      u.weight = h->raw_weights ? 1.0 : 1.0 - (double)h->deg[bi];
     } else {
       bi = edges[2 * (uix - B)];
       bj = edges[2 * (uix - B) + 1];
@@ -755,6 +756,28 @@ extern "C" int gprf_set_edges(gprf_handle h, int E, const int* edges, int shard_
   h->have_structure = false;
   h->units_built = false;
   if ((int)h->block_ptr_h.size() == h->B + 1 && h->B > 0) {
+    int rc = rebuild_units(h, h->stream);
+    if (rc != GPRF_OK) return rc;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
+  return GPRF_OK;
+}
+
+// Evaluate only the units with mask != 0 (NULL: all units / the shard of gprf_set_edges again).
+// raw_weights != 0: every active unit counts once (no (1 - deg_i) factors), so that a mask holding a
+// single unit returns that unit's own (ll, gradients) - llgrad_unary / llgrad_joint of gprf.py:299-330
+// on the live structure.
+extern "C" int gprf_set_unit_mask(gprf_handle h, const unsigned char* mask, int n_units, int raw_weights) {
+  if (!h) return GPRF_ERR_ARG;
+  if (mask && n_units != h->B + h->E) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  h->use_explicit_mask = (mask != nullptr);
+  if (mask) h->explicit_mask.assign(mask, mask + n_units);
+  h->raw_weights = (mask != nullptr) && raw_weights != 0;
+  h->res_static_dirty = true;
+  h->have_structure = false;
+  h->units_built = false;
+  if (!h->host_blocks_stale && (int)h->block_ptr_h.size() == h->B + 1 && h->B > 0) {
     int rc = rebuild_units(h, h->stream);
     if (rc != GPRF_OK) return rc;
     CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -1271,6 +1294,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   C.adj_side = h->dAdjSide;
   C.edges = h->dResEdges;
   C.deg = h->dResDeg;
+  C.raw = h->raw_weights ? 1 : 0;
   C.active = h->res_have_mask ? h->dResActive : nullptr;
   C.ll_u = h->dResLL;
   C.gth_u = h->dResGth;

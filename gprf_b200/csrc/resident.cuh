@@ -1738,6 +1738,7 @@ struct ResCombine {
   const int* adj_side;
   const int* edges;
   const int* deg;                  // per block
+  int raw;                         // masked evaluation with unit weights (gprf_set_unit_mask)
   const unsigned char* active;     // per unit or nullptr
   const double* ll_u;
   const double* gth_u;
@@ -1762,7 +1763,7 @@ __global__ void k_res_combine(ResCombine C, double* out, int want_gx, int want_c
       double wgt;
       if (u < C.B) {
         s = C.block_ptr[u + 1] - C.block_ptr[u];
-        wgt = 1.0 - (double)C.deg[u];
+        wgt = C.raw ? 1.0 : 1.0 - (double)C.deg[u];
       } else {
         const int i = C.edges[2 * (u - C.B)], j = C.edges[2 * (u - C.B) + 1];
         s = (C.block_ptr[i + 1] - C.block_ptr[i]) + (C.block_ptr[j + 1] - C.block_ptr[j]);
@@ -1794,7 +1795,7 @@ __global__ void k_res_combine(ResCombine C, double* out, int want_gx, int want_c
   const int lp = (int)(pos - C.block_ptr[bq]);
   double g[3] = {0.0, 0.0, 0.0};
   if (!C.active || C.active[bq]) {
-    const double wgt = 1.0 - (double)C.deg[bq];
+    const double wgt = C.raw ? 1.0 : 1.0 - (double)C.deg[bq];
     const double* p = C.gx_u + (long long)bq * GX_STRIDE + (long long)lp * 3;
     g[0] += wgt * p[0];
     g[1] += wgt * p[1];

@@ -20,6 +20,8 @@ to the host numpy result on the construction-time X (see ``partition_probe``);
 any other ``block_fn`` is called on the host exactly like the reference does.
 """
 import ctypes as C
+import os
+import warnings
 from collections import defaultdict
 
 import numpy as np
@@ -70,6 +72,10 @@ class GPRF(object):
         self.device = device
         self.unit_shard = unit_shard
         self.device_blocks = device_blocks
+        # runtime guard of the on-device re-blocking: every k-th re-blocked evaluation is checked
+        # against block_fn(X) on the host (0 = only the construction-time proof)
+        self.verify_reblock_every = int(os.environ.get("GPRF_VERIFY_REBLOCK", "0"))
+        self._reblock_count = 0
         self._lib = None
         self._h = None
         self._device_part = None
@@ -155,6 +161,8 @@ class GPRF(object):
         self._lib = None
         self._h = None
         self._device_part = None
+        self.__dict__.setdefault("verify_reblock_every", 0)
+        self.__dict__.setdefault("_reblock_count", 0)
         self._open()
         if self.device_blocks and self.block_fn is not None:
             self._setup_device_partitioner()
@@ -221,6 +229,14 @@ class GPRF(object):
                              "weight function, but currently wfn_params=%s" % self.cov.wfn_params)
         return np.ascontiguousarray(np.concatenate([[self.noise_var], np.asarray(self.cov.wfn_params, dtype=float),
                                                     np.asarray(self.cov.dfn_params, dtype=float)]), dtype=np.float64)
+
+    def _device_blocks_match_host(self):
+        """Runtime guard of the on-device re-blocking (block_clustering.py:17-26,
+        pdtree_clustering.py:65-77): the device-held membership of the current X against block_fn(X)."""
+        self._block_idxs = None
+        dev = self.block_idxs
+        host = self.block_fn(self.X)
+        return len(dev) == len(host) and all(np.array_equal(a, b) for a, b in zip(dev, host))
 
     def update_covs(self, covs):
         """gprf.py:160-167."""
@@ -323,7 +339,8 @@ class GPRF(object):
         failed = C.c_int(-1)
         gX = np.empty(Xc.shape, dtype=np.float64) if grad_X else None
         gC = np.empty(len(th), dtype=np.float64) if grad_cov else None
-        if self._blocks_stale:
+        reblocked = self._blocks_stale
+        if reblocked:
             fn = self._lib.gprf_llgrad_reblock      # update_X's re-blocking happens on the GPU
             self._blocks_stale = False
             self._blocks_key = None
@@ -332,6 +349,17 @@ class GPRF(object):
         rc = fn(self._h, _lib.ptr(Xc), _lib.ptr(th), len(th), int(grad_X), int(grad_cov),
                 C.byref(ll), _lib.ptr(gX), _lib.ptr(gC), C.byref(failed))
         self._check(rc, failed.value)
+        if reblocked and self.verify_reblock_every > 0:
+            self._reblock_count += 1
+            if self._reblock_count % self.verify_reblock_every == 0 and not self._device_blocks_match_host():
+                # the device partition is no longer the reference's: from here on block_fn runs on the
+                # host (block assignment only - the evaluation itself stays on the GPU), and this
+                # evaluation is redone with the host's blocks
+                warnings.warn("gprf_b200: device re-blocking differs from block_fn(X); block assignment "
+                              "falls back to the host block_fn", RuntimeWarning)
+                self._device_part = None
+                self.block_idxs = self.block_fn(self.X)
+                return self.llgrad(parallel=parallel, local=local, **kwargs)
         gradX = gX if grad_X else np.zeros((0, 0))
         gradCov = gC.reshape((1, -1)) if grad_cov else np.zeros((0, 0))
         return np.float64(ll.value), gradX, gradCov
@@ -497,14 +525,53 @@ class GPRF(object):
             sub.close()
         return float(ll), (gX if grad_X else np.zeros(())), (gC.reshape(-1) if grad_cov else np.zeros(()))
 
+    def set_unit_mask(self, mask=None, raw_weights=False):
+        """Restrict the evaluations to the units with mask != 0 (units: blocks 0..B-1, then the edges
+        in ``neighbors`` order); ``None`` restores all units.  ``raw_weights``: every active unit counts
+        once instead of with (1 - deg_i)  (gprf_set_unit_mask)."""
+        self._sync_blocks()
+        self._sync_edges(self._edges_for(True))
+        if mask is None:
+            self._check(self._lib.gprf_set_unit_mask(self._h, None, 0, 0))
+            return
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        if m.shape != (self.n_blocks + len(self._keep_edges[1]),):
+            raise ValueError("mask must have one entry per unit (%d blocks + %d edges)"
+                             % (self.n_blocks, len(self._keep_edges[1])))
+        self._check(self._lib.gprf_set_unit_mask(self._h, _lib.ptr(m), len(m), int(bool(raw_weights))))
+
+    def _masked_unit(self, unit, rows, **kwargs):
+        """One unit of the live structure through the normal evaluation path (unit mask, weight 1)."""
+        grad_X, grad_cov = bool(kwargs.get("grad_X", False)), bool(kwargs.get("grad_cov", False))
+        mask = np.zeros(self.n_blocks + len(self.neighbors), dtype=np.uint8)
+        mask[unit] = 1
+        self.set_unit_mask(mask, raw_weights=True)
+        try:
+            ll, gX, gC = self.llgrad(grad_X=grad_X, grad_cov=grad_cov)
+        finally:
+            self.set_unit_mask(None)
+        return float(ll), (gX[rows] if grad_X else np.zeros(())), (gC.reshape(-1) if grad_cov else np.zeros(()))
+
     def llgrad_unary(self, i, sparse=False, **kwargs):
+        """gprf.py:299-308, on the live structure: the unit mask selects block i, nothing is re-created."""
         idx = self.block_idxs[i]
-        return self.gaussian_llgrad(self.X[idx], self.Y[idx], **kwargs)
+        if len(idx) == 0:
+            return self.gaussian_llgrad(self.X[idx], self.Y[idx], **kwargs)
+        return self._masked_unit(int(i), idx, **kwargs)
 
     def llgrad_joint(self, i, j, sparse=False, **kwargs):
+        """gprf.py:310-330.  An edge of ``neighbors`` runs as that pair unit of the live structure
+        (block i's factor is shared as in a full evaluation); any other pair goes through
+        gaussian_llgrad on the stacked rows."""
         ii, jj = self.block_idxs[i], self.block_idxs[j]
-        return self.gaussian_llgrad(np.vstack([self.X[ii], self.X[jj]]),
-                                    np.vstack([self.Y[ii], self.Y[jj]]), **kwargs)
+        try:
+            e = self.neighbors.index((i, j))
+        except ValueError:
+            e = -1
+        if e < 0 or len(ii) + len(jj) == 0:
+            return self.gaussian_llgrad(np.vstack([self.X[ii], self.X[jj]]),
+                                        np.vstack([self.Y[ii], self.Y[jj]]), **kwargs)
+        return self._masked_unit(self.n_blocks + e, np.concatenate([ii, jj]), **kwargs)
 
     # -- prediction (gprf.py:593-672) ---------------------------------------------
     def block_precisions(self, Y=None):
@@ -646,13 +713,18 @@ class GPRF(object):
         for (i, j) in inside:
             cnt[i] += 1
             cnt[j] += 1
-        sub = GPRF(self._Xc(), self._Yc, None, self.cov, self.noise_var, block_idxs=self.block_idxs,
-                   neighbors=inside, device=self.device)
+        B = self.n_blocks
+        mask = np.zeros(B + len(self.neighbors), dtype=np.uint8)
+        mask[blocks] = 1
+        eidx = [e for e, (i, j) in enumerate(self.neighbors) if i in bset and j in bset]
+        mask[[B + e for e in eidx]] = 1
+        self.set_unit_mask(mask, raw_weights=True)
         try:
-            sub.llgrad()
-            lls, _ = sub.unit_results()
+            self.llgrad()
+            lls_all, _ = self.unit_results()
         finally:
-            sub.close()
+            self.set_unit_mask(None)
+        lls = np.concatenate([lls_all[:B], lls_all[[B + e for e in eidx]]]) if eidx else lls_all[:B]
         B = self.n_blocks
         ll = float(np.sum(lls[B:B + len(inside)])) if inside else 0.0
         ll += float(np.sum([(1 - cnt[b]) * lls[b] for b in blocks]))

@@ -70,6 +70,13 @@ int gprf_set_edges(gprf_handle h, int n_edges, const int* edges, int shard_rank,
                    int shard_world);
 int gprf_set_blocks(gprf_handle h, int n_blocks, const long long* block_ptr,
                     const long long* perm);
+/* Restrict the evaluations to the units with mask != 0 (mask[B+E]; NULL restores
+ * all units / the shard selected by gprf_set_edges).  With raw_weights != 0 every
+ * active unit counts once instead of with (1 - deg_i): a mask holding one unit
+ * then returns that unit's own objective and gradients, which is how
+ * GPRF.llgrad_unary / llgrad_joint (gprf.py:299-330) and subset evaluations run on
+ * the live structure. */
+int gprf_set_unit_mask(gprf_handle h, const unsigned char* mask, int n_units, int raw_weights);
 
 /* Device-side partitioners: block membership is recomputed from X on the GPU,
  * bit-exact with the reference's numpy expressions.
