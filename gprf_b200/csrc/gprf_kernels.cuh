@@ -1116,4 +1116,62 @@ __global__ void k_block_maxk(const double* X, int dx, const long long* perm, con
   }
 }
 
+
+// out (s x dy, row major) = L Y_unit for one unit after its factorisation: L is the lower triangle of
+// the unit's working matrix M (row major, leading dimension sp), Y_unit the unit's rows of Y (n x dy) in
+// unit order.  The dense branch of the reference's sample_y (synthetic.py:106-114: y = chol(K) z): the
+// draw z is uploaded as "Y", the objective-only evaluation factors K, this kernel applies L.
+// grid: one CTA (256 threads) per 64 output rows; tiles of 64 x 64 through shared memory, plain DFMA
+// (n^2 dy flops, once per data set - not on the evaluation path).
+#ifndef GPRF_FUSED_ONLY
+__global__ void __launch_bounds__(256) k_unit_lmul(const double* M, int sp, int s, const double* Y, int dy,
+                                                   const long long* perm, int a_start, double* out) {
+  constexpr int KT = 32;
+  __shared__ double sL[64][KT + 1];
+  __shared__ double sY[KT][65];
+  const int r0 = blockIdx.x * 64;
+  const int tid = threadIdx.x;
+  const int tr = tid >> 4, tc = tid & 15;        // thread: rows tr + 16 i, columns tc + 16 j
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < r0 + 64 && k0 < s; k0 += KT) {
+    for (int e = tid; e < 64 * KT; e += 256) {
+      const int r = e / KT, c = e % KT;
+      const int gr = r0 + r, gc = k0 + c;
+      sL[r][c] = (gr < s && gc <= gr) ? M[(long long)gr * sp + gc] : 0.0;
+    }
+    for (int e = tid; e < KT * 64; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      const int yr_ = k0 + r;
+      sY[r][c] = (yr_ < s && c < dy) ? Y[perm[a_start + yr_] * dy + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < KT; ++k) {
+      double lv[4], yv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) lv[i] = sL[tr + 16 * i][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) yv[j] = sY[k][tc + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(lv[i], yv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gr = r0 + tr + 16 * i, gc = tc + 16 * j;
+      if (gr < s && gc < dy) out[(long long)gr * dy + gc] = acc[i][j];
+    }
+}
+
+#endif  // GPRF_FUSED_ONLY
+
 }  // namespace gprf

@@ -1675,6 +1675,30 @@ extern "C" int gprf_debug_unit(gprf_handle h, int unit, int* s, int* sp, int* yr
   return GPRF_OK;
 }
 
+// out_host (s x dy) = L_unit Y_unit of the last evaluation's factorisation (tile pipeline; the unit must
+// be active and dy <= 64).  See k_unit_lmul.
+extern "C" int gprf_unit_lmul(gprf_handle h, int unit, double* out_host) {
+  if (!h || !out_host) return GPRF_ERR_ARG;
+  if (!h->have_structure || h->last_resident) return GPRF_ERR_NO_STRUCTURE;
+  if (unit < 0 || unit >= h->U || h->dy > 64) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  const UnitDesc& u = h->units[unit];
+  if (!u.active || u.s == 0) return GPRF_OK;
+  if (unit >= h->B) {
+    h->err = "gprf_unit_lmul is defined for block units";
+    return GPRF_ERR_ARG;
+  }
+  double* d_out = nullptr;
+  CUDA_OK(cudaMalloc((void**)&d_out, (size_t)u.s * h->dy * sizeof(double)));
+  k_unit_lmul<<<(u.s + 63) / 64, 256, 0, h->stream>>>(h->arena + u.m_off, u.sp, u.s, h->dY, h->dy, h->dPerm, u.a_start, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_out, (size_t)u.s * h->dy * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_out);
+  CUDA_OK(e);
+  return GPRF_OK;
+}
+
 extern "C" int gprf_kernel_matrix(gprf_handle h, const double* X1, long long n1, const double* X2, long long n2,
                                   const double* theta, int ncov, double* K) {
   if (!h || !X1 || !theta || !K || n1 < 0) return GPRF_ERR_ARG;

@@ -27,10 +27,44 @@ def _se_gram(X, lscales, signal_var):
     return r2
 
 
-def sample_y(X, cov, noise_var, yd):
-    """GP-prior draw Y = chol(K + nv I) Z with Z = randn(n, yd) (dense branch, n < 40000)."""
+def sample_y_device(X, cov, noise_var, yd, device=0, Z=None):
+    """GP-prior draw Y = jitchol(K + nv I) Z on the GPU, any covariance family, any n whose n x n
+    matrix fits in HBM (8 n^2 bytes twice: n = 20500 needs 7 GB, n = 80500 about 105 GB of the 180).
+
+    One unit holding every point runs through the batched Cholesky of the evaluation path (kernel
+    matrix generated in the factorisation's epilogues, jitter rule of gpy_linalg.py:77-97), then
+    ``gprf_unit_lmul`` applies L to the draw.  This is the dense branch of the reference's sample_y
+    (synthetic.py:106-114) for n < 40000 AND the stated replacement of its CHOLMOD branch
+    (synthetic.py:115-135, n >= 40000): the sparse factorisation there is an approximation of this
+    exact draw (kernel entries beyond 4 lengthscales dropped) whose samples depend on CHOLMOD's
+    fill-reducing permutation, so the golden runs with n >= 40000 cannot be reproduced by anyone
+    without that library; the exact draw can.
+    """
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n = X.shape[0]
+    if Z is None:
+        Z = np.random.randn(n, yd)
+    g = GPRF(X, np.ascontiguousarray(Z), None, cov, noise_var, block_idxs=[np.arange(n)], neighbors=[],
+             device=device, device_blocks=False)
+    try:
+        g.set_resident(False)
+        g.llgrad()
+        Y = np.empty((n, yd), dtype=np.float64)
+        g._check(g._lib.gprf_unit_lmul(g._h, 0, Y.ctypes.data))
+    finally:
+        g.close()
+    return Y
+
+
+def sample_y(X, cov, noise_var, yd, device=None):
+    """GP-prior draw Y = chol(K + nv I) Z with Z = randn(n, yd) (synthetic.py:103-137).
+    ``device`` = CUDA ordinal: on the GPU (sample_y_device).  ``device=None``: host numpy, as the
+    reference's dense branch does it - the synthetic (euclidean, se) family only; this is what the
+    CPU-only legs (bench.py --impl reference, the oracle tests) use to build their input data."""
+    if device is not None:
+        return sample_y_device(X, cov, noise_var, yd, device=device)
     if cov.dfn_str != "euclidean" or cov.wfn_str != "se":
-        raise NotImplementedError("host sampling is provided for the synthetic (euclidean, se) family")
+        raise NotImplementedError("host sampling covers the synthetic (euclidean, se) family; pass device=")
     K = _se_gram(np.asarray(X, dtype=float), cov.dfn_params, cov.wfn_params[0])
     K[np.diag_indices_from(K)] += noise_var
     L, info = lapack.dpotrf(K, lower=1)
@@ -40,21 +74,22 @@ def sample_y(X, cov, noise_var, yd):
     return np.dot(L, Z)
 
 
-def sample_synthetic(seed=1, n=400, xd=2, yd=10, lscale=0.1, noise_var=0.01):
+def sample_synthetic(seed=1, n=400, xd=2, yd=10, lscale=0.1, noise_var=0.01, device=None):
     if seed >= 1000:
         raise NotImplementedError("shaped synthetic sets (seed >= 1000) are not provided")
     np.random.seed(seed)
     X = np.random.rand(n, xd)
     cov = GPCov(wfn_params=[1.0], dfn_params=[lscale, lscale], dfn_str="euclidean", wfn_str="se")
-    return X, sample_y(X, cov, noise_var, yd), cov
+    return X, sample_y(X, cov, noise_var, yd, device=device), cov
 
 
 class SampledData(object):
     """Train/test split, noisy observed locations, grid blocks and the location prior."""
 
-    def __init__(self, noise_var=0.01, n=30, ntrain=20, lscale=0.5, obs_std=0.05, yd=10, seed=1):
+    def __init__(self, noise_var=0.01, n=30, ntrain=20, lscale=0.5, obs_std=0.05, yd=10, seed=1, device=None):
         self.noise_var, self.n, self.ntrain, self.lscale, self.obs_std = noise_var, n, ntrain, lscale, obs_std
-        Xfull, Yfull, self.cov = sample_synthetic(n=n, noise_var=noise_var, yd=yd, lscale=lscale, seed=seed)
+        Xfull, Yfull, self.cov = sample_synthetic(n=n, noise_var=noise_var, yd=yd, lscale=lscale, seed=seed,
+                                                  device=device)
         self.SX, self.SY = Xfull[:ntrain, :], Yfull[:ntrain, :]
         self.Xtest, self.Ytest = Xfull[ntrain:, :], Yfull[ntrain:, :]
         np.random.seed(seed)
@@ -125,10 +160,10 @@ class SampledData(object):
         return ll, -resid / self.obs_std ** 2
 
 
-def readme_dataset(ntrain=10000, nblocks=100, ntest=500, yd=50, seed=0, noise_var=0.01):
+def readme_dataset(ntrain=10000, nblocks=100, ntest=500, yd=50, seed=0, noise_var=0.01, device=None):
     """The reference's README / results configuration: lscale = 6/sqrt(n), obs_std = 2/sqrt(n)
     (gprfopt_analyze.py:206-207), grid blocks, 8-connected edges."""
     sd = SampledData(noise_var=noise_var, n=ntrain + ntest, ntrain=ntrain, lscale=6.0 / np.sqrt(ntrain),
-                     obs_std=2.0 / np.sqrt(ntrain), yd=yd, seed=seed)
+                     obs_std=2.0 / np.sqrt(ntrain), yd=yd, seed=seed, device=device)
     sd.set_centers(grid_centers(nblocks))
     return sd

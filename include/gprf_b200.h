@@ -159,6 +159,11 @@ int gprf_debug_unit(gprf_handle h, int unit, int* s, int* sp, int* yr,
 
 /* Device time of the kernels of the last evaluation, in milliseconds
  * (CUDA events on the launching stream), and the number of kernel launches. */
+/* out (s x dy, row major) = L Y_unit for a block unit, L the Cholesky factor the last evaluation
+ * computed for it (jitter rule included) and Y_unit the unit's rows of the Y given to gprf_create.
+ * The dense branch of the reference's sample_y (synthetic.py:106-114, y = jitchol(K) z): upload the
+ * normal draw z as Y, evaluate the objective of the one-block structure, call this. */
+int gprf_unit_lmul(gprf_handle h, int unit, double* out);
 int gprf_last_timing(gprf_handle h, float* ms, int* launches);
 
 /* Debug: timeline of the fused kernel, 512 (tag, %globaltimer ns) pairs per CTA.
