@@ -1174,4 +1174,56 @@ __global__ void __launch_bounds__(256) k_unit_lmul(const double* M, int sp, int 
 
 #endif  // GPRF_FUSED_ONLY
 
+
+// ---- optimiser glue (gprfopt.py:396-409, run_seismic.py:157-179) ------------------------------------------------
+// The L-BFGS callback of the reference's drivers turns (ll, gradX) into the minimiser's (f, g):
+//   f = -(ll + x_prior(X)),   g = -(gradX + d x_prior / dX) * grad_scale
+// with an independent Gaussian prior per coordinate, x_prior = -1/2 sum_pd ivar_d (X_pd - mean_pd)^2 + const
+// (gprfopt.py:172-182; run_seismic.py:363-371 with one std per column; grad_scale = (1, 1, 100) is the
+// seismic driver's depth rescaling).  Applied in place to out = [ll, grad theta (5), gradX (n dx)] after the
+// combination, so that only (f, g) crosses PCIe and the host does no pass over n x dx arrays.  The
+// quadratic form is reduced in a fixed order (per-CTA partials, summed by the last CTA to finish).
+struct PriorParams {
+  const double* X;
+  const double* mean;
+  double ivar[MAX_DX], gscale[MAX_DX];
+  long long n;
+  int dx, want_gx;
+  double* partial;          // gridDim.x
+  unsigned* counter;        // zero before the launch; reset by the last CTA
+};
+#ifndef GPRF_FUSED_ONLY
+__global__ void __launch_bounds__(256) k_x_prior(PriorParams Q, double* out) {
+  __shared__ double red[256];
+  __shared__ bool last;
+  const long long tot = Q.n * Q.dx;
+  double q = 0.0;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < tot; e += (long long)gridDim.x * 256) {
+    const int d = (int)(e % Q.dx);
+    const double r = Q.X[e] - Q.mean[e];
+    q += Q.ivar[d] * r * r;
+    if (Q.want_gx) out[1 + MAX_NCOV + e] = -(out[1 + MAX_NCOV + e] - Q.ivar[d] * r) * Q.gscale[d];
+  }
+  red[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    Q.partial[blockIdx.x] = red[0];
+    __threadfence();
+    last = atomicAdd(Q.counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += Q.partial[b];
+    out[0] = -(out[0] - 0.5 * s);
+    *Q.counter = 0u;
+  }
+}
+#endif  // GPRF_FUSED_ONLY
+
 }  // namespace gprf

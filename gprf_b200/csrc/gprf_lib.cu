@@ -71,6 +71,12 @@ struct gprf_ctx {
   std::vector<unsigned char> explicit_mask, lpt, seen;
   bool use_explicit_mask = false, adj_dirty = true, blocks_from_device = false;
   bool raw_weights = false;        // masked evaluations: every active unit counts with weight 1
+  // optimiser glue (gprf_set_x_prior / gprf_neg_objective)
+  double* dPriorMean = nullptr;    // n x dx
+  double* dPriorPartial = nullptr;
+  unsigned* dPriorCounter = nullptr;
+  double prior_ivar[MAX_DX] = {0, 0, 0}, prior_gscale[MAX_DX] = {1, 1, 1};
+  bool have_prior = false, prior_apply = false;
   int shard_rank = 0, shard_world = 1;
   bool keep_kinv = false;          // store K^-1 tiles (gprf_set_keep_kinv)
   bool share_on = true;            // edges reuse block i's factor tiles (gprf_set_factor_reuse)
@@ -399,6 +405,7 @@ extern "C" int gprf_destroy(gprf_handle h) {
   cudaFree(h->dResExports); cudaFree(h->dResScratch); cudaFree(h->dResLL); cudaFree(h->dResGth); cudaFree(h->dResGx);
   cudaFree(h->dResInfo); cudaFree(h->dResOrderB); cudaFree(h->dResOrderP); cudaFree(h->dResCounts); cudaFree(h->dResReady);
   cudaFree(h->dResEdges); cudaFree(h->dResDeg); cudaFree(h->dResActive); cudaFree(h->dResDbg); cudaFree(h->dResListPtr);
+  cudaFree(h->dPriorMean); cudaFree(h->dPriorPartial); cudaFree(h->dPriorCounter);
   if (h->hResStatus) cudaFreeHost(h->hResStatus);
   if (h->hUnits) cudaFreeHost(h->hUnits);
   if (h->hList) cudaFreeHost(h->hList);
@@ -874,6 +881,28 @@ extern "C" int gprf_set_tree_partitioner(gprf_handle h, int n_nodes, const doubl
 
 static int res_sync_static(gprf_ctx* h);
 static int res_alloc(gprf_ctx* h, int grid);
+
+// f = -(ll + x_prior), g = -(gradX + prior gradient) * grad_scale, in place on out_dev (k_x_prior)
+static int apply_prior(gprf_ctx* h, const double* X_dev, double* out_dev, int grad_X, cudaStream_t st) {
+  if (!h->prior_apply) return GPRF_OK;
+  PriorParams Q;
+  Q.X = X_dev;
+  Q.mean = h->dPriorMean;
+  for (int d = 0; d < MAX_DX; ++d) {
+    Q.ivar[d] = h->prior_ivar[d];
+    Q.gscale[d] = h->prior_gscale[d];
+  }
+  Q.n = h->n;
+  Q.dx = h->dx;
+  Q.want_gx = grad_X ? 1 : 0;
+  Q.partial = h->dPriorPartial;
+  Q.counter = h->dPriorCounter;
+  const long long tot = (long long)h->n * h->dx;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((tot + 255) / 256, 2LL * h->n_sm));
+  k_x_prior<<<grid, 256, 0, st>>>(Q, out_dev);
+  CUDA_OK(cudaGetLastError());
+  return GPRF_OK;
+}
 static void res_plan_params(gprf_ctx* h, res::PlanParams* Q);
 
 // Block membership of X_dev on the device: assignment kernel, stable radix sort, bounds.
@@ -1307,6 +1336,9 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   const unsigned gc = 1 + (grad_X ? (unsigned)((h->plen + 255) / 256) : 0);
   LAUNCH(12, (res::k_res_combine<<<gc, 256, 0, st>>>(C, out_dev, grad_X ? 1 : 0, grad_cov ? 1 : 0, nullptr)));
   CUDA_OK(cudaGetLastError());
+  rc = apply_prior(h, X_dev, out_dev, grad_X, st);
+  if (rc != GPRF_OK) return rc;
+  if (h->prior_apply) ++launches;
   if (launches_out) *launches_out = launches;
   return GPRF_OK;
 }
@@ -1412,6 +1444,10 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
       LAUNCH(7, (k_combine_gradx<<<(unsigned)((h->plen + tb - 1) / tb), tb, 0, st>>>(C, out_dev + 1 + MAX_NCOV)));
     }
     CUDA_OK(cudaGetLastError());
+    {
+      int prc = apply_prior(h, X_dev, out_dev, grad_X, st);
+      if (prc != GPRF_OK) return prc;
+    }
     CUDA_OK(cudaEventRecord(h->ev1, st));
     if (host_out) CUDA_OK(cudaMemcpyAsync(host_out, out_dev, outlen * sizeof(double), cudaMemcpyDeviceToHost, st));
     return GPRF_OK;
@@ -1471,6 +1507,9 @@ static int run_eval(gprf_ctx* h, const double* X_dev, const double* theta, int n
     nfail = *h->hNfail;
   }
   if (any_retry) {
+    // (entries of out no block covers are not rewritten by the combination: cleared so that the prior
+    // epilogue, which works in place, is not applied to them twice)
+    if (h->prior_apply) CUDA_OK(cudaMemsetAsync(out_dev, 0, outlen * sizeof(double), st));
     rc = combine();
     if (rc != GPRF_OK) return rc;
     CUDA_OK(cudaStreamSynchronize(st));
@@ -1555,6 +1594,45 @@ extern "C" int gprf_llgrad_reblock(gprf_handle h, const double* X, const double*
     for (int t = 0; t < ncov; ++t) gradTheta[t] = h->hOut[1 + t];
   if (grad_X) memcpy(gradX, h->hOut + 1 + MAX_NCOV, xb);
   return GPRF_OK;
+}
+
+// ---- optimiser glue ---------------------------------------------------------------------------------------------
+extern "C" int gprf_set_x_prior(gprf_handle h, const double* mean, const double* inv_var, const double* grad_scale) {
+  if (!h) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  if (!mean) {
+    h->have_prior = false;
+    return GPRF_OK;
+  }
+  if (!inv_var) return GPRF_ERR_ARG;
+  const size_t nb = (size_t)h->n * h->dx * sizeof(double);
+  if (!h->dPriorMean) CUDA_OK(cudaMalloc((void**)&h->dPriorMean, std::max<size_t>(nb, 8)));
+  if (!h->dPriorPartial) CUDA_OK(cudaMalloc((void**)&h->dPriorPartial, (size_t)2 * h->n_sm * sizeof(double)));
+  if (!h->dPriorCounter) {
+    CUDA_OK(cudaMalloc((void**)&h->dPriorCounter, sizeof(unsigned)));
+    CUDA_OK(cudaMemset(h->dPriorCounter, 0, sizeof(unsigned)));
+  }
+  CUDA_OK(cudaMemcpy(h->dPriorMean, mean, nb, cudaMemcpyHostToDevice));
+  for (int d = 0; d < h->dx; ++d) {
+    h->prior_ivar[d] = inv_var[d];
+    h->prior_gscale[d] = grad_scale ? grad_scale[d] : 1.0;
+  }
+  h->have_prior = true;
+  return GPRF_OK;
+}
+
+extern "C" int gprf_neg_objective(gprf_handle h, const double* X, const double* theta, int ncov, int grad_cov,
+                                  int reblock, double* f, double* g, double* gradTheta, int* failed_unit) {
+  if (!h || !X || !theta || !f || !g) return GPRF_ERR_ARG;
+  if (!h->have_prior) {
+    h->err = "gprf_neg_objective: no prior set (gprf_set_x_prior)";
+    return GPRF_ERR_ARG;
+  }
+  h->prior_apply = true;
+  const int rc = reblock ? gprf_llgrad_reblock(h, X, theta, ncov, 1, grad_cov, f, g, gradTheta, failed_unit)
+                         : gprf_llgrad(h, X, theta, ncov, 1, grad_cov, f, g, gradTheta, failed_unit);
+  h->prior_apply = false;
+  return rc;
 }
 
 extern "C" int gprf_unit_results(gprf_handle h, double* ll_units, double* jitter_units) {

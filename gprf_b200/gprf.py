@@ -152,7 +152,7 @@ class GPRF(object):
         d = self.__dict__.copy()
         d["_block_idxs"] = self.block_idxs          # materialise device-held blocks
         for k in ("_lib", "_h", "_edges_key", "_blocks_key", "_Yc", "_keep_edges", "_keep_blocks",
-                  "_device_part", "_blocks_stale"):
+                  "_device_part", "_blocks_stale", "_prior_const"):
             d.pop(k, None)
         return d
 
@@ -539,6 +539,53 @@ class GPRF(object):
             raise ValueError("mask must have one entry per unit (%d blocks + %d edges)"
                              % (self.n_blocks, len(self._keep_edges[1])))
         self._check(self._lib.gprf_set_unit_mask(self._h, _lib.ptr(m), len(m), int(bool(raw_weights))))
+
+    # -- optimiser glue (gprfopt.py:396-409, run_seismic.py:157-179) --------------------------------------
+    def set_x_prior(self, mean, std, grad_scale=None):
+        """Independent Gaussian prior on the locations, N(mean_pd, std_d^2) (gprfopt.py:172-182 with
+        one std; run_seismic.py:363-371 with one per column).  ``grad_scale``: per-column factor of the
+        returned gradient (the seismic driver optimises depth / 100).  ``mean=None`` removes it."""
+        if mean is None:
+            self._check(self._lib.gprf_set_x_prior(self._h, None, None, None))
+            self._prior_const = None
+            return
+        m = np.ascontiguousarray(mean, dtype=np.float64)
+        if m.shape != self._shape:
+            raise ValueError("prior mean has shape %s, expected %s" % (m.shape, self._shape))
+        dx = self._shape[1]
+        sd = np.ascontiguousarray(np.broadcast_to(np.asarray(std, dtype=np.float64), (dx,)))
+        gs = np.ascontiguousarray(np.broadcast_to(np.asarray(1.0 if grad_scale is None else grad_scale,
+                                                             dtype=np.float64), (dx,)))
+        iv = np.ascontiguousarray(1.0 / sd ** 2)
+        self._check(self._lib.gprf_set_x_prior(self._h, _lib.ptr(m), _lib.ptr(iv), _lib.ptr(gs)))
+        n = self._shape[0]
+        self._prior_const = -.5 * n * (dx * np.log(2 * np.pi) + np.sum(np.log(sd ** 2)))
+
+    def neg_objective(self, X, grad_cov=False):
+        """One L-BFGS callback evaluation: ``update_X(X)`` + ``llgrad(grad_X=True)`` + the location prior,
+        returned as the minimiser wants it, f = -(ll + x_prior(X)) and g = -(gradX + prior gradient) *
+        grad_scale, both formed on the device (gprf_neg_objective).  Also returns d ll / d theta
+        ((1, ncov) or zeros((0, 0))) for the host's log-theta chain rule."""
+        if getattr(self, "_prior_const", None) is None:
+            raise RuntimeError("neg_objective needs set_x_prior first")
+        self.update_X(X)
+        Xc = self._Xc()
+        if not self._blocks_stale:
+            self._sync_blocks()
+        self._sync_edges(self._edges_for(True))
+        th = self._theta()
+        f = C.c_double()
+        failed = C.c_int(-1)
+        g = np.empty(Xc.shape, dtype=np.float64)
+        gC = np.empty(len(th), dtype=np.float64) if grad_cov else None
+        reblock = self._blocks_stale
+        if reblock:
+            self._blocks_stale = False
+            self._blocks_key = None
+        rc = self._lib.gprf_neg_objective(self._h, _lib.ptr(Xc), _lib.ptr(th), len(th), int(grad_cov), int(reblock),
+                                          C.byref(f), _lib.ptr(g), _lib.ptr(gC), C.byref(failed))
+        self._check(rc, failed.value)
+        return f.value - self._prior_const, g, (gC.reshape((1, -1)) if grad_cov else np.zeros((0, 0)))
 
     def _masked_unit(self, unit, rows, **kwargs):
         """One unit of the live structure through the normal evaluation path (unit mask, weight 1)."""

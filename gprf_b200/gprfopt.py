@@ -59,10 +59,17 @@ def _collapse_cov_grad(g, C0):
 
 
 def do_optimization(d, gprf, X0, C0, sdata, method="l-bfgs-b", maxsec=3600, parallel=False, maxiter=200,
-                    max_evals=None, save_steps=True, verbose=False):
+                    max_evals=None, save_steps=True, verbose=False, fused=True):
     """gprfopt.py:322-432.  Returns the list of (step, seconds, objective) that is also written to
-    ``log.txt``.  ``max_evals`` (not in the reference) stops after that many callback evaluations."""
+    ``log.txt``.  ``max_evals`` (not in the reference) stops after that many callback evaluations.
+    ``fused``: with a GPRF that offers ``neg_objective`` the location prior (gprfopt.py:172-182), the sum
+    with the likelihood gradient and the sign change happen on the device in the evaluation's epilogue
+    (same arithmetic, gprf_neg_objective); only (f, g) come back."""
     grad_X, grad_C = X0 is not None, C0 is not None
+    fused = bool(fused and grad_X and hasattr(gprf, "neg_objective") and hasattr(sdata, "X_obs")
+                 and hasattr(sdata, "obs_std"))
+    if fused:
+        gprf.set_x_prior(sdata.X_obs, sdata.obs_std)
     x0 = X0.flatten() if grad_X else np.array(())
     c0 = np.log(C0.flatten()) * COV_SCALE if grad_C else np.array(())
     full0 = np.concatenate([x0, c0])
@@ -79,7 +86,8 @@ def do_optimization(d, gprf, X0, C0, sdata, method="l-bfgs-b", maxsec=3600, para
             xx, xc = x[:len(x0)], x[len(x0):] / COV_SCALE
             if grad_X:
                 XX = xx.reshape(X0.shape)
-                gprf.update_X(XX)
+                if not fused:
+                    gprf.update_X(XX)
                 if save_steps:
                     np.save(os.path.join(d, "step_%05d_X.npy" % step), XX)
             if grad_C:
@@ -88,9 +96,14 @@ def do_optimization(d, gprf, X0, C0, sdata, method="l-bfgs-b", maxsec=3600, para
                 gprf.update_covs(FC)
                 if save_steps:
                     np.save(os.path.join(d, "step_%05d_cov.npy" % step), FC)
-            ll, gX, gC = gprf.llgrad(local=True, grad_X=grad_X, grad_cov=grad_C, parallel=parallel)
             parts = []
-            if grad_X:
+            if fused:
+                f_neg, g_neg, gC = gprf.neg_objective(XX, grad_cov=grad_C)
+                ll = -f_neg
+                parts.append(-g_neg.reshape(-1))
+            else:
+                ll, gX, gC = gprf.llgrad(local=True, grad_X=grad_X, grad_cov=grad_C, parallel=parallel)
+            if grad_X and not fused:
                 pl, pg = sdata.x_prior(xx)
                 ll += pl
                 parts.append(gX.flatten() + pg)

@@ -92,6 +92,8 @@ def make_x_prior(means, prior_std):
         n = X.shape[0]
         ll = -.5 * np.sum(r.flatten() ** 2) - .5 * n * (3 * np.log(2 * np.pi) + np.sum(np.log(prior_std ** 2)))
         return ll, -r2.reshape(X.shape)
+    x_prior.means = np.asarray(means, dtype=np.float64)          # lets the driver move the prior to the device
+    x_prior.prior_std = np.asarray(prior_std, dtype=np.float64)
     return x_prior
 
 
@@ -162,8 +164,16 @@ def setup_seismic(X_true, SY, cov, obs_std, seed=0, block_size=300, threshold=1.
 def do_optimization(d, gprf, X0, C0, cov_prior, x_prior, maxsec=3600, parallel=False, sparse=False, max_evals=None,
                     maxiter=None, save_steps=True, verbose=False):
     """run_seismic.py:92-215.  Returns the (step, seconds, objective) rows also written to ``log.txt``.
-    ``max_evals`` / ``maxiter`` / ``save_steps`` are additions for bounded test and bench runs."""
+    ``max_evals`` / ``maxiter`` / ``save_steps`` are additions for bounded test and bench runs.
+    When ``x_prior`` comes from ``make_x_prior`` and the GPRF offers ``neg_objective``, the prior, the
+    depth rescaling of the gradient and the sign change run on the device (gprf_neg_objective)."""
     gradX, gradC = X0 is not None, C0 is not None
+    fused = bool(gradX and not sparse and hasattr(gprf, "neg_objective") and hasattr(x_prior, "means"))
+    if fused:
+        dxs = np.shape(X0)[1]
+        gs = np.ones(dxs)
+        gs[2] = DEPTH_SCALE
+        gprf.set_x_prior(x_prior.means, np.broadcast_to(x_prior.prior_std, (dxs,)), grad_scale=gs)
     if gradX:
         X0 = np.array(X0, dtype=np.float64)
         X0[:, 2] /= DEPTH_SCALE
@@ -187,7 +197,8 @@ def do_optimization(d, gprf, X0, C0, cov_prior, x_prior, maxsec=3600, parallel=F
             if gradX:
                 XX = xx.reshape(X0.shape).copy()
                 XX[:, 2] *= DEPTH_SCALE
-                gprf.update_X(XX)
+                if not fused:
+                    gprf.update_X(XX)
                 if save_steps:
                     np.save(os.path.join(d, "step_%05d_X.npy" % step), XX)
             else:
@@ -198,13 +209,19 @@ def do_optimization(d, gprf, X0, C0, cov_prior, x_prior, maxsec=3600, parallel=F
                 if save_steps:
                     np.save(os.path.join(d, "step_%05d_cov.npy" % step), FC)
             try:
-                ll, gX, gC = gprf.llgrad(local=True, grad_X=gradX, grad_cov=gradC, parallel=parallel, **kw)
+                if fused:
+                    f_neg, g_neg, gC = gprf.neg_objective(XX, grad_cov=gradC)
+                    ll = -f_neg
+                else:
+                    ll, gX, gC = gprf.llgrad(local=True, grad_X=gradX, grad_cov=gradC, parallel=parallel, **kw)
             except Exception as e:            # run_seismic.py:153-155: any failure is a huge objective
                 if verbose:
                     print("fail", e)
                 return 1e10, np.random.randn(*x.shape)
             parts = []
-            if gradX:
+            if fused:
+                parts.append(-g_neg.reshape(-1))
+            elif gradX:
                 gX = np.array(gX)
                 gX[:, 2] *= DEPTH_SCALE
                 prior_ll, prior_grad = x_prior(XX)

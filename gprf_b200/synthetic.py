@@ -56,6 +56,31 @@ def sample_y_device(X, cov, noise_var, yd, device=0, Z=None):
     return Y
 
 
+def sample_y_local(X, cov, noise_var, yd, block_idxs, device=0, Z=None):
+    """Draw from the block-local model: independently per block, Y_b = jitchol(K_bb + nv I) Z_b
+    (the parity data of the n = 200000 shape, where an exact draw of the full GP
+    is out of reach).  All blocks are factored by ONE device evaluation."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n = X.shape[0]
+    if Z is None:
+        Z = np.random.randn(n, yd)
+    g = GPRF(X, np.ascontiguousarray(Z), None, cov, noise_var, block_idxs=block_idxs, neighbors=[], device=device,
+             device_blocks=False)
+    Y = np.zeros((n, yd), dtype=np.float64)
+    try:
+        g.set_resident(False)
+        g.llgrad()
+        for b, idx in enumerate(block_idxs):
+            if len(idx) == 0:
+                continue
+            out = np.empty((len(idx), yd), dtype=np.float64)
+            g._check(g._lib.gprf_unit_lmul(g._h, b, out.ctypes.data))
+            Y[idx] = out
+    finally:
+        g.close()
+    return Y
+
+
 def sample_y(X, cov, noise_var, yd, device=None):
     """GP-prior draw Y = chol(K + nv I) Z with Z = randn(n, yd) (synthetic.py:103-137).
     ``device`` = CUDA ordinal: on the GPU (sample_y_device).  ``device=None``: host numpy, as the

@@ -131,6 +131,17 @@ int gprf_llgrad_device(gprf_handle h, const double* X_dev, const double* theta,
 /* Per-unit results of the last evaluation (llgrad_unary / llgrad_joint,
  * gprf.py:299-330): ll_units[B+E]; jitter_units[B+E] (0 = none); either may
  * be NULL. */
+/* Optimiser glue (gprfopt.py:396-409; run_seismic.py:157-179).  gprf_set_x_prior uploads an
+ * independent Gaussian prior on the locations (mean n x dx; inv_var and grad_scale per column,
+ * grad_scale NULL = 1; mean NULL removes the prior).  gprf_neg_objective then returns what the
+ * reference's L-BFGS callback hands to scipy,
+ *     f = -(ll + x_prior(X)) up to the prior's constant,  g = -(gradX + d x_prior/dX) * grad_scale,
+ * formed on the device in the combination epilogue, so that only (f, g) come back and the host makes
+ * no pass over n x dx arrays.  gradTheta (when grad_cov) is the plain d ll / d theta for the host's
+ * log-theta chain rule.  reblock != 0: block membership is recomputed from X on the device first. */
+int gprf_set_x_prior(gprf_handle h, const double* mean, const double* inv_var, const double* grad_scale);
+int gprf_neg_objective(gprf_handle h, const double* X, const double* theta, int ncov, int grad_cov,
+                       int reblock, double* f, double* g, double* gradTheta, int* failed_unit);
 int gprf_unit_results(gprf_handle h, double* ll_units, double* jitter_units);
 
 /* Replaces GPRF.compute_neighbors (gprf.py:119-150): for every block pair

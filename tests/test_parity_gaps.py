@@ -125,7 +125,15 @@ def test_n200k_pair_gradients_on_the_real_structure():
     gradients against the oracle."""
     import bench
     from gprf_b200 import GPRF
+    from gprf_b200.synthetic import sample_y_local
     wl = bench.make_workload("cfg5")
+    # parity data as SURVEY.md section 8d asks: Y drawn from the block-local model (per-block dense
+    # sample on the device) instead of the throughput runs' white noise
+    rng = np.random.RandomState(5)
+    wl = dict(wl, Y=sample_y_local(wl["X"], wl["cov"], wl["noise_var"], 50, wl["block_idxs"], device=0,
+                                   Z=rng.randn(wl["X"].shape[0], 50)))
+    b0 = wl["block_idxs"][3]
+    assert abs(np.var(wl["Y"][b0]) - 1.0) < 0.2            # prior variance s2 + nv = 1.01
     g = GPRF(wl["X"], wl["Y"], wl["block_fn"], wl["cov"], wl["noise_var"], block_idxs=wl["block_idxs"],
              neighbors=wl["neighbors"])
     o = oracle_for(wl, wl["neighbors"])
@@ -246,4 +254,46 @@ def test_runtime_guard_of_device_reblocking(monkeypatch):
     assert_parity(want, got, "guard")
     g.update_X(X3)
     assert_parity(want, g.llgrad(grad_X=True), "after the guard")
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["euclid_se", "lld_m32"])
+def test_neg_objective_equals_host_glue(name):
+    """gprf_neg_objective (prior, sum with the likelihood gradient, column rescaling and sign on the
+    device) against the reference's host formulas (gprfopt.py:172-182,396-409; run_seismic.py:157-179,
+    363-371), on the resident path, on the tile pipeline and through a jitter retry."""
+    from gprf_b200 import GPRF
+    from test_gpu_parity import build_pair
+    from test_oracle_props import COVS as CV
+    dx = CV[name][1]
+    o, g = build_pair(name, [60, 75, 90, 40, 110], [(1, 0), (2, 1), (3, 2), (4, 3), (4, 0)], dy=50, seed=9)
+    rng = np.random.RandomState(1)
+    mean = o.X + 0.01 * rng.randn(*o.X.shape)
+    std = np.array([0.02, 0.03, 0.5])[:dx]
+    gs = np.array([1.0, 1.0, 100.0])[:dx]
+    n = o.X.shape[0]
+
+    def host(X, grad_cov):
+        ll, gX, gC = o.llgrad(grad_X=True, grad_cov=grad_cov)
+        r = (X - mean) / std
+        pl = -.5 * np.sum(r ** 2) - .5 * n * (dx * np.log(2 * np.pi) + np.sum(np.log(std ** 2)))
+        return -(ll + pl), -(gX - r / std) * gs, gC
+
+    g.set_x_prior(mean, std, grad_scale=gs)
+    for resident in (True, False):
+        g.set_resident(resident)
+        for grad_cov in (False, True):
+            f, gg, gC = g.neg_objective(o.X, grad_cov=grad_cov)
+            wf, wg, wC = host(o.X, grad_cov)
+            assert abs(f - wf) <= LL_RTOL * abs(wf), (resident, grad_cov)
+            assert np.abs(gg - wg).max() <= GRAD_RTOL * np.abs(wg).max()
+            if grad_cov:
+                assert np.all(np.abs(gC - wC) <= GRAD_RTOL * np.maximum(np.abs(wC), 1e-3 * np.abs(wC).max()))
+        assert (g.resident_stats()[1] == 0) if resident else True
+    # plain llgrad is unaffected by the prior
+    g.set_resident(True)
+    assert_parity(o.llgrad(grad_X=True), g.llgrad(grad_X=True), "plain after prior")
+    g.set_x_prior(None, None)
+    with pytest.raises(RuntimeError):
+        g.neg_objective(o.X)
     g.close()
