@@ -460,6 +460,18 @@ def lbfgs_full_run():
     return out
 
 
+def kernel_sources_sha16():
+    """Hash of the CUDA sources (the stamp of profiles/ncu_traffic.json)."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "gprf_b200", "csrc")
+    for fn in sorted(os.listdir(csrc)):
+        if fn.endswith((".cu", ".cuh")):
+            with open(os.path.join(csrc, fn), "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def roofline_from_profile(fam, sizes_local, dy, peak_tflops, peak_note):
     """Dominant kernel family of one evaluation.  Units of up to FUSED_NT tiles run the whole pipeline
     in k_unit_fused (algorithmic flops s^3 + 4 s^2 dy each); larger ones go through the per-family
@@ -562,13 +574,25 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
     else:
         sizes_local = sizes
     roof = roofline_from_profile(fam, sizes_local, DY, peak, peak_note)
-    try:        # DRAM bytes of the dominant kernel's launch, recorded from an ncu --set full capture (1 GPU)
+    # DRAM bytes of the dominant kernel, from an ncu --set full capture of THIS source state (1 GPU):
+    # profiles/ncu_traffic.json is stamped with a hash of the kernel sources and ignored on a mismatch.
+    # On the resident path the dominant kernel's one launch IS the evaluation (the other three launches
+    # move < 1 MB), so the figure is per evaluation.
+    try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            ent = json.load(f).get(wl_name, {}).get(roof["kernel"])
+            tj = json.load(f)
+        ent = tj.get(wl_name, {}).get(roof["kernel"])
         if ent and world == 1:
-            roof["traffic"] = ent["bytes"]
-            roof["traffic_unit"] = "bytes per launch (dram read + write)"
-            roof["traffic_source"] = ent["source"]
+            if ent.get("sources_sha16", kernel_sources_sha16()) == kernel_sources_sha16():
+                roof["traffic"] = ent["bytes"]
+                roof["traffic_unit"] = ent.get("unit", "bytes per launch (dram read + write)")
+                roof["traffic_source"] = ent["source"]
+                if "algorithmic_bytes" in ent:
+                    roof["traffic_algorithmic_bytes"] = ent["algorithmic_bytes"]
+            else:
+                roof["traffic"] = None
+                roof["traffic_source"] = ("profiles/ncu_traffic.json was captured from other kernel sources (%s); "
+                                          "re-run scripts/gpu_job_ncu.sh" % ent.get("sources_sha16"))
     except (IOError, OSError, ValueError):
         pass
     roof["eval_tflops"] = flops_eval / (ms_per_step * 1e-3) * 1e-12

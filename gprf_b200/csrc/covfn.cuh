@@ -74,7 +74,9 @@ __device__ __forceinline__ double exp_neg(double x) {
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   const double scale = __hiloint2double((ni + 1023) << 20, 0);
-  return (x > 708.0) ? 0.0 : p * scale;
+  // NaN in, NaN out (fmax above would swallow it): a NaN coordinate must poison K and fail the
+  // factorisation as it does in the reference, not produce a finite objective
+  return (x > 708.0) ? 0.0 : ((x != x) ? x : p * scale);
 }
 
 template <int WFN>

@@ -128,6 +128,7 @@ struct gprf_ctx {
   bool res_static_dirty = true;    // edges / degrees / unit mask have to be uploaded again
   bool last_resident = false;      // the last evaluation ran on the resident path
   bool plan_fused = false;         // the launch plan of the next resident evaluation is already on the device
+  int pending_part_launches = 0;   // re-blocking launches of gprf_reblock_device, counted into the next evaluation
   bool bucket_small = true;        // single-CTA bucketing for small problems (GPRF_BUCKET_SMALL=0: cub radix sort)
   long long res_evals = 0, res_fallbacks = 0;
   int res_last_status = 0;
@@ -1047,8 +1048,10 @@ extern "C" int gprf_reblock_device(gprf_handle h, const double* X_dev, void* str
   if (!h || !X_dev) return GPRF_ERR_ARG;
   CUDA_OK(cudaSetDevice(h->device));
   h->have_structure = false;
-  if (res_eligible(h)) return reblock_launch(h, X_dev, (cudaStream_t)stream);   // host view on demand
-  return reblock_device(h, X_dev, (cudaStream_t)stream);
+  const int rc = res_eligible(h) ? reblock_launch(h, X_dev, (cudaStream_t)stream)   // host view on demand
+                                 : reblock_device(h, X_dev, (cudaStream_t)stream);
+  if (rc == GPRF_OK) h->pending_part_launches = h->part_launches;
+  return rc;
 }
 
 extern "C" int gprf_reblock(gprf_handle h, const double* X) {
@@ -1245,8 +1248,8 @@ static int res_alloc(gprf_ctx* h, int grid) {
     CUDA_OK(cudaMalloc((void**)&h->dResOrderB, cu * sizeof(int)));
     CUDA_OK(cudaMalloc((void**)&h->dResOrderP, cu * sizeof(int)));
     CUDA_OK(cudaMalloc((void**)&h->dResCounts, 8 * sizeof(int)));
-    CUDA_OK(cudaMalloc((void**)&h->dResReady, cu * sizeof(int)));
-    CUDA_OK(cudaMemset(h->dResReady, 0, cu * sizeof(int)));
+    CUDA_OK(cudaMalloc((void**)&h->dResReady, 2 * cu * sizeof(int)));
+    CUDA_OK(cudaMemset(h->dResReady, 0, 2 * cu * sizeof(int)));
     h->res_epoch = 0;
     CUDA_OK(cudaMemset(h->dResLL, 0, cu * sizeof(double)));
     CUDA_OK(cudaMemset(h->dResGth, 0, cu * MAX_NCOV * sizeof(double)));
@@ -1305,6 +1308,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   // debug timeline (gprf_debug_trace with >= n_sm CTAs)
   P.trace = (h->dTrace && h->capTrace >= (size_t)h->n_sm * 2 * res::RTRACE_SLOTS) ? h->dTrace : nullptr;
   P.ready = h->dResReady;
+  P.ready2 = h->dResReady + h->capResU;
   P.epoch = ++h->res_epoch;
   P.order = h->dResOrderB;
   P.n_order = h->dResCounts + 0;
@@ -1533,6 +1537,8 @@ extern "C" int gprf_llgrad_device(gprf_handle h, const double* X_dev, const doub
     rc = run_eval(h, X_dev, theta, ncov, grad_X, grad_cov, out_dev, st, failed_unit);
     if (rc != GPRF_OK) return rc;
   }
+  h->last_launches += h->pending_part_launches;
+  h->pending_part_launches = 0;
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   if (h->profile) h->prof_resolve();
   return GPRF_OK;

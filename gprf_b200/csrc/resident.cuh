@@ -118,7 +118,8 @@ struct ResParams {
   double* gx_u;                 // per unit x GX_STRIDE
   int* info;                    // per unit: 1 + first failing local row
   int* status;
-  int* ready;                   // per block: == epoch once the block unit's exports are complete
+  int* ready;                   // per block: == epoch once the block unit's factor exports (W, Z, alpha, K, scalars) are complete
+  int* ready2;                  // per block: == epoch once K^-1 (written by the block's gradient phase) is complete too
   int epoch;
   int dbg_unit, dbg_phase;      // debug dump of R1 / R2 after a phase (-1: off)
   double* dbg_out;              // 2 x (160 x 160) doubles
@@ -1006,7 +1007,9 @@ static __device__ __noinline__ void ph_v(const ResParams& P, const Ctx& c) {
         mk<false, true>(acc[i], c.oR2 + rtri(row) * RBLK, RBLK, pb, ab * RBLK, 0, row + 1, nj, L);
       }
     }
+    rtrace(P, c, 40);
     __syncthreads();
+    rtrace(P, c, 41);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = w + i * RNW;
@@ -1450,6 +1453,14 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
   rtrace(P, c, 5);
   ph_ypart<R1>(P, c, stage, nyc);
   rtrace(P, c, 6);
+  if (c.is_export) {
+    // Everything this block's pairs need before THEIR gradient phase is exported: release them now
+    // (measured: the CTAs that start with a pair waited 87 us for the whole block unit, 75 us of it
+    // the parent's own work).  K^-1 follows in ph_grad under the second flag.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(P.ready + c.bj, P.epoch);
+  }
   if (!c.want_grad) {
     __syncthreads();
     return;
@@ -1476,6 +1487,12 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
     rtrace(P, c, 8);
     ph_alpha_i<R1>(P, c, stage);
     asm volatile("fence.proxy.async;\n" ::: "memory");   // alpha_i rows
+  }
+  if (c.pair) {                  // K_ii^-1 of the parent (its gradient phase): long done by now
+    if (tid == 0) {
+      while (atomicAdd(P.ready2 + c.bi, 0) != P.epoch) __nanosleep(100);
+      __threadfence();
+    }
   }
   __syncthreads();
   rtrace(P, c, 9);
@@ -1525,7 +1542,9 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
     if (bi >= 0) {
       // the parent block's unit (earlier in the queue, possibly still running on another SM)
       if (threadIdx.x == 0) {
-        while (atomicAdd(P.ready + bi, 0) != P.epoch) __nanosleep(100);
+        // (a pair with an empty second block copies block i's final results: second flag)
+        const int* flag = (b == 0 ? P.ready2 : P.ready) + bi;
+        while (atomicAdd(const_cast<int*>(flag), 0) != P.epoch) __nanosleep(100);
         __threadfence();
       }
       __syncthreads();
@@ -1543,7 +1562,10 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
     if (cls == 2) {
       if (threadIdx.x == 0) {
         atomicOr(P.status, ST_OVERFLOW);
-        if (bi < 0) atomicExch(P.ready + bj, P.epoch);     // nobody may wait forever; the tile pipeline redoes it
+        if (bi < 0) {                                        // nobody may wait forever; the tile pipeline redoes it
+          atomicExch(P.ready + bj, P.epoch);
+          atomicExch(P.ready2 + bj, P.epoch);
+        }
       }
       continue;
     }
@@ -1557,7 +1579,10 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
       if (threadIdx.x < MAX_NCOV) P.gth_u[(long long)uid * MAX_NCOV + threadIdx.x] = 0.0;
       __threadfence();
       __syncthreads();
-      if (threadIdx.x == 0) atomicExch(P.ready + bj, P.epoch);
+      if (threadIdx.x == 0) {
+        atomicExch(P.ready + bj, P.epoch);
+        atomicExch(P.ready2 + bj, P.epoch);
+      }
       continue;
     }
     const bool r1g = cls == 1;
@@ -1586,10 +1611,10 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
     __syncthreads();
     if (r1g) run_unit<DFN, WFN, R1Glob>(P, *ctx, stage);
     else run_unit<DFN, WFN, R1Smem>(P, *ctx, stage);
-    if (bi < 0) {                  // exports complete: release the block's pairs
+    if (bi < 0) {                  // all exports complete
       __threadfence();
       __syncthreads();
-      if (threadIdx.x == 0) atomicExch(P.ready + bj, P.epoch);
+      if (threadIdx.x == 0) atomicExch(P.ready2 + bj, P.epoch);
     }
   }
 }

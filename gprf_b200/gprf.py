@@ -670,12 +670,15 @@ class GPRF(object):
         gp = self
         dy = np.asarray(Yc).shape[1]
 
-        def kernel_fn(A, B):
-            return kern_gp.kernel(A, B)         # X2 given: cross kernel without noise (gprf.py:341-342)
+        def kernel_fn(A, B):                    # Kstar, Kss: the TRAINING covariance (predict_tree, gprf.py:649-654)
+            return gp.kernel(A, B)              # X2 given: cross kernel without noise (gprf.py:341-342)
+
+        def prior_kernel_fn(A, B):              # test_cov enters the prior covariance only (gprf.py:599-605,621)
+            return kern_gp.kernel(A, B)
 
         def predict(Xstar, test_noise_var=0.0, local=False):
             Xstar = np.ascontiguousarray(Xstar, dtype=np.float64)
-            prior_cov = kernel_fn(Xstar, Xstar) + np.eye(Xstar.shape[0]) * test_noise_var
+            prior_cov = prior_kernel_fn(Xstar, Xstar) + np.eye(Xstar.shape[0]) * test_noise_var
             prior_prec = np.linalg.inv(prior_cov)
             prior_mean = np.zeros((Xstar.shape[0], dy))
             source_blocks = set()

@@ -207,10 +207,12 @@ class OracleGPRF(object):
         return ll, gradX, gradCov
 
 
-def _bcm_predict(gp, kernel_fn, block_Kinvs, block_Alphas, dy, Xstar, test_noise_var):
+def _bcm_predict(gp, kernel_fn, block_Kinvs, block_Alphas, dy, Xstar, test_noise_var, prior_kernel_fn=None):
     """Body of the closure returned by train_predictor (gprf.py:619-670): Bayesian-committee
-    fusion of the per-block GP predictions of the test points' own block and its neighbours."""
-    prior_cov = kernel_fn(Xstar, Xstar)
+    fusion of the per-block GP predictions of the test points' own block and its neighbours.
+    ``prior_kernel_fn`` (test_cov, gprf.py:599-605,621) enters the prior covariance only; Kstar and Kss
+    use the training covariance (predict_tree, gprf.py:649-654)."""
+    prior_cov = (prior_kernel_fn or kernel_fn)(Xstar, Xstar)
     prior_cov = prior_cov + np.eye(prior_cov.shape[0]) * test_noise_var
     prior_prec = np.linalg.inv(prior_cov)
     prior_mean = np.zeros((Xstar.shape[0], dy))
@@ -253,10 +255,14 @@ def _train_predictor(self, test_cov=None, Y=None):
         block_Alphas.append(np.dot(Kinv, Y[idxs]))
 
     def kernel_fn(A, B):
+        return kern.kernel_matrix(A, B, self.cov)
+
+    def prior_kernel_fn(A, B):
         return kern.kernel_matrix(A, B, tcov)
 
     def predict(Xstar, test_noise_var=0.0, local=False):
-        return _bcm_predict(self, kernel_fn, block_Kinvs, block_Alphas, Y.shape[1], Xstar, test_noise_var)
+        return _bcm_predict(self, kernel_fn, block_Kinvs, block_Alphas, Y.shape[1], Xstar, test_noise_var,
+                            prior_kernel_fn=prior_kernel_fn)
     return predict
 
 

@@ -1,2 +1,1 @@
-python scripts/golden_diag.py > gpurun_out/r02_golden_runs_device_sampling.txt 2>&1; tail -3 gpurun_out/r02_golden_runs_device_sampling.txt
-python -m pytest tests -m gpu -x -q > gpurun_out/r02ac_tests.txt 2>&1; tail -4 gpurun_out/r02ac_tests.txt
+python scripts/trace_resident.py cfg2 gpurun_out/r02af_unit_times.txt > gpurun_out/r02af_trace_cfg2.txt 2>&1; tail -2 gpurun_out/r02af_trace_cfg2.txt

@@ -46,6 +46,45 @@ def test_oracle_prediction_error_sane():
     assert noisy[0] > smse                          # wrong locations predict worse
 
 
+def test_oracle_test_cov_enters_the_prior_only():
+    """gprf.py:599-605,621 vs :649-654: test_cov builds the prior covariance; the per-block messages
+    (Kstar, Kss) keep the training covariance.  With one block and the prior's extra precision removed,
+    the posterior mean is therefore independent of test_cov only through that prior term."""
+    from oracle import synthetic as osyn
+    from oracle.kernels import GPCov as OCov
+    sd = osyn.SampledData(noise_var=0.01, n=160, ntrain=120, lscale=0.3, obs_std=0.01, yd=3, seed=1)
+    sd.set_centers(np.array([[0.5, 0.5]]))
+    g = sd.build_gprf(local_dist=1.0)
+    other = OCov(wfn_params=[2.5], dfn_params=[0.11, 0.11], dfn_str="euclidean", wfn_str="se")
+    Xs = sd.Xtest[:6]
+    m0, c0 = g.train_predictor()(Xs)
+    m1, c1 = g.train_predictor(test_cov=other)(Xs)
+    # one source block: final precision = inv(prior_cov) + inv(cov) - inv(Kss); only the first term changes
+    from oracle import kernels as kern
+    d_prec = np.linalg.inv(c1) - np.linalg.inv(c0)
+    want = np.linalg.inv(kern.kernel_matrix(Xs, Xs, other)) - np.linalg.inv(kern.kernel_matrix(Xs, Xs, g.cov))
+    assert np.allclose(d_prec, want, rtol=1e-5, atol=1e-6 * np.abs(want).max())
+    assert not np.allclose(m0, m1)
+
+
+@pytest.mark.gpu
+def test_predictor_test_cov_cuda_matches_oracle():
+    from oracle import synthetic as osyn
+    from gprf_b200 import synthetic as psyn
+    from gprf_b200 import GPCov
+    from oracle.kernels import GPCov as OCov
+    so, sp = small_data(osyn), small_data(psyn)
+    go, gp = so.build_gprf(local_dist=0.4), sp.build_gprf(local_dist=0.4)
+    th = dict(wfn_params=[1.7], dfn_params=[0.2, 0.25], dfn_str="euclidean", wfn_str="se")
+    po, pp = go.train_predictor(test_cov=OCov(**th)), gp.train_predictor(test_cov=GPCov(**th))
+    Xs = so.Xtest[:9]
+    for tnv in (0.0, 0.01):
+        mo, co = po(Xs, test_noise_var=tnv)
+        mp, cp = pp(Xs, test_noise_var=tnv)
+        assert np.abs(mo - mp).max() <= 1e-7 * np.abs(mo).max()
+        assert np.abs(co - cp).max() <= 1e-7 * np.abs(co).max()
+
+
 @pytest.mark.gpu
 def test_predictor_cuda_matches_oracle(tmp_path):
     from oracle import synthetic as osyn
