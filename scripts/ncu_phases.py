@@ -31,9 +31,11 @@ def phase_ranges():
 
 def main():
     src_csv, obj = sys.argv[1:3]
-    ncu_lines.MAIN_FROM = 395
-    table = ncu_lines.line_table(obj, "k_resident")
     marks = phase_ranges()
+    # frames above the first phase function are helpers (fragment loads, mk_loop, cov_frag ...): an
+    # instruction is attributed to the innermost frame that lies in a phase function
+    ncu_lines.MAIN_FROM = min(l for l, nm in marks if nm.startswith("ph_"))
+    table = ncu_lines.line_table(obj, "k_resident")
 
     def phase(line):
         name = "helpers"
