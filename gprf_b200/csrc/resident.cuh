@@ -559,6 +559,7 @@ static __device__ __noinline__ void ph_schur(const ResParams& P, const Ctx& c) {
   const int ab = c.ab, bb = c.bb;
   const typename R1::T r1 = R1::get(c);
   // task list: rows descending (longest first), column groups of nearly equal width (<= 4)
+  rtrace(P, c, 45);
   int t = 0;
   for (int row = bb - 1; row >= 0; --row) {
     const int ng = (row + 4) >> 2;
@@ -586,6 +587,7 @@ static __device__ __noinline__ void ph_schur(const ResParams& P, const Ctx& c) {
       }
     }
   }
+  rtrace(P, c, 46);
   __syncthreads();
 }
 
@@ -927,6 +929,7 @@ static __device__ __noinline__ void ph_t(const ResParams& P, const Ctx& c, Stage
 #pragma unroll
     for (int i = 0; i < 4; ++i) zero4(acc[i]);
     staged_rows(stage, g_smem + oF, nF, c.pexp + EXP_W, ab, tri_len, rtri, ahead, [&](int k0, int k1, const double*) {
+      rtrace(P, c, 42);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int t = w + i * RNW;
@@ -965,7 +968,9 @@ static __device__ __noinline__ void ph_t(const ResParams& P, const Ctx& c, Stage
       }
     });
     ahead = false;
+    rtrace(P, c, 43);
     __syncthreads();
+    rtrace(P, c, 44);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = w + i * RNW;

@@ -18,7 +18,8 @@ import bench  # noqa: E402
 SLOTS = 512
 NAMES = {2: "P1 L_ji", 3: "P2 S", 4: "P3a chol", 5: "P3b inv", 6: "P4 Y-part", 7: "P6a T", 8: "P6b V",
          9: "P7 alpha_i", 10: "P8 G/grad", 11: "finalize", 19: "P8 piece barrier", 20: "P8 table+issue", 21: "P8 tma wait",
-         22: "P8 warp0 tasks", 30: "chol: barrier wait", 31: "chol: panel + diag update", 32: "chol: diag block", 33: "gather", 34: "P1 cov K_ji", 35: "P1 wait W_i", 36: "P4 R=Y-LZ", 37: "P4 Z=W R + stores", 40: "V: warp 0 products", 41: "V: barrier wait"}
+         22: "P8 warp0 tasks", 30: "chol: barrier wait", 31: "chol: panel + diag update", 32: "chol: diag block", 33: "gather", 34: "P1 cov K_ji", 35: "P1 wait W_i", 36: "P4 R=Y-LZ", 37: "P4 Z=W R + stores", 40: "V: warp 0 products", 41: "V: barrier wait", 42: "T: wait for W_i (TMA)", 43: "T: warp 0 products",
+         44: "T: barrier wait", 45: "S: entry", 46: "S: warp 0 tasks"}
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 wl = bench.make_workload(name)
 R = bench.Runner(torch, None, wl, 0, 1, 0)
