@@ -274,3 +274,29 @@ def test_single_cta_bucketing_equals_radix_sort_path(monkeypatch):
     for (a, la), (b, lb) in zip(res["1"], res["0"]):
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
         assert la == lb - 4, (la, lb)          # 3 cub launches + bounds + plan -> 1
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_resident_random_structures(seed):
+    """Randomised structures (block sizes 0..160 incl. multiples of 8 +-1, random edge sets with repeated
+    parents, every covariance family by turns): resident path == oracle, and the static unit lists cover
+    every unit exactly once whatever the number of CTAs they are dealt to."""
+    rng = np.random.RandomState(100 + seed)
+    name = sorted(COVS)[seed % len(COVS)]
+    B = int(rng.randint(3, 14))
+    pool = [0, 1, 7, 8, 9, 15, 16, 17, 63, 64, 65, 100, 127, 128, 129, 159, 160]
+    sizes = [int(pool[rng.randint(len(pool))]) if rng.rand() < 0.5 else int(rng.randint(1, 161)) for _ in range(B)]
+    pairs = [(i, j) for i in range(B) for j in range(i)]
+    rng.shuffle(pairs)
+    edges = pairs[:int(rng.randint(1, min(len(pairs), 3 * B) + 1))]
+    o, g = build_pair(name, sizes, edges, dy=int(rng.choice([1, 7, 50, 64])), seed=seed)
+    kw = dict(grad_X=True, grad_cov=True)
+    got = g.llgrad(**kw)
+    assert g.resident_stats() == (1, 0, 0), (sizes, edges)
+    assert_parity(o.llgrad(**kw), got, "random structure %d (%s)" % (seed, name))
+    lls, _ = g.unit_results()
+    for e, (i, j) in enumerate(edges):
+        if sizes[i] + sizes[j] == 0:
+            continue
+        ref = o.llgrad_joint(i, j)[0]
+        assert abs(lls[B + e] - ref) <= 1e-9 * max(1.0, abs(ref)), (e, i, j, sizes[i], sizes[j])
