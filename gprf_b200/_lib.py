@@ -94,4 +94,4 @@ def load():
 
 def ptr(a):
     """Host pointer of a C-contiguous numpy array (or None)."""
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    return None if a is None else a.ctypes.data          # plain integer: c_void_p arguments accept it

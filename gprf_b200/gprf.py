@@ -50,7 +50,43 @@ def _edge_array(edges):
     return np.ascontiguousarray(np.asarray(edges, dtype=np.int32).reshape(-1, 2))
 
 
+class _EdgeList(list):
+    """The list behind ``GPRF.neighbors``: an ordinary list of (i, j) tuples that counts its
+    mutations, so that the per-evaluation check "is the device's edge list still current?" is O(1)
+    and an in-place edit (``gprf.neighbors[k] = ...``, ``.append``, ...) still reaches the device.
+    (Rebuilding an int32 array from 342 tuples and comparing its bytes cost 135 us per evaluation.)"""
+
+    def __init__(self, *args):
+        super(_EdgeList, self).__init__(*args)
+        self.version = 0
+
+    def _bump(name):          # noqa: N805
+        base = getattr(list, name)
+
+        def method(self, *args, **kwargs):
+            self.version += 1
+            return base(self, *args, **kwargs)
+        method.__name__ = name
+        return method
+
+    for _name in ("__setitem__", "__delitem__", "__iadd__", "__imul__", "append", "extend", "insert", "pop",
+                  "remove", "clear", "sort", "reverse"):
+        locals()[_name] = _bump(_name)
+    del _name, _bump
+
+    def __reduce__(self):     # pickles as a plain list
+        return (list, (list(self),))
+
+
 class GPRF(object):
+
+    @property
+    def neighbors(self):
+        return self._neighbors
+
+    @neighbors.setter
+    def neighbors(self, value):
+        self._neighbors = value if isinstance(value, _EdgeList) else _EdgeList(value)
 
     def __init__(self, X, Y, block_fn, cov, noise_var, kernelized=False, dy=None,
                  neighbor_threshold=1e-3, nonstationary=False, nonstationary_prec=False,
@@ -157,7 +193,11 @@ class GPRF(object):
         return d
 
     def __setstate__(self, d):
+        if "neighbors" in d:                       # pickles written before ``neighbors`` became a property
+            d["_neighbors"] = d.pop("neighbors")
         self.__dict__ = d
+        if "_neighbors" in d:
+            self._neighbors = _EdgeList(d["_neighbors"])
         self._lib = None
         self._h = None
         self._device_part = None
@@ -282,12 +322,13 @@ class GPRF(object):
         return self._all_pairs
 
     def _sync_edges(self, edges):
-        # keyed on the CONTENTS (an in-place edit of self.neighbors must reach the device); the
-        # (1 - deg) weights of gprf.py:253-264 are derived from this edge list
-        e = _edge_array(edges)
-        key = e.tobytes()
+        # O(1) check: ``neighbors`` is an _EdgeList (identity + mutation count); the all-pairs list of
+        # local=False is internal and never edited.  The (1 - deg) weights of gprf.py:253-264 are
+        # derived on the device from this edge list.
+        key = (id(edges), getattr(edges, "version", -1), len(edges))
         if key == self._edges_key:
             return
+        e = _edge_array(edges)
         rank, world = self.unit_shard if self.unit_shard is not None else (0, 1)
         self._check(self._lib.gprf_set_edges(self._h, len(e), _lib.ptr(e), int(rank), int(world)))
         self._edges_key = key
