@@ -972,7 +972,7 @@ static int reblock_launch(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
         res_alloc(h, std::max(1, std::min(h->B + h->E, h->n_sm))) == GPRF_OK) {
       bp.enabled = 1;
       res_plan_params(h, &bp.Q);
-      smb = std::max(smb, (size_t)(h->B + h->E) * sizeof(int));
+      smb += res::res_plan_smem(h->B, h->E, BK_WARPS * 32);
       h->plan_fused = true;
     }
     if (smb > 200 * 1024) {
@@ -1278,7 +1278,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   } else {
     res::PlanParams Q;
     res_plan_params(h, &Q);
-    const size_t plan_sm = (size_t)(B + E) * sizeof(int);
+    const size_t plan_sm = res::res_plan_smem(B, E, 512);
     if (plan_sm > 48 * 1024)
       cudaFuncSetAttribute(res::k_res_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_sm);
     LAUNCH(9, (res::k_res_plan<<<1, 512, plan_sm, st>>>(Q)));

@@ -153,7 +153,7 @@ __global__ void k_block_bounds(const int* keys, const int* idx_sorted, long long
 // `plan` set it goes on to build the resident path's launch plan (resident.cuh) in the same launch.
 // Warp w owns the contiguous point range [w L, (w + 1) L): (1) per-warp histograms, (2) per block a
 // prefix over the warps, (3) every warp places its points in order, ranks inside a group of 32 by
-// __match_any_sync.  Shared memory: BK_WARPS x B ints + (B + 1) ints.
+// __match_any_sync.  Shared memory: BK_WARPS x B ints + (B + 1) ints (+ B + E ints for the plan).
 constexpr int BK_WARPS = 32;
 constexpr int BK_MAXB = 1024;
 constexpr long long BK_MAXN = 1 << 18;
@@ -165,25 +165,44 @@ __global__ void __launch_bounds__(BK_WARPS * 32, 1)
 k_bucket_small(const int* owner, long long n, int B, long long* block_ptr, long long* perm64, int* pos_block,
                BucketPlan plan) {
   extern __shared__ int bk_sh[];
-  int* wh = bk_sh;                       // [BK_WARPS][B]: counts, then running positions
-  int* start = bk_sh + BK_WARPS * B;     // [B + 1]
+  int* wh = bk_sh;                       // [BK_WARPS][B]: counts, then exclusive prefixes over the warps
+  int* start = bk_sh + BK_WARPS * B;     // [B + 1]: block totals, then block starts
+  int* plan_sh = start + B + 1;          // (B + E) ints for the plan
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   for (int e = tid; e < BK_WARPS * B; e += blockDim.x) wh[e] = 0;
   __syncthreads();
   const long long L = (n + BK_WARPS - 1) / BK_WARPS;
   const long long p0 = w * L, p1 = p0 + L < n ? p0 + L : n;
-  for (long long p = p0 + lane; p < p1; p += 32) atomicAdd(&wh[w * B + owner[p]], 1);
+  // the warp's owners: the first BK_PRE rounds stay in registers for the placement pass
+  constexpr int BK_PRE = 16;
+  int own[BK_PRE];
+#pragma unroll
+  for (int k = 0; k < BK_PRE; ++k) {
+    const long long p = p0 + lane + 32 * k;
+    own[k] = p < p1 ? owner[p] : -1;
+  }
+#pragma unroll
+  for (int k = 0; k < BK_PRE; ++k)
+    if (own[k] >= 0) atomicAdd(&wh[w * B + own[k]], 1);
+  for (long long p = p0 + lane + 32 * BK_PRE; p < p1; p += 32) atomicAdd(&wh[w * B + owner[p]], 1);
   __syncthreads();
-  // block totals -> exclusive scan (one warp, B <= 1024: 32 per lane) -> per-warp running positions
+  // per block: exclusive prefix over the warps (in place) and the block total
+  for (int b = tid; b < B; b += blockDim.x) {
+    int c = 0;
+#pragma unroll 8
+    for (int v = 0; v < BK_WARPS; ++v) {
+      const int x = wh[v * B + b];
+      wh[v * B + b] = c;
+      c += x;
+    }
+    start[b] = c;
+  }
+  __syncthreads();
+  // block totals -> block starts (one warp, B <= 1024: up to 32 per lane)
   if (w == 0) {
     const int per = (B + 31) / 32;
     int tot = 0;
-    for (int b = lane * per; b < min(B, (lane + 1) * per); ++b) {
-      int c = 0;
-      for (int v = 0; v < BK_WARPS; ++v) c += wh[v * B + b];
-      start[b] = c;
-      tot += c;
-    }
+    for (int b = lane * per; b < min(B, (lane + 1) * per); ++b) tot += start[b];
     int pre = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -200,20 +219,9 @@ k_bucket_small(const int* owner, long long n, int B, long long* block_ptr, long 
   }
   __syncthreads();
   for (int b = tid; b <= B; b += blockDim.x) block_ptr[b] = start[b];
-  for (int b = tid; b < B; b += blockDim.x) {
-    int at = start[b];
-    for (int v = 0; v < BK_WARPS; ++v) {
-      const int c = wh[v * B + b];
-      wh[v * B + b] = at;
-      at += c;
-    }
-  }
-  __syncthreads();
-  for (long long q0 = p0; q0 < p1; q0 += 32) {
-    const long long p = q0 + lane;
-    const bool live = p < p1;
-    const int o = live ? owner[p] : -1 - lane;                 // dead lanes: distinct keys
-    const unsigned grp = __match_any_sync(0xffffffffu, o);
+  // placement: every warp walks its points in order; rank inside a group of 32 by __match_any_sync
+  auto place = [&](long long q0, int o, bool live) {
+    const unsigned grp = __match_any_sync(0xffffffffu, live ? o : -1 - lane);      // dead lanes: distinct keys
     const int rank = __popc(grp & ((1u << lane) - 1u));
     const int leader = __ffs(grp) - 1;
     int base = 0;
@@ -223,15 +231,26 @@ k_bucket_small(const int* owner, long long n, int B, long long* block_ptr, long 
     }
     base = __shfl_sync(0xffffffffu, base, leader);
     if (live) {
-      perm64[base + rank] = p;
-      pos_block[base + rank] = o;
+      const int pos = start[o] + base + rank;
+      perm64[pos] = q0 + lane;
+      pos_block[pos] = o;
     }
     __syncwarp();
+  };
+#pragma unroll
+  for (int k = 0; k < BK_PRE; ++k) {
+    const long long q0 = p0 + 32 * k;
+    if (q0 < p1) place(q0, own[k], own[k] >= 0);
+  }
+  for (long long q0 = p0 + 32 * BK_PRE; q0 < p1; q0 += 32) {
+    const long long p = q0 + lane;
+    const bool live = p < p1;
+    place(q0, live ? owner[p] : 0, live);
   }
   if (plan.enabled) {
     __threadfence_block();
     __syncthreads();                     // block_ptr (global, this CTA's own writes) is read back by the plan
-    res::res_plan_body(plan.Q, bk_sh);
+    res::res_plan_body(plan.Q, plan_sh);
   }
 }
 

@@ -447,6 +447,9 @@ __device__ __forceinline__ double2 cov_frag(const ResParams& P, const Ctx& c, co
 }
 
 __device__ __forceinline__ int tri_len(int r) { return r + 1; }
+// Task of warp w in round i when tasks are ordered by length: rounds alternate direction (snake), so
+// that every warp's tasks add up to about the same length (a phase lasts as long as its most loaded warp).
+__device__ __forceinline__ int snake_task(int w, int i) { return i * RNW + ((i & 1) ? RNW - 1 - w : w); }
 // n columns in ng = ceil(n / 4) groups of nearly equal width (<= 4): first column of group g
 __device__ __forceinline__ int grp_lo(int g, int n, int ng) { return (g * n) / ng; }
 
@@ -775,7 +778,7 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
     double2 z[YSLOTS][2];
 #pragma unroll
     for (int i = 0; i < YSLOTS; ++i) {
-      const int t = w + i * RNW;
+      const int t = snake_task(w, i);
       z[i][0] = z[i][1] = make_double2(0.0, 0.0);
       if (t < ntask) {
         const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
@@ -797,7 +800,7 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
       tma_wait(stage);
 #pragma unroll
       for (int i = 0; i < YSLOTS; ++i) {
-        const int t = w + i * RNW;
+        const int t = snake_task(w, i);
         if (t < ntask) {
           const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
           const int nj = min(2, ny - yl0);
@@ -818,7 +821,7 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
     rtrace(P, c, 36);
 #pragma unroll
     for (int i = 0; i < YSLOTS; ++i) {
-      const int t = w + i * RNW;
+      const int t = snake_task(w, i);
       if (t < ntask) {
         const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
 #pragma unroll
@@ -830,7 +833,7 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
     // Z = W_S R  (held in registers until every read of R is done)
 #pragma unroll
     for (int i = 0; i < YSLOTS; ++i) {
-      const int t = w + i * RNW;
+      const int t = snake_task(w, i);
       if (t < ntask) {
         const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
         const int nj = min(2, ny - yl0);
@@ -849,7 +852,7 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < YSLOTS; ++i) {
-      const int t = w + i * RNW;
+      const int t = snake_task(w, i);
       if (t < ntask) {
         const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
 #pragma unroll
@@ -865,7 +868,9 @@ static __device__ __noinline__ void ph_ypart(const ResParams& P, const Ctx& c, S
     rtrace(P, c, 37);
     // alpha_j = W_S^T Z
     if (c.want_grad) {
-      for (int t = w; t < ntask; t += RNW) {
+      for (int i = 0; i * RNW < ntask; ++i) {
+        const int t = snake_task(w, i);
+        if (t >= ntask) continue;
         const int row = t / ngy, yl0 = ((t + row + row / ngy) % ngy) * 2;     // output groups rotated by row
         const int nj = min(2, ny - yl0);
         double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
@@ -1002,7 +1007,7 @@ static __device__ __noinline__ void ph_v(const ResParams& P, const Ctx& c) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       zero4(acc[i]);
-      const int t = w + i * RNW;
+      const int t = snake_task(w, i);
       if (t < ntask) {
         const int row = rhi - 1 - t / ng, gq = (t % ng + t / ng + (t / ng) / ng) % ng;     // longest rows first, groups rotated
         const int c0 = grp_lo(gq, ab, ng), nj = grp_lo(gq + 1, ab, ng) - c0;
@@ -1017,7 +1022,7 @@ static __device__ __noinline__ void ph_v(const ResParams& P, const Ctx& c) {
     rtrace(P, c, 41);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int t = w + i * RNW;
+      const int t = snake_task(w, i);
       if (t < ntask) {
         const int row = rhi - 1 - t / ng, gq = (t % ng + t / ng + (t / ng) / ng) % ng;
         const int c0 = grp_lo(gq, ab, ng), nj = grp_lo(gq + 1, ab, ng) - c0;
@@ -1372,19 +1377,62 @@ static __device__ __noinline__ void ph_finalize(const ResParams& P, const Ctx& c
 #pragma unroll
   for (int t = 0; t < MAX_NCOV; ++t) th[t] = 0.0;
   const double coef = (WFN == WFN_SE) ? -2.0 : -3.0;         // w'(r)/r = coef * (k or k / (1 + sqrt3 r))
-  for (int t = tid; t < nr * 8; t += RNT) {
-    const int rb = t >> 3, g0 = t & 7;
-    double o[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
-    for (int gi = 0; gi < rowcnt[rb]; ++gi) {
-      const double* tp = c.taskp + ((long long)rb * MAXG + gi) * TASKP + g0 * 8;
+  // Two lanes per point: the even one sums the point's row records (8 doubles per task of its block row),
+  // the odd one its column records (4 doubles per block below it) - all of them L2 round trips, issued
+  // four records at a time; the pair is joined by a shuffle.  Fixed order => bit-reproducible.
+  for (int t2 = tid; t2 < ((nr * 16 + 31) & ~31); t2 += RNT) {
+    const int t = t2 >> 1, half = t2 & 1;
+    const bool live = t < nr * 8;
+    const int rb = live ? t >> 3 : 0, g0 = t & 7;
+    double o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (live && half == 0) {
+      const int cnt = rowcnt[rb];
+      const double* tp = c.taskp + ((long long)rb * MAXG) * TASKP + g0 * 8;
+      int gi = 0;
+      for (; gi + 4 <= cnt; gi += 4) {
+        double2 v[4][4];
 #pragma unroll
-      for (int n = 0; n < 8; ++n) o[n] += tp[n];
-    }
-    for (int r2 = rb; r2 < nr; ++r2) {
-      const double* pc = c.colp + (long long)(rtri(r2) + rb) * COLP + g0 * 4;
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int n = 0; n < 4; ++n) cc[n] += pc[n];
+          for (int n = 0; n < 4; ++n) v[u][n] = *reinterpret_cast<const double2*>(tp + (long long)(gi + u) * TASKP + 2 * n);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            o[2 * n] += v[u][n].x;
+            o[2 * n + 1] += v[u][n].y;
+          }
+      }
+      for (; gi < cnt; ++gi)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) o[n] += tp[(long long)gi * TASKP + n];
+    } else if (live) {
+      int r2 = rb;
+      for (; r2 + 4 <= nr; r2 += 4) {
+        double2 v[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int n = 0; n < 2; ++n)
+            v[u][n] = *reinterpret_cast<const double2*>(c.colp + (long long)(rtri(r2 + u) + rb) * COLP + g0 * 4 + 2 * n);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          o[0] += v[u][0].x;
+          o[1] += v[u][0].y;
+          o[2] += v[u][1].x;
+          o[3] += v[u][1].y;
+        }
+      }
+      for (; r2 < nr; ++r2) {
+        const double* pc = c.colp + (long long)(rtri(r2) + rb) * COLP + g0 * 4;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) o[n] += pc[n];
+      }
     }
+    double cc[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) cc[n] = __shfl_xor_sync(0xffffffffu, o[n], 1);     // even lanes receive the column sums
+    if (!live || half != 0) continue;
     double gxv[3];
     if (DFN == DFN_EUCLIDEAN) {
 #pragma unroll
@@ -1645,6 +1693,11 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
 // Launch plan on the device (one CTA): which blocks have to be factored, the pair units in
 // descending size order (longest first on the dynamic queue), the fit check.  No host round trip:
 // block sizes never leave the GPU.
+constexpr int PLAN_NKEY = 3 * BMAXB + 5 * BMAXB + 1;       // values of the pairs' cost key 3 ab + 5 bb
+// shared memory of res_plan_body for a CTA of nt threads: need[B] | key[E] | histograms | bucket starts
+__host__ __device__ inline size_t res_plan_smem(int B, int E, int nt) {
+  return ((size_t)B + E + (size_t)(nt / 32 + 1) * PLAN_NKEY + 1) * sizeof(int);
+}
 struct PlanParams {
   const long long* block_ptr;
   const int* edges;
@@ -1659,7 +1712,7 @@ struct PlanParams {
 };
 
 #ifndef GPRF_RES_KERNEL_ONLY
-// One CTA (any size); sh: (B + E) ints of shared memory.  Also called at the end of the single-CTA
+// One CTA (a multiple of 32 threads); sh: res_plan_smem(B, E, blockDim.x) bytes of shared memory.  Also called at the end of the single-CTA
 // bucketing kernel of partition.cuh (k_bucket_small), which saves a launch per evaluation.
 __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
   int* need = sh;
@@ -1680,7 +1733,8 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
     const int a = (int)(Q.block_ptr[i + 1] - Q.block_ptr[i]);
     const int b = (int)(Q.block_ptr[j + 1] - Q.block_ptr[j]);
     // cost key: measured pair times fit 11.5 ab + 19.0 bb - 228 us (8-blocks of block i / block j)
-    key[e] = act ? (b > 0 ? 3 * ((a + 7) >> 3) + 5 * ((b + 7) >> 3) : 0) : -1;
+    // (clamped: a structure with oversized blocks is handed to the tile pipeline, but the plan still runs)
+    key[e] = act ? (b > 0 ? min(PLAN_NKEY - 1, 3 * ((a + 7) >> 3) + 5 * ((b + 7) >> 3)) : 0) : -1;
     if (act) {
       need[i] = 1;                      // benign race: everybody writes 1
       if (b > 0 && res_class((a + 7) >> 3, (b + 7) >> 3) == 2) s_over = 1;
@@ -1711,8 +1765,12 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
     }
     if (tid == 0) s_nb = nb;
   }
-  for (int e = tid; e < Q.E; e += nt)
-    if (key[e] >= 0) atomicAdd(&s_np, 1);
+  {
+    int mine = 0;
+    for (int e = tid; e < Q.E; e += nt) mine += key[e] >= 0 ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((tid & 31) == 0 && mine) atomicAdd(&s_np, mine);
+  }
   __syncthreads();
   const int G = Q.G, nb = s_nb, np_ = s_np;
   const int kb = nb / G, rb = nb % G, q = np_ / G, rem = np_ % G, mB = G - rem;
@@ -1725,23 +1783,57 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
       Q.order[lptr(w) + k / G] = bq;
     }
   }
-  // pairs: rank sort by (size descending, id ascending); S lanes share an edge's comparisons
+  // pairs by (cost key descending, id ascending): the key takes at most PLAN_NKEY values, so a stable
+  // counting sort does it in O(E) (the O(E^2) rank sort it replaces was 45 000 of the kernel's 60 000
+  // warp instructions at E = 342, ~10 us on the one SM that runs the plan).  Warp v owns the contiguous
+  // edge range [v Le, (v + 1) Le): per-warp histograms, per bucket a prefix over the warps, the bucket
+  // starts, then every warp places its edges in order (ranks inside a group of 32 by __match_any_sync).
   {
-    int S = 1;
-    while (S < 32 && 2 * S * Q.E <= nt) S *= 2;
-    const int sub = tid & (S - 1);
-    for (int e0 = 0; e0 < Q.E; e0 += nt / S) {
-      const int e = e0 + tid / S;
-      const int ke = e < Q.E ? key[e] : -1;
-      int rank = 0;
-      if (ke >= 0) {
-        for (int f = sub; f < Q.E; f += S) {
-          const int kf = key[f];
-          rank += (kf > ke || (kf == ke && f < e)) ? 1 : 0;
-        }
+    int* kh = sh + Q.B + Q.E;                       // [nwarp][PLAN_NKEY] counts -> prefixes
+    const int nwarp = nt >> 5, wv = tid >> 5, lane = tid & 31;
+    int* kstart = kh + nwarp * PLAN_NKEY;           // [PLAN_NKEY + 1]
+    for (int e = tid; e < nwarp * PLAN_NKEY; e += nt) kh[e] = 0;
+    __syncthreads();
+    const int Le = (Q.E + nwarp - 1) / nwarp;
+    const int e0 = wv * Le, e1 = min(Q.E, e0 + Le);
+    for (int e = e0 + lane; e < e1; e += 32)
+      if (key[e] >= 0) atomicAdd(&kh[wv * PLAN_NKEY + (PLAN_NKEY - 1 - key[e])], 1);     // bucket 0 = largest key
+    __syncthreads();
+    for (int kb2 = tid; kb2 < PLAN_NKEY; kb2 += nt) {
+      int cnt = 0;
+      for (int v = 0; v < nwarp; ++v) {
+        const int x = kh[v * PLAN_NKEY + kb2];
+        kh[v * PLAN_NKEY + kb2] = cnt;
+        cnt += x;
       }
-      for (int o = 1; o < S; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
-      if (ke >= 0 && sub == 0) {
+      kstart[kb2] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {                                  // PLAN_NKEY = 161 totals -> starts
+      int at = 0;
+      for (int kb2 = 0; kb2 < PLAN_NKEY; ++kb2) {
+        const int cnt = kstart[kb2];
+        kstart[kb2] = at;
+        at += cnt;
+      }
+    }
+    __syncthreads();
+    for (int q0 = e0; q0 < e1; q0 += 32) {
+      const int e = q0 + lane;
+      const int ke = e < e1 ? key[e] : -1;
+      const bool live = ke >= 0;
+      const int bk = live ? PLAN_NKEY - 1 - ke : -1 - lane;
+      const unsigned grp = __match_any_sync(0xffffffffu, bk);
+      const int within = __popc(grp & ((1u << lane) - 1u));
+      const int leader = __ffs(grp) - 1;
+      int base = 0;
+      if (live && lane == leader) {
+        base = kh[wv * PLAN_NKEY + bk];
+        kh[wv * PLAN_NKEY + bk] = base + __popc(grp);
+      }
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (live) {
+        const int rank = kstart[bk] + base + within;
         int w, round;
         if (rank < mB * q) {
           round = rank / mB;
@@ -1755,6 +1847,7 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
         }
         Q.order[lptr(w) + nblk(w) + round] = Q.B + e;
       }
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -1768,7 +1861,7 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
 }
 
 __global__ void k_res_plan(PlanParams Q) {
-  extern __shared__ int sh[];          // need[B] | key[E]
+  extern __shared__ int sh[];          // res_plan_smem(B, E, blockDim.x) bytes
   res_plan_body(Q, sh);
 }
 
