@@ -180,3 +180,38 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "n=2000" in d["config"]["workload"]
+
+
+def test_edge_list_counts_mutations():
+    """GPRF.neighbors is a list that counts its mutations (the O(1) currency check of the device's edge
+    list): every in-place edit bumps the version, reads do not, and it pickles as a plain list."""
+    import pickle
+    from gprf_b200.gprf import _EdgeList
+    e = _EdgeList([(1, 0), (2, 1)])
+    v0 = e.version
+    assert e[0] == (1, 0) and len(e) == 2 and list(e) == [(1, 0), (2, 1)] and e.version == v0
+    steps = [lambda: e.append((3, 2)), lambda: e.__setitem__(0, (2, 0)), lambda: e.extend([(4, 3)]),
+             lambda: e.insert(1, (3, 1)), lambda: e.sort(), lambda: e.reverse(), lambda: e.pop(),
+             lambda: e.remove(e[0]), lambda: e.__delitem__(0)]
+    for k, f in enumerate(steps):
+        f()
+        assert e.version == v0 + k + 1
+    e += [(5, 4)]
+    assert isinstance(e, _EdgeList) and e.version == v0 + len(steps) + 1
+    e.clear()
+    assert len(e) == 0 and e.version == v0 + len(steps) + 2
+    back = pickle.loads(pickle.dumps(_EdgeList([(1, 0)])))
+    assert type(back) is list and back == [(1, 0)]
+
+
+def test_traffic_figure_is_stamped_with_the_kernel_sources():
+    """bench.py takes roofline.traffic from profiles/ncu_traffic.json only when that file was captured
+    from the CUDA sources in the tree (hash stamp)."""
+    import json
+    import bench
+    sha = bench.kernel_sources_sha16()
+    assert len(sha) == 16 and sha == bench.kernel_sources_sha16()
+    tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    ent = tj["cfg2"]["resident"]
+    assert set(("bytes", "sources_sha16", "source", "algorithmic_bytes")) <= set(ent)
+    assert ent["bytes"] < 3.5 * ent["algorithmic_bytes"]
