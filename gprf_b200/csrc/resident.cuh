@@ -612,6 +612,7 @@ __device__ __forceinline__ void chol_diag_block(int blk, int wd, int row0, bool 
       A[r][2 * cp] = t.x;
       A[r][2 * cp + 1] = t.y;
     }
+  __syncwarp();                                  // every lane has read the block before any lane writes into it
   const int f = chol8_full(A, wv, lane);
   if (lane == 0 && f != 0 && *S_FAIL == 0) *S_FAIL = row0 + f;
   if (lane < 8) {

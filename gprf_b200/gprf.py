@@ -664,17 +664,26 @@ class GPRF(object):
     # -- prediction (gprf.py:593-672) ---------------------------------------------
     def block_precisions(self, Y=None):
         """Per block: (K_b + nv I)^-1 and Alpha_b = K_b^-1 Y_b, computed by the device pipeline
-        (a local-GP evaluation with the K^-1 tiles kept: jitchol -> triangular inverse -> U U^T,
-        the dpotri route of gpy_linalg.py:219-240) and read back once."""
-        Yc = self.Y if Y is None else Y
+        (jitchol -> triangular inverse -> U U^T, the dpotri route of gpy_linalg.py:219-240).  With the
+        GPRF's own Y this runs on the live handle: one evaluation of the block units only (unit mask,
+        K^-1 tiles kept), no second context; another Y needs its own upload and therefore its own handle."""
         blocks = self.block_idxs
-        sub = GPRF(np.ascontiguousarray(self.X, dtype=np.float64), np.ascontiguousarray(Yc, dtype=np.float64), None,
-                   self.cov, self.noise_var, block_idxs=blocks, neighbors=[], device=self.device)
+        if Y is not None and Y is not self.Y:
+            sub = GPRF(np.ascontiguousarray(self.X, dtype=np.float64), np.ascontiguousarray(Y, dtype=np.float64), None,
+                       self.cov, self.noise_var, block_idxs=blocks, neighbors=[], device=self.device)
+            try:
+                return sub.block_precisions()
+            finally:
+                sub.close()
+        B = self.n_blocks
+        mask = np.zeros(B + len(self.neighbors), dtype=np.uint8)
+        mask[:B] = 1
+        self.set_unit_mask(mask, raw_weights=True)
+        self.set_keep_kinv(True)
         try:
-            sub.set_keep_kinv(True)
-            sub.llgrad(grad_X=True)
+            self.llgrad(grad_X=True)
             Kinvs, Alphas = [], []
-            dy = sub._Yc.shape[1]
+            dy = self._Yc.shape[1]
             for b, idx in enumerate(blocks):
                 s = len(idx)
                 if s == 0:
@@ -682,15 +691,16 @@ class GPRF(object):
                     Alphas.append(np.zeros((0, dy)))
                     continue
                 sz, sp, yr = C.c_int(), C.c_int(), C.c_int()
-                sub._check(sub._lib.gprf_debug_unit(sub._h, b, C.byref(sz), C.byref(sp), C.byref(yr), None, None, None))
+                self._check(self._lib.gprf_debug_unit(self._h, b, C.byref(sz), C.byref(sp), C.byref(yr), None, None, None))
                 M = np.empty((sp.value + yr.value, sp.value))
                 Al = np.empty((sp.value, yr.value))
-                sub._check(sub._lib.gprf_debug_unit(sub._h, b, None, None, None, _lib.ptr(M), _lib.ptr(Al), None))
+                self._check(self._lib.gprf_debug_unit(self._h, b, None, None, None, _lib.ptr(M), _lib.ptr(Al), None))
                 L = np.tril(M[:s, :s])
                 Kinvs.append(L + np.tril(L, -1).T)
                 Alphas.append(np.array(Al[:s, :dy]))
         finally:
-            sub.close()
+            self.set_keep_kinv(False)
+            self.set_unit_mask(None)
         return Kinvs, Alphas
 
     def train_predictor(self, test_cov=None, Y=None):
