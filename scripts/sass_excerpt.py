@@ -50,9 +50,9 @@ for f in funcs[1:]:
     a = [k for k, l in enumerate(lines) if 'BAR.ARV' in l][-1]
     out.append("## ... the producer side of the Cholesky look-ahead (named barrier 1: BAR.ARV by warp 0, BAR.SYNC by the workers)")
     out += [clean(l) for l in lines[max(0, a - 3):a + 3]] + [""]
-    d = [k for k, l in enumerate(lines) if 'CCTL' in l or 'DISCARD' in l.upper()]
+    d = [k for k, l in enumerate(lines) if 'CCTL.E.RML2' in l]
     if d:
-        out.append("## ... dead scratch dropped from the L2 (discard.global.L2)")
+        out.append("## ... dead scratch dropped from the L2 (discard.global.L2 = CCTL.E.RML2, %d of them)" % len(d))
         out += [clean(l) for l in lines[max(0, d[0] - 2):d[0] + 3]]
     break
 open(os.path.join(ROOT, "profiles", "r02_sass_excerpt_shipped_so.txt"), "w").write("\n".join(out) + "\n")
