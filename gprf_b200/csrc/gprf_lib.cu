@@ -17,6 +17,7 @@
 #include "resident.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <queue>
+#include <mutex>
 
 using namespace gprf;
 
@@ -1362,6 +1363,12 @@ static int try_resident(gprf_ctx* h, const double* X_dev, const double* theta, i
     return rc;
   }
   int launches = 0;
+  // One resident launch per process at a time: its CTAs wait for each other (a pair spins on its parent
+  // block's flag), which is only safe while the whole grid can become resident.  Two handles driven from
+  // two host threads are serialised here (the evaluation is synchronous anyway); the kernel's watchdog
+  // (ST_TIMEOUT) covers what a mutex cannot (other processes on the same GPU).
+  static std::mutex res_mutex;
+  std::lock_guard<std::mutex> res_lock(res_mutex);
   CUDA_OK(cudaEventRecord(h->ev0, st));
   rc = run_resident(h, X_dev, cp, grad_X, grad_cov, out_dev, st, &launches);
   if (rc != GPRF_OK) return rc;

@@ -80,7 +80,13 @@ constexpr long long SCR_R1 = SCR_KJJ + (long long)RTRI * RBLK;                  
 constexpr long long SCR_STRIDE = SCR_R1 + (long long)EMAXB * EMAXB * RBLK;
 constexpr int GX_STRIDE = 2 * EMAXB * 8 * 3;           // per-unit gradX rows (padded local order)
 
-enum { ST_OVERFLOW = 1, ST_NOTPD = 2 };
+enum { ST_OVERFLOW = 1, ST_NOTPD = 2, ST_TIMEOUT = 4 };
+// Watchdog of the kernel's spin waits (a parent block's flag, a TMA's mbarrier): after ~2 s (a launch takes
+// 0.5 ms) the wait gives up and sets ST_TIMEOUT - the evaluation's results are then discarded and it is
+// redone by the tile pipeline, like a structure that does not fit.  It turns any scheduling or
+// synchronisation fault (e.g. two resident launches on one GPU whose CTAs wait for each other's SMs)
+// from a hung process into a visible fallback (gprf_resident_stats).
+constexpr long long SPIN_LIMIT_CYCLES = 4000000000LL;
 
 __host__ __device__ __forceinline__ int rtri(int i) { return i * (i + 1) / 2; }
 // shared memory, in whole 8x8 blocks:  MISC | XS | R1 | R2 | F | WB
@@ -224,6 +230,7 @@ __device__ __forceinline__ void for_desc(int n, F&& f) {
 struct Stage {
   uint64_t* bar;
   unsigned par;
+  int* status;                  // the evaluation's status word (watchdog)
 };
 __device__ __forceinline__ void tma_issue(const Stage& S, double* dst, const double* src, int nblk) {
   asm volatile("fence.proxy.async;\n" ::: "memory");      // generic-proxy writes (this CTA's, or acquired) before the copy
@@ -231,8 +238,29 @@ __device__ __forceinline__ void tma_issue(const Stage& S, double* dst, const dou
   mbar_expect_tx(S.bar, bytes);
   bulk_g2s(dst, src, bytes, S.bar);
 }
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tma_wait(Stage& S) {
-  mbar_wait(S.bar, S.par & 1u);
+  if (!mbar_try(S.bar, S.par & 1u)) {
+    const long long t0 = clock64();
+    while (!mbar_try(S.bar, S.par & 1u)) {
+      if (clock64() - t0 > SPIN_LIMIT_CYCLES) {
+        if (S.status) atomicOr(S.status, ST_TIMEOUT);
+        break;
+      }
+    }
+  }
   S.par ^= 1u;
 }
 
@@ -1544,7 +1572,14 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
   }
   if (c.pair) {                  // K_ii^-1 of the parent (its gradient phase): long done by now
     if (tid == 0) {
-      while (atomicAdd(P.ready2 + c.bi, 0) != P.epoch) __nanosleep(100);
+      const long long t0 = clock64();
+      while (atomicAdd(P.ready2 + c.bi, 0) != P.epoch) {
+        __nanosleep(100);
+        if (clock64() - t0 > SPIN_LIMIT_CYCLES) {
+          atomicOr(P.status, ST_TIMEOUT);
+          break;
+        }
+      }
       __threadfence();
     }
   }
@@ -1581,6 +1616,7 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
   Stage stage;
   stage.bar = reinterpret_cast<uint64_t*>(MISC);
   stage.par = 0;
+  stage.status = Pk.status;
   int* s_unit = reinterpret_cast<int*>(MISC + 4);
   Ctx* ctx = reinterpret_cast<Ctx*>(MISC + MISC_CTX);
   ResParams* Ps = reinterpret_cast<ResParams*>(MISC + MISC_PARAMS);
@@ -1615,7 +1651,14 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
       if (threadIdx.x == 0) {
         // (a pair with an empty second block copies block i's final results: second flag)
         const int* flag = (b == 0 ? P.ready2 : P.ready) + bi;
-        while (atomicAdd(const_cast<int*>(flag), 0) != P.epoch) __nanosleep(100);
+        const long long t0 = clock64();
+        while (atomicAdd(const_cast<int*>(flag), 0) != P.epoch) {
+          __nanosleep(100);
+          if (clock64() - t0 > SPIN_LIMIT_CYCLES) {
+            atomicOr(P.status, ST_TIMEOUT);
+            break;
+          }
+        }
         __threadfence();
       }
       __syncthreads();

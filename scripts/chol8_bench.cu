@@ -20,7 +20,7 @@ __global__ void k_bench(long long* out, int reps) {
   for (int i = 0; i < reps; ++i) {
     for (int e = lane; e < 64; e += 32) g_smem[2048 + e] = g_smem[1024 + e];
     __syncwarp();
-    chol_diag_block(2048, 3072, 0);
+    chol_diag_block(2048, 3072, 0, true);
     __syncwarp();
   }
   long long t1 = clock64();

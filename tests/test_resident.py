@@ -300,3 +300,36 @@ def test_resident_random_structures(seed):
             continue
         ref = o.llgrad_joint(i, j)[0]
         assert abs(lls[B + e] - ref) <= 1e-9 * max(1.0, abs(ref)), (e, i, j, sizes[i], sizes[j])
+
+
+@pytest.mark.timeout(120)
+def test_two_handles_from_two_threads():
+    """Two GPRF objects evaluated concurrently from two host threads (ctypes releases the GIL): resident
+    launches are serialised per process - their CTAs wait for each other's results, so two grids must not
+    compete for the SMs - and every evaluation returns the single-threaded result, bit for bit."""
+    import threading
+    o1, g1 = build_pair("euclid_se", [90, 100, 80, 110, 95, 70], [(1, 0), (2, 1), (3, 2), (4, 3), (5, 4), (5, 0)], dy=50, seed=3)
+    o2, g2 = build_pair("euclid_m32", [60, 120, 100, 85], [(1, 0), (2, 1), (3, 2), (3, 0)], dy=50, seed=4)
+    kw = dict(grad_X=True, grad_cov=True)
+    want = [g1.llgrad(**kw), g2.llgrad(**kw)]
+    assert_parity(o1.llgrad(**kw), want[0], "thread 1 reference")
+    assert_parity(o2.llgrad(**kw), want[1], "thread 2 reference")
+    errors = []
+
+    def work(g, ref):
+        try:
+            for _ in range(60):
+                got = g.llgrad(**kw)
+                if not (got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])):
+                    errors.append("result changed")
+                    return
+        except Exception as exc:        # noqa: BLE001
+            errors.append(repr(exc))
+    ts = [threading.Thread(target=work, args=(g1, want[0])), threading.Thread(target=work, args=(g2, want[1]))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(100)
+    assert not any(t.is_alive() for t in ts), "an evaluation hangs"
+    assert errors == []
+    assert g1.resident_stats()[1] == 0 and g2.resident_stats()[1] == 0
