@@ -333,7 +333,13 @@ class Runner(object):
         self.pool_d = [torch.tensor(x, dtype=torch.float64, device=self.dev) for x in self.pool_h]
         self.step_no = 0
         self.Xd = self.pool_d[0]
-        self.out = torch.zeros(self.outlen, dtype=torch.float64, device=self.dev)
+        # [status | ll, grad theta (5), gradX]: at N > 1 the evaluation's status word travels with the
+        # results through the all-reduce (no host round trip before the collective)
+        self.out_s = torch.zeros(self.outlen + 1, dtype=torch.float64, device=self.dev)
+        self.out = self.out_s[1:]
+        self.status_h = torch.zeros(1, dtype=torch.float64).pin_memory()
+        self.Xe2e = torch.empty((self.n, self.dx), dtype=torch.float64, device=self.dev)
+        self.sync_redos = 0
         self.Xh = torch.empty((self.n, self.dx), dtype=torch.float64).pin_memory()
         self.outh = torch.empty(self.outlen, dtype=torch.float64).pin_memory()
         self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
@@ -343,14 +349,39 @@ class Runner(object):
     def flush_l2(self):
         self.flush_buf.zero_()
 
-    def device_step(self, reblock=False):
+    def device_step(self, reblock=False, Xd=None, force_sync=False):
+        """One evaluation with X resident in HBM.  N = 1: gprf_llgrad_device (one host round trip for the
+        status word).  N > 1: gprf_llgrad_device_nosync + ONE all-reduce of [status | results]; the caller
+        synchronises and calls check_status()."""
         st = self.torch.cuda.current_stream(self.dev)
         self.step_no += 1
-        self.Xd = self.pool_d[self.step_no % len(self.pool_d)] if reblock else self.pool_d[0]
-        self.g.llgrad_device(self.Xd.data_ptr(), self.out.data_ptr(), st.cuda_stream,
-                             grad_X=True, grad_cov=self.grad_cov, reblock=reblock)
-        if self.world > 1:
-            self.dist.all_reduce(self.out)
+        if Xd is None:
+            Xd = self.pool_d[self.step_no % len(self.pool_d)] if reblock else self.pool_d[0]
+        self.Xd = Xd
+        if self.world == 1 or force_sync:
+            self.g.llgrad_device(Xd.data_ptr(), self.out.data_ptr(), st.cuda_stream,
+                                 grad_X=True, grad_cov=self.grad_cov, reblock=reblock)
+            if self.world > 1:
+                self.out_s[0] = 0.0
+                self.dist.all_reduce(self.out_s)
+                self.status_h.zero_()
+            return
+        self.g.llgrad_device(Xd.data_ptr(), self.out.data_ptr(), st.cuda_stream, grad_X=True, grad_cov=self.grad_cov,
+                             reblock=reblock, status_dev_ptr=self.out_s.data_ptr())
+        self.dist.all_reduce(self.out_s)
+        self.status_h.copy_(self.out_s[:1], non_blocking=True)
+
+    def check_status(self):
+        """After the stream has drained (N > 1): a non-zero reduced status means some rank's evaluation has
+        to be redone by the synchronous path (jitter rule / tile pipeline) - on every rank."""
+        if self.world > 1 and self.status_h[0].item() != 0.0:
+            st = self.torch.cuda.current_stream(self.dev)
+            self.g.llgrad_device(self.Xd.data_ptr(), self.out.data_ptr(), st.cuda_stream,
+                                 grad_X=True, grad_cov=self.grad_cov, reblock=False)
+            self.out_s[0] = 0.0
+            self.dist.all_reduce(self.out_s)
+            st.synchronize()
+            self.sync_redos += 1
 
     def timed_device_steps(self, k):
         torch = self.torch
@@ -363,6 +394,7 @@ class Runner(object):
             self.device_step(reblock=self.reblock)
             e1.record()
             e1.synchronize()
+            self.check_status()
             total += e0.elapsed_time(e1)
             launches += self.g.last_timing()[1] + (1 if self.world > 1 else 0)
         return total, launches
@@ -378,10 +410,11 @@ class Runner(object):
             return self.g.llgrad(grad_X=True, grad_cov=self.grad_cov)
         self.g.update_X(X_host)
         self.Xh.numpy()[...] = X_host
-        self.Xd.copy_(self.Xh, non_blocking=True)
-        self.device_step(reblock=self.g._device_part is not None)
+        self.Xe2e.copy_(self.Xh, non_blocking=True)
+        self.device_step(reblock=self.g._device_part is not None, Xd=self.Xe2e)
         self.outh.copy_(self.out, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
+        self.check_status()
         return self.outh[0].item()
 
     def e2e_bytes(self):
@@ -406,7 +439,7 @@ class Runner(object):
         acc = {}
         for _ in range(reps):
             self.flush_l2()
-            self.device_step(reblock=self.reblock)
+            self.device_step(reblock=self.reblock, force_sync=True)     # the per-family events are resolved by the synchronous entry
             for k, (ms, nl) in self.g.family_timing().items():
                 a = acc.setdefault(k, [0.0, 0])
                 a[0] += ms / reps
@@ -461,12 +494,13 @@ def lbfgs_full_run():
 
 
 def kernel_sources_sha16():
-    """Hash of the CUDA sources (the stamp of profiles/ncu_traffic.json)."""
+    """Hash of the device code (every kernel lives in a .cuh header; the .cu files hold the host plan
+    and the C-ABI) - the stamp of profiles/ncu_traffic.json."""
     import hashlib
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "gprf_b200", "csrc")
     for fn in sorted(os.listdir(csrc)):
-        if fn.endswith((".cu", ".cuh")):
+        if fn.endswith(".cuh"):
             with open(os.path.join(csrc, fn), "rb") as f:
                 h.update(f.read())
     return h.hexdigest()[:16]
@@ -603,7 +637,7 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
         barrier()
         e0.record()
         for _ in range(10):
-            dist.all_reduce(R.out)
+            dist.all_reduce(R.out_s)
         e1.record()
         e1.synchronize()
         ta = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=R.dev)
@@ -612,7 +646,8 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
     roof["factor_reuse"] = dict(zip(("pair_units", "tile_tasks_saved"), R.g.factor_reuse_stats()))
     if ar_ms is not None:
         roof["allreduce_ms"] = ar_ms
-        roof["allreduce_bytes"] = int(R.out.numel() * 8)
+        roof["allreduce_bytes"] = int(R.out_s.numel() * 8)
+        roof["sync_redos"] = R.sync_redos
     ev, fb, _ = R.g.resident_stats()
     roof["resident_path"] = {"evaluations": ev, "handed_to_tile_pipeline": fb}
     res = {"wl": wl, "reblock": R.reblock, "ms_per_step": ms_per_step, "value": 1e3 / ms_per_step, "launches": launches // steps,

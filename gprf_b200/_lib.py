@@ -32,6 +32,8 @@ _SIGNATURES = {
     "gprf_set_edges": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "gprf_set_unit_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "gprf_unit_lmul": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "gprf_llgrad_device_nosync": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gprf_set_x_prior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gprf_neg_objective": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),

@@ -1264,7 +1264,7 @@ static int res_alloc(gprf_ctx* h, int grid) {
 
 // Enqueue one evaluation on the resident path.  out_dev = [ll, grad theta (5), gradX (n dx)].
 static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, int grad_X, int grad_cov,
-                        double* out_dev, cudaStream_t st, int* launches_out) {
+                        double* out_dev, cudaStream_t st, int* launches_out, double* status_dev = nullptr) {
   int rc = res_sync_static(h);
   if (rc != GPRF_OK) return rc;
   const int B = h->B, E = h->E;
@@ -1339,7 +1339,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   C.dx = h->dx;
   C.plen = h->plen;
   const unsigned gc = 1 + (grad_X ? (unsigned)((h->plen + 255) / 256) : 0);
-  LAUNCH(12, (res::k_res_combine<<<gc, 256, 0, st>>>(C, out_dev, grad_X ? 1 : 0, grad_cov ? 1 : 0, nullptr)));
+  LAUNCH(12, (res::k_res_combine<<<gc, 256, 0, st>>>(C, out_dev, grad_X ? 1 : 0, grad_cov ? 1 : 0, status_dev)));
   CUDA_OK(cudaGetLastError());
   rc = apply_prior(h, X_dev, out_dev, grad_X, st);
   if (rc != GPRF_OK) return rc;
@@ -1548,6 +1548,49 @@ extern "C" int gprf_llgrad_device(gprf_handle h, const double* X_dev, const doub
   h->pending_part_launches = 0;
   CUDA_OK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   if (h->profile) h->prof_resolve();
+  return GPRF_OK;
+}
+
+// Device-resident evaluation WITHOUT a host round trip: on the resident path the launches are enqueued on
+// `stream` and the call returns at once; the evaluation's status word is written (as a double, 0 = ok) to
+// *status_dev by the combination kernel, next to the results in out_dev.  Meant for multi-GPU use
+// (gprf.py:218-233 runs the units in a process pool): the status travels inside the all-reduce of the packed
+// results, the host synchronises once after the collective, and only when the reduced status is non-zero
+// (a unit needs the jitter rule, a block does not fit) every rank repeats the evaluation with
+// gprf_llgrad_device.  *enqueued = 1: asynchronous; 0: the structure is not of the resident kind, the
+// evaluation ran synchronously (tile pipeline, jitter rule and errors as in gprf_llgrad_device) and
+// *status_dev is 0.
+extern "C" int gprf_llgrad_device_nosync(gprf_handle h, const double* X_dev, const double* theta, int ncov,
+                                         int grad_X, int grad_cov, double* out_dev, double* status_dev, void* stream,
+                                         int* enqueued, int* failed_unit) {
+  if (!h || !X_dev || !theta || !out_dev || !status_dev || !enqueued) return GPRF_ERR_ARG;
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  *enqueued = 0;
+  if (failed_unit) *failed_unit = -1;
+  if (res_eligible(h) && h->dev_blocks_valid && h->plen > 0) {
+    CovParams cp;
+    int rc = make_cov(h, theta, ncov, &cp);
+    if (rc != GPRF_OK) {
+      h->err = "theta must have 2 + (number of lengthscales) entries";
+      return rc;
+    }
+    int launches = 0;
+    CUDA_OK(cudaEventRecord(h->ev0, st));
+    rc = run_resident(h, X_dev, cp, grad_X, grad_cov, out_dev, st, &launches, status_dev);
+    if (rc != GPRF_OK) return rc;
+    CUDA_OK(cudaEventRecord(h->ev1, st));
+    h->res_evals++;
+    h->res_last_status = 0;               // unknown to the host; the caller reports failures by redoing
+    h->last_launches = launches + h->pending_part_launches;
+    h->pending_part_launches = 0;
+    h->last_resident = true;
+    *enqueued = 1;
+    return GPRF_OK;
+  }
+  int rc = gprf_llgrad_device(h, X_dev, theta, ncov, grad_X, grad_cov, out_dev, stream, failed_unit);
+  if (rc != GPRF_OK) return rc;
+  CUDA_OK(cudaMemsetAsync(status_dev, 0, sizeof(double), st));
   return GPRF_OK;
 }
 

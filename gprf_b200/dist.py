@@ -120,21 +120,43 @@ class ShardedGPRF(GPRF):
         self._Xd.copy_(self._Xh, non_blocking=True)
         stream = torch.cuda.current_stream(dev)
         used = 2 + _lib.MAX_NCOV + (n * dx if grad_X else 0)
-        error = None
-        try:
-            self.llgrad_device(self._Xd.data_ptr(), self._out.data_ptr() + 8, stream.cuda_stream, local=local,
-                               grad_X=grad_X, grad_cov=grad_cov,
-                               reblock=self._blocks_stale and self._device_part is not None)
-            self._out[0] = 0.0
-        except Exception as exc:          # any failure: flag it, still take part in the collective
-            error = exc
-            self._out[:used].zero_()
-            self._out[0] = 1.0
-        dist.all_reduce(self._out[:used])
-        self._outh[:used].copy_(self._out[:used], non_blocking=True)
-        stream.synchronize()
+        # Slot 0 carries the status: on the resident path the device writes it (no host round trip before
+        # the collective), otherwise the host does.  A non-zero sum after the all-reduce means that some
+        # rank needs the jitter rule / the tile pipeline or failed: then EVERY rank repeats the evaluation
+        # synchronously (same decision everywhere - the reduced status is the same on every rank).
+        reblock = self._blocks_stale and self._device_part is not None
+
+        def evaluate(sync):
+            error = None
+            try:
+                if sync:
+                    self.llgrad_device(self._Xd.data_ptr(), self._out.data_ptr() + 8, stream.cuda_stream, local=local,
+                                       grad_X=grad_X, grad_cov=grad_cov, reblock=reblock and not self._reblocked)
+                    self._out[0] = 0.0
+                else:
+                    self.llgrad_device(self._Xd.data_ptr(), self._out.data_ptr() + 8, stream.cuda_stream, local=local,
+                                       grad_X=grad_X, grad_cov=grad_cov, reblock=reblock,
+                                       status_dev_ptr=self._out.data_ptr())
+                    self._reblocked = reblock
+            except Exception as exc:          # any failure: flag it, still take part in the collective
+                error = exc
+                self._out[:used].zero_()
+                self._out[0] = 1e6
+            dist.all_reduce(self._out[:used])
+            self._outh[:used].copy_(self._out[:used], non_blocking=True)
+            stream.synchronize()
+            return error
+
+        # Every rank takes the same path through the collectives: the decisions below depend on the
+        # REDUCED status only (>= 1e6: some rank raised; otherwise non-zero: some rank's device status).
+        self._reblocked = False
+        error = evaluate(sync=False)
+        status = self._outh[0].item()
+        if 0.0 < status < 1e6:
+            error = evaluate(sync=True)
+            status = self._outh[0].item()
         if error is not None:
             raise error
-        if self._outh[0].item() != 0.0:
+        if status != 0.0:
             raise LinAlgError("the evaluation failed on another rank (e.g. a unit was not positive definite)")
         return unpack(self._outh.numpy()[1:], n, dx, 2 + len(self.cov.dfn_params), grad_X, grad_cov)

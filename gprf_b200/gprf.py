@@ -406,13 +406,18 @@ class GPRF(object):
         return np.float64(ll.value), gradX, gradCov
 
     def llgrad_device(self, X_dev_ptr, out_dev_ptr, stream_ptr=0, local=True, grad_X=False, grad_cov=False,
-                      reblock=False):
+                      reblock=False, status_dev_ptr=None):
         """Device-resident variant (gprf_llgrad_device): X already in HBM at ``X_dev_ptr``
         (n x dx doubles), results left in HBM at ``out_dev_ptr`` as
         [ll, grad_theta (5, zero padded), gradX (n*dx)].  Pointers are plain integers
         (e.g. ``tensor.data_ptr()``, ``torch.cuda.current_stream().cuda_stream``).
         ``reblock`` recomputes block membership from the device X first (needs the
-        on-device partitioner); otherwise the current blocks are used."""
+        on-device partitioner); otherwise the current blocks are used.
+        ``status_dev_ptr`` (a device double): no host round trip - on the resident path the launches
+        are only enqueued and the evaluation's status (0 = ok) is written there by the device
+        (gprf_llgrad_device_nosync); returns True when the evaluation is still in flight.  The caller
+        synchronises, reads the status (e.g. after an all-reduce that carried it) and repeats the call
+        without ``status_dev_ptr`` when it is non-zero."""
         self._sync_edges(self._edges_for(local))
         if reblock:
             if self._device_part is None:
@@ -427,10 +432,18 @@ class GPRF(object):
             self._sync_blocks()
         th = self._theta()
         failed = C.c_int(-1)
+        if status_dev_ptr is not None:
+            enq = C.c_int(0)
+            rc = self._lib.gprf_llgrad_device_nosync(self._h, C.c_void_p(X_dev_ptr), _lib.ptr(th), len(th), int(grad_X),
+                                                     int(grad_cov), C.c_void_p(out_dev_ptr), C.c_void_p(status_dev_ptr),
+                                                     C.c_void_p(stream_ptr), C.byref(enq), C.byref(failed))
+            self._check(rc, failed.value)
+            return bool(enq.value)
         rc = self._lib.gprf_llgrad_device(self._h, C.c_void_p(X_dev_ptr), _lib.ptr(th), len(th), int(grad_X),
                                           int(grad_cov), C.c_void_p(out_dev_ptr), C.c_void_p(stream_ptr),
                                           C.byref(failed))
         self._check(rc, failed.value)
+        return False
 
     def unit_results(self):
         """Per-unit log-likelihoods and applied jitter of the last evaluation

@@ -142,6 +142,15 @@ int gprf_llgrad_device(gprf_handle h, const double* X_dev, const double* theta,
 int gprf_set_x_prior(gprf_handle h, const double* mean, const double* inv_var, const double* grad_scale);
 int gprf_neg_objective(gprf_handle h, const double* X, const double* theta, int ncov, int grad_cov,
                        int reblock, double* f, double* g, double* gradTheta, int* failed_unit);
+/* gprf_llgrad_device without the host round trip (resident path): launches are enqueued on `stream`, the
+ * status word of the evaluation is written as a double (0 = ok) to *status_dev by the combination kernel.
+ * For multi-GPU use (replaces the Pool of gprf.py:218-233): the status travels inside the all-reduce of
+ * the packed results; when the reduced status is non-zero every rank repeats the evaluation with
+ * gprf_llgrad_device (jitter rule / oversized blocks).  *enqueued = 0: the structure is not of the
+ * resident kind and the evaluation ran synchronously. */
+int gprf_llgrad_device_nosync(gprf_handle h, const double* X_dev, const double* theta, int ncov,
+                              int grad_X, int grad_cov, double* out_dev, double* status_dev, void* stream,
+                              int* enqueued, int* failed_unit);
 int gprf_unit_results(gprf_handle h, double* ll_units, double* jitter_units);
 
 /* Replaces GPRF.compute_neighbors (gprf.py:119-150): for every block pair
