@@ -220,8 +220,18 @@ k_bucket_small(const int* owner, long long n, int B, long long* block_ptr, long 
   __syncthreads();
   for (int b = tid; b <= B; b += blockDim.x) block_ptr[b] = start[b];
   // placement: every warp walks its points in order; rank inside a group of 32 by __match_any_sync
+  int kbits = 1;
+  while ((1 << kbits) < B) ++kbits;
   auto place = [&](long long q0, int o, bool live) {
-    const unsigned grp = __match_any_sync(0xffffffffu, live ? o : -1 - lane);      // dead lanes: distinct keys
+    // lanes holding the same owner: one ballot per key bit (__match_any_sync costs ~1500 cycles per call
+    // with ~27 distinct keys among the 32 lanes: measured 19 000 -> 13 000 cycles for this pass)
+    unsigned grp = __ballot_sync(0xffffffffu, live);
+    for (int bit = 0; bit < kbits; ++bit) {
+      const bool one = (o >> bit) & 1;
+      const unsigned mb = __ballot_sync(0xffffffffu, one);
+      grp &= one ? mb : ~mb;
+    }
+    if (!live) grp = 1u << lane;
     const int rank = __popc(grp & ((1u << lane) - 1u));
     const int leader = __ffs(grp) - 1;
     int base = 0;

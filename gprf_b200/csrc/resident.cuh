@@ -1894,6 +1894,30 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
       __syncwarp();
     }
   }
+  // A CTA without a block unit starts with a pair and waits for that pair's parent: put the pair with the
+  // smallest parent block (the first to be released) in front.  These CTAs carry one pair more than the
+  // others and finish last, so what they wait at the start is on the launch's critical path.
+  __threadfence_block();
+  __syncthreads();
+  for (int w = tid; w < G; w += nt) {
+    if (nblk(w) != 0) continue;
+    const int beg = lptr(w), cnt = lptr(w + 1) - beg;
+    int best = 0, bs = 0x7fffffff;
+    for (int k = 0; k < cnt; ++k) {
+      const int e = Q.order[beg + k] - Q.B;
+      const int i = Q.edges[2 * e];
+      const int sz = (int)(Q.block_ptr[i + 1] - Q.block_ptr[i]);
+      if (sz < bs) {
+        bs = sz;
+        best = k;
+      }
+    }
+    if (best != 0) {
+      const int t0 = Q.order[beg];
+      Q.order[beg] = Q.order[beg + best];
+      Q.order[beg + best] = t0;
+    }
+  }
   __syncthreads();
   if (tid == 0) {
     Q.counts[0] = s_nb + s_np;
