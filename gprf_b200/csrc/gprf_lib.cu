@@ -123,6 +123,7 @@ struct gprf_ctx {
 
   // resident (shared-memory) unit path, resident.cuh
   bool res_enable = true;
+  long long res_spin_limit = res::SPIN_LIMIT_CYCLES;   // watchdog of the resident kernel's spin waits (cycles)
   bool dev_blocks_valid = false;   // dPerm / dPosBlock / dBlockPtr describe the current blocks
   bool host_blocks_stale = false;  // ... and are newer than block_ptr_h / the unit descriptors
   cudaStream_t blocks_stream = nullptr;   // stream the device-held blocks were last written on
@@ -322,6 +323,10 @@ extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, in
   }
   if (const char* e = getenv("GPRF_PANEL_ORDER")) h->panel_order = atoi(e);
   if (const char* e = getenv("GPRF_RESIDENT")) h->res_enable = atoi(e) != 0;
+  if (const char* e = getenv("GPRF_RES_WATCHDOG_S")) {
+    const double sec = atof(e);
+    if (sec > 0) h->res_spin_limit = (long long)(sec * 2.0e9);
+  }
   if (const char* e = getenv("GPRF_BUCKET_SMALL")) h->bucket_small = atoi(e) != 0;
   CUDA_OK(cudaMallocHost((void**)&h->hResStatus, 4 * sizeof(int)));
   if (const char* e = getenv("GPRF_FUSED_SHARE_MIN")) h->fused_share_min = atoi(e);
@@ -1303,6 +1308,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   P.gx_u = h->dResGx;
   P.info = h->dResInfo;
   P.status = h->dResCounts + 4;
+  P.spin_limit = h->res_spin_limit;
   P.dbg_unit = h->res_dbg_unit;
   P.dbg_phase = h->res_dbg_phase;
   P.dbg_out = h->dResDbg;

@@ -86,6 +86,8 @@ enum { ST_OVERFLOW = 1, ST_NOTPD = 2, ST_TIMEOUT = 4 };
 // redone by the tile pipeline, like a structure that does not fit.  It turns any scheduling or
 // synchronisation fault (e.g. two resident launches on one GPU whose CTAs wait for each other's SMs)
 // from a hung process into a visible fallback (gprf_resident_stats).
+// The limit travels in ResParams::spin_limit (cycles; GPRF_RES_WATCHDOG_S seconds in the environment, for runs
+// under compute-sanitizer, where a launch takes minutes).
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000LL;
 
 __host__ __device__ __forceinline__ int rtri(int i) { return i * (i + 1) / 2; }
@@ -124,6 +126,7 @@ struct ResParams {
   double* gx_u;                 // per unit x GX_STRIDE
   int* info;                    // per unit: 1 + first failing local row
   int* status;
+  long long spin_limit;         // watchdog of the spin waits, in SM cycles
   int* ready;                   // per block: == epoch once the block unit's factor exports (W, Z, alpha, K, scalars) are complete
   int* ready2;                  // per block: == epoch once K^-1 (written by the block's gradient phase) is complete too
   int epoch;
@@ -231,6 +234,7 @@ struct Stage {
   uint64_t* bar;
   unsigned par;
   int* status;                  // the evaluation's status word (watchdog)
+  long long spin_limit;
 };
 __device__ __forceinline__ void tma_issue(const Stage& S, double* dst, const double* src, int nblk) {
   asm volatile("fence.proxy.async;\n" ::: "memory");      // generic-proxy writes (this CTA's, or acquired) before the copy
@@ -255,7 +259,7 @@ __device__ __forceinline__ void tma_wait(Stage& S) {
   if (!mbar_try(S.bar, S.par & 1u)) {
     const long long t0 = clock64();
     while (!mbar_try(S.bar, S.par & 1u)) {
-      if (clock64() - t0 > SPIN_LIMIT_CYCLES) {
+      if (clock64() - t0 > S.spin_limit) {
         if (S.status) atomicOr(S.status, ST_TIMEOUT);
         break;
       }
@@ -1575,7 +1579,7 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
       const long long t0 = clock64();
       while (atomicAdd(P.ready2 + c.bi, 0) != P.epoch) {
         __nanosleep(100);
-        if (clock64() - t0 > SPIN_LIMIT_CYCLES) {
+        if (clock64() - t0 > P.spin_limit) {
           atomicOr(P.status, ST_TIMEOUT);
           break;
         }
@@ -1617,6 +1621,7 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
   stage.bar = reinterpret_cast<uint64_t*>(MISC);
   stage.par = 0;
   stage.status = Pk.status;
+  stage.spin_limit = Pk.spin_limit;
   int* s_unit = reinterpret_cast<int*>(MISC + 4);
   Ctx* ctx = reinterpret_cast<Ctx*>(MISC + MISC_CTX);
   ResParams* Ps = reinterpret_cast<ResParams*>(MISC + MISC_PARAMS);
@@ -1654,7 +1659,7 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
         const long long t0 = clock64();
         while (atomicAdd(const_cast<int*>(flag), 0) != P.epoch) {
           __nanosleep(100);
-          if (clock64() - t0 > SPIN_LIMIT_CYCLES) {
+          if (clock64() - t0 > P.spin_limit) {
             atomicOr(P.status, ST_TIMEOUT);
             break;
           }

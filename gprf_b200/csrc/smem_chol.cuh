@@ -89,6 +89,7 @@ __device__ __forceinline__ void smem_potrf_trtri(double* S, double* S2, double* 
                                                  int* fail_out, int row0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, q = lane & 3;
+  int first_fail = 0;                       // warp 0: first bad pivot so far (kept in a register, stored once at the end)
   for (int J = 0; J < nb; ++J) {
     // (a) diagonal block, warp 0
     if (warp == 0) {
@@ -107,7 +108,7 @@ __device__ __forceinline__ void smem_potrf_trtri(double* S, double* S2, double* 
         for (int v = 0; v < 8; ++v) a[v] = (v == r) ? 1.0 : 0.0;
       }
       const int f = chol8_inv8(a, w, lane);
-      if (lane == 0 && f != 0 && *fail_out == 0) *fail_out = row0 + 8 * J + f;
+      if (f != 0 && first_fail == 0) first_fail = row0 + 8 * J + f;
       if (lane < 8) {
         double* dl = S + (8 * J + r) * ld + 8 * J;
         double* du = S2 + (8 * J + r) * ld + 8 * J;
@@ -173,6 +174,10 @@ __device__ __forceinline__ void smem_potrf_trtri(double* S, double* S2, double* 
       *reinterpret_cast<double2*>(S2 + (8 * K + g) * ld + 8 * I + 2 * q) = make_double2(-o0, -o1);
     }
     __syncthreads();
+  }
+  if (threadIdx.x == 0 && first_fail != 0) {       // (volatile: the load must not be hoisted above the thread test)
+    volatile int* fo = fail_out;
+    if (*fo == 0) *fo = first_fail;
   }
 }
 
