@@ -123,6 +123,8 @@ struct gprf_ctx {
 
   // resident (shared-memory) unit path, resident.cuh
   bool res_enable = true;
+  bool res_defer = true, res_sort_blocks = true;       // GPRF_RES_DEFER / GPRF_RES_SORTBLK
+  bool res_early = true;                               // pairs start once the parent's W is exported (GPRF_RES_EARLY=0: wait for all factor exports)
   long long res_spin_limit = res::SPIN_LIMIT_CYCLES;   // watchdog of the resident kernel's spin waits (cycles)
   bool dev_blocks_valid = false;   // dPerm / dPosBlock / dBlockPtr describe the current blocks
   bool host_blocks_stale = false;  // ... and are newer than block_ptr_h / the unit descriptors
@@ -323,6 +325,9 @@ extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, in
   }
   if (const char* e = getenv("GPRF_PANEL_ORDER")) h->panel_order = atoi(e);
   if (const char* e = getenv("GPRF_RESIDENT")) h->res_enable = atoi(e) != 0;
+  if (const char* e = getenv("GPRF_RES_EARLY")) h->res_early = atoi(e) != 0;
+  if (const char* e = getenv("GPRF_RES_DEFER")) h->res_defer = atoi(e) != 0;
+  if (const char* e = getenv("GPRF_RES_SORTBLK")) h->res_sort_blocks = atoi(e) != 0;
   if (const char* e = getenv("GPRF_RES_WATCHDOG_S")) {
     const double sec = atof(e);
     if (sec > 0) h->res_spin_limit = (long long)(sec * 2.0e9);
@@ -1230,6 +1235,7 @@ static void res_plan_params(gprf_ctx* h, res::PlanParams* Q) {
   Q->B = h->B;
   Q->E = h->E;
   Q->G = std::max(1, std::min(h->B + h->E, h->n_sm));
+  Q->sort_blocks = h->res_sort_blocks ? 1 : 0;
   Q->list_ptr = h->dResListPtr;
   Q->order = h->dResOrderB;        // sized for all units
   Q->counts = h->dResCounts;
@@ -1254,8 +1260,8 @@ static int res_alloc(gprf_ctx* h, int grid) {
     CUDA_OK(cudaMalloc((void**)&h->dResOrderB, cu * sizeof(int)));
     CUDA_OK(cudaMalloc((void**)&h->dResOrderP, cu * sizeof(int)));
     CUDA_OK(cudaMalloc((void**)&h->dResCounts, 8 * sizeof(int)));
-    CUDA_OK(cudaMalloc((void**)&h->dResReady, 2 * cu * sizeof(int)));
-    CUDA_OK(cudaMemset(h->dResReady, 0, 2 * cu * sizeof(int)));
+    CUDA_OK(cudaMalloc((void**)&h->dResReady, 3 * cu * sizeof(int)));
+    CUDA_OK(cudaMemset(h->dResReady, 0, 3 * cu * sizeof(int)));
     h->res_epoch = 0;
     CUDA_OK(cudaMemset(h->dResLL, 0, cu * sizeof(double)));
     CUDA_OK(cudaMemset(h->dResGth, 0, cu * MAX_NCOV * sizeof(double)));
@@ -1309,6 +1315,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   P.info = h->dResInfo;
   P.status = h->dResCounts + 4;
   P.spin_limit = h->res_spin_limit;
+  P.defer_ok = h->res_defer ? 1 : 0;
   P.dbg_unit = h->res_dbg_unit;
   P.dbg_phase = h->res_dbg_phase;
   P.dbg_out = h->dResDbg;
@@ -1316,6 +1323,7 @@ static int run_resident(gprf_ctx* h, const double* X_dev, const CovParams& cp, i
   P.trace = (h->dTrace && h->capTrace >= (size_t)h->n_sm * 2 * res::RTRACE_SLOTS) ? h->dTrace : nullptr;
   P.ready = h->dResReady;
   P.ready2 = h->dResReady + h->capResU;
+  P.ready0 = h->res_early ? h->dResReady + 2 * h->capResU : nullptr;
   P.epoch = ++h->res_epoch;
   P.order = h->dResOrderB;
   P.n_order = h->dResCounts + 0;

@@ -127,8 +127,11 @@ struct ResParams {
   int* info;                    // per unit: 1 + first failing local row
   int* status;
   long long spin_limit;         // watchdog of the spin waits, in SM cycles
+  int defer_ok;                 // a pair whose parent is still running starts with its own K_ji (GPRF_RES_DEFER)
   int* ready;                   // per block: == epoch once the block unit's factor exports (W, Z, alpha, K, scalars) are complete
   int* ready2;                  // per block: == epoch once K^-1 (written by the block's gradient phase) is complete too
+  int* ready0;                  // per block: == epoch once W = L^-1 and the saved covariance values are exported (all a pair
+                                // needs for L_ji, S and its factorisation); nullptr: pairs start on `ready`
   int epoch;
   int dbg_unit, dbg_phase;      // debug dump of R1 / R2 after a phase (-1: off)
   double* dbg_out;              // 2 x (160 x 160) doubles
@@ -310,6 +313,7 @@ __device__ __forceinline__ int first_piece(int cap, int nrows, RowLen rowlen) {
 // were demoted to local memory and the lane offsets recomputed at every use).
 struct Ctx {
   int uid, bi, bj, a, b, ab, bb, nr, nyb, pair, is_export, nF, want_grad, dx, dy, r1g;
+  int defer;                        // pair whose parent was not ready at the start: W_i is requested in ph_lji, after K_ji
   int oXS, oR1, oR2, oF;            // offsets (doubles) into the dynamic shared memory
   long long ia, ja;
   double* R1g;                      // R1 in this CTA's scratch (units of res_class 1)
@@ -543,7 +547,19 @@ static __device__ __noinline__ void ph_lji(const ResParams& P, const Ctx& c, Sta
   }
   __syncthreads();
   rtrace(P, c, 34);
-  tma_wait(stage);                    // W_i, issued by run_unit into [R2 | F]
+  if (c.defer && threadIdx.x == 0) {  // the parent was still running when this unit started
+    const long long t0 = clock64();
+    while (atomicAdd(P.ready0 + c.bi, 0) != P.epoch) {
+      __nanosleep(100);
+      if (clock64() - t0 > P.spin_limit) {
+        atomicOr(P.status, ST_TIMEOUT);
+        break;
+      }
+    }
+    __threadfence();
+    tma_issue(stage, g_smem + c.oR2, c.pexp + EXP_W, rtri(ab));
+  }
+  tma_wait(stage);                    // W_i, issued by run_unit (or just now) into [R2 | F]
   rtrace(P, c, 35);
   // L_ji(row, c0 .. c0+3) = sum_{k <= c} K_ji(row, k) W_i(c, k)^T, in place: rounds of whole rows; every
   // task of a round holds its blocks until all of the round's reads are done
@@ -784,6 +800,13 @@ static __device__ __noinline__ void ph_chol_inv(const ResParams& P, const Ctx& c
     const double* src = g_smem + R2;
     for (int e = tid; e < rtri(bb) * RBLK / 2; e += RNT)
       reinterpret_cast<double2*>(dst)[e] = reinterpret_cast<const double2*>(src)[e];
+    if (P.ready0) {
+      // The pairs of this block can start now: L_ji, S and the factorisation of S need W_i only; Z_i, the
+      // alpha rows and the scalars follow under `ready` (the pair waits for it before it requests Z_i).
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicExch(P.ready0 + c.bj, P.epoch);
+    }
   }
 }
 
@@ -1522,7 +1545,7 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
   const int tid = threadIdx.x;
   rtrace(P, c, 1);
   // W_i on its way into [R2 | F] (both still unused; res_class guarantees that all of it fits)
-  if (c.pair && tid == 0) tma_issue(stage, g_smem + c.oR2, c.pexp + EXP_W, rtri(c.ab));
+  if (c.pair && tid == 0 && !c.defer) tma_issue(stage, g_smem + c.oR2, c.pexp + EXP_W, rtri(c.ab));
   ph_gather<DFN>(P, c);
   rtrace(P, c, 33);
   if (c.pair) ph_lji<DFN, WFN, R1>(P, c, stage);
@@ -1533,7 +1556,20 @@ __device__ __forceinline__ void run_unit(const ResParams& P, const Ctx& c, Stage
   rtrace(P, c, 3);
   // Z_i (all of it, or its first piece) travels into F while S is factored
   const int nyc = max(1, min(c.nyb, c.nF / max(c.ab, c.bb)));
-  if (c.pair && tid == 0) tma_issue(stage, g_smem + c.oF, c.pexp + EXP_ZY, min(nyc, c.nyb) * c.ab);
+  if (c.pair && tid == 0) {
+    if (P.ready0) {              // started on the first flag: Z_i, alpha_i and the scalars come with the second
+      const long long t0 = clock64();
+      while (atomicAdd(P.ready + c.bi, 0) != P.epoch) {
+        __nanosleep(100);
+        if (clock64() - t0 > P.spin_limit) {
+          atomicOr(P.status, ST_TIMEOUT);
+          break;
+        }
+      }
+      __threadfence();
+    }
+    tma_issue(stage, g_smem + c.oF, c.pexp + EXP_ZY, min(nyc, c.nyb) * c.ab);
+  }
   ph_chol_inv(P, c);
   dbg_dump(P, c, 4);
   rtrace(P, c, 5);
@@ -1651,20 +1687,27 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
       ia = P.block_ptr[bi];
       a = (int)(P.block_ptr[bi + 1] - ia);
     }
+    int defer = 0;                  // (thread 0)
     if (bi >= 0) {
       // the parent block's unit (earlier in the queue, possibly still running on another SM)
       if (threadIdx.x == 0) {
         // (a pair with an empty second block copies block i's final results: second flag)
-        const int* flag = (b == 0 ? P.ready2 : P.ready) + bi;
-        const long long t0 = clock64();
-        while (atomicAdd(const_cast<int*>(flag), 0) != P.epoch) {
-          __nanosleep(100);
-          if (clock64() - t0 > P.spin_limit) {
-            atomicOr(P.status, ST_TIMEOUT);
-            break;
+        const int* flag = (b == 0 ? P.ready2 : (P.ready0 ? P.ready0 : P.ready)) + bi;
+        if (b != 0 && P.ready0 && P.defer_ok && atomicAdd(const_cast<int*>(flag), 0) != P.epoch) {
+          // Not released yet: the pair starts anyway - its coordinate records and K_ji do not need the
+          // parent - and waits in ph_lji, just before it requests W_i.
+          defer = 1;
+        } else {
+          const long long t0 = clock64();
+          while (atomicAdd(const_cast<int*>(flag), 0) != P.epoch) {
+            __nanosleep(100);
+            if (clock64() - t0 > P.spin_limit) {
+              atomicOr(P.status, ST_TIMEOUT);
+              break;
+            }
           }
+          __threadfence();
         }
-        __threadfence();
       }
       __syncthreads();
     }
@@ -1682,6 +1725,7 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
       if (threadIdx.x == 0) {
         atomicOr(P.status, ST_OVERFLOW);
         if (bi < 0) {                                        // nobody may wait forever; the tile pipeline redoes it
+          if (P.ready0) atomicExch(P.ready0 + bj, P.epoch);
           atomicExch(P.ready + bj, P.epoch);
           atomicExch(P.ready2 + bj, P.epoch);
         }
@@ -1699,6 +1743,7 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) {
+        if (P.ready0) atomicExch(P.ready0 + bj, P.epoch);
         atomicExch(P.ready + bj, P.epoch);
         atomicExch(P.ready2 + bj, P.epoch);
       }
@@ -1710,6 +1755,7 @@ __global__ void __launch_bounds__(RNT, 1) k_resident(ResParams Pk) {
       c.uid = uid; c.bi = bi; c.bj = bj; c.a = a; c.b = b; c.ab = ab; c.bb = bb; c.nr = ab + bb;
       c.nyb = P.nyb; c.pair = ab > 0; c.is_export = bi < 0; c.want_grad = P.want_grad; c.dx = P.dx; c.dy = P.dy;
       c.r1g = r1g;
+      c.defer = defer;
       c.ia = ia; c.ja = ja;
       c.oXS = OFF_XS;
       c.oR1 = OFF_XS + res_xs_blocks(ab, bb) * RBLK;
@@ -1753,6 +1799,7 @@ struct PlanParams {
   const unsigned char* active;     // per unit (B + E), or nullptr = all
   int B, E;
   int G;                           // CTAs of the resident launch
+  int sort_blocks;                 // block units in size order (GPRF_RES_SORTBLK=0: in id order)
   int* order;                      // out: the CTAs' unit lists, back to back
   int* list_ptr;                   // out: G + 1 list bounds
   int* counts;                     // out: [n units, n block units, -, -]
@@ -1768,6 +1815,7 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
   int* key = sh + Q.B;
   const int tid = threadIdx.x, nt = blockDim.x;
   __shared__ int s_over, s_nb, s_np;
+  __shared__ int s_bstart[BMAXB + 2];
   if (tid == 0) {
     s_over = 0;
     s_nb = 0;
@@ -1800,19 +1848,56 @@ __device__ __forceinline__ void res_plan_body(const PlanParams& Q, int* sh) {
   // blocks take ~75 us on 100 CTAs while the other 48 wait for them, so every CTA is "busy" until
   // then): 545 us against a mean load of 430.  Here the CTAs that must take one pair more get the
   // SMALLEST pairs, and inside each class the pairs are dealt in snake order (large with small).
-  //   blocks: the k-th needed block -> CTA k % G, slot k / G (ascending id, all about the same size)
+  //   blocks: the k-th needed block in (size class, id) order -> CTA k % G, slot k / G
   //   pairs by rank r (size descending): q = np / G, rem = np % G; the first (G - rem) q ranks go to
   //   CTAs 0 .. G-rem-1 (q each), the rest to CTAs G-rem .. G-1 (q + 1 each)
   if (tid < 32) {
-    int nb = 0;
+    // need[bq] = 1 + the block's index among the needed blocks in (size class ascending, id ascending) order: the
+    // CTAs are filled from 0 upwards and CTA 0 also gets the LARGEST pairs (below), so the smallest blocks
+    // go where the pairs are heaviest (the block-carrying CTAs with the top pairs end the launch: measured
+    // 493 us against 451 for the mean block-carrying CTA; a block unit takes 46 + 2.5 us per 8 points).
+    constexpr int NCLS = BMAXB + 2;                  // size classes 0 .. BMAXB, oversized
+    for (int v = tid; v < NCLS; v += 32) s_bstart[v] = 0;
+    __syncwarp();
+    auto cls = [&](int bq) {
+      return Q.sort_blocks ? min(NCLS - 1, (int)((Q.block_ptr[bq + 1] - Q.block_ptr[bq] + 7) >> 3)) : 0;
+    };
+    for (int b0 = 0; b0 < Q.B; b0 += 32) {
+      const int bq = b0 + tid;
+      if (bq < Q.B && need[bq]) atomicAdd(&s_bstart[cls(bq)], 1);
+    }
+    __syncwarp();
+    if (tid == 0) {
+      int at = 0;
+      for (int v = 0; v < NCLS; ++v) {
+        const int cnt = s_bstart[v];
+        s_bstart[v] = at;
+        at += cnt;
+      }
+      s_nb = at;
+    }
+    __syncwarp();
     for (int b0 = 0; b0 < Q.B; b0 += 32) {
       const int bq = b0 + tid;
       const bool f = bq < Q.B && need[bq];
-      const unsigned m = __ballot_sync(0xffffffffu, f);
-      if (f) need[bq] = 1 + nb + __popc(m & ((1u << tid) - 1u));      // 1 + its index among the needed blocks
-      nb += __popc(m);
+      const int v = f ? cls(bq) : 0;
+      unsigned grp = __ballot_sync(0xffffffffu, f);              // lanes with a needed block of the same class
+      for (int bit = 0; bit < 5; ++bit) {
+        const bool one = (v >> bit) & 1;
+        const unsigned mb = __ballot_sync(0xffffffffu, one);
+        grp &= one ? mb : ~mb;
+      }
+      if (!f) grp = 1u << tid;
+      const int leader = __ffs(grp) - 1;
+      int base = 0;
+      if (f && tid == leader) {
+        base = s_bstart[v];
+        s_bstart[v] = base + __popc(grp);
+      }
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (f) need[bq] = 1 + base + __popc(grp & ((1u << tid) - 1u));
+      __syncwarp();
     }
-    if (tid == 0) s_nb = nb;
   }
   {
     int mine = 0;
