@@ -493,14 +493,18 @@ def lbfgs_full_run():
     return out
 
 
-def kernel_sources_sha16():
-    """Hash of the device code (every kernel lives in a .cuh header; the .cu files hold the host plan
-    and the C-ABI) - the stamp of profiles/ncu_traffic.json."""
+RESIDENT_SOURCES = ("resident.cuh", "covfn.cuh", "tile_gemm.cuh", "smem_chol.cuh")
+
+
+def kernel_sources_sha16(files=None):
+    """Hash of device code - the stamp of profiles/ncu_traffic.json.  Every kernel lives in a .cuh header (the
+    .cu files hold the host plan and the C-ABI); ``files`` = the headers one kernel is compiled from (k_resident:
+    RESIDENT_SOURCES, the include closure of gprf_resident.cu), default all of them."""
     import hashlib
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "gprf_b200", "csrc")
     for fn in sorted(os.listdir(csrc)):
-        if fn.endswith(".cuh"):
+        if fn.endswith(".cuh") and (files is None or fn in files):
             with open(os.path.join(csrc, fn), "rb") as f:
                 h.update(f.read())
     return h.hexdigest()[:16]
@@ -617,7 +621,8 @@ def measure(torch, dist, args, wl_name, rank, world, local_rank, steps, warmup, 
             tj = json.load(f)
         ent = tj.get(wl_name, {}).get(roof["kernel"])
         if ent and world == 1:
-            if ent.get("sources_sha16", kernel_sources_sha16()) == kernel_sources_sha16():
+            sha = kernel_sources_sha16(RESIDENT_SOURCES if roof["kernel"] == "resident" else None)
+            if ent.get("sources_sha16", sha) == sha:
                 roof["traffic"] = ent["bytes"]
                 roof["traffic_unit"] = ent.get("unit", "bytes per launch (dram read + write)")
                 roof["traffic_source"] = ent["source"]

@@ -123,6 +123,7 @@ struct gprf_ctx {
 
   // resident (shared-memory) unit path, resident.cuh
   bool res_enable = true;
+  int bucket_split = -1;                               // placement CTAs of the split bucketing launch (GPRF_BUCKET_SPLIT; 0: one CTA, -1: one per 4096 points, at most 8)
   bool res_defer = true, res_sort_blocks = true;       // GPRF_RES_DEFER / GPRF_RES_SORTBLK
   bool res_early = true;                               // pairs start once the parent's W is exported (GPRF_RES_EARLY=0: wait for all factor exports)
   long long res_spin_limit = res::SPIN_LIMIT_CYCLES;   // watchdog of the resident kernel's spin waits (cycles)
@@ -326,6 +327,7 @@ extern "C" int gprf_create(gprf_handle* out, int device, long long n, int dx, in
   if (const char* e = getenv("GPRF_PANEL_ORDER")) h->panel_order = atoi(e);
   if (const char* e = getenv("GPRF_RESIDENT")) h->res_enable = atoi(e) != 0;
   if (const char* e = getenv("GPRF_RES_EARLY")) h->res_early = atoi(e) != 0;
+  if (const char* e = getenv("GPRF_BUCKET_SPLIT")) h->bucket_split = std::max(-1, std::min(8, atoi(e)));
   if (const char* e = getenv("GPRF_RES_DEFER")) h->res_defer = atoi(e) != 0;
   if (const char* e = getenv("GPRF_RES_SORTBLK")) h->res_sort_blocks = atoi(e) != 0;
   if (const char* e = getenv("GPRF_RES_WATCHDOG_S")) {
@@ -978,20 +980,26 @@ static int reblock_launch(gprf_ctx* h, const double* X_dev, cudaStream_t st) {
     // one CTA: stable bucketing + bounds, and the resident path's launch plan when that path follows
     BucketPlan bp;
     memset(&bp, 0, sizeof(bp));
-    size_t smb = ((size_t)BK_WARPS * B + B + 1) * sizeof(int);
+    size_t smp = 0;                      // the plan's share
     if (B == h->B && res_eligible(h) && res_sync_static(h) == GPRF_OK &&
         res_alloc(h, std::max(1, std::min(h->B + h->E, h->n_sm))) == GPRF_OK) {
       bp.enabled = 1;
       res_plan_params(h, &bp.Q);
-      smb += res::res_plan_smem(h->B, h->E, BK_WARPS * 32);
+      smp = res::res_plan_smem(h->B, h->E, BK_WARPS * 32);
       h->plan_fused = true;
     }
+    // split launch (CTA 0: totals + plan, CTAs 1 .. npl: placement over BK_WARPS * npl sub-ranges) when there
+    // are enough points for the finer ranges and their histograms fit; else one CTA does everything
+    int npl = (n >= 4096) ? (h->bucket_split >= 0 ? h->bucket_split : (int)std::min<long long>(8, n / 4096)) : 0;
+    while (npl > 0 && ((size_t)BK_WARPS * npl * B + B + 1) * sizeof(int) > 160 * 1024) npl >>= 1;
+    size_t smb = npl > 0 ? std::max(((size_t)BK_WARPS * npl * B + B + 1) * sizeof(int), ((size_t)B + 1) * sizeof(int) + smp)
+                         : ((size_t)BK_WARPS * B + B + 1) * sizeof(int) + smp;
     if (smb > 200 * 1024) {
       h->err = "bucket kernel: structure too large for one CTA";
       return GPRF_ERR_ARG;
     }
     if (smb > 48 * 1024) cudaFuncSetAttribute(k_bucket_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
-    k_bucket_small<<<1, BK_WARPS * 32, smb, st>>>(h->dOwner, n, B, h->dBlockPtr, h->dPerm, h->dPosBlock, bp);
+    k_bucket_small<<<1 + npl, BK_WARPS * 32, smb, st>>>(h->dOwner, n, B, h->dBlockPtr, h->dPerm, h->dPosBlock, bp);
     CUDA_OK(cudaGetLastError());
     h->part_launches = 2;
   } else {

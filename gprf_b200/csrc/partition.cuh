@@ -161,18 +161,68 @@ struct BucketPlan {
   int enabled;
   res::PlanParams Q;
 };
+// Launch geometry: ONE CTA does everything (gridDim.x == 1), or 1 + npl CTAs split the work - CTA 0 counts
+// the blocks' totals, writes block_ptr and builds the launch plan (which needs the block SIZES only), while
+// CTAs 1 .. npl place the points: the point range is cut into BK_WARPS * npl sub-ranges, every placement CTA
+// builds the histograms of ALL sub-ranges (redundantly; 10^4 shared-memory atomics) and places its own
+// BK_WARPS of them.  Same permutation by construction (sub-ranges in order, points of a sub-range in order);
+// the placement pass (6.6 us as one chain of n / 32 / BK_WARPS steps per warp) and the plan (~7 us) then
+// overlap instead of following each other.
+__device__ __forceinline__ void bucket_starts(int* start, int B) {     // block totals -> block starts (warp 0)
+  const int lane = threadIdx.x & 31;
+  const int per = (B + 31) / 32;
+  int tot = 0;
+  for (int b = lane * per; b < min(B, (lane + 1) * per); ++b) tot += start[b];
+  int pre = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, pre, o);
+    if (lane >= o) pre += v;
+  }
+  int at = pre - tot;
+  for (int b = lane * per; b < min(B, (lane + 1) * per); ++b) {
+    const int c = start[b];
+    start[b] = at;
+    at += c;
+  }
+  if (lane == 31) start[B] = pre;
+}
+
 __global__ void __launch_bounds__(BK_WARPS * 32, 1)
 k_bucket_small(const int* owner, long long n, int B, long long* block_ptr, long long* perm64, int* pos_block,
                BucketPlan plan) {
   extern __shared__ int bk_sh[];
-  int* wh = bk_sh;                       // [BK_WARPS][B]: counts, then exclusive prefixes over the warps
-  int* start = bk_sh + BK_WARPS * B;     // [B + 1]: block totals, then block starts
-  int* plan_sh = start + B + 1;          // (B + E) ints for the plan
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  for (int e = tid; e < BK_WARPS * B; e += blockDim.x) wh[e] = 0;
+  const bool split = gridDim.x > 1;
+  if (split && blockIdx.x == 0) {
+    // totals + plan
+    int* start = bk_sh;                  // [B + 1]
+    int* plan_sh = start + B + 1;        // (B + E) ints + the plan's histograms
+    for (int b = tid; b <= B; b += blockDim.x) start[b] = 0;
+    __syncthreads();
+    for (long long p = tid; p < n; p += blockDim.x) atomicAdd(&start[owner[p]], 1);
+    __syncthreads();
+    if (w == 0) bucket_starts(start, B);
+    __syncthreads();
+    for (int b = tid; b <= B; b += blockDim.x) block_ptr[b] = start[b];
+    if (plan.enabled) {
+      __threadfence_block();
+      __syncthreads();                   // block_ptr (global, this CTA's own writes) is read back by the plan
+      res::res_plan_body(plan.Q, plan_sh);
+    }
+    return;
+  }
+  const int npl = split ? (int)gridDim.x - 1 : 1;          // placement CTAs
+  const int cta = split ? (int)blockIdx.x - 1 : 0;
+  const int R = BK_WARPS * npl;                             // sub-ranges
+  int* wh = bk_sh;                       // [R][B]: counts, then exclusive prefixes over the sub-ranges
+  int* start = bk_sh + R * B;            // [B + 1]: block totals, then block starts
+  int* plan_sh = start + B + 1;          // (B + E) ints for the plan (single-CTA launch)
+  for (int e = tid; e < R * B; e += blockDim.x) wh[e] = 0;
   __syncthreads();
-  const long long L = (n + BK_WARPS - 1) / BK_WARPS;
-  const long long p0 = w * L, p1 = p0 + L < n ? p0 + L : n;
+  const long long L = (n + R - 1) / R;
+  const int mine = cta * BK_WARPS + w;   // the sub-range this warp places
+  const long long p0 = mine * L < n ? mine * L : n, p1 = p0 + L < n ? p0 + L : n;
   // the warp's owners: the first BK_PRE rounds stay in registers for the placement pass
   constexpr int BK_PRE = 16;
   int own[BK_PRE];
@@ -183,14 +233,20 @@ k_bucket_small(const int* owner, long long n, int B, long long* block_ptr, long 
   }
 #pragma unroll
   for (int k = 0; k < BK_PRE; ++k)
-    if (own[k] >= 0) atomicAdd(&wh[w * B + own[k]], 1);
-  for (long long p = p0 + lane + 32 * BK_PRE; p < p1; p += 32) atomicAdd(&wh[w * B + owner[p]], 1);
+    if (own[k] >= 0) atomicAdd(&wh[mine * B + own[k]], 1);
+  for (long long p = p0 + lane + 32 * BK_PRE; p < p1; p += 32) atomicAdd(&wh[mine * B + owner[p]], 1);
+  // (split launch) the other placement CTAs' sub-ranges: every CTA needs all the histograms
+  for (int r = w; r < R; r += BK_WARPS) {
+    if (r == mine || r / BK_WARPS == cta) continue;
+    const long long q0 = r * L < n ? r * L : n, q1 = q0 + L < n ? q0 + L : n;
+    for (long long p = q0 + lane; p < q1; p += 32) atomicAdd(&wh[r * B + owner[p]], 1);
+  }
   __syncthreads();
-  // per block: exclusive prefix over the warps (in place) and the block total
+  // per block: exclusive prefix over the sub-ranges (in place) and the block total
   for (int b = tid; b < B; b += blockDim.x) {
     int c = 0;
 #pragma unroll 8
-    for (int v = 0; v < BK_WARPS; ++v) {
+    for (int v = 0; v < R; ++v) {
       const int x = wh[v * B + b];
       wh[v * B + b] = c;
       c += x;
@@ -198,27 +254,10 @@ k_bucket_small(const int* owner, long long n, int B, long long* block_ptr, long 
     start[b] = c;
   }
   __syncthreads();
-  // block totals -> block starts (one warp, B <= 1024: up to 32 per lane)
-  if (w == 0) {
-    const int per = (B + 31) / 32;
-    int tot = 0;
-    for (int b = lane * per; b < min(B, (lane + 1) * per); ++b) tot += start[b];
-    int pre = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, pre, o);
-      if (lane >= o) pre += v;
-    }
-    int at = pre - tot;
-    for (int b = lane * per; b < min(B, (lane + 1) * per); ++b) {
-      const int c = start[b];
-      start[b] = at;
-      at += c;
-    }
-    if (lane == 31) start[B] = pre;
-  }
+  if (w == 0) bucket_starts(start, B);
   __syncthreads();
-  for (int b = tid; b <= B; b += blockDim.x) block_ptr[b] = start[b];
+  if (!split)
+    for (int b = tid; b <= B; b += blockDim.x) block_ptr[b] = start[b];
   // placement: every warp walks its points in order; rank inside a group of 32 by __match_any_sync
   int kbits = 1;
   while ((1 << kbits) < B) ++kbits;
@@ -236,8 +275,8 @@ k_bucket_small(const int* owner, long long n, int B, long long* block_ptr, long 
     const int leader = __ffs(grp) - 1;
     int base = 0;
     if (live && lane == leader) {
-      base = wh[w * B + o];
-      wh[w * B + o] = base + __popc(grp);
+      base = wh[mine * B + o];
+      wh[mine * B + o] = base + __popc(grp);
     }
     base = __shfl_sync(0xffffffffu, base, leader);
     if (live) {
@@ -257,7 +296,7 @@ k_bucket_small(const int* owner, long long n, int B, long long* block_ptr, long 
     const bool live = p < p1;
     place(q0, live ? owner[p] : 0, live);
   }
-  if (plan.enabled) {
+  if (!split && plan.enabled) {
     __threadfence_block();
     __syncthreads();                     // block_ptr (global, this CTA's own writes) is read back by the plan
     res::res_plan_body(plan.Q, plan_sh);

@@ -2099,19 +2099,44 @@ __global__ void k_res_combine(ResCombine C, double* out, int want_gx, int want_c
     g[1] += wgt * p[1];
     g[2] += wgt * p[2];
   }
-  for (int aidx = C.adj_ptr[bq]; aidx < C.adj_ptr[bq + 1]; ++aidx) {
-    const int e = C.adj_edge[aidx];
-    if (C.active && !C.active[C.B + e]) continue;
-    int off = 0;
-    if (C.adj_side[aidx]) {
-      const int i = C.edges[2 * e];
-      const int a = (int)(C.block_ptr[i + 1] - C.block_ptr[i]);
-      off = ((a + 7) >> 3) * 8;
+  // The block's edges, four at a time: every stage of the chain  adjacency -> edge -> size of block i -> row of
+  // the pair's gradient  is loaded for all four before the next stage starts (as one loop per edge the five
+  // dependent L2 round trips per edge made this kernel a 12 us latency chain); the sums keep the edge order.
+  const int a_end = C.adj_ptr[bq + 1];
+  for (int a0 = C.adj_ptr[bq]; a0 < a_end; a0 += 4) {
+    bool on[4];
+    int e[4], ib[4], off[4];
+    double v[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      on[u] = a0 + u < a_end;
+      e[u] = on[u] ? C.adj_edge[a0 + u] : 0;
+      ib[u] = (on[u] && C.adj_side[a0 + u]) ? 0 : -1;
     }
-    const double* p = C.gx_u + (long long)(C.B + e) * GX_STRIDE + (long long)(off + lp) * 3;
-    g[0] += p[0];
-    g[1] += p[1];
-    g[2] += p[2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (on[u] && C.active && !C.active[C.B + e[u]]) on[u] = false;
+      if (on[u] && ib[u] == 0) ib[u] = C.edges[2 * e[u]];
+      else ib[u] = -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      off[u] = ib[u] >= 0 ? (((int)(C.block_ptr[ib[u] + 1] - C.block_ptr[ib[u]]) + 7) >> 3) * 8 : 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double* p = C.gx_u + (long long)(C.B + e[u]) * GX_STRIDE + (long long)(off[u] + lp) * 3;
+      v[u][0] = on[u] ? p[0] : 0.0;
+      v[u][1] = on[u] ? p[1] : 0.0;
+      v[u][2] = on[u] ? p[2] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (on[u]) {
+        g[0] += v[u][0];
+        g[1] += v[u][1];
+        g[2] += v[u][2];
+      }
+    }
   }
   const long long n = C.perm[pos];
   for (int d = 0; d < C.dx; ++d) out[1 + MAX_NCOV + n * C.dx + d] = g[d];

@@ -209,8 +209,9 @@ def test_traffic_figure_is_stamped_with_the_kernel_sources():
     from the CUDA sources in the tree (hash stamp)."""
     import json
     import bench
-    sha = bench.kernel_sources_sha16()
-    assert len(sha) == 16 and sha == bench.kernel_sources_sha16()
+    sha = bench.kernel_sources_sha16(bench.RESIDENT_SOURCES)
+    assert len(sha) == 16 and sha == bench.kernel_sources_sha16(bench.RESIDENT_SOURCES)
+    assert sha != bench.kernel_sources_sha16()               # (all headers: the other kernels' stamp)
     tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     ent = tj["cfg2"]["resident"]
     assert set(("bytes", "sources_sha16", "source", "algorithmic_bytes")) <= set(ent)

@@ -235,18 +235,20 @@ def test_resident_sharded_partial_sums():
     assert_parity(o.llgrad(**kw), full, "full")
 
 
-def test_single_cta_bucketing_equals_radix_sort_path(monkeypatch):
-    """Re-blocking of small problems runs in ONE CTA (stable counting sort + bounds + the resident
-    path's launch plan, partition.cuh: k_bucket_small); GPRF_BUCKET_SMALL=0 keeps the cub radix sort +
-    k_block_bounds + k_res_plan launches.  Same block lists (bit-exact against numpy, empty blocks
-    included), same results to the last bit, three launches fewer."""
+@pytest.mark.parametrize("n,ncenters", [(2500, 36), (4200, 64)])
+def test_single_cta_bucketing_equals_radix_sort_path(monkeypatch, n, ncenters):
+    """Re-blocking of small problems (stable counting sort + bounds + the resident path's launch plan,
+    partition.cuh: k_bucket_small) runs in ONE CTA, or from 4096 points on as a split launch (CTA 0: block
+    totals + plan, four more CTAs: placement over finer sub-ranges; GPRF_BUCKET_SPLIT=0 keeps the one CTA);
+    GPRF_BUCKET_SMALL=0 keeps the cub radix sort + k_block_bounds + k_res_plan launches.  Same block lists
+    (bit-exact against numpy, empty blocks included), same results to the last bit, three launches fewer."""
     from gprf_b200 import GPRF, GPCov, Blocker, grid_centers
     from oracle.blocking import Blocker as OB, grid_centers as ogc
     rng = np.random.RandomState(8)
-    n, dy = 2500, 50
+    dy = 50
     Y = rng.randn(n, dy)
-    bl = Blocker(grid_centers(36))
-    bo = OB(np.asarray(ogc(36)))
+    bl = Blocker(grid_centers(ncenters))
+    bo = OB(np.asarray(ogc(ncenters)))
     th = dict(wfn_params=[1.0], dfn_params=[0.1, 0.1], dfn_str="euclidean", wfn_str="se")
     res = {}
     Xs = []
@@ -255,8 +257,10 @@ def test_single_cta_bucketing_equals_radix_sort_path(monkeypatch):
         if step == 1:
             X[:, 0] *= 0.6                     # leaves the right-hand blocks empty
         Xs.append(X)
-    for mode in ("1", "0"):
-        monkeypatch.setenv("GPRF_BUCKET_SMALL", mode)
+    modes = (("1", "4"), ("1", "0"), ("0", "4"))
+    for mode in modes:
+        monkeypatch.setenv("GPRF_BUCKET_SMALL", mode[0])
+        monkeypatch.setenv("GPRF_BUCKET_SPLIT", mode[1])
         g = GPRF(Xs[0], Y, bl.block_clusters, GPCov(**th), 0.01, neighbors=bl.neighbors())
         assert g._device_part == "grid"
         out = []
@@ -271,9 +275,10 @@ def test_single_cta_bucketing_equals_radix_sort_path(monkeypatch):
             out.append((r, launches))
         res[mode] = out
         g.close()
-    for (a, la), (b, lb) in zip(res["1"], res["0"]):
-        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
-        assert la == lb - 4, (la, lb)          # 3 cub launches + bounds + plan -> 1
+    for mode in modes[1:]:
+        for (a, la), (b, lb) in zip(res[modes[0]], res[mode]):
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+            assert la == (lb - 4 if mode[0] == "0" else lb), (la, lb)          # 3 cub launches + bounds + plan -> 1
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
