@@ -232,13 +232,19 @@ int gprf_family_timing(gprf_handle h, float* ms, int* launches);
 const char* gprf_family_name(int fam);
 
 /* ---- resident path (gprf_b200/csrc/resident.cuh) -------------------------------------------------
- * Units of small blocks (<= 128 points per block, dy <= 64) are evaluated by one CTA each, entirely
+ * Units of small blocks (<= 160 points per block, dy <= 64) are evaluated by one CTA each, entirely
  * out of shared memory: block units export their factor, pair units factor only the Schur complement
  * of block j on top of block i's exported factor (the reference computes an independent pdinv per
  * unit, gprf.py:299-330; same values to rounding).  Tried automatically by gprf_llgrad*,
  * with ONE host synchronisation per evaluation; an evaluation in which a unit does not fit or a
  * Cholesky pivot fails (the jitter rule, gpy_linalg.py:77-97) is re-run by the tile pipeline.
- * gprf_set_resident(h, 0) switches it off (env GPRF_RESIDENT=0 likewise). */
+ * gprf_set_resident(h, 0) switches it off (env GPRF_RESIDENT=0 likewise).
+ * Environment switches read at gprf_create (diagnostics and A/B runs; the defaults are the measured best):
+ *   GPRF_RES_EARLY=0      pairs wait for all of the parent block's factor exports instead of W alone
+ *   GPRF_RES_DEFER=0      a pair whose parent is still running waits at its start instead of after its own K_ji
+ *   GPRF_RES_SORTBLK=0    block units are dealt to the CTAs in id order instead of size order
+ *   GPRF_BUCKET_SPLIT=k   placement CTAs of the re-blocking launch (0: one CTA does everything; default one per 4096 points)
+ *   GPRF_RES_WATCHDOG_S=s limit of the kernel's spin waits (default ~2 s; raise it under compute-sanitizer) */
 int gprf_set_resident(gprf_handle h, int on);
 int gprf_resident_stats(gprf_handle h, long long* evals, long long* fallbacks, int* last_status);
 /* Layout constants of the resident path's export records (tests): returns their number. */
