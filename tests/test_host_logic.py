@@ -216,3 +216,5 @@ def test_traffic_figure_is_stamped_with_the_kernel_sources():
     ent = tj["cfg2"]["resident"]
     assert set(("bytes", "sources_sha16", "source", "algorithmic_bytes")) <= set(ent)
     assert ent["bytes"] < 3.5 * ent["algorithmic_bytes"]
+    # the committed figure belongs to the committed sources (otherwise bench.py reports traffic: null)
+    assert ent["sources_sha16"] == sha, "profiles/ncu_traffic.json is stale: re-capture (scripts/gpu_job_r02_final.sh)"
