@@ -2100,8 +2100,8 @@ __global__ void k_res_combine(ResCombine C, double* out, int want_gx, int want_c
     g[2] += wgt * p[2];
   }
   // The block's edges, four at a time: every stage of the chain  adjacency -> edge -> size of block i -> row of
-  // the pair's gradient  is loaded for all four before the next stage starts (as one loop per edge the five
-  // dependent L2 round trips per edge made this kernel a 12 us latency chain); the sums keep the edge order.
+  // the pair's gradient  is loaded for all four before the next stage starts; the sums keep the edge order.
+  // (Measured: the kernel stays at 12.7 us - CTA 0's walk over the unit records is what bounds it.)
   const int a_end = C.adj_ptr[bq + 1];
   for (int a0 = C.adj_ptr[bq]; a0 < a_end; a0 += 4) {
     bool on[4];
